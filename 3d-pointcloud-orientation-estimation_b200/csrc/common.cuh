@@ -1,0 +1,62 @@
+// common.cuh — shared helpers of libpcoe (error reporting, launch accounting, small device utils).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "pcoe.h"
+
+namespace pcoe {
+
+// thread-local error text + process-wide launch counter (defined in api.cu)
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline int fail(pcoe_status st, const char* fmt, ...) {
+  char buf[480];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  set_error("%s", buf);
+  return (int)st;
+}
+
+// Checks the launch that was just enqueued (cudaPeekAtLastError is legal during graph capture).
+inline int check_launch(const char* what) {
+  count_launch();
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // clear
+    return fail(PCOE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  }
+  return PCOE_OK;
+}
+
+#define PCOE_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return ::pcoe::fail(PCOE_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));       \
+  } while (0)
+
+#define PCOE_TRY(expr)        \
+  do {                        \
+    int rc_ = (expr);         \
+    if (rc_ != PCOE_OK) return rc_; \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Squared distance with the operation order and roundings of torch.sum((a - b) ** 2, -1):
+// three rounded subtractions, three rounded squares, ((x+y)+z).  No FMA contraction.
+__device__ __forceinline__ float sqdist_rn(float ax, float ay, float az, float bx, float by,
+                                           float bz) {
+  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+}  // namespace pcoe

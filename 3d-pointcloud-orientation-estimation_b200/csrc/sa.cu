@@ -1,0 +1,361 @@
+// sa.cu — pcoe_sa_forward / pcoe_sa_backward: the set-abstraction MLP
+// (PointNetSetAbstraction.forward, models/pointnet_pp_8dir.py:21-43, and its autograd).
+//
+// Forward (train):   L1 gather->GEMM->y1,stats | bn1 | L2 relu(bn(y1))->GEMM->y2,stats | bn2 |
+//                    L3 relu(bn(y2))->GEMM->y3,stats,group max/min | bn3 | out = relu(a*sel+b)
+// Backward (train):  reduce(gm,sums3) | consts3 | wgrad3, dgrad3->dz2,sums2 | consts2 |
+//                    wgrad2, dgrad2->dz1,sums1 | consts1 | wgrad1, dgrad1->scatter-add
+// Conv biases are not added in train mode: BatchNorm subtracts the batch mean, which cancels a
+// per-channel constant exactly; they only shift running_mean (and enter eval mode).
+#include "sa_common.cuh"
+#include "sa_layout.h"
+
+namespace pcoe {
+
+// ---- small kernels ---------------------------------------------------------------------------
+
+// batch statistics -> affine (scale, shift), saved (mean, invstd), running-stat update
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ bias, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float eps, float momentum, int train,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float b = bias ? bias[c] : 0.f;
+  if (train) {
+    const double mean = sums[c] / count;
+    double var = sums[C + c] / count - mean * mean;  // biased, as BatchNorm normalises
+    var = var < 0.0 ? 0.0 : var;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    mean_out[c] = (float)mean;
+    invstd_out[c] = invstd;
+    if (running_mean) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)(mean + (double)b);
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else {
+    const float invstd = 1.f / sqrtf(running_var[c] + eps);
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] + (b - running_mean[c]) * sc;
+    if (mean_out) { mean_out[c] = running_mean[c] - b; invstd_out[c] = invstd; }
+  }
+}
+
+// out = relu(a * (a >= 0 ? ymax : ymin) + b), slot = the matching arg, ysel = the selected y
+__global__ void sa_out_finalize_kernel(const float* __restrict__ ymax, const float* __restrict__ ymin,
+                                       const uint8_t* __restrict__ amax, const uint8_t* __restrict__ amin,
+                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                       size_t total, int C, float* __restrict__ out,
+                                       uint8_t* __restrict__ slot, float* __restrict__ ysel) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const float a = scale[c];
+    const bool up = a >= 0.f;
+    const float ys = up ? ymax[e] : ymin[e];
+    out[e] = fmaxf(fmaf(ys, a, shift[c]), 0.f);
+    if (slot) { slot[e] = up ? amax[e] : amin[e]; ysel[e] = ys; }
+  }
+}
+
+// gm = grad_out * [out > 0];  sums3 = (sum gm, sum gm * xhat(ysel)) per channel
+__global__ void bwd_last_reduce_kernel(const float* __restrict__ grad_out, const float* __restrict__ out,
+                                       const float* __restrict__ ysel, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, int G, int C, int groups_per_block,
+                                       float* __restrict__ gm, double* __restrict__ sums) {
+  const int g0 = blockIdx.x * groups_per_block, g1 = min(G, g0 + groups_per_block);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mu = mean[c], is = invstd[c];
+    float s0 = 0.f, s1 = 0.f;
+    for (int g = g0; g < g1; ++g) {
+      const size_t e = (size_t)g * C + c;
+      const float v = out[e] > 0.f ? grad_out[e] : 0.f;
+      gm[e] = v;
+      s0 += v;
+      s1 = fmaf(v, (ysel[e] - mu) * is, s1);
+    }
+    atomicAdd(sums + c, (double)s0);
+    atomicAdd(sums + C + c, (double)s1);
+  }
+}
+
+// (sum dz, sum dz*xhat) -> BN-backward constants (a,p,q) + parameter gradients
+__global__ void bn_bwd_consts_kernel(const double* __restrict__ sums, double count, int C,
+                                     const float* __restrict__ scale, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, float* __restrict__ a,
+                                     float* __restrict__ p, float* __restrict__ q,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s0 = sums[c], s1 = sums[C + c];
+  const double m1 = s0 / count, m2 = s1 / count;
+  const double av = scale[c];
+  const double pv = -av * (double)invstd[c] * m2;
+  a[c] = (float)av;
+  p[c] = (float)pv;
+  q[c] = (float)(-av * m1 - pv * (double)mean[c]);
+  if (dgamma) dgamma[c] = (float)s1;
+  if (dbeta) dbeta[c] = (float)s0;
+  if (dbias) dbias[c] = 0.f;  // exactly cancelled by the batch-mean subtraction
+}
+
+// ---- launch helpers --------------------------------------------------------------------------
+
+template <class AProd, class Epi, bool BT>
+static int launch_nt(const AProd& ap, const float* Bmat, int ldb, const Epi& epi, int M, int Ncols,
+                     int Kdim, cudaStream_t st, const char* what) {
+  if (Ncols > 64) {
+    auto k = gemm_nt_kernel<AProd, Epi, 8, BT>;
+    static bool attr = false;
+    if (!attr) {
+      PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_nt_smem<8>()));
+      attr = true;
+    }
+    dim3 grid(ceil_div(M, kBM), ceil_div(Ncols, 128));
+    k<<<grid, 256, gemm_nt_smem<8>(), st>>>(ap, Bmat, ldb, epi, M, Ncols, Kdim);
+  } else {
+    auto k = gemm_nt_kernel<AProd, Epi, 4, BT>;
+    static bool attr = false;
+    if (!attr) {
+      PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_nt_smem<4>()));
+      attr = true;
+    }
+    dim3 grid(ceil_div(M, kBM), 1);
+    k<<<grid, 256, gemm_nt_smem<4>(), st>>>(ap, Bmat, ldb, epi, M, Ncols, Kdim);
+  }
+  return check_launch(what);
+}
+
+template <class PProd, class QProd>
+static int launch_tn(const PProd& pp, const QProd& qp, float* out, int ldo, int M, int Ca, int Cb,
+                     cudaStream_t st, const char* what) {
+  const int ta = ceil_div(Ca, 64), tb = ceil_div(Cb, 64);
+  int splits = ceil_div(kNumSMs * 4, ta * tb);
+  const int max_splits = ceil_div(M, kWgRows * 4);
+  splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
+  int rps = ceil_div(ceil_div(M, splits), kWgRows) * kWgRows;
+  splits = ceil_div(M, rps);
+  dim3 grid(ta, tb, splits);
+  gemm_tn_kernel<PProd, QProd><<<grid, 256, 0, st>>>(pp, qp, out, ldo, M, Ca, Cb, rps);
+  return check_launch(what);
+}
+
+static int validate(const pcoe_sa_desc* d) {
+  if (!d) return fail(PCOE_ERR_NULL, "sa: desc is NULL");
+  if (d->B <= 0 || d->N <= 0 || d->S <= 0 || d->K <= 0 || d->D < 0 || d->C1 <= 0 || d->C2 <= 0 || d->C3 <= 0)
+    return fail(PCOE_ERR_BAD_SHAPE, "sa: B=%d N=%d S=%d K=%d D=%d C=(%d,%d,%d)", d->B, d->N, d->S, d->K,
+                d->D, d->C1, d->C2, d->C3);
+  if (d->group_all && (d->S != 1 || d->K != d->N))
+    return fail(PCOE_ERR_BAD_SHAPE, "sa: group_all needs S=1 and K=N (S=%d K=%d N=%d)", d->S, d->K, d->N);
+  if (d->K > 128 || (d->K & (d->K - 1)))
+    return fail(PCOE_ERR_UNSUPPORTED, "sa: K=%d must be a power of two <= 128", d->K);
+  if (d->train && (long long)d->B * d->S * d->K < 2)
+    return fail(PCOE_ERR_BAD_SHAPE, "sa: train-mode BatchNorm needs more than 1 value per channel");
+  if (d->precision != PCOE_PRECISION_FP32 && d->precision != PCOE_PRECISION_BF16)
+    return fail(PCOE_ERR_UNSUPPORTED, "sa: precision=%d", d->precision);
+  return PCOE_OK;
+}
+
+template <typename TY>
+static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float* new_xyz, const int32_t* nbr,
+                           const float* feats, const pcoe_sa_params& P, float* out, void* saved,
+                           void* workspace, cudaStream_t st) {
+  const SaLayout L = sa_layout(d);
+  char* sv = (char*)saved;
+  char* ws = (char*)workspace;
+  const int M = L.M, G = L.G, Cin = 3 + d.D;
+  const int Cs[3] = {d.C1, d.C2, d.C3};
+  const bool train = d.train != 0;
+
+  // pre-BN activations: saved for backward in train mode, transient otherwise
+  TY* y[3];
+  for (int l = 0; l < 3; ++l) y[l] = train ? (TY*)(sv + L.sv_y[l]) : (l < 2 ? (TY*)(ws + L.ws_y[l]) : nullptr);
+  float *scale[3], *shift[3], *mean[3], *invstd[3];
+  for (int l = 0; l < 3; ++l) {
+    char* base = train ? sv + L.sv_stat[l] : ws + L.ws_stat[l];
+    scale[l] = (float*)base; shift[l] = scale[l] + Cs[l]; mean[l] = shift[l] + Cs[l]; invstd[l] = mean[l] + Cs[l];
+  }
+  double* sums[3];
+  for (int l = 0; l < 3; ++l) sums[l] = train ? (double*)(ws + L.ws_sums[l]) : nullptr;
+  if (train) PCOE_CUDA(cudaMemsetAsync(ws + L.ws_sums[0], 0, L.ws_sums_bytes, st));
+  float* ymax = (float*)(ws + L.ws_ymax);
+  float* ymin = (float*)(ws + L.ws_ymin);
+  uint8_t* amax = (uint8_t*)(ws + L.ws_amax);
+  uint8_t* amin = (uint8_t*)(ws + L.ws_amin);
+
+  auto finalize = [&](int l) -> int {
+    bn_finalize_kernel<<<ceil_div(Cs[l], 128), 128, 0, st>>>(sums[l], (double)M, Cs[l], P.gamma[l], P.beta[l],
+        P.bias[l], P.running_mean[l], P.running_var[l], d.eps, d.momentum, d.train, scale[l], shift[l],
+        mean[l], invstd[l]);
+    return check_launch("bn_finalize_kernel");
+  };
+  if (!train) for (int l = 0; l < 3; ++l) PCOE_TRY(finalize(l));
+
+  GatherProd gp{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, Cin};
+  PCOE_TRY((launch_nt<GatherProd, StoreStatsEpi<TY>, false>(gp, P.W[0], Cin, StoreStatsEpi<TY>{y[0], sums[0], d.C1},
+                                                           M, d.C1, Cin, st, "sa_fwd_l1")));
+  if (train) PCOE_TRY(finalize(0));
+  BnReluProd<TY> p1{y[0], scale[0], shift[0], M, d.C1};
+  PCOE_TRY((launch_nt<BnReluProd<TY>, StoreStatsEpi<TY>, false>(p1, P.W[1], d.C1, StoreStatsEpi<TY>{y[1], sums[1], d.C2},
+                                                               M, d.C2, d.C1, st, "sa_fwd_l2")));
+  if (train) PCOE_TRY(finalize(1));
+  BnReluProd<TY> p2{y[1], scale[1], shift[1], M, d.C2};
+  GroupEpi<TY> ge{y[2], sums[2], ymax, ymin, amax, amin, d.C3, d.K};
+  PCOE_TRY((launch_nt<BnReluProd<TY>, GroupEpi<TY>, false>(p2, P.W[2], d.C2, ge, M, d.C3, d.C2, st, "sa_fwd_l3")));
+  if (train) PCOE_TRY(finalize(2));
+
+  const size_t total = (size_t)G * d.C3;
+  int blocks = (int)((total + 255) / 256);
+  blocks = blocks > kNumSMs * 8 ? kNumSMs * 8 : blocks;
+  sa_out_finalize_kernel<<<blocks, 256, 0, st>>>(ymax, ymin, amax, amin, scale[2], shift[2], total, d.C3, out,
+                                                train ? (uint8_t*)(sv + L.sv_slot) : nullptr,
+                                                train ? (float*)(sv + L.sv_ysel) : nullptr);
+  return check_launch("sa_out_finalize_kernel");
+}
+
+template <typename TY>
+static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float* new_xyz, const int32_t* nbr,
+                            const float* feats, const pcoe_sa_params& P, const float* out, const float* grad_out,
+                            const void* saved, float* grad_feats, const pcoe_sa_grads& Gr, void* workspace,
+                            cudaStream_t st) {
+  const SaLayout L = sa_layout(d);
+  const char* sv = (const char*)saved;
+  char* ws = (char*)workspace;
+  const int M = L.M, G = L.G, Cin = 3 + d.D;
+  const int Cs[3] = {d.C1, d.C2, d.C3};
+  const int Kin[3] = {Cin, d.C1, d.C2};
+
+  const TY* y[3];
+  const float *scale[3], *shift[3], *mean[3], *invstd[3];
+  for (int l = 0; l < 3; ++l) {
+    y[l] = (const TY*)(sv + L.sv_y[l]);
+    scale[l] = (const float*)(sv + L.sv_stat[l]); shift[l] = scale[l] + Cs[l];
+    mean[l] = shift[l] + Cs[l]; invstd[l] = mean[l] + Cs[l];
+  }
+  const uint8_t* slot = (const uint8_t*)(sv + L.sv_slot);
+  const float* ysel = (const float*)(sv + L.sv_ysel);
+
+  double* bs[3];
+  float *ca[3], *cp[3], *cq[3];
+  for (int l = 0; l < 3; ++l) {
+    bs[l] = (double*)(ws + L.wb_sums[l]);
+    ca[l] = (float*)(ws + L.wb_consts[l]); cp[l] = ca[l] + Cs[l]; cq[l] = cp[l] + Cs[l];
+  }
+  float* gm = (float*)(ws + L.wb_gm);
+  TY* dz[2] = {(TY*)(ws + L.wb_dz[0]), (TY*)(ws + L.wb_dz[1])};
+
+  PCOE_CUDA(cudaMemsetAsync(ws + L.wb_sums[0], 0, L.wb_sums_bytes, st));
+  for (int l = 0; l < 3; ++l)
+    PCOE_CUDA(cudaMemsetAsync(Gr.dW[l], 0, sizeof(float) * (size_t)Cs[l] * Kin[l], st));
+  if (d.D > 0 && grad_feats)
+    PCOE_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)d.B * d.N * d.D, st));
+
+  auto consts = [&](int l) -> int {
+    bn_bwd_consts_kernel<<<ceil_div(Cs[l], 128), 128, 0, st>>>(bs[l], (double)M, Cs[l], scale[l], mean[l],
+        invstd[l], ca[l], cp[l], cq[l], Gr.dgamma[l], Gr.dbeta[l], Gr.dbias[l]);
+    return check_launch("bn_bwd_consts_kernel");
+  };
+
+  {
+    const int gpb = ceil_div(G, kNumSMs * 2);
+    bwd_last_reduce_kernel<<<ceil_div(G, gpb), 256, 0, st>>>(grad_out, out, ysel, mean[2], invstd[2], G, d.C3,
+                                                            gpb, gm, bs[2]);
+    PCOE_TRY(check_launch("bwd_last_reduce_kernel"));
+  }
+  PCOE_TRY(consts(2));
+
+  // layer 3
+  DyLastProd<TY> dy3{gm, slot, y[2], ca[2], cp[2], cq[2], M, d.C3, d.K};
+  BnReluProd<TY> x2{y[1], scale[1], shift[1], M, d.C2};
+  PCOE_TRY((launch_tn(dy3, x2, Gr.dW[2], d.C2, M, d.C3, d.C2, st, "sa_bwd_wgrad3")));
+  MaskStatsEpi<TY> me2{y[1], scale[1], shift[1], mean[1], invstd[1], dz[1], bs[1], d.C2};
+  PCOE_TRY((launch_nt<DyLastProd<TY>, MaskStatsEpi<TY>, true>(dy3, P.W[2], d.C2, me2, M, d.C2, d.C3, st, "sa_bwd_dgrad3")));
+  PCOE_TRY(consts(1));
+
+  // layer 2
+  DyProd<TY> dy2{dz[1], y[1], ca[1], cp[1], cq[1], M, d.C2};
+  BnReluProd<TY> x1{y[0], scale[0], shift[0], M, d.C1};
+  PCOE_TRY((launch_tn(dy2, x1, Gr.dW[1], d.C1, M, d.C2, d.C1, st, "sa_bwd_wgrad2")));
+  MaskStatsEpi<TY> me1{y[0], scale[0], shift[0], mean[0], invstd[0], dz[0], bs[0], d.C1};
+  PCOE_TRY((launch_nt<DyProd<TY>, MaskStatsEpi<TY>, true>(dy2, P.W[1], d.C1, me1, M, d.C1, d.C2, st, "sa_bwd_dgrad2")));
+  PCOE_TRY(consts(0));
+
+  // layer 1
+  DyProd<TY> dy1{dz[0], y[0], ca[0], cp[0], cq[0], M, d.C1};
+  GatherProd x0{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, Cin};
+  PCOE_TRY((launch_tn(dy1, x0, Gr.dW[0], Cin, M, d.C1, Cin, st, "sa_bwd_wgrad1")));
+  if (d.D > 0 && grad_feats) {
+    ScatterEpi se{grad_feats, nbr, d.N, d.S, d.K, d.D, d.group_all};
+    PCOE_TRY((launch_nt<DyProd<TY>, ScatterEpi, true>(dy1, P.W[0], Cin, se, M, Cin, d.C1, st, "sa_bwd_dgrad1")));
+  }
+  return PCOE_OK;
+}
+
+}  // namespace pcoe
+
+using namespace pcoe;
+
+extern "C" size_t pcoe_sa_saved_bytes(const pcoe_sa_desc* desc) {
+  if (validate(desc) != PCOE_OK) return 0;
+  return sa_layout(*desc).saved_bytes;
+}
+
+extern "C" size_t pcoe_sa_workspace_bytes(const pcoe_sa_desc* desc) {
+  if (validate(desc) != PCOE_OK) return 0;
+  return sa_layout(*desc).workspace_bytes;
+}
+
+extern "C" int pcoe_sa_forward(const pcoe_sa_desc* desc, const float* xyz, const float* new_xyz,
+                               const int32_t* nbr, const float* feats, const pcoe_sa_params* params,
+                               float* out, void* saved, size_t saved_bytes, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  PCOE_TRY(validate(desc));
+  const pcoe_sa_desc& d = *desc;
+  if (!xyz || !params || !out || !workspace) return fail(PCOE_ERR_NULL, "sa_forward: NULL pointer");
+  if (!d.group_all && (!new_xyz || !nbr)) return fail(PCOE_ERR_NULL, "sa_forward: new_xyz/nbr is NULL");
+  if (d.D > 0 && !feats) return fail(PCOE_ERR_NULL, "sa_forward: feats is NULL but D=%d", d.D);
+  for (int l = 0; l < 3; ++l)
+    if (!params->W[l] || !params->gamma[l] || !params->beta[l] || !params->running_mean[l] || !params->running_var[l])
+      return fail(PCOE_ERR_NULL, "sa_forward: parameter pointer of layer %d is NULL", l + 1);
+  const SaLayout L = sa_layout(d);
+  if (d.train && (!saved || saved_bytes < L.saved_bytes))
+    return fail(PCOE_ERR_WORKSPACE, "sa_forward: saved buffer %zu < %zu bytes", saved_bytes, L.saved_bytes);
+  if (workspace_bytes < L.workspace_bytes)
+    return fail(PCOE_ERR_WORKSPACE, "sa_forward: workspace %zu < %zu bytes", workspace_bytes, L.workspace_bytes);
+  if (d.precision == PCOE_PRECISION_BF16)
+    return sa_forward_impl<__nv_bfloat16>(d, xyz, new_xyz, nbr, feats, *params, out, saved, workspace, (cudaStream_t)stream);
+  return sa_forward_impl<float>(d, xyz, new_xyz, nbr, feats, *params, out, saved, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int pcoe_sa_backward(const pcoe_sa_desc* desc, const float* xyz, const float* new_xyz,
+                                const int32_t* nbr, const float* feats, const pcoe_sa_params* params,
+                                const float* out, const float* grad_out, const void* saved,
+                                size_t saved_bytes, float* grad_feats, const pcoe_sa_grads* grads,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  PCOE_TRY(validate(desc));
+  const pcoe_sa_desc& d = *desc;
+  if (!d.train) return fail(PCOE_ERR_UNSUPPORTED, "sa_backward: only defined for a train-mode forward");
+  if (!xyz || !params || !out || !grad_out || !saved || !grads || !workspace)
+    return fail(PCOE_ERR_NULL, "sa_backward: NULL pointer");
+  if (!d.group_all && (!new_xyz || !nbr)) return fail(PCOE_ERR_NULL, "sa_backward: new_xyz/nbr is NULL");
+  if (d.D > 0 && !feats) return fail(PCOE_ERR_NULL, "sa_backward: feats is NULL but D=%d", d.D);
+  for (int l = 0; l < 3; ++l)
+    if (!params->W[l] || !grads->dW[l]) return fail(PCOE_ERR_NULL, "sa_backward: W/dW of layer %d is NULL", l + 1);
+  const SaLayout L = sa_layout(d);
+  if (saved_bytes < L.saved_bytes)
+    return fail(PCOE_ERR_WORKSPACE, "sa_backward: saved buffer %zu < %zu bytes", saved_bytes, L.saved_bytes);
+  if (workspace_bytes < L.workspace_bytes)
+    return fail(PCOE_ERR_WORKSPACE, "sa_backward: workspace %zu < %zu bytes", workspace_bytes, L.workspace_bytes);
+  if (d.precision == PCOE_PRECISION_BF16)
+    return sa_backward_impl<__nv_bfloat16>(d, xyz, new_xyz, nbr, feats, *params, out, grad_out, saved, grad_feats,
+                                           *grads, workspace, (cudaStream_t)stream);
+  return sa_backward_impl<float>(d, xyz, new_xyz, nbr, feats, *params, out, grad_out, saved, grad_feats, *grads,
+                                 workspace, (cudaStream_t)stream);
+}

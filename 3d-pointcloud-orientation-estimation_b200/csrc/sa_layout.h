@@ -1,0 +1,60 @@
+// sa_layout.h — byte offsets inside the `saved` and `workspace` buffers of pcoe_sa_forward /
+// pcoe_sa_backward.  Everything is 256-byte aligned; forward and backward share one workspace
+// (the regions overlap in time, not in use).
+#pragma once
+#include "common.cuh"
+
+namespace pcoe {
+
+struct SaLayout {
+  int M, G;        // rows = B*S*K, groups = B*S
+  size_t esz;      // bytes per stored activation element (4 fp32, 2 bf16)
+  // saved (train only)
+  size_t sv_y[3], sv_stat[3], sv_slot, sv_ysel, saved_bytes;
+  // workspace, forward
+  size_t ws_sums[3], ws_sums_bytes, ws_ymax, ws_ymin, ws_amax, ws_amin, ws_y[2], ws_stat[3];
+  // workspace, backward
+  size_t wb_sums[3], wb_sums_bytes, wb_consts[3], wb_gm, wb_dz[2];
+  size_t workspace_bytes;
+};
+
+inline SaLayout sa_layout(const pcoe_sa_desc& d) {
+  SaLayout L;
+  L.M = d.B * d.S * d.K;
+  L.G = d.B * d.S;
+  L.esz = d.precision == PCOE_PRECISION_BF16 ? 2 : 4;
+  const int C[3] = {d.C1, d.C2, d.C3};
+  auto take = [](size_t& cur, size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
+
+  size_t s = 0;
+  for (int l = 0; l < 3; ++l) L.sv_y[l] = take(s, (size_t)L.M * C[l] * L.esz);
+  for (int l = 0; l < 3; ++l) L.sv_stat[l] = take(s, sizeof(float) * 4 * C[l]);
+  L.sv_slot = take(s, (size_t)L.G * d.C3);
+  L.sv_ysel = take(s, sizeof(float) * (size_t)L.G * d.C3);
+  L.saved_bytes = d.train ? s : 0;
+
+  size_t f = 0;
+  for (int l = 0; l < 3; ++l) L.ws_sums[l] = take(f, sizeof(double) * 2 * C[l]);
+  L.ws_sums_bytes = f - L.ws_sums[0];
+  L.ws_ymax = take(f, sizeof(float) * (size_t)L.G * d.C3);
+  L.ws_ymin = take(f, sizeof(float) * (size_t)L.G * d.C3);
+  L.ws_amax = take(f, (size_t)L.G * d.C3);
+  L.ws_amin = take(f, (size_t)L.G * d.C3);
+  for (int l = 0; l < 3; ++l) L.ws_stat[l] = take(f, sizeof(float) * 4 * C[l]);
+  L.ws_y[0] = L.ws_y[1] = 0;
+  if (!d.train)
+    for (int l = 0; l < 2; ++l) L.ws_y[l] = take(f, (size_t)L.M * C[l] * L.esz);
+
+  size_t b = 0;
+  for (int l = 0; l < 3; ++l) L.wb_sums[l] = take(b, sizeof(double) * 2 * C[l]);
+  L.wb_sums_bytes = b - L.wb_sums[0];
+  for (int l = 0; l < 3; ++l) L.wb_consts[l] = take(b, sizeof(float) * 3 * C[l]);
+  L.wb_gm = take(b, sizeof(float) * (size_t)L.G * d.C3);
+  for (int l = 0; l < 2; ++l) L.wb_dz[l] = take(b, (size_t)L.M * C[l] * L.esz);
+  if (!d.train) b = 0;
+
+  L.workspace_bytes = f > b ? f : b;
+  return L;
+}
+
+}  // namespace pcoe

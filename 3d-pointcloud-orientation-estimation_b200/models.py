@@ -1,0 +1,196 @@
+"""Drop-in model classes: same constructors, ``forward(xyz)`` contracts and ``state_dict`` keys as
+the reference, with the three set-abstraction layers running in libpcoe.
+
+    PointNetPP8Dir          models/pointnet_pp_8dir.py:58-85      logits (B,8)
+    PointNetPPVonMises      models/pointnet_pp_vonMises.py:8-38   mu (B,), kappa (B,)
+    PointNetPPMvM           models/pointnet_pp_mvM.py:30-127      mu, kappa, weight (B,K)
+    PointNetPPXYZ           models/Pointnet_pp_xyz.py:47-90       two unit vectors (B,3)
+    PointNetPP              models/pointnet_pp.py:45-68           (B,3)
+    PointNetPPXYZ_Schedmit  models/Pointnet_pp_xyz_Schedmit.py:47-92   two unit vectors (B,3)
+    PointNetPPFwd           models/pointnet_pp_Fwd.py:77-98       unit vector (B,3) (device randperm)
+
+The 1024->512->256 trunk and the heads (1.3 MFLOP per cloud) stay ordinary torch modules - the
+boundary SURVEY.md draws - so optimizers, clipping and checkpoints work unchanged.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .sa import PointNetSetAbstraction
+
+# 8 horizontal directions, 45 degree steps starting from the original "forward" [0,0,-1]
+# (values of models/pointnet_pp_8dir.py:46-55; imported by train_8dir_KL.py:14)
+DIRS_8 = torch.tensor([[math.sin(math.radians(45 * k)), 0.0, -math.cos(math.radians(45 * k))] for k in range(8)],
+                      dtype=torch.float64).mul(1e4).round().div(1e4).float() + 0.0
+
+
+class _Backbone(nn.Module):
+    """sa1/sa2/sa3 + fc1/fc2 with the reference's attribute names."""
+
+    def __init__(self, norm: str = "bn", p_drop: float = 0.5, sa_kwargs: dict | None = None):
+        super().__init__()
+        kw = dict(sa_kwargs or {})
+        self.sa1 = PointNetSetAbstraction(128, 32, 0, [64, 64, 128], **kw)
+        self.sa2 = PointNetSetAbstraction(32, 32, 128, [128, 128, 256], **kw)
+        self.sa3 = PointNetSetAbstraction(None, None, 256, [256, 512, 1024], group_all=True,
+                                          **{k: v for k, v in kw.items() if k == "precision"})
+        # registration order = the reference's, so state_dict() iterates identically
+        self.fc1 = nn.Linear(1024, 512)
+        if norm == "bn":
+            self.bn1 = nn.BatchNorm1d(512)
+        else:
+            self.ln1 = nn.LayerNorm(512)
+        self.fc2 = nn.Linear(512, 256)
+        if norm == "bn":
+            self.bn2 = nn.BatchNorm1d(256)
+        else:
+            self.ln2 = nn.LayerNorm(256)
+        self.drop = nn.Dropout(p_drop)
+
+    def _sa_features(self, xyz: torch.Tensor) -> torch.Tensor:
+        B = xyz.size(0)
+        l1_xyz, l1_pts = self.sa1(xyz, None)
+        l2_xyz, l2_pts = self.sa2(l1_xyz, l1_pts)
+        _, l3_pts = self.sa3(l2_xyz, l2_pts)
+        return l3_pts.view(B, -1)
+
+    def _bn_trunk(self, xyz: torch.Tensor) -> torch.Tensor:
+        x = self._sa_features(xyz)
+        x = F.relu(self.bn1(self.fc1(x)))
+        x = F.relu(self.bn2(self.fc2(x)))
+        return self.drop(x)
+
+
+class PointNetPP8Dir(_Backbone):
+    def __init__(self, **sa_kwargs):
+        super().__init__("bn", 0.5, sa_kwargs)
+        self.fc3 = nn.Linear(256, 8)
+
+    def forward(self, xyz):
+        return self.fc3(self._bn_trunk(xyz))
+
+
+class PointNetPPVonMises(_Backbone):
+    def __init__(self, **sa_kwargs):
+        super().__init__("bn", 0.5, sa_kwargs)
+        self.fc3 = nn.Linear(256, 2)
+
+    def forward(self, xyz):
+        out = self.fc3(self._bn_trunk(xyz))
+        mu = torch.tanh(out[:, 0]) * math.pi
+        kappa = F.softplus(out[:, 1])
+        return mu, kappa
+
+
+class PointNetPP(_Backbone):
+    def __init__(self, **sa_kwargs):
+        super().__init__("bn", 0.5, sa_kwargs)
+        self.fc3 = nn.Linear(256, 3)
+
+    def forward(self, x):
+        return self.fc3(self._bn_trunk(x))
+
+
+class PointNetPPFwd(_Backbone):
+    """The reference draws its random subset on the device in this variant (pointnet_pp_Fwd.py:44-47)."""
+
+    def __init__(self, **sa_kwargs):
+        sa_kwargs.setdefault("sampler", "randperm_device")
+        super().__init__("bn", 0.5, sa_kwargs)
+        self.fc3 = nn.Linear(256, 3)
+
+    def forward(self, xyz):
+        return F.normalize(self.fc3(self._bn_trunk(xyz)), dim=1)
+
+
+class PointNetPPXYZ(_Backbone):
+    def __init__(self, **sa_kwargs):
+        super().__init__("bn", 0.5, sa_kwargs)
+        self.head_x = nn.Linear(256, 3)
+        self.head_y = nn.Linear(256, 3)
+
+    def forward(self, x):
+        feat = self._bn_trunk(x)
+        return F.normalize(self.head_x(feat), p=2, dim=1), F.normalize(self.head_y(feat), p=2, dim=1)
+
+
+class PointNetPPXYZ_Schedmit(_Backbone):
+    def __init__(self, **sa_kwargs):
+        super().__init__("bn", 0.5, sa_kwargs)
+        self.head_y = nn.Linear(256, 3)
+        self.head_z = nn.Linear(256, 3)
+
+    def forward(self, x):
+        feat = self._bn_trunk(x)
+        return F.normalize(self.head_y(feat), p=2, dim=1), F.normalize(self.head_z(feat), p=2, dim=1)
+
+
+def _maybe_transpose_xyz(xyz: torch.Tensor) -> torch.Tensor:
+    """Accept (B,N,3) or (B,3,N); return (B,N,3).  Same acceptance rule and errors as
+    models/pointnet_pp_mvM.py:15-27 (which goes to (B,3,N) and straight back, :77)."""
+    assert xyz.dim() == 3, f"xyz should be 3D tensor, got {xyz.shape}"
+    B, A, Cc = xyz.shape
+    if Cc == 3:
+        return xyz
+    if A == 3:
+        return xyz.transpose(1, 2).contiguous()
+    raise ValueError(f"xyz must be (B,N,3) or (B,3,N), got {xyz.shape}")
+
+
+class PointNetPPMvM(_Backbone):
+    """Mixture-of-von-Mises head.  The three host synchronisations of the reference forward
+    (isfinite prints and the ``(norm < 1e-3).any()`` branch, :98,108,118) are removed: the fallback
+    ``where`` is applied unconditionally, which is value- and gradient-identical."""
+
+    def __init__(self, max_K: int = 4, kappa_max: float = 80.0, p_drop: float = 0.4, temp: float = 0.7, **sa_kwargs):
+        super().__init__("ln", p_drop, sa_kwargs)
+        self.max_K = max_K
+        self.kappa_max = float(kappa_max)
+        self.temp = float(temp)
+        hidden = 256
+        self.head_pi = nn.Linear(hidden, max_K)
+        self.head_mu = nn.Linear(hidden, max_K * 2)
+        self.head_kappa = nn.Linear(hidden, max_K)
+        nn.init.zeros_(self.head_pi.weight)
+        nn.init.zeros_(self.head_pi.bias)
+        nn.init.zeros_(self.head_mu.weight)
+        nn.init.zeros_(self.head_mu.bias)
+        nn.init.constant_(self.head_kappa.bias, 0.0)
+
+    def _global_feat(self, xyz_bn3: torch.Tensor) -> torch.Tensor:
+        x = self._sa_features(xyz_bn3)
+        x = self.drop(F.relu(self.ln1(self.fc1(x))))
+        x = self.drop(F.relu(self.ln2(self.fc2(x))))
+        return x
+
+    def forward(self, xyz: torch.Tensor):
+        feat = self._global_feat(_maybe_transpose_xyz(xyz))
+        weight = F.softmax(self.head_pi(feat) / self.temp, dim=-1)
+        mu_raw = self.head_mu(feat).view(-1, self.max_K, 2)
+        mu_unit = F.normalize(mu_raw, dim=-1, eps=1e-4)
+        c, s = mu_unit[..., 0], mu_unit[..., 1]
+        norm = torch.sqrt(c * c + s * s)
+        mask = norm < 1e-3
+        c = torch.where(mask, torch.ones_like(c), c)
+        s = torch.where(mask, torch.zeros_like(s), s)
+        mu = torch.atan2(s, c)
+        kappa = F.softplus(self.head_kappa(feat)) + 1e-6
+        if self.kappa_max is not None:
+            kappa = kappa.clamp_max(self.kappa_max)
+        return mu, kappa, weight
+
+
+@torch.no_grad()
+def mvm_density_on_grid(mu, kappa, weight, num=360, device=None):
+    """Mixture density on [0, 2*pi).  Reference: models/pointnet_pp_mvM.py:130-144."""
+    device = device or mu.device
+    theta = torch.linspace(0.0, 2 * math.pi, steps=num, device=device, dtype=mu.dtype)[:-1]
+    th = theta[None, None, :]
+    vm = torch.exp(kappa[..., None] * torch.cos(th - mu[..., None])) / (2 * math.pi * torch.i0(kappa[..., None]))
+    p = (weight[..., None] * vm).sum(dim=1)
+    p = p / (p.sum(dim=-1, keepdim=True) + 1e-8)
+    return theta.squeeze(), p

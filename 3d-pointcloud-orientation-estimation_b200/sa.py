@@ -1,0 +1,219 @@
+"""Drop-in ``PointNetSetAbstraction`` and the ``models/base.py`` helpers, backed by libpcoe.
+
+Reference: models/pointnet_pp_8dir.py:6-43 (the canonical SA layer; byte-identical copies live in
+Pointnet_pp_xyz.py, pointnet_pp.py, Pointnet_pp_xyz_Schedmit.py, pointnet_pp_Fwd.py) and
+models/base.py:4-35.  Constructor signature, attribute names (npoint, nsample, group_all, convs,
+bns) and therefore the ``state_dict`` layout are the reference's; the extra keyword-only arguments
+select what the reference hard-codes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+_DEFAULT_PRECISION = "fp32"
+
+
+def set_default_precision(p: str) -> None:
+    """'fp32' (CUDA-core fp32 GEMMs, the parity mode) or 'bf16' (tcgen05 bf16 operands, fp32 accumulate)."""
+    global _DEFAULT_PRECISION
+    if p not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _DEFAULT_PRECISION = p
+
+
+def get_default_precision() -> str:
+    return _DEFAULT_PRECISION
+
+
+# ------------------------------------------------------------------------------------------------
+# models/base.py helpers (same names, same argument meaning)
+# ------------------------------------------------------------------------------------------------
+def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """points (B,N,C), idx (B,S) or (B,S,K) -> gathered points.  Reference: models/base.py:4-18."""
+    if idx.dim() == 2:
+        return ops.gather_points(points, idx.to(torch.int32))
+    B, S, K = idx.shape
+    return ops.gather_points(points, idx.reshape(B, S * K).to(torch.int32)).view(B, S, K, -1)
+
+
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """(B,N,M) squared distances.  Reference: models/base.py:20-27.  Kept for API completeness
+    (device torch ops); the hot path never materialises this matrix."""
+    dist = -2 * torch.matmul(src, dst.transpose(2, 1))
+    dist += torch.sum(src ** 2, dim=-1).unsqueeze(-1)
+    dist += torch.sum(dst ** 2, dim=-1).unsqueeze(1)
+    return dist
+
+
+def query_ball_point(new_xyz: torch.Tensor, xyz: torch.Tensor, nsample: int) -> torch.Tensor:
+    """kNN indices (B,S,nsample) int64 (the reference's misnamed helper, models/base.py:29-35)."""
+    return ops.knn_int32(new_xyz, xyz, nsample).long()
+
+
+# ------------------------------------------------------------------------------------------------
+_workspaces: dict = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _fill3(arr, tensors):
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+
+
+class _SAFunction(torch.autograd.Function):
+    """pcoe_sa_forward / pcoe_sa_backward as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, nbr, feats, module, *params):
+        # params = (W1,b1,g1,be1, W2,b2,g2,be2, W3,b3,g3,be3)
+        lib = _lib.load()
+        B, N, _ = xyz.shape
+        group_all = module.group_all
+        S = 1 if group_all else new_xyz.size(1)
+        K = N if group_all else nbr.size(2)
+        D = 0 if feats is None else feats.size(2)
+        Ws, bs, gs, bes = params[0::4], params[1::4], params[2::4], params[3::4]
+        train = module.training
+        desc = _lib.SADesc(B=B, N=N, S=S, K=K, D=D, C1=Ws[0].size(0), C2=Ws[1].size(0), C3=Ws[2].size(0),
+                           group_all=int(group_all), train=int(train),
+                           precision=_lib.PRECISION_BF16 if module.precision == "bf16" else _lib.PRECISION_FP32,
+                           eps=module.bns[0].eps, momentum=module.bns[0].momentum or 0.1)
+        P = _lib.SAParams()
+        _fill3(P.W, Ws); _fill3(P.bias, bs); _fill3(P.gamma, gs); _fill3(P.beta, bes)
+        _fill3(P.running_mean, [bn.running_mean for bn in module.bns])
+        _fill3(P.running_var, [bn.running_var for bn in module.bns])
+        sv_bytes = lib.pcoe_sa_saved_bytes(C.byref(desc))
+        ws_bytes = lib.pcoe_sa_workspace_bytes(C.byref(desc))
+        if ws_bytes == 0:
+            _lib.check(lib.pcoe_sa_forward(C.byref(desc), None, None, None, None, C.byref(P), None, None, 0, None, 0, None))
+        saved = torch.empty(sv_bytes, dtype=torch.uint8, device=xyz.device) if train else None
+        ws = _workspace(xyz.device, ws_bytes)
+        out = torch.empty(B, S, Ws[2].size(0), dtype=torch.float32, device=xyz.device)
+        _lib.check(lib.pcoe_sa_forward(C.byref(desc), xyz.data_ptr(), ops._ptr(new_xyz), ops._ptr(nbr),
+                                       ops._ptr(feats), C.byref(P), out.data_ptr(), ops._ptr(saved), sv_bytes,
+                                       ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+        if train:
+            for bn in module.bns:
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked.add_(1)
+        ctx.desc, ctx.P, ctx.train = desc, P, train
+        ctx.has_feats = feats is not None
+        ctx.param_shapes = [p.shape for p in params]
+        ctx.save_for_backward(xyz, new_xyz, nbr, feats, out, saved, *Ws)
+        ctx.keep = (bs, gs, bes, [bn.running_mean for bn in module.bns], [bn.running_var for bn in module.bns])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if not ctx.train:
+            raise NotImplementedError("pcoe: backward through an eval-mode set-abstraction layer is not implemented "
+                                      "(the reference never trains with BatchNorm in eval mode)")
+        lib = _lib.load()
+        xyz, new_xyz, nbr, feats, out, saved, W1, W2, W3 = ctx.saved_tensors
+        desc, P = ctx.desc, ctx.P
+        dev = xyz.device
+        grads = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.param_shapes]
+        G = _lib.SAGrads()
+        _fill3(G.dW, grads[0::4]); _fill3(G.dbias, grads[1::4]); _fill3(G.dgamma, grads[2::4]); _fill3(G.dbeta, grads[3::4])
+        gfeats = torch.empty_like(feats) if (ctx.has_feats and ctx.needs_input_grad[3]) else None
+        ws = _workspace(dev, lib.pcoe_sa_workspace_bytes(C.byref(desc)))
+        _lib.check(lib.pcoe_sa_backward(C.byref(desc), xyz.data_ptr(), ops._ptr(new_xyz), ops._ptr(nbr),
+                                        ops._ptr(feats), C.byref(P), out.data_ptr(),
+                                        grad_out.contiguous().data_ptr(), saved.data_ptr(), saved.numel(),
+                                        ops._ptr(gfeats), C.byref(G), ws.data_ptr(), ws.numel(),
+                                        torch.cuda.current_stream().cuda_stream))
+        return (None, None, None, gfeats, None, *grads)
+
+
+class PointNetSetAbstraction(nn.Module):
+    """Sample -> group -> centre -> 3 x (1x1 conv, BatchNorm, ReLU) -> max over neighbours.
+
+    Positional arguments are the reference's (models/pointnet_pp_8dir.py:7).  Keyword-only extras:
+
+    sampler   'randperm_host' (default; the reference: ``torch.randperm(N)[:npoint]`` per cloud on the
+              CPU generator, :28 - index-exact under the same ``torch.manual_seed``), 'randperm_device'
+              (same distribution drawn by a CUDA kernel, no host work; pointnet_pp_Fwd.py:44-47),
+              or 'fps' (true farthest-point sampling, PointNet++Demo.py:8-29).
+    grouper   'knn' (default; what the reference's ``query_ball_point`` computes, base.py:29-35) or
+              'ball' (radius query of PointNet++Demo.py:49-70; needs ``radius``).
+    precision 'fp32' | 'bf16' | None (= pcoe default at call time).
+    """
+
+    def __init__(self, npoint, nsample, in_channel, mlp_channels, group_all=False, *,
+                 sampler: str = "randperm_host", grouper: str = "knn", radius: float | None = None,
+                 precision: str | None = None):
+        super().__init__()
+        if len(mlp_channels) != 3:
+            raise NotImplementedError("pcoe: the fused set-abstraction kernels implement the reference's 3-layer MLP")
+        if sampler not in ("randperm_host", "randperm_device", "fps"):
+            raise ValueError(f"unknown sampler {sampler!r}")
+        if grouper not in ("knn", "ball") or (grouper == "ball" and radius is None):
+            raise ValueError("grouper must be 'knn' or 'ball' (with radius)")
+        self.npoint = npoint
+        self.nsample = nsample
+        self.group_all = group_all
+        self.sampler, self.grouper, self.radius = sampler, grouper, radius
+        self._precision = precision
+        self._calls = 0
+        self.last_fps_idx = None
+        self.last_group_idx = None
+
+        last_ch = in_channel + 3
+        self.convs = nn.ModuleList()
+        self.bns = nn.ModuleList()
+        for out_ch in mlp_channels:
+            self.convs.append(nn.Conv2d(last_ch, out_ch, 1))
+            self.bns.append(nn.BatchNorm2d(out_ch))
+            last_ch = out_ch
+
+    @property
+    def precision(self) -> str:
+        return self._precision or _DEFAULT_PRECISION
+
+    def _sample(self, xyz: torch.Tensor) -> torch.Tensor:
+        B, N, _ = xyz.shape
+        if self.sampler == "randperm_host":
+            idx = torch.stack([torch.randperm(N)[:self.npoint] for _ in range(B)])
+            return idx.to(torch.int32).to(xyz.device, non_blocking=True)
+        if self.sampler == "randperm_device":
+            self._calls += 1
+            return ops.random_subset(B, N, self.npoint, torch.initial_seed(), (id(self) << 20) ^ self._calls, xyz.device)
+        return ops.farthest_point_sample(xyz, self.npoint).to(torch.int32)
+
+    def forward(self, xyz, points, fps_idx=None):
+        if xyz.dim() != 3 or xyz.size(-1) != 3:
+            raise ValueError(f"xyz must be (B,N,3), got {tuple(xyz.shape)}")
+        if not xyz.is_cuda:
+            raise RuntimeError("pcoe: PointNetSetAbstraction runs on CUDA only (no CPU fallback); move the model and "
+                               "inputs to a B200")
+        xyz = xyz.contiguous().float()
+        feats = None if points is None else points.contiguous().float()
+        params = []
+        for conv, bn in zip(self.convs, self.bns):
+            params += [conv.weight, conv.bias, bn.weight, bn.bias]
+        if self.group_all:
+            new_xyz = torch.zeros(xyz.size(0), 1, 3, device=xyz.device)
+            out = _SAFunction.apply(xyz, None, None, feats, self, *params)
+            return new_xyz, out
+        idx32 = self._sample(xyz) if fps_idx is None else fps_idx.to(torch.int32).to(xyz.device)
+        new_xyz = ops.gather_points(xyz, idx32)
+        if self.grouper == "knn":
+            nbr = ops.knn_int32(new_xyz, xyz, self.nsample)
+        else:
+            nbr = ops.ball_query_int32(self.radius, self.nsample, xyz, new_xyz)
+        self.last_fps_idx, self.last_group_idx = idx32, nbr
+        out = _SAFunction.apply(xyz, new_xyz, nbr, feats, self, *params)
+        return new_xyz, out

@@ -1,0 +1,202 @@
+/*
+ * pcoe.h — C ABI of libpcoe.so: the B200 (sm_100a) PointNet++ set-abstraction hot path of
+ * 0xPabloxx/3d-pointcloud-orientation-estimation.
+ *
+ * The reference is pure Python/PyTorch and has no FFI; each entry point below names the reference
+ * function (file:line under the reference root) whose arithmetic it replaces.  A maintainer binds
+ * these with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - tensors are dense, row-major, with the shapes given in the comments;
+ *   - indices are int32 on this side (the Python layer widens to int64 where the reference exposes them);
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (no device
+ *     synchronisation, no allocation, CUDA-graph capturable);
+ *   - every call returns 0 on success or a negative pcoe_status; the message of the last failure
+ *     on the calling thread is available from pcoe_last_error();
+ *   - the library never keeps a caller pointer after the call returns.
+ */
+#ifndef PCOE_H_
+#define PCOE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCOE_VERSION 100 /* 0.1.0 */
+
+typedef enum pcoe_status {
+  PCOE_OK = 0,
+  PCOE_ERR_BAD_SHAPE = -1,     /* non-positive / inconsistent dimensions                       */
+  PCOE_ERR_UNSUPPORTED = -2,   /* a size or mode this build has no kernel for                  */
+  PCOE_ERR_NULL = -3,          /* a required pointer is NULL                                   */
+  PCOE_ERR_CUDA = -4,          /* a CUDA runtime call or launch failed                         */
+  PCOE_ERR_WORKSPACE = -5      /* workspace / saved buffer smaller than *_bytes() reports       */
+} pcoe_status;
+
+int pcoe_version(void);
+/* Thread-local, NUL-terminated description of the most recent failing call on this thread. */
+const char* pcoe_last_error(void);
+/* Number of kernels this library has enqueued since load (all threads); used by bench.py for
+ * its `gpu_launches` claim. */
+uint64_t pcoe_launch_count(void);
+
+/* --------------------------------------------------------------------------------------------
+ * Sampling
+ * ------------------------------------------------------------------------------------------ */
+
+/* Farthest-point sampling.  Replaces farthest_point_sample(), PointNet++Demo.py:8-29.
+ *   xyz       [B,N,3] f32
+ *   start_idx [B] i32 first centroid of every cloud (the reference draws it with torch.randint,
+ *             :20); NULL = index 0 for every cloud
+ *   out_idx   [B,S] i32   indices in visiting order (out_idx[b,0] == start_idx[b])
+ *   out_xyz   [B,S,3] f32 the sampled coordinates, or NULL
+ * Bit-exact contract: distances are ((dx*dx)+(dy*dy))+(dz*dz) with individually rounded fp32
+ * operations, running minimum starts at 1e10, arg-max ties resolve to the lowest index. */
+int pcoe_fps_f32(const float* xyz, int B, int N, int S, const int32_t* start_idx,
+                 int32_t* out_idx, float* out_xyz, void* stream);
+
+/* Gather of sampled centroids.  Replaces index_points(xyz, fps_idx) with a (B,S) index,
+ * models/base.py:4-14 (call site models/pointnet_pp_8dir.py:29).
+ *   src [B,N,C] f32, idx [B,S] i32 -> out [B,S,C] f32.  Fails (BAD_SHAPE) only on shapes;
+ *   an out-of-range index is clamped into [0,N) (the reference would raise IndexError). */
+int pcoe_gather_points_f32(const float* src, int B, int N, int C, const int32_t* idx, int S,
+                           float* out, void* stream);
+
+/* Uniform random subset without replacement drawn on the device (partial Fisher-Yates, Philox-
+ * style counter RNG keyed by (seed, call offset, cloud)).  Same distribution as the reference's
+ * torch.randperm(N)[:S] (models/pointnet_pp_8dir.py:28; the on-device variant is
+ * models/pointnet_pp_Fwd.py:44-47) but a different random stream: use the host-replayed
+ * permutation (Python layer, sampler="randperm_host") when index parity with a seeded reference
+ * run is required.   out_idx [B,S] i32. */
+int pcoe_random_subset(int B, int N, int S, uint64_t seed, uint64_t offset, int32_t* out_idx,
+                       void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Grouping
+ * ------------------------------------------------------------------------------------------ */
+
+/* k nearest neighbours of every centroid.  Replaces query_ball_point(new_xyz, xyz, nsample) =
+ * square_distance + topk(largest=False, sorted=False), models/base.py:20-35.
+ *   xyz [B,N,3] f32, new_xyz [B,S,3] f32 -> out_idx [B,S,K] i32.
+ * The reference's order inside a row is unspecified (sorted=False); this kernel writes ascending
+ * distance, ties by ascending index.  Distances are the direct sum of squared differences in
+ * fp32.  Requires 1 <= K <= min(N, 128). */
+int pcoe_knn_f32(const float* xyz, const float* new_xyz, int B, int N, int S, int K,
+                 int32_t* out_idx, void* stream);
+
+/* Radius ball query.  Replaces query_ball_point(radius, nsample, xyz, new_xyz),
+ * PointNet++Demo.py:49-70: the first `nsample` point indices (ascending index) whose squared
+ * distance is NOT greater than (float)(radius*radius); short rows are padded with the row's
+ * first hit; a row with no hit is filled with N (as the reference does).
+ * Distances as in pcoe_fps_f32 (bit-exact contract).  out_idx [B,S,nsample] i32. */
+int pcoe_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N, int S, int nsample,
+                        double radius, int32_t* out_idx, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Set abstraction: gather + centre + 3 x (1x1 conv -> BatchNorm -> ReLU) + max over neighbours
+ * Replaces PointNetSetAbstraction.forward, models/pointnet_pp_8dir.py:21-43 (identical copies in
+ * models/Pointnet_pp_xyz.py:22-44, pointnet_pp.py, Pointnet_pp_xyz_Schedmit.py, pointnet_pp_Fwd.py)
+ * and its autograd.
+ * ------------------------------------------------------------------------------------------ */
+
+enum { PCOE_PRECISION_FP32 = 0, PCOE_PRECISION_BF16 = 1 };
+
+typedef struct pcoe_sa_desc {
+  int32_t B;          /* clouds                                                               */
+  int32_t N;          /* points per cloud entering the layer                                  */
+  int32_t S;          /* centroids per cloud (1 when group_all)                               */
+  int32_t K;          /* neighbours per centroid (N when group_all); power of two, 1..128     */
+  int32_t D;          /* feature channels of `feats` (0 = none); conv input width is 3 + D     */
+  int32_t C1, C2, C3; /* output widths of the three 1x1 convolutions                          */
+  int32_t group_all;  /* 1: one group of all N points, absolute xyz (pointnet_pp_8dir.py:23-26) */
+  int32_t train;      /* 1: batch statistics + running-stat update; 0: running statistics     */
+  int32_t precision;  /* PCOE_PRECISION_FP32 (CUDA-core fp32) or PCOE_PRECISION_BF16 (tcgen05) */
+  float eps;          /* BatchNorm eps (1e-5 in the reference)                                */
+  float momentum;     /* BatchNorm momentum (0.1 in the reference)                            */
+} pcoe_sa_desc;
+
+/* Parameters of the three conv+BN stages, PyTorch layouts: W[l] is Conv2d.weight (Cout,Cin,1,1)
+ * = row-major [Cout][Cin]; running_* are updated in place when desc.train != 0. */
+typedef struct pcoe_sa_params {
+  const float* W[3];
+  const float* bias[3];
+  const float* gamma[3];
+  const float* beta[3];
+  float* running_mean[3];
+  float* running_var[3];
+} pcoe_sa_params;
+
+/* Gradients written by pcoe_sa_backward (all overwritten, not accumulated), same layouts. */
+typedef struct pcoe_sa_grads {
+  float* dW[3];
+  float* dbias[3];
+  float* dgamma[3];
+  float* dbeta[3];
+} pcoe_sa_grads;
+
+/* Bytes of the `saved` buffer (forward -> backward state: pre-BN activations, batch statistics,
+ * arg-max slots) and of the transient `workspace`.  Both must be 256-byte aligned. */
+size_t pcoe_sa_saved_bytes(const pcoe_sa_desc* desc);
+size_t pcoe_sa_workspace_bytes(const pcoe_sa_desc* desc);
+
+/*   xyz     [B,N,3] f32     coordinates entering the layer
+ *   new_xyz [B,S,3] f32     centroids (ignored when group_all)
+ *   nbr     [B,S,K] i32     neighbour indices into N (ignored when group_all)
+ *   feats   [B,N,D] f32     or NULL when D == 0
+ *   out     [B,S,C3] f32    max-pooled features = the reference's second return value
+ *   saved / workspace       see above; `saved` may be NULL when desc.train == 0 */
+int pcoe_sa_forward(const pcoe_sa_desc* desc, const float* xyz, const float* new_xyz,
+                    const int32_t* nbr, const float* feats, const pcoe_sa_params* params,
+                    float* out, void* saved, size_t saved_bytes, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/*   grad_out   [B,S,C3] f32   gradient w.r.t. `out`
+ *   out        [B,S,C3] f32   the forward result (ReLU mask)
+ *   grad_feats [B,N,D] f32    overwritten; NULL when D == 0
+ * Only defined for a forward that ran with desc.train != 0 (the reference never back-propagates
+ * through eval-mode BatchNorm). */
+int pcoe_sa_backward(const pcoe_sa_desc* desc, const float* xyz, const float* new_xyz,
+                     const int32_t* nbr, const float* feats, const pcoe_sa_params* params,
+                     const float* out, const float* grad_out, const void* saved,
+                     size_t saved_bytes, float* grad_feats, const pcoe_sa_grads* grads,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Losses (value and gradient in one launch; gradients are d loss[b] / d input[b,...])
+ * ------------------------------------------------------------------------------------------ */
+
+enum { PCOE_VM_SINGLE = 0, PCOE_VM_MULTI = 1 };
+
+/* Elementwise KL(vM(mu_p,kappa_p) || vM(mu_q,kappa_q)).
+ *   variant PCOE_VM_SINGLE: kl_von_mises, train_single_peak_vonMises_KL.py:23-28
+ *           (no clamp, no wrap, A:=0 for kappa_p<=1e-6, fp32 overflow of I0 -> NaN/inf as there)
+ *   variant PCOE_VM_MULTI : kl_von_mises, train_multi_peaks_vonMises_KL.py:38-52
+ *           (kappa clamped to [1e-6,500], delta wrapped to [-pi,pi))
+ *   all arrays [n] f32; dmu / dkappa may be NULL. */
+int pcoe_vm_kl_fwd_bwd(const float* mu_p, const float* kappa_p, const float* mu_q,
+                       const float* kappa_q, int n, int variant, float* loss, float* dmu,
+                       float* dkappa, void* stream);
+
+/* Matched mixture loss.  Replaces match_loss, train_multi_peaks_vonMises_KL.py:54-81 including
+ * the host scipy.optimize.linear_sum_assignment (minimum over the <= 24 permutations).
+ *   mu,kappa,w [B,Kmax] f32; gt [B,Kmax,gt_stride] f32 with (mu,kappa) in columns 0,1;
+ *   K_gt [B] i32 (<=0 -> loss 0, no gradient); Kmax <= 4.
+ *   loss [B]; dmu,dkappa,dw [B,Kmax] (may be NULL); perm [B,Kmax] i32 matched gt column per
+ *   predicted component (-1 beyond K), may be NULL. */
+int pcoe_mvm_match_fwd_bwd(const float* mu, const float* kappa, const float* w, const float* gt,
+                           int gt_stride, const int32_t* K_gt, int B, int Kmax, float* loss,
+                           float* dmu, float* dkappa, float* dw, int32_t* perm, void* stream);
+
+/* Soft-label cross entropy -(p * log_softmax(logits)).sum(1).  Replaces
+ * kl_loss_per_sample_from_logits, train_8dir_KL.py:60-68.  logits,p [B,C] f32, C <= 64. */
+int pcoe_soft_ce_fwd_bwd(const float* logits, const float* p, int B, int C, float* loss,
+                         float* dlogits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCOE_H_ */
