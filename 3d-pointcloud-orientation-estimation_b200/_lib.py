@@ -41,6 +41,8 @@ SIGNATURES = {
     "pcoe_version": (_I, []),
     "pcoe_last_error": (C.c_char_p, []),
     "pcoe_launch_count": (_U64, []),
+    "pcoe_profile_enable": (_I, [_I]),
+    "pcoe_profile_report": (_I, [C.c_char_p, _SZ]),
     "pcoe_fps_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "pcoe_gather_points_f32": (_I, [_P, _I, _I, _I, _P, _I, _P, _P]),
     "pcoe_random_subset": (_I, [_I, _I, _I, _U64, _U64, _P, _P]),
@@ -92,3 +94,18 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(load().pcoe_launch_count())
+
+
+def profile(enable: bool) -> None:
+    check(load().pcoe_profile_enable(int(enable)))
+
+
+def profile_report() -> dict:
+    """{kernel name: (launches, total_ms)} since the last report; synchronises on the recorded events."""
+    buf = C.create_string_buffer(1 << 16)
+    check(load().pcoe_profile_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(",", 2)
+        out[name] = (int(n), float(ms))
+    return out

@@ -2,6 +2,10 @@
 #include "common.cuh"
 #include <atomic>
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 namespace pcoe {
 
@@ -17,7 +21,61 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+// ---- per-kernel timing ------------------------------------------------------------------------
+struct ProfRec { const char* what; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+int profile_begin(const char* what, cudaStream_t st) {
+  if (!g_prof_on) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{what, nullptr, nullptr};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+
+void profile_end(int slot, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot >= 0 && slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].b, st);
+}
+
 }  // namespace pcoe
+
+extern "C" int pcoe_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(pcoe::g_prof_mu);
+  pcoe::g_prof_on = on != 0;
+  return PCOE_OK;
+}
+
+extern "C" int pcoe_profile_report(char* buf, size_t cap) {
+  using namespace pcoe;
+  if (!buf || cap == 0) return fail(PCOE_ERR_NULL, "profile_report: buffer is NULL");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.b);
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.what];
+      e.first += 1;
+      e.second += ms;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& kv : agg) {
+    int n = snprintf(buf + off, cap - off, "%s,%d,%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    if (n < 0 || (size_t)n >= cap - off) break;
+    off += (size_t)n;
+  }
+  return PCOE_OK;
+}
 
 extern "C" int pcoe_version(void) { return PCOE_VERSION; }
 extern "C" const char* pcoe_last_error(void) { return pcoe::g_error; }

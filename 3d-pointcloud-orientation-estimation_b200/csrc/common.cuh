@@ -22,6 +22,10 @@ inline int fail(pcoe_status st, const char* fmt, ...) {
   return (int)st;
 }
 
+// Optional per-kernel CUDA-event timing (pcoe_profile_enable): begin/end events around a launch.
+int profile_begin(const char* what, cudaStream_t st);   // returns slot or -1 when disabled
+void profile_end(int slot, cudaStream_t st);
+
 // Checks the launch that was just enqueued (cudaPeekAtLastError is legal during graph capture).
 inline int check_launch(const char* what) {
   count_launch();
@@ -32,6 +36,18 @@ inline int check_launch(const char* what) {
   }
   return PCOE_OK;
 }
+
+// Brackets one kernel launch: `LaunchScope ls("name", st); kernel<<<...>>>(...); return ls.done();`
+struct LaunchScope {
+  const char* what;
+  cudaStream_t st;
+  int slot;
+  LaunchScope(const char* w, cudaStream_t s) : what(w), st(s), slot(profile_begin(w, s)) {}
+  int done() {
+    if (slot >= 0) profile_end(slot, st);
+    return check_launch(what);
+  }
+};
 
 #define PCOE_CUDA(call)                                                                  \
   do {                                                                                   \

@@ -159,8 +159,9 @@ extern "C" int pcoe_knn_f32(const float* xyz, const float* new_xyz, int B, int N
   if (smem > 48 * 1024)
     PCOE_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(S, kGroupWarps * kCentroidsPerWarp), B);
+  LaunchScope ls("knn_kernel", (cudaStream_t)stream);
   knn_kernel<<<grid, kGroupWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, K, out_idx);
-  return check_launch("knn_kernel");
+  return ls.done();
 }
 
 extern "C" int pcoe_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N, int S,
@@ -175,6 +176,7 @@ extern "C" int pcoe_ball_query_f32(const float* xyz, const float* new_xyz, int B
     PCOE_CUDA(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const float r2 = (float)(radius * radius);  // Python double r**2, cast to the tensor dtype
   dim3 grid(ceil_div(S, kGroupWarps * kCentroidsPerWarp), B);
+  LaunchScope ls("ball_query_kernel", (cudaStream_t)stream);
   ball_query_kernel<<<grid, kGroupWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, nsample, r2, out_idx);
-  return check_launch("ball_query_kernel");
+  return ls.done();
 }

@@ -237,9 +237,10 @@ extern "C" int pcoe_vm_kl_fwd_bwd(const float* mu_p, const float* kappa_p, const
     return fail(PCOE_ERR_UNSUPPORTED, "vm_kl: variant=%d", variant);
   if (n == 0) return PCOE_OK;
   if (!mu_p || !kappa_p || !mu_q || !kappa_q || !loss) return fail(PCOE_ERR_NULL, "vm_kl: NULL pointer");
+  LaunchScope ls("vm_kl_kernel", (cudaStream_t)stream);
   vm_kl_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(mu_p, kappa_p, mu_q, kappa_q, n,
                                                                    variant, loss, dmu, dkappa);
-  return check_launch("vm_kl_kernel");
+  return ls.done();
 }
 
 extern "C" int pcoe_mvm_match_fwd_bwd(const float* mu, const float* kappa, const float* w,
@@ -251,9 +252,10 @@ extern "C" int pcoe_mvm_match_fwd_bwd(const float* mu, const float* kappa, const
   if (Kmax > 4) return fail(PCOE_ERR_UNSUPPORTED, "mvm_match: Kmax=%d > 4", Kmax);
   if (B == 0) return PCOE_OK;
   if (!mu || !kappa || !w || !gt || !K_gt || !loss) return fail(PCOE_ERR_NULL, "mvm_match: NULL pointer");
+  LaunchScope ls("mvm_match_kernel", (cudaStream_t)stream);
   mvm_match_kernel<<<ceil_div(B, 64), 64, 0, (cudaStream_t)stream>>>(mu, kappa, w, gt, gt_stride, K_gt,
                                                                      B, Kmax, loss, dmu, dkappa, dw, perm);
-  return check_launch("mvm_match_kernel");
+  return ls.done();
 }
 
 extern "C" int pcoe_soft_ce_fwd_bwd(const float* logits, const float* p, int B, int C, float* loss,
@@ -262,6 +264,7 @@ extern "C" int pcoe_soft_ce_fwd_bwd(const float* logits, const float* p, int B, 
   if (C > 64) return fail(PCOE_ERR_UNSUPPORTED, "soft_ce: C=%d > 64", C);
   if (B == 0) return PCOE_OK;
   if (!logits || !p || !loss) return fail(PCOE_ERR_NULL, "soft_ce: NULL pointer");
+  LaunchScope ls("soft_ce_kernel", (cudaStream_t)stream);
   soft_ce_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(logits, p, B, C, loss, dlogits);
-  return check_launch("soft_ce_kernel");
+  return ls.done();
 }

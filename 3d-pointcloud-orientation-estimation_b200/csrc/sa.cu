@@ -111,6 +111,7 @@ __global__ void bn_bwd_consts_kernel(const double* __restrict__ sums, double cou
 template <class AProd, class Epi, bool BT>
 static int launch_nt(const AProd& ap, const float* Bmat, int ldb, const Epi& epi, int M, int Ncols,
                      int Kdim, cudaStream_t st, const char* what) {
+  LaunchScope ls(what, st);
   if (Ncols > 64) {
     auto k = gemm_nt_kernel<AProd, Epi, 8, BT>;
     static bool attr = false;
@@ -130,7 +131,7 @@ static int launch_nt(const AProd& ap, const float* Bmat, int ldb, const Epi& epi
     dim3 grid(ceil_div(M, kBM), 1);
     k<<<grid, 256, gemm_nt_smem<4>(), st>>>(ap, Bmat, ldb, epi, M, Ncols, Kdim);
   }
-  return check_launch(what);
+  return ls.done();
 }
 
 template <class PProd, class QProd>
@@ -143,8 +144,9 @@ static int launch_tn(const PProd& pp, const QProd& qp, float* out, int ldo, int 
   int rps = ceil_div(ceil_div(M, splits), kWgRows) * kWgRows;
   splits = ceil_div(M, rps);
   dim3 grid(ta, tb, splits);
+  LaunchScope ls(what, st);
   gemm_tn_kernel<PProd, QProd><<<grid, 256, 0, st>>>(pp, qp, out, ldo, M, Ca, Cb, rps);
-  return check_launch(what);
+  return ls.done();
 }
 
 static int validate(const pcoe_sa_desc* d) {
@@ -191,10 +193,11 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
   uint8_t* amin = (uint8_t*)(ws + L.ws_amin);
 
   auto finalize = [&](int l) -> int {
+    LaunchScope ls("bn_finalize_kernel", st);
     bn_finalize_kernel<<<ceil_div(Cs[l], 128), 128, 0, st>>>(sums[l], (double)M, Cs[l], P.gamma[l], P.beta[l],
         P.bias[l], P.running_mean[l], P.running_var[l], d.eps, d.momentum, d.train, scale[l], shift[l],
         mean[l], invstd[l]);
-    return check_launch("bn_finalize_kernel");
+    return ls.done();
   };
   if (!train) for (int l = 0; l < 3; ++l) PCOE_TRY(finalize(l));
 
@@ -214,10 +217,11 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
   const size_t total = (size_t)G * d.C3;
   int blocks = (int)((total + 255) / 256);
   blocks = blocks > kNumSMs * 8 ? kNumSMs * 8 : blocks;
+  LaunchScope ls("sa_out_finalize_kernel", st);
   sa_out_finalize_kernel<<<blocks, 256, 0, st>>>(ymax, ymin, amax, amin, scale[2], shift[2], total, d.C3, out,
                                                 train ? (uint8_t*)(sv + L.sv_slot) : nullptr,
                                                 train ? (float*)(sv + L.sv_ysel) : nullptr);
-  return check_launch("sa_out_finalize_kernel");
+  return ls.done();
 }
 
 template <typename TY>
@@ -258,16 +262,18 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
     PCOE_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)d.B * d.N * d.D, st));
 
   auto consts = [&](int l) -> int {
+    LaunchScope ls("bn_bwd_consts_kernel", st);
     bn_bwd_consts_kernel<<<ceil_div(Cs[l], 128), 128, 0, st>>>(bs[l], (double)M, Cs[l], scale[l], mean[l],
         invstd[l], ca[l], cp[l], cq[l], Gr.dgamma[l], Gr.dbeta[l], Gr.dbias[l]);
-    return check_launch("bn_bwd_consts_kernel");
+    return ls.done();
   };
 
   {
     const int gpb = ceil_div(G, kNumSMs * 2);
+    LaunchScope ls("bwd_last_reduce_kernel", st);
     bwd_last_reduce_kernel<<<ceil_div(G, gpb), 256, 0, st>>>(grad_out, out, ysel, mean[2], invstd[2], G, d.C3,
                                                             gpb, gm, bs[2]);
-    PCOE_TRY(check_launch("bwd_last_reduce_kernel"));
+    PCOE_TRY(ls.done());
   }
   PCOE_TRY(consts(2));
 

@@ -97,6 +97,7 @@ template <int PPT>
 static int launch_fps(const float* xyz, int B, int N, int S, const int32_t* start, int32_t* out_idx,
                       float* out_xyz, int threads, cudaStream_t st) {
   size_t smem = (size_t)N * 3 * sizeof(float);
+  LaunchScope ls("fps_kernel", st);
   if (smem <= 200 * 1024) {
     auto k = fps_kernel<PPT, true>;
     if (smem > 48 * 1024)
@@ -105,7 +106,7 @@ static int launch_fps(const float* xyz, int B, int N, int S, const int32_t* star
   } else {
     fps_kernel<PPT, false><<<B, threads, 0, st>>>(xyz, N, S, start, out_idx, out_xyz);
   }
-  return check_launch("fps_kernel");
+  return ls.done();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -191,8 +192,9 @@ extern "C" int pcoe_gather_points_f32(const float* src, int B, int N, int C, con
   size_t total = (size_t)B * S * C;
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  LaunchScope ls("gather_points_kernel", (cudaStream_t)stream);
   gather_points_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, N, C, idx, S, out, total);
-  return check_launch("gather_points_kernel");
+  return ls.done();
 }
 
 extern "C" int pcoe_random_subset(int B, int N, int S, uint64_t seed, uint64_t offset,
@@ -204,6 +206,7 @@ extern "C" int pcoe_random_subset(int B, int N, int S, uint64_t seed, uint64_t o
   if (smem > 200 * 1024) return fail(PCOE_ERR_UNSUPPORTED, "random_subset: N=%d too large", N);
   if (smem > 48 * 1024)
     PCOE_CUDA(cudaFuncSetAttribute(random_subset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchScope ls("random_subset_kernel", (cudaStream_t)stream);
   random_subset_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(N, S, seed, offset, out_idx);
-  return check_launch("random_subset_kernel");
+  return ls.done();
 }

@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py - training throughput of the PointNet++ set-abstraction hot path on B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # this repo's CUDA path
+    python bench.py --impl reference --steps 5 --warmup 1     # the reference algorithm on host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one optimisation step of the reference's training loop on one synthetic batch
+(zero_grad -> forward -> loss -> backward -> [grad all-reduce] -> clip_grad_norm_ (mvM only) -> Adam),
+train_multi_peaks_vonMises_KL.py:221-236.  Workload at N=1 = BASELINE.json configs[1]
+(PointNetPPMvM, 64 clouds x 1024 points per GPU); weak scaling over GPUs.
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM, device-side sampler, CUDA-event
+timed, L2 flushed between steps.  `e2e`: the drop-in module called with HOST tensors - pinned-host
+xyz + targets copied H2D every step, the reference's host-side randperm sampling, loss read back D2H.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {  # name -> (kind, model class, clouds per GPU, points)
+    "c1": ("vonmises", "PointNetPPVonMises", 16, 1024),
+    "c2": ("mvm", "PointNetPPMvM", 64, 1024),
+    "c3": ("8dir", "PointNetPP8Dir", 32, 2048),
+    "c4": ("xyz", "PointNetPPXYZ", 32, 8192),
+}
+WORKLOAD_NAMES = {
+    "c1": "PointNet++ SSG single-peak von Mises KL head, 16 x 1024 pts per GPU, train step",
+    "c2": "PointNet++ multi-peak mvM KL head (pointnet_pp_mvM.py), 64 x 1024 pts per GPU, train step",
+    "c3": "PointNet++ 8-direction head, 32 x 2048 pts per GPU, train step",
+    "c4": "Pointnet_pp_xyz at 8192 pts/cloud, 32 clouds per GPU, train step",
+}
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=float(p["hbm_gbs"]), tensor=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json; bf16 sustained figure: kernel timed inside a long step)")
+    except Exception:
+        return dict(hbm=6650.0, tensor=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if not (t0 - 0.1 <= ts <= t1 + 0.3):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def sa_shapes(B: int, N: int):
+    """(rows M, Cin, C1, C2, C3, N_in, S, K) of the three SA layers (pointnet_pp_8dir.py:65-67)."""
+    return [(B * 128 * 32, 3, 64, 64, 128, N, 128, 32), (B * 32 * 32, 131, 128, 128, 256, 128, 32, 32),
+            (B * 32, 259, 256, 512, 1024, 32, 1, 32)]
+
+
+def kernel_work(B: int, N: int) -> dict:
+    """Algorithmic work per STEP of every libpcoe kernel name (DESIGN.md 'Kernels'): FLOPs for the
+    GEMM kernels (2*M*Cin*Cout, no padding/recompute), bytes for the sampling/grouping kernels."""
+    sh = sa_shapes(B, N)
+    f = lambda a, b: float(sum(2.0 * s[0] * s[a] * s[b] for s in sh))
+    w = {
+        "sa_fwd_l1": ("tensor", f(1, 2)), "sa_fwd_l2": ("tensor", f(2, 3)), "sa_fwd_l3": ("tensor", f(3, 4)),
+        "sa_bwd_wgrad3": ("tensor", f(3, 4)), "sa_bwd_dgrad3": ("tensor", f(3, 4)),
+        "sa_bwd_wgrad2": ("tensor", f(2, 3)), "sa_bwd_dgrad2": ("tensor", f(2, 3)),
+        "sa_bwd_wgrad1": ("tensor", f(1, 2)),
+        "sa_bwd_dgrad1": ("tensor", float(sum(2.0 * s[0] * (s[1] - 3) * s[2] for s in sh[1:]))),
+    }
+    grp = float(sum(B * (12 * s[5] + 12 * s[6] + 4 * s[6] * s[7]) for s in sh[:2]))
+    smp = float(sum(B * (12 * s[5] + 4 * s[6] + 12 * s[6]) for s in sh[:2]))
+    w["knn_kernel"] = ("hbm", grp)
+    w["ball_query_kernel"] = ("hbm", grp)
+    w["fps_kernel"] = ("hbm", smp)
+    w["random_subset_kernel"] = ("hbm", float(sum(B * 4 * s[6] for s in sh[:2])))
+    w["gather_points_kernel"] = ("hbm", float(sum(B * (4 * s[6] + 24 * s[6]) for s in sh[:2])))
+    return w
+
+
+def make_targets(kind: str, B: int, pcoe, batch: int):
+    syn = pcoe.synthetic
+    if kind == "mvm":
+        gt, K = syn.mvm_targets(B, batch)
+        return (gt, K.to(dtype=__import__("torch").int32))
+    if kind == "vonmises":
+        return syn.vm_targets(B, batch)
+    if kind == "8dir":
+        return (syn.dir8_targets(B, pcoe.DIRS_8, batch),)
+    return ()
+
+
+def loss_of(kind: str, res, tg, pcoe):
+    if kind == "mvm":
+        return pcoe.match_loss(res[0], res[1], res[2], tg[0], None, tg[1]).mean()
+    if kind == "vonmises":
+        return pcoe.kl_von_mises(res[0], res[1], tg[0], tg[1]).mean()
+    if kind == "8dir":
+        return pcoe.kl_loss_per_sample_from_logits(res, tg[0]).mean()
+    return sum((r ** 2).sum() for r in res)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference algorithm (oracle port, torch CPU) on the box's host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import pcoe
+    from oracle.step import OracleTrainer
+    kind, cls, B, N = CONFIGS[args.config]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1000)
+    model = getattr(pcoe, cls)()                       # construction only (CPU): reference-identical init
+    tr = OracleTrainer(kind, model.state_dict())
+    batches = [(pcoe.synthetic.clouds(1, B, N, i), tuple(t.long() if not t.is_floating_point() else t
+                                                        for t in make_targets(kind, B, pcoe, i))) for i in range(4)]
+    torch.manual_seed(42)
+    for i in range(args.warmup):
+        tr.step(*batches[i % 4])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        tr.step(*batches[i % 4])
+    dt = time.perf_counter() - t0
+    v = B * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "train clouds/sec (1024 pts, fwd+bwd)", "value": v, "unit": "clouds/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[args.config], "clouds_per_step": B, "points": N},
+        "cpu_baseline": {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full steps of {B} clouds (oracle port of the reference step, torch CPU)"},
+        "e2e": {"value": v, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import pcoe
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - this framework has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    kind, cls, B, N = CONFIGS[args.config]
+    pcoe.set_default_precision(args.precision)
+    peaks = load_peaks()
+
+    torch.manual_seed(1000)
+    model = getattr(pcoe, cls)(sampler="randperm_device").to(dev).train()
+    engine = pcoe.dp.DataParallel(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    params = [p for p in model.parameters()]
+    NB = 8                                               # distinct synthetic batches, rotated
+    host = [(pcoe.synthetic.clouds(1, B, N, rank * NB + i).pin_memory(),
+             tuple(t.pin_memory() for t in make_targets(kind, B, pcoe, rank * NB + i))) for i in range(NB)]
+    resident = [(x.to(dev), tuple(t.to(dev) for t in tg)) for x, tg in host]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(xyz, tg):
+        engine.zero_grad()
+        res = model(xyz)
+        loss = loss_of(kind, res, tg, pcoe)
+        loss.backward()
+        engine.allreduce_grads()
+        if kind == "mvm":
+            torch.nn.utils.clip_grad_norm_(params, 1.0, foreach=True)
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timed region ---------------------------------------------------------
+    for i in range(args.warmup):
+        step(*resident[i % NB])
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = pcoe._lib.launch_count()
+    t_wall0 = time.time()
+    for i in range(args.steps):
+        flush.zero_()                                     # L2 flush, outside the event pair
+        ev[i][0].record()
+        step(*resident[i % NB])
+        ev[i][1].record()
+    barrier()
+    t_wall1 = time.time()
+    launches = pcoe._lib.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    value = world * B * args.steps / (dev_ms / 1e3)
+
+    # ---- end-to-end through the public API with host buffers ------------------------------------
+    for m in (model.sa1, model.sa2):
+        m.sampler = "randperm_host"                       # the reference's host-generator sampling (index-exact)
+    h2d = host[0][0].numel() * 4 + sum(t.numel() * t.element_size() for t in host[0][1]) + B * (128 + 32) * 4
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(2):
+        float(step(host[i][0].to(dev, non_blocking=True), tuple(t.to(dev, non_blocking=True) for t in host[i][1])))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        x, tg = host[i % NB]
+        loss = step(x.to(dev, non_blocking=True), tuple(t.to(dev, non_blocking=True) for t in tg))
+        float(loss)                                       # D2H read of the step's result
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(t.item())
+    for m in (model.sa1, model.sa2):
+        m.sampler = "randperm_device"
+
+    # ---- per-kernel CUDA-event profile of the same step (rank 0) -> roofline ---------------------
+    roofline, kernels = None, {}
+    if rank == 0:
+        barrier_local = torch.cuda.synchronize
+        barrier_local()
+    psteps = 3
+    pcoe._lib.profile(True)
+    for i in range(psteps):
+        flush.zero_()
+        step(*resident[i % NB])
+    torch.cuda.synchronize()
+    pcoe._lib.profile(False)
+    rep = pcoe._lib.profile_report()
+    if rank == 0:
+        work = kernel_work(B, N)
+        tot_ms = sum(ms for _, ms in rep.values())
+        for name, (n, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+            ent = {"launches_per_step": n / psteps, "ms_per_step": ms / psteps, "share_of_libpcoe_time": ms / tot_ms}
+            if name in work:
+                bound, amount = work[name]
+                ach = amount / (ms / psteps * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+                ent.update(bound=bound, achieved=ach, unit="TFLOP/s" if bound == "tensor" else "GB/s",
+                           frac=ach / peaks[bound])
+            kernels[name] = ent
+        top = next((n for n in kernels if "achieved" in kernels[n]), None)
+        if top:
+            k = kernels[top]
+            roofline = {"kernel": top, "bound": k["bound"], "achieved": k["achieved"], "peak": peaks[k["bound"]],
+                        "unit": k["unit"], "frac": k["frac"], "traffic": None, "peak_source": peaks["source"],
+                        "avg_launch_ms": k["ms_per_step"] / k["launches_per_step"],
+                        "share_of_libpcoe_time": k["share_of_libpcoe_time"]}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.step import OracleTrainer
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        tr = OracleTrainer(kind, {k: v.detach().cpu() for k, v in model.state_dict().items()})
+        cb = [(x.clone(), tuple(t.long() if not t.is_floating_point() else t.clone() for t in tg)) for x, tg in host[:2]]
+        tr.step(*cb[0])
+        n_cpu = 4
+        t0 = time.perf_counter()
+        for i in range(n_cpu):
+            tr.step(*cb[i % 2])
+        dt = time.perf_counter() - t0
+        cpu = {"value": B * n_cpu / dt, "unit": "clouds/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} full steps of {B} clouds after 1 warm-up (oracle port of the reference step, torch CPU fp32)"}
+
+    if rank == 0:
+        line = {
+            "metric": "train clouds/sec (1024 pts, fwd+bwd)", "value": value, "unit": "clouds/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[args.config], "clouds_per_gpu": B, "points": N,
+                       "global_clouds_per_step": B * world, "parallelism": f"dp{world}",
+                       "step": "zero_grad+fwd+loss+bwd+allreduce+clip+Adam", "sampler_value": "randperm_device",
+                       "sampler_e2e": "randperm_host (reference-faithful)", "precision": args.precision,
+                       "l2": "512 MiB buffer written between timed steps (flush outside the event pair)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "gpu_launches_per_step": launches / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+            "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps,
+            "grad_allreduce_bytes": engine.grads.nbytes() if world > 1 else 0,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
+    ap.add_argument("--precision", choices=["fp32", "bf16"], default=os.environ.get("PCOE_PRECISION", "fp32"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,13 @@ const char* pcoe_last_error(void);
  * its `gpu_launches` claim. */
 uint64_t pcoe_launch_count(void);
 
+/* Per-kernel timing for bench.py's roofline line: when enabled every kernel this library enqueues
+ * is bracketed by CUDA events on its stream.  pcoe_profile_report synchronises on those events and
+ * writes "name,launches,total_ms\n" lines (NUL-terminated, truncated to cap) into the HOST buffer
+ * `buf_host`, then clears the records.  Not for use during CUDA-graph capture. */
+int pcoe_profile_enable(int on);
+int pcoe_profile_report(char* buf_host, size_t cap);
+
 /* --------------------------------------------------------------------------------------------
  * Sampling
  * ------------------------------------------------------------------------------------------ */

@@ -77,7 +77,7 @@ def sa_features(sd: dict, xyz: torch.Tensor, fps1, fps2, training=True, update_b
     return l3.reshape(xyz.shape[0], -1)
 
 
-def _bn_trunk(sd, feat, training, update_buffers):
+def _bn_trunk(sd, feat, training, update_buffers, dropout_p=0.0):
     x = feat
     for fc, bn in (("fc1", "bn1"), ("fc2", "bn2")):
         x = x @ sd[f"{fc}.weight"].t() + sd[f"{fc}.bias"]
@@ -85,19 +85,21 @@ def _bn_trunk(sd, feat, training, update_buffers):
         if not update_buffers:
             rm, rv = rm.clone(), rv.clone()
         x = F.relu(F.batch_norm(x, rm, rv, sd[f"{bn}.weight"], sd[f"{bn}.bias"], training, 0.1, 1e-5))
-    return x  # dropout: parity runs use p=0 / eval (identity)
+    return F.dropout(x, dropout_p, training) if dropout_p > 0 else x   # parity runs use p=0
 
 
-def _ln_trunk(sd, feat):
+def _ln_trunk(sd, feat, training=True, dropout_p=0.0):
     x = feat
     for fc, ln in (("fc1", "ln1"), ("fc2", "ln2")):
         x = x @ sd[f"{fc}.weight"].t() + sd[f"{fc}.bias"]
         x = F.relu(F.layer_norm(x, x.shape[-1:], sd[f"{ln}.weight"], sd[f"{ln}.bias"], 1e-5))
+        if dropout_p > 0:
+            x = F.dropout(x, dropout_p, training)      # applied after both layers (pointnet_pp_mvM.py:82-83)
     return x
 
 
 def model_forward(kind: str, sd: dict, xyz: torch.Tensor, fps1, fps2, training=True, update_buffers=True,
-                  record=None, kappa_max=80.0, temp=0.7, max_K=4):
+                  record=None, kappa_max=80.0, temp=0.7, max_K=4, dropout_p=0.0):
     """Heads (dropout treated as identity):
       'vonmises' pointnet_pp_vonMises.py:26-38 | '8dir' pointnet_pp_8dir.py:76-85 | 'pp' pointnet_pp.py:59-68
       'xyz' Pointnet_pp_xyz.py:68-90 | 'schedmit' Pointnet_pp_xyz_Schedmit.py:68-90 | 'fwd' pointnet_pp_Fwd.py:89-98
@@ -105,7 +107,7 @@ def model_forward(kind: str, sd: dict, xyz: torch.Tensor, fps1, fps2, training=T
     feat = sa_features(sd, xyz, fps1, fps2, training, update_buffers, record)
     lin = lambda name, x: x @ sd[f"{name}.weight"].t() + sd[f"{name}.bias"]
     if kind == "mvm":
-        h = _ln_trunk(sd, feat)
+        h = _ln_trunk(sd, feat, training, dropout_p)
         weight = F.softmax(lin("head_pi", h) / temp, dim=-1)
         mu_raw = lin("head_mu", h).view(-1, max_K, 2)
         unit = F.normalize(mu_raw, dim=-1, eps=1e-4)
@@ -117,7 +119,7 @@ def model_forward(kind: str, sd: dict, xyz: torch.Tensor, fps1, fps2, training=T
         if kappa_max is not None:
             kappa = kappa.clamp_max(kappa_max)
         return torch.atan2(s, c), kappa, weight
-    h = _bn_trunk(sd, feat, training, update_buffers)
+    h = _bn_trunk(sd, feat, training, update_buffers, dropout_p)
     if kind == "vonmises":
         o = lin("fc3", h)
         return torch.tanh(o[:, 0]) * math.pi, F.softplus(o[:, 1])

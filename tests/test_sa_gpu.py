@@ -1,0 +1,129 @@
+"""Set-abstraction kernels (pcoe_sa_forward/backward through the drop-in module) vs the reference's
+recorded results (tests/golden/sa.npz) and vs the fp64 oracle at the model's real layer shapes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sa_torch
+
+pytestmark = pytest.mark.gpu
+
+# fp32 (CUDA-core) mode gates; the teacher-forced backward sees the same routing as the oracle
+# gradients are discontinuous in the forward values (arg-max / ReLU re-routing between fp32 and fp64):
+# SURVEY 7.3 measures 7.4e-4 for an exact-arithmetic fp32 implementation at the deepest weight
+FWD_RTOL, GRAD_REL = 2e-5, 2e-3
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _build(pcoe, g, tag, cuda, precision="fp32"):
+    B, N, S, K, D, c1, c2, c3, ga = g[f"{tag}_cfg"].tolist()
+    layer = pcoe.PointNetSetAbstraction(S or None, K or None, D, [c1, c2, c3], group_all=bool(ga), precision=precision)
+    sd = {k[len(tag) + 5:]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith(f"{tag}_sd0.")}
+    layer.load_state_dict(sd, strict=True)
+    return layer.to(cuda), (B, N, S, K, D, ga)
+
+
+@pytest.mark.parametrize("tag", ["small", "nofeat", "sa2", "gall"])
+def test_sa_golden_train_forward_backward_buffers(pcoe, golden, cuda, tag):
+    g = golden("sa")
+    layer, (B, N, S, K, D, ga) = _build(pcoe, g, tag, cuda)
+    layer.train()
+    xyz = torch.from_numpy(g[f"{tag}_xyz"]).to(cuda)
+    pts = torch.from_numpy(g[f"{tag}_pts"]).to(cuda).requires_grad_(True) if D else None
+    fps = None if ga else torch.from_numpy(g[f"{tag}_fps"]).to(cuda)
+    new_xyz, out = layer(xyz, pts, fps_idx=fps)
+    if not ga:   # T1: the kNN kernel reproduces the reference's neighbour sets on the recorded centroids
+        assert np.array_equal(np.sort(layer.last_group_idx.cpu().numpy(), -1), np.sort(g[f"{tag}_grp"], -1))
+    assert out.shape == tuple(g[f"{tag}_out"].shape)
+    assert torch.allclose(out.cpu(), torch.from_numpy(g[f"{tag}_out"]), rtol=1e-4, atol=2e-5)
+    out.backward(torch.from_numpy(g[f"{tag}_gout"]).to(cuda))
+    for name, p in layer.named_parameters():
+        want = torch.from_numpy(g[f"{tag}_grad.{name}"])
+        if name.startswith("convs") and name.endswith("bias"):
+            assert float(p.grad.abs().max()) == 0.0            # cancelled exactly; the reference has rounding noise
+            continue
+        assert _rel(p.grad, want) < 2e-3, name                 # the fp32 reference itself is ~1e-3 from fp64 here
+    if D:
+        assert _rel(pts.grad, torch.from_numpy(g[f"{tag}_gpts"])) < 2e-3
+    for k in g.files:
+        if k.startswith(f"{tag}_sd1."):
+            got = layer.state_dict()[k[len(tag) + 5:]].cpu()
+            assert torch.allclose(got.float(), torch.from_numpy(g[k]).float(), rtol=1e-5, atol=1e-6), k
+
+
+@pytest.mark.parametrize("tag", ["small", "nofeat", "sa2", "gall"])
+def test_sa_golden_eval_forward(pcoe, golden, cuda, tag):
+    g = golden("sa")
+    layer, (B, N, S, K, D, ga) = _build(pcoe, g, tag, cuda)
+    sd = layer.state_dict()
+    for k in g.files:                                          # eval output was recorded after one train step
+        if k.startswith(f"{tag}_sd1."):
+            sd[k[len(tag) + 5:]] = torch.from_numpy(g[k]).to(cuda)
+    layer.load_state_dict(sd)
+    layer.eval()
+    xyz = torch.from_numpy(g[f"{tag}_xyz"]).to(cuda)
+    pts = torch.from_numpy(g[f"{tag}_pts"]).to(cuda) if D else None
+    fps = None if ga else torch.from_numpy(g[f"{tag}_fps"]).to(cuda)
+    with torch.no_grad():
+        _, out = layer(xyz, pts, fps_idx=fps)
+    assert torch.allclose(out.cpu(), torch.from_numpy(g[f"{tag}_out_eval"]), rtol=1e-4, atol=2e-5)
+    rm_before = layer.bns[0].running_mean.clone()
+    with torch.no_grad():
+        layer(xyz, pts, fps_idx=fps)
+    assert torch.equal(rm_before, layer.bns[0].running_mean)   # eval never touches the buffers
+
+
+@pytest.mark.parametrize("shape", ["sa1", "sa2", "sa3"])
+def test_sa_vs_fp64_oracle_at_model_shapes(pcoe, cuda, shape):
+    """T2 (teacher-forced): same indices, same weights, fp64 oracle; fp32 kernels must be fp32-accurate."""
+    torch.manual_seed(3)
+    B = 8
+    cfg = dict(sa1=(1024, 128, 32, 0, [64, 64, 128], False), sa2=(128, 32, 32, 128, [128, 128, 256], False),
+               sa3=(32, None, None, 256, [256, 512, 1024], True))[shape]
+    N, S, K, D, mlp, ga = cfg
+    layer = pcoe.PointNetSetAbstraction(S, K, D, mlp, group_all=ga).to(cuda).train()
+    with torch.no_grad():
+        for bn in layer.bns:
+            bn.weight.uniform_(-0.5, 1.5)
+            bn.bias.uniform_(-0.2, 0.2)
+    g = torch.Generator().manual_seed(17)
+    xyz = torch.randn(B, N, 3, generator=g)
+    xyz = xyz / xyz.norm(dim=-1).amax(1).view(B, 1, 1)
+    pts = torch.randn(B, N, D, generator=g) if D else None
+    sd0 = sa_torch.clone_state({f"sa.{k}": v for k, v in layer.state_dict().items()}, dtype=torch.float64, requires_grad=True)
+    fps = None if ga else torch.stack([torch.randperm(N, generator=g)[:S] for _ in range(B)])
+    pts_c = pts.to(cuda).requires_grad_(True) if D else None
+    _, out = layer(xyz.to(cuda), pts_c, fps_idx=None if ga else fps.to(cuda))
+    grp = None if ga else layer.last_group_idx.long().cpu()
+    opts = pts.double().requires_grad_(True) if D else None
+    _, oy, _ = sa_torch.set_abstraction(sd0, "sa", xyz.double(), opts, group_all=ga, nsample=K, fps_idx=fps, group_idx=grp)
+    assert _rel(out, oy) < FWD_RTOL
+    gout = torch.randn(out.shape, generator=g)
+    out.backward(gout.to(cuda))
+    oy.backward(gout.double())
+    for name, p in layer.named_parameters():
+        if name.startswith("convs") and name.endswith("bias"):
+            continue
+        # sa1 has 8*128*128 maxima over 32 rows each: a handful of fp32-vs-fp64 arg-max / ReLU flips
+        # each re-route one O(1) gradient element (measured 2.2e-3 on bns.1.bias), hence the wider gate
+        assert _rel(p.grad, sd0[f"sa.{name}"].grad) < (5e-3 if shape == "sa1" else GRAD_REL), name
+    if D:
+        assert _rel(pts_c.grad, opts.grad) < GRAD_REL
+    for i in range(3):
+        for buf in ("running_mean", "running_var"):
+            assert torch.allclose(getattr(layer.bns[i], buf).cpu().double(), sd0[f"sa.bns.{i}.{buf}"], rtol=1e-5, atol=1e-6)
+        assert int(layer.bns[i].num_batches_tracked) == 1
+
+
+def test_sa_errors(pcoe, cuda):
+    layer = pcoe.PointNetSetAbstraction(None, None, 0, [8, 8, 8], group_all=True).to(cuda).train()
+    with pytest.raises(NotImplementedError):
+        layer(torch.zeros(2, 48, 3, device=cuda), None)        # 48 points: group size not a power of two
+    with pytest.raises(ValueError, match="more than 1 value per channel"):
+        layer(torch.zeros(1, 1, 3, device=cuda), None)         # the reference's BatchNorm raises the same
+    with pytest.raises(ValueError):
+        layer(torch.zeros(2, 3, 32, device=cuda), None)        # (B,3,N) is not accepted by the SA layer
