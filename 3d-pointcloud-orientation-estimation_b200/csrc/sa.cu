@@ -8,7 +8,9 @@
 // Conv biases are not added in train mode: BatchNorm subtracts the batch mean, which cancels a
 // per-channel constant exactly; they only shift running_mean (and enter eval mode).
 #include "sa_common.cuh"
+#include "sa_tc.cuh"
 #include "sa_layout.h"
+#include <type_traits>
 
 namespace pcoe {
 
@@ -149,6 +151,57 @@ static int launch_tn(const PProd& pp, const QProd& qp, float* out, int ldo, int 
   return ls.done();
 }
 
+template <class AProd, class Epi>
+static int launch_nt_tc(const AProd& ap, const __nv_bfloat16* Bw, int ldb, int brows, const Epi& epi, int M,
+                        int Ncols, int Kdim, cudaStream_t st, const char* what) {
+  auto k = tc_gemm_nt_kernel<AProd, Epi>;
+  static bool attr = false;
+  if (!attr) {
+    PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcNtSmem));
+    attr = true;
+  }
+  dim3 grid(ceil_div(M, kTcTile), ceil_div(Ncols, kTcN));
+  LaunchScope ls(what, st);
+  k<<<grid, 256, kTcNtSmem, st>>>(ap, Bw, ldb, brows, epi, M, Ncols, Kdim);
+  return ls.done();
+}
+
+template <class PProd, class QProd>
+static int launch_tn_tc(const PProd& pp, const QProd& qp, float* out, int ldo, int M, int Ca, int Cb,
+                        cudaStream_t st, const char* what) {
+  auto k = tc_gemm_tn_kernel<PProd, QProd>;
+  static bool attr = false;
+  if (!attr) {
+    PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcTnSmem));
+    attr = true;
+  }
+  const int ta = ceil_div(Ca, 128), tb = ceil_div(Cb, 128);
+  int splits = ceil_div(kNumSMs * 2, ta * tb);
+  const int max_splits = ceil_div(M, 128);
+  splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
+  const int rps = ceil_div(ceil_div(M, splits), 128) * 128;
+  splits = ceil_div(M, rps);
+  dim3 grid(ta, tb, splits);
+  LaunchScope ls(what, st);
+  k<<<grid, 256, kTcTnSmem, st>>>(pp, qp, out, ldo, M, Ca, Cb, rps);
+  return ls.done();
+}
+
+// bf16 copies of the three weight matrices (and their transposes for dgrad), tensor-core path only
+static int convert_weights(const pcoe_sa_desc& d, const SaLayout& L, const pcoe_sa_params& P, char* base,
+                           cudaStream_t st) {
+  const int Cs[3] = {d.C1, d.C2, d.C3}, Kin[3] = {3 + d.D, d.C1, d.C2};
+  for (int l = 0; l < 3; ++l) {
+    const int total = L.wb_rows[l] * L.wb_k[l] + L.wbt_rows[l] * L.wbt_k[l];
+    LaunchScope ls("convert_weights_kernel", st);
+    convert_weights_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(
+        P.W[l], Cs[l], Kin[l], (__nv_bfloat16*)(base + L.wb_off[l]), L.wb_rows[l], L.wb_k[l],
+        (__nv_bfloat16*)(base + L.wbt_off[l]), L.wbt_rows[l], L.wbt_k[l]);
+    PCOE_TRY(ls.done());
+  }
+  return PCOE_OK;
+}
+
 static int validate(const pcoe_sa_desc* d) {
   if (!d) return fail(PCOE_ERR_NULL, "sa: desc is NULL");
   if (d->B <= 0 || d->N <= 0 || d->S <= 0 || d->K <= 0 || d->D < 0 || d->C1 <= 0 || d->C2 <= 0 || d->C3 <= 0)
@@ -165,7 +218,7 @@ static int validate(const pcoe_sa_desc* d) {
   return PCOE_OK;
 }
 
-template <typename TY>
+template <typename TY, bool TC>
 static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float* new_xyz, const int32_t* nbr,
                            const float* feats, const pcoe_sa_params& P, float* out, void* saved,
                            void* workspace, cudaStream_t st) {
@@ -201,17 +254,28 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
   };
   if (!train) for (int l = 0; l < 3; ++l) PCOE_TRY(finalize(l));
 
+  const int Kin[3] = {Cin, d.C1, d.C2};
+  char* wbase = train ? sv : ws;   // bf16 weight copies live with the saved state in train mode
+  if (TC) PCOE_TRY(convert_weights(d, L, P, wbase, st));
+  auto nt = [&](const auto& ap, int l, const auto& epi, const char* what) -> int {
+    using AP = std::decay_t<decltype(ap)>;
+    using EP = std::decay_t<decltype(epi)>;
+    if constexpr (TC)
+      return launch_nt_tc<AP, EP>(ap, (const __nv_bfloat16*)(wbase + L.wb_off[l]), L.wb_k[l], L.wb_rows[l], epi, M,
+                                  Cs[l], Kin[l], st, what);
+    else
+      return launch_nt<AP, EP, false>(ap, P.W[l], Kin[l], epi, M, Cs[l], Kin[l], st, what);
+  };
+
   GatherProd gp{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, Cin};
-  PCOE_TRY((launch_nt<GatherProd, StoreStatsEpi<TY>, false>(gp, P.W[0], Cin, StoreStatsEpi<TY>{y[0], sums[0], d.C1},
-                                                           M, d.C1, Cin, st, "sa_fwd_l1")));
+  PCOE_TRY(nt(gp, 0, StoreStatsEpi<TY>{y[0], sums[0], d.C1}, "sa_fwd_l1"));
   if (train) PCOE_TRY(finalize(0));
   BnReluProd<TY> p1{y[0], scale[0], shift[0], M, d.C1};
-  PCOE_TRY((launch_nt<BnReluProd<TY>, StoreStatsEpi<TY>, false>(p1, P.W[1], d.C1, StoreStatsEpi<TY>{y[1], sums[1], d.C2},
-                                                               M, d.C2, d.C1, st, "sa_fwd_l2")));
+  PCOE_TRY(nt(p1, 1, StoreStatsEpi<TY>{y[1], sums[1], d.C2}, "sa_fwd_l2"));
   if (train) PCOE_TRY(finalize(1));
   BnReluProd<TY> p2{y[1], scale[1], shift[1], M, d.C2};
   GroupEpi<TY> ge{y[2], sums[2], ymax, ymin, amax, amin, d.C3, d.K};
-  PCOE_TRY((launch_nt<BnReluProd<TY>, GroupEpi<TY>, false>(p2, P.W[2], d.C2, ge, M, d.C3, d.C2, st, "sa_fwd_l3")));
+  PCOE_TRY(nt(p2, 2, ge, "sa_fwd_l3"));
   if (train) PCOE_TRY(finalize(2));
 
   const size_t total = (size_t)G * d.C3;
@@ -224,7 +288,7 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
   return ls.done();
 }
 
-template <typename TY>
+template <typename TY, bool TC>
 static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float* new_xyz, const int32_t* nbr,
                             const float* feats, const pcoe_sa_params& P, const float* out, const float* grad_out,
                             const void* saved, float* grad_feats, const pcoe_sa_grads& Gr, void* workspace,
@@ -277,29 +341,44 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   }
   PCOE_TRY(consts(2));
 
+  // dgrad: dx_prev[M x Kin[l]] = dy_l[M x Cs[l]] * W_l ;  wgrad: dW_l[Cs[l] x Kin[l]] = dy_l^T x_prev
+  auto dgrad = [&](const auto& ap, int l, const auto& epi, const char* what) -> int {
+    using AP = std::decay_t<decltype(ap)>;
+    using EP = std::decay_t<decltype(epi)>;
+    if constexpr (TC)
+      return launch_nt_tc<AP, EP>(ap, (const __nv_bfloat16*)(sv + L.wbt_off[l]), L.wbt_k[l], L.wbt_rows[l], epi, M,
+                                  Kin[l], Cs[l], st, what);
+    else
+      return launch_nt<AP, EP, true>(ap, P.W[l], Kin[l], epi, M, Kin[l], Cs[l], st, what);
+  };
+  auto wgrad = [&](const auto& pp, const auto& qp, int l, const char* what) -> int {
+    if constexpr (TC) return launch_tn_tc(pp, qp, Gr.dW[l], Kin[l], M, Cs[l], Kin[l], st, what);
+    else return launch_tn(pp, qp, Gr.dW[l], Kin[l], M, Cs[l], Kin[l], st, what);
+  };
+
   // layer 3
   DyLastProd<TY> dy3{gm, slot, y[2], ca[2], cp[2], cq[2], M, d.C3, d.K};
   BnReluProd<TY> x2{y[1], scale[1], shift[1], M, d.C2};
-  PCOE_TRY((launch_tn(dy3, x2, Gr.dW[2], d.C2, M, d.C3, d.C2, st, "sa_bwd_wgrad3")));
+  PCOE_TRY(wgrad(dy3, x2, 2, "sa_bwd_wgrad3"));
   MaskStatsEpi<TY> me2{y[1], scale[1], shift[1], mean[1], invstd[1], dz[1], bs[1], d.C2};
-  PCOE_TRY((launch_nt<DyLastProd<TY>, MaskStatsEpi<TY>, true>(dy3, P.W[2], d.C2, me2, M, d.C2, d.C3, st, "sa_bwd_dgrad3")));
+  PCOE_TRY(dgrad(dy3, 2, me2, "sa_bwd_dgrad3"));
   PCOE_TRY(consts(1));
 
   // layer 2
   DyProd<TY> dy2{dz[1], y[1], ca[1], cp[1], cq[1], M, d.C2};
   BnReluProd<TY> x1{y[0], scale[0], shift[0], M, d.C1};
-  PCOE_TRY((launch_tn(dy2, x1, Gr.dW[1], d.C1, M, d.C2, d.C1, st, "sa_bwd_wgrad2")));
+  PCOE_TRY(wgrad(dy2, x1, 1, "sa_bwd_wgrad2"));
   MaskStatsEpi<TY> me1{y[0], scale[0], shift[0], mean[0], invstd[0], dz[0], bs[0], d.C1};
-  PCOE_TRY((launch_nt<DyProd<TY>, MaskStatsEpi<TY>, true>(dy2, P.W[1], d.C1, me1, M, d.C1, d.C2, st, "sa_bwd_dgrad2")));
+  PCOE_TRY(dgrad(dy2, 1, me1, "sa_bwd_dgrad2"));
   PCOE_TRY(consts(0));
 
   // layer 1
   DyProd<TY> dy1{dz[0], y[0], ca[0], cp[0], cq[0], M, d.C1};
   GatherProd x0{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, Cin};
-  PCOE_TRY((launch_tn(dy1, x0, Gr.dW[0], Cin, M, d.C1, Cin, st, "sa_bwd_wgrad1")));
+  PCOE_TRY(wgrad(dy1, x0, 0, "sa_bwd_wgrad1"));
   if (d.D > 0 && grad_feats) {
     ScatterEpi se{grad_feats, nbr, d.N, d.S, d.K, d.D, d.group_all};
-    PCOE_TRY((launch_nt<DyProd<TY>, ScatterEpi, true>(dy1, P.W[0], Cin, se, M, Cin, d.C1, st, "sa_bwd_dgrad1")));
+    PCOE_TRY(dgrad(dy1, 0, se, "sa_bwd_dgrad1"));
   }
   return PCOE_OK;
 }
@@ -336,8 +415,8 @@ extern "C" int pcoe_sa_forward(const pcoe_sa_desc* desc, const float* xyz, const
   if (workspace_bytes < L.workspace_bytes)
     return fail(PCOE_ERR_WORKSPACE, "sa_forward: workspace %zu < %zu bytes", workspace_bytes, L.workspace_bytes);
   if (d.precision == PCOE_PRECISION_BF16)
-    return sa_forward_impl<__nv_bfloat16>(d, xyz, new_xyz, nbr, feats, *params, out, saved, workspace, (cudaStream_t)stream);
-  return sa_forward_impl<float>(d, xyz, new_xyz, nbr, feats, *params, out, saved, workspace, (cudaStream_t)stream);
+    return sa_forward_impl<__nv_bfloat16, true>(d, xyz, new_xyz, nbr, feats, *params, out, saved, workspace, (cudaStream_t)stream);
+  return sa_forward_impl<float, false>(d, xyz, new_xyz, nbr, feats, *params, out, saved, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int pcoe_sa_backward(const pcoe_sa_desc* desc, const float* xyz, const float* new_xyz,
@@ -360,8 +439,8 @@ extern "C" int pcoe_sa_backward(const pcoe_sa_desc* desc, const float* xyz, cons
   if (workspace_bytes < L.workspace_bytes)
     return fail(PCOE_ERR_WORKSPACE, "sa_backward: workspace %zu < %zu bytes", workspace_bytes, L.workspace_bytes);
   if (d.precision == PCOE_PRECISION_BF16)
-    return sa_backward_impl<__nv_bfloat16>(d, xyz, new_xyz, nbr, feats, *params, out, grad_out, saved, grad_feats,
+    return sa_backward_impl<__nv_bfloat16, true>(d, xyz, new_xyz, nbr, feats, *params, out, grad_out, saved, grad_feats,
                                            *grads, workspace, (cudaStream_t)stream);
-  return sa_backward_impl<float>(d, xyz, new_xyz, nbr, feats, *params, out, grad_out, saved, grad_feats, *grads,
+  return sa_backward_impl<float, false>(d, xyz, new_xyz, nbr, feats, *params, out, grad_out, saved, grad_feats, *grads,
                                  workspace, (cudaStream_t)stream);
 }

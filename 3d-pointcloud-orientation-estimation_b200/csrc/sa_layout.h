@@ -15,6 +15,9 @@ struct SaLayout {
   size_t ws_sums[3], ws_sums_bytes, ws_ymax, ws_ymin, ws_amax, ws_amin, ws_y[2], ws_stat[3];
   // workspace, backward
   size_t wb_sums[3], wb_sums_bytes, wb_consts[3], wb_gm, wb_dz[2];
+  // bf16 weight copies (tensor-core path): offsets relative to `saved` (train) or `workspace` (eval)
+  size_t wb_off[3], wbt_off[3];
+  int wb_rows[3], wb_k[3], wbt_rows[3], wbt_k[3];
   size_t workspace_bytes;
 };
 
@@ -31,6 +34,18 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   for (int l = 0; l < 3; ++l) L.sv_stat[l] = take(s, sizeof(float) * 4 * C[l]);
   L.sv_slot = take(s, (size_t)L.G * d.C3);
   L.sv_ysel = take(s, sizeof(float) * (size_t)L.G * d.C3);
+  const bool tc = d.precision == PCOE_PRECISION_BF16;
+  const int Kin[3] = {3 + d.D, d.C1, d.C2};
+  for (int l = 0; l < 3; ++l) {
+    L.wb_rows[l] = (int)align_up(C[l], 128);   L.wb_k[l] = (int)align_up(Kin[l], 64);
+    L.wbt_rows[l] = (int)align_up(Kin[l], 128); L.wbt_k[l] = (int)align_up(C[l], 64);
+    L.wb_off[l] = L.wbt_off[l] = 0;
+  }
+  if (tc && d.train)
+    for (int l = 0; l < 3; ++l) {
+      L.wb_off[l] = take(s, (size_t)2 * L.wb_rows[l] * L.wb_k[l]);
+      L.wbt_off[l] = take(s, (size_t)2 * L.wbt_rows[l] * L.wbt_k[l]);
+    }
   L.saved_bytes = d.train ? s : 0;
 
   size_t f = 0;
@@ -42,8 +57,14 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   L.ws_amin = take(f, (size_t)L.G * d.C3);
   for (int l = 0; l < 3; ++l) L.ws_stat[l] = take(f, sizeof(float) * 4 * C[l]);
   L.ws_y[0] = L.ws_y[1] = 0;
-  if (!d.train)
+  if (!d.train) {
     for (int l = 0; l < 2; ++l) L.ws_y[l] = take(f, (size_t)L.M * C[l] * L.esz);
+    if (tc)
+      for (int l = 0; l < 3; ++l) {
+        L.wb_off[l] = take(f, (size_t)2 * L.wb_rows[l] * L.wb_k[l]);
+        L.wbt_off[l] = take(f, (size_t)2 * L.wbt_rows[l] * L.wbt_k[l]);
+      }
+  }
 
   size_t b = 0;
   for (int l = 0; l < 3; ++l) L.wb_sums[l] = take(b, sizeof(double) * 2 * C[l]);

@@ -251,6 +251,12 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     value = world * B * args.steps / (dev_ms / 1e3)
 
+    if args.timed_only:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": dev_ms / args.steps, "gpu_launches": int(launches),
+                              "precision": args.precision, "timed_only": True}), flush=True)
+        return
+
     # ---- end-to-end through the public API with host buffers ------------------------------------
     for m in (model.sa1, model.sa2):
         m.sampler = "randperm_host"                       # the reference's host-generator sampling (index-exact)
@@ -357,6 +363,8 @@ def main():
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
     ap.add_argument("--precision", choices=["fp32", "bf16"], default=os.environ.get("PCOE_PRECISION", "fp32"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timed-only", action="store_true",
+                    help="warm-up + timed region only (for ncu captures): no e2e / per-kernel / CPU legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

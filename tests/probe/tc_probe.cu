@@ -1,0 +1,133 @@
+// tc_probe.cu — stand-alone check of the tcgen05 / TMEM primitives and the SWIZZLE_128B operand
+// layouts in csrc/tc_common.cuh against a CPU GEMM.  Build: nvcc -gencode arch=compute_100a,code=sm_100a
+// -I<csrc> tc_probe.cu -o tc_probe ; run on a B200: prints max |error| per case (exact inputs -> 0).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "tc_common.cuh"
+
+using namespace pcoe::tc;
+
+// mode 0: D[128 x N] = A[128 x K] * B[N x K]^T   (both K-major)
+// mode 1: D[128 x N] = P[K x 128]^T * Q[K x N]   (both MN-major; K = contraction rows)
+// swap : exchange LBO/SBO in the MN-major descriptors (layout hypothesis test)
+__global__ void probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                             float* __restrict__ D, int N, int K, int mode, int swap) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* sA;
+  uint8_t* sB;
+  if (mode == 0) {
+    sA = smem;                              // K/64 tiles of [128 x 64]
+    sB = smem + (size_t)(K / 64) * 128 * 128;  // K/64 tiles of [N x 64]
+    for (int e = tid; e < 128 * K; e += blockDim.x) {
+      int r = e / K, c = e % K;
+      *(__nv_bfloat16*)(sA + (size_t)(c / 64) * 128 * 128 + sw128_off(r, c % 64)) = A[e];
+    }
+    for (int e = tid; e < N * K; e += blockDim.x) {
+      int r = e / K, c = e % K;
+      *(__nv_bfloat16*)(sB + (size_t)(c / 64) * N * 128 + sw128_off(r, c % 64)) = B[e];
+    }
+  } else {
+    sA = smem;                              // 2 tiles of [K x 64]   (P is [K][128])
+    sB = smem + (size_t)2 * K * 128;        // N/64 tiles of [K x 64] (Q is [K][N])
+    for (int e = tid; e < K * 128; e += blockDim.x) {
+      int r = e / 128, c = e % 128;
+      *(__nv_bfloat16*)(sA + (size_t)(c / 64) * K * 128 + sw128_off(r, c % 64)) = A[e];
+    }
+    for (int e = tid; e < K * N; e += blockDim.x) {
+      int r = e / N, c = e % N;
+      *(__nv_bfloat16*)(sB + (size_t)(c / 64) * K * 128 + sw128_off(r, c % 64)) = B[e];
+    }
+  }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc<256>(&tmem_base);
+  if (tid == 0) mbar_init(&mbar, 1);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base;
+
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N, mode == 1, mode == 1);
+    bool acc = false;
+    if (mode == 0) {
+      for (int kb = 0; kb < K / 64; ++kb)
+        for (int ks = 0; ks < 4; ++ks) {
+          uint64_t ad = make_desc_sw128(smem_u32(sA + (size_t)kb * 128 * 128) + ks * 32, 16, 1024);
+          uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)kb * N * 128) + ks * 32, 16, 1024);
+          mma_bf16(tmem, ad, bd, idesc, acc);
+          acc = true;
+        }
+    } else {
+      for (int ks = 0; ks < K / 16; ++ks) {
+        uint32_t lbo = (uint32_t)K * 128, sbo = 1024;
+        if (swap) { uint32_t t = lbo; lbo = sbo; sbo = t; }
+        uint64_t ad = make_desc_sw128(smem_u32(sA) + ks * 2048, lbo, sbo);
+        uint64_t bd = make_desc_sw128(smem_u32(sB) + ks * 2048, lbo, sbo);
+        mma_bf16(tmem, ad, bd, idesc, acc);
+        acc = true;
+      }
+    }
+    mma_commit(&mbar);
+  }
+  mbar_wait(&mbar, 0);
+  fence_after_sync();
+  if (warp < 4) {
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      for (int i = 0; i < 32; ++i) D[(size_t)(warp * 32 + (tid & 31)) * N + c0 + i] = v[i];
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+static float frand_exact() { return (float)((rand() % 9) - 4) * 0.25f; }
+
+static double run_case(int mode, int N, int K, int swap) {
+  const int an = 128 * K, bn = N * K;
+  std::vector<float> fa(an), fb(bn);
+  std::vector<__nv_bfloat16> ha(an), hb(bn);
+  for (int i = 0; i < an; ++i) { fa[i] = frand_exact(); ha[i] = __float2bfloat16(fa[i]); }
+  for (int i = 0; i < bn; ++i) { fb[i] = frand_exact(); hb[i] = __float2bfloat16(fb[i]); }
+  __nv_bfloat16 *dA, *dB; float* dD;
+  cudaMalloc(&dA, an * 2); cudaMalloc(&dB, bn * 2); cudaMalloc(&dD, 128 * N * 4);
+  cudaMemcpy(dA, ha.data(), an * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, hb.data(), bn * 2, cudaMemcpyHostToDevice);
+  cudaMemset(dD, 0xFF, 128 * N * 4);
+  size_t smem = (size_t)(128 + N) * K * 2 + 1024;
+  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, mode, swap);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  CUDA error: %s\n", cudaGetErrorString(e)); exit(2); }
+  std::vector<float> hd(128 * N);
+  cudaMemcpy(hd.data(), dD, 128 * N * 4, cudaMemcpyDeviceToHost);
+  double worst = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      double ref = 0;
+      for (int k = 0; k < K; ++k)
+        ref += mode == 0 ? (double)fa[m * K + k] * fb[n * K + k] : (double)fa[k * 128 + m] * fb[k * N + n];
+      double err = fabs(ref - (double)hd[m * N + n]);
+      if (!(err <= worst)) worst = err;   // NaN-propagating max
+    }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return worst;
+}
+
+int main() {
+  srand(1);
+  const int Ns[] = {64, 128, 256}, Ks[] = {64, 128, 192};
+  for (int N : Ns)
+    for (int K : Ks) printf("K-major   N=%3d K=%3d  max_err=%g\n", N, K, run_case(0, N, K, 0));
+  for (int swap = 0; swap < 2; ++swap)
+    for (int N : Ns)
+      for (int K : Ks) printf("MN-major  N=%3d K=%3d swap=%d max_err=%g\n", N, K, swap, run_case(1, N, K, swap));
+  return 0;
+}
