@@ -10,11 +10,12 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
        -I"$root/include" -I"$here" "$@")
 objs=()
 pids=()
+# newest header (any change to a shared header rebuilds every object)
+newest_hdr="$(ls -t "$here"/*.cuh "$here"/*.h "$root/include/pcoe.h" "$here/build.sh" 2>/dev/null | head -1)"
 for src in "$here"/*.cu; do
   obj="$here/build/$(basename "${src%.cu}").o"
   objs+=("$obj")
-  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$here/common.cuh" -nt "$obj" || "$root/include/pcoe.h" -nt "$obj" \
-        || ( -f "$here/sa_common.cuh" && "$here/sa_common.cuh" -nt "$obj" ) ]]; then
+  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$newest_hdr" -nt "$obj" ]]; then
     "$NVCC" "${FLAGS[@]}" -c "$src" -o "$obj" &
     pids+=($!)
   fi

@@ -38,10 +38,15 @@ __device__ __forceinline__ void load_cloud_soa(const float* __restrict__ cloud, 
   }
 }
 
-// kNN: per-warp sorted list (ascending distance) in shared memory, K/32 entries per lane.
-// A candidate enters only if it is strictly closer than the current K-th entry; points are
-// visited in ascending index so equal distances keep the lower index (matches a stable top-k).
-__global__ void __launch_bounds__(kGroupWarps * 32)
+// kNN by selection, one warp per centroid.  The cloud is walked in chunks of 1024 points: every lane
+// holds 32 squared distances of the chunk in registers (point = chunk + slot*32 + lane, so the
+// shared-memory reads are conflict free) next to its share of the running K-best list.  The K-th
+// smallest distance T of (list U chunk) is found by a 31-step bitwise search on the fp32 bit pattern
+// (distances are >= +0, so unsigned order == float order; one REDUX per step), then the new list =
+// every entry below T plus the lowest-index entries equal to T.  No sorting, no serial insertion.
+// Rows come out in ascending point index (the reference's topk(sorted=False) order is unspecified).
+template <int KR>   // list slots per lane, K <= 32*KR
+__global__ void __launch_bounds__(1024)
 knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S, int K,
            int32_t* __restrict__ out_idx) {
   extern __shared__ float smem_f[];
@@ -49,57 +54,98 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int
   float* sy = sx + N;
   float* sz = sy + N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* list_d = sz + N + warp * K;
-  int32_t* list_i = reinterpret_cast<int32_t*>(sz + N + kGroupWarps * K) + warp * K;
+  const int nwarps = blockDim.x >> 5;
+  uint32_t* list_d = reinterpret_cast<uint32_t*>(sz + N) + warp * (32 * KR);
+  int32_t* list_i = reinterpret_cast<int32_t*>(sz + N + nwarps * 32 * KR) + warp * (32 * KR);
+  constexpr uint32_t kInf = 0x7F800000u;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   const int b = blockIdx.y;
   load_cloud_soa(xyz + (size_t)b * N * 3, N, sx, sy, sz);
   __syncthreads();
 
-  const int s_begin = (blockIdx.x * kGroupWarps + warp) * kCentroidsPerWarp;
-  for (int s = s_begin; s < min(s_begin + kCentroidsPerWarp, S); ++s) {
+  // one centroid per warp (high occupancy hides the REDUX / shared-memory latency of the search)
+  for (int s = blockIdx.x * nwarps + warp; s < S; s += gridDim.x * nwarps) {
     const float* c = new_xyz + ((size_t)b * S + s) * 3;
     const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
-    for (int e = lane; e < K; e += 32) { list_d[e] = INFINITY; list_i[e] = -1; }
-    __syncwarp();
-    float kth = INFINITY;
-    int filled = 0;  // number of real entries (<= K)
-    for (int base = 0; base < N; base += 32) {
-      const int i = base + lane;
-      float d = INFINITY;
-      if (i < N) d = sqdist_rn(sx[i], sy[i], sz[i], cx, cy, cz);
-      unsigned pass = __ballot_sync(0xFFFFFFFFu, i < N && (d < kth || filled < K));
-      while (pass) {
-        const int src = __ffs(pass) - 1;
-        pass &= pass - 1;
-        const float dv = __shfl_sync(0xFFFFFFFFu, d, src);
-        const int iv = base + src;
-        if (!(dv < kth || filled < K)) continue;  // threshold moved since the ballot
-        // position = number of entries with distance <= dv (they all have a lower index)
-        int pos = 0;
-        for (int e0 = 0; e0 < K; e0 += 32) {
-          int e = e0 + lane;
-          pos += __popc(__ballot_sync(0xFFFFFFFFu, e < K && list_d[e] <= dv));
-        }
-        // shift [pos, K-1) up by one, highest chunk first so reads precede overwrites
-        for (int e0 = ((K - 1) / 32) * 32; e0 >= 0; e0 -= 32) {
-          int e = e0 + lane;
-          float pd = 0.f; int pi = 0;
-          bool mv = e < K && e > pos;
-          if (mv) { pd = list_d[e - 1]; pi = list_i[e - 1]; }
-          __syncwarp();
-          if (mv) { list_d[e] = pd; list_i[e] = pi; }
-          __syncwarp();
-        }
-        if (lane == 0) { list_d[pos] = dv; list_i[pos] = iv; }
-        __syncwarp();
-        if (filled < K) ++filled;
-        kth = (filled == K) ? list_d[K - 1] : INFINITY;
+    uint32_t ld[KR];
+    int32_t li[KR];
+#pragma unroll
+    for (int j = 0; j < KR; ++j) { ld[j] = kInf; li[j] = -1; }
+    uint32_t kth = kInf;   // current K-th smallest distance (bits); kInf while the list is not full
+
+    for (int base = 0; base < N; base += 1024) {
+      uint32_t d[32];
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int i = base + q * 32 + lane;
+        uint32_t v = kInf;
+        if (i < N) v = __float_as_uint(sqdist_rn(sx[i], sy[i], sz[i], cx, cy, cz));
+        // later chunks: an entry that is not below the current K-th can never enter (ties keep the lower index)
+        if (v >= kth) v = kInf;
+        d[q] = v;
+        any |= v != kInf;
       }
+      if (!__any_sync(0xFFFFFFFFu, any)) continue;
+
+      // T = K-th smallest of list U chunk
+      uint32_t T = 0;
+#pragma unroll 1
+      for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) cnt += d[q] < cand;
+#pragma unroll
+        for (int j = 0; j < KR; ++j) cnt += ld[j] < cand;
+        if (__reduce_add_sync(0xFFFFFFFFu, cnt) < K) T = cand;
+      }
+      int less = 0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) less += d[q] < T;
+#pragma unroll
+      for (int j = 0; j < KR; ++j) less += ld[j] < T;
+      const int need_eq = K - __reduce_add_sync(0xFFFFFFFFu, less);   // >= 1
+
+      // rebuild the list in ascending index order: old list entries first (lower indices), then the chunk
+      int out_n = 0, eq_n = 0;
+#pragma unroll
+      for (int j = 0; j < KR; ++j) {
+        const bool eq = ld[j] == T && T != kInf;
+        const unsigned meq = __ballot_sync(0xFFFFFFFFu, eq);
+        const bool sel = ld[j] < T || (eq && eq_n + __popc(meq & lt_mask) < need_eq);
+        const unsigned msel = __ballot_sync(0xFFFFFFFFu, sel);
+        if (sel) { const int pos = out_n + __popc(msel & lt_mask); list_d[pos] = ld[j]; list_i[pos] = li[j]; }
+        out_n += __popc(msel);
+        eq_n += __popc(meq);
+      }
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const bool eq = d[q] == T && T != kInf;
+        const unsigned meq = __ballot_sync(0xFFFFFFFFu, eq);
+        const bool sel = d[q] < T || (eq && eq_n + __popc(meq & lt_mask) < need_eq);
+        const unsigned msel = __ballot_sync(0xFFFFFFFFu, sel);
+        if (sel) { const int pos = out_n + __popc(msel & lt_mask); list_d[pos] = d[q]; list_i[pos] = base + q * 32 + lane; }
+        out_n += __popc(msel);
+        eq_n += __popc(meq);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < KR; ++j) {
+        const int e = j * 32 + lane;
+        ld[j] = e < out_n ? list_d[e] : kInf;
+        li[j] = e < out_n ? list_i[e] : -1;
+      }
+      __syncwarp();
+      kth = out_n >= K ? T : kInf;
     }
     int32_t* o = out_idx + ((size_t)b * S + s) * K;
-    for (int e = lane; e < K; e += 32) o[e] = list_i[e];
-    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < KR; ++j) {
+      const int e = j * 32 + lane;
+      if (e < K) o[e] = li[j];
+    }
   }
 }
 
@@ -138,8 +184,8 @@ ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_x
   }
 }
 
-static int group_smem(int N, int K, size_t* smem) {
-  *smem = (size_t)N * 3 * sizeof(float) + (size_t)kGroupWarps * K * 8;
+static int group_smem(int N, int K, size_t* smem, int warps = kGroupWarps) {
+  *smem = (size_t)N * 3 * sizeof(float) + (size_t)warps * ((K + 31) / 32 * 32) * 8;
   return *smem <= 200 * 1024;
 }
 
@@ -155,13 +201,19 @@ extern "C" int pcoe_knn_f32(const float* xyz, const float* new_xyz, int B, int N
   if (K > 128) return fail(PCOE_ERR_UNSUPPORTED, "knn: K=%d > 128", K);
   if (!xyz || !new_xyz || !out_idx) return fail(PCOE_ERR_NULL, "knn: NULL pointer");
   size_t smem;
-  if (!group_smem(N, K, &smem)) return fail(PCOE_ERR_UNSUPPORTED, "knn: N=%d does not fit shared memory", N);
-  if (smem > 48 * 1024)
-    PCOE_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(S, kGroupWarps * kCentroidsPerWarp), B);
-  LaunchScope ls("knn_kernel", (cudaStream_t)stream);
-  knn_kernel<<<grid, kGroupWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, K, out_idx);
-  return ls.done();
+  const int warps = N <= 2048 ? 8 : (N <= 4096 ? 16 : 32);   // big clouds: fewer CTAs re-stage the cloud
+  if (!group_smem(N, K, &smem, warps)) return fail(PCOE_ERR_UNSUPPORTED, "knn: N=%d does not fit shared memory", N);
+  dim3 grid(ceil_div(S, warps), B);
+#define PCOE_KNN(KR_)                                                                                       \
+  {                                                                                                         \
+    if (smem > 48 * 1024)                                                                                   \
+      PCOE_CUDA(cudaFuncSetAttribute(knn_kernel<KR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    LaunchScope ls("knn_kernel", (cudaStream_t)stream);                                                     \
+    knn_kernel<KR_><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, K, out_idx); \
+    return ls.done();                                                                                       \
+  }
+  if (K <= 32) PCOE_KNN(1) else if (K <= 64) PCOE_KNN(2) else PCOE_KNN(4)
+#undef PCOE_KNN
 }
 
 extern "C" int pcoe_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N, int S,

@@ -9,6 +9,8 @@
 // per-channel constant exactly; they only shift running_mean (and enter eval mode).
 #include "sa_common.cuh"
 #include "sa_tc.cuh"
+#include "sa_tc2.cuh"
+#include "sa_tc3.cuh"
 #include "sa_layout.h"
 #include <type_traits>
 
@@ -108,6 +110,19 @@ __global__ void bn_bwd_consts_kernel(const double* __restrict__ sums, double cou
   if (dbias) dbias[c] = 0.f;  // exactly cancelled by the batch-mean subtraction
 }
 
+// per-layer kernel names for the profile report: sa1 = no input features, sa3 = group-all, sa2 = the rest
+enum { kF1, kF2, kF3, kBL3, kBL2, kBL1, kWG3, kDG3, kWG2, kDG2, kWG1, kDG1, kNumNames };
+static const char* kname(const pcoe_sa_desc& d, int which) {
+  static const char* t[3][kNumNames] = {
+      {"sa1_fwd_l1", "sa1_fwd_l2", "sa1_fwd_l3", "sa1_bwd_l3", "sa1_bwd_l2", "sa1_bwd_l1", "sa1_bwd_wgrad3",
+       "sa1_bwd_dgrad3", "sa1_bwd_wgrad2", "sa1_bwd_dgrad2", "sa1_bwd_wgrad1", "sa1_bwd_dgrad1"},
+      {"sa2_fwd_l1", "sa2_fwd_l2", "sa2_fwd_l3", "sa2_bwd_l3", "sa2_bwd_l2", "sa2_bwd_l1", "sa2_bwd_wgrad3",
+       "sa2_bwd_dgrad3", "sa2_bwd_wgrad2", "sa2_bwd_dgrad2", "sa2_bwd_wgrad1", "sa2_bwd_dgrad1"},
+      {"sa3_fwd_l1", "sa3_fwd_l2", "sa3_fwd_l3", "sa3_bwd_l3", "sa3_bwd_l2", "sa3_bwd_l1", "sa3_bwd_wgrad3",
+       "sa3_bwd_dgrad3", "sa3_bwd_wgrad2", "sa3_bwd_dgrad2", "sa3_bwd_wgrad1", "sa3_bwd_dgrad1"}};
+  return t[d.group_all ? 2 : (d.D == 0 ? 0 : 1)][which];
+}
+
 // ---- launch helpers --------------------------------------------------------------------------
 
 template <class AProd, class Epi, bool BT>
@@ -187,7 +202,8 @@ static int launch_tn_tc(const PProd& pp, const QProd& qp, float* out, int ldo, i
   return ls.done();
 }
 
-// bf16 copies of the three weight matrices (and their transposes for dgrad), tensor-core path only
+// bf16 copies of the three weight matrices (and their transposes for dgrad), tensor-core path only.
+// On the v2 path layer 1 uses the "features first" channel order [feats(D) | xyz(3)].
 static int convert_weights(const pcoe_sa_desc& d, const SaLayout& L, const pcoe_sa_params& P, char* base,
                            cudaStream_t st) {
   const int Cs[3] = {d.C1, d.C2, d.C3}, Kin[3] = {3 + d.D, d.C1, d.C2};
@@ -196,10 +212,64 @@ static int convert_weights(const pcoe_sa_desc& d, const SaLayout& L, const pcoe_
     LaunchScope ls("convert_weights_kernel", st);
     convert_weights_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(
         P.W[l], Cs[l], Kin[l], (__nv_bfloat16*)(base + L.wb_off[l]), L.wb_rows[l], L.wb_k[l],
-        (__nv_bfloat16*)(base + L.wbt_off[l]), L.wbt_rows[l], L.wbt_k[l]);
+        (__nv_bfloat16*)(base + L.wbt_off[l]), L.wbt_rows[l], L.wbt_k[l], (L.v2 && l == 0) ? d.D : -1);
     PCOE_TRY(ls.done());
   }
   return PCOE_OK;
+}
+
+// ---- v2 (persistent, register-epilogue) launchers ------------------------------------------------
+static int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+static int v2_grid(int M, size_t smem, int tcols) {
+  int occ = (int)((size_t)227 * 1024 / (smem + 1024));
+  occ = occ > 512 / tcols ? 512 / tcols : occ;
+  occ = occ > 2 ? 2 : (occ < 1 ? 1 : occ);
+  const int tiles = ceil_div(M, 128);
+  return tiles < kNumSMs * occ ? tiles : kNumSMs * occ;
+}
+
+template <class Prod, class Epi>
+static int launch_fwd_v2(const Prod& prod, const __nv_bfloat16* Wb, int ldw, int wrows, const Epi& epi, int M,
+                         int ncols, int kin, cudaStream_t st, const char* what) {
+  const int kpad = ldw, kmma = ceil_div(kin, 16) * 16, nmma = ceil_div(ncols, 16) * 16;
+  const int wr = min(wrows, ceil_div(nmma, 8) * 8), tcols = pow2_cols(2 * (ceil_div(ncols, 32) * 32));
+  const size_t smem = 1024 + (size_t)(kpad / 64) * (128 * 128 + wr * 128) + 4 * 256 * sizeof(float);
+  const int tiles = ceil_div(M, 128), grid = tiles < kNumSMs ? tiles : kNumSMs;   // one persistent CTA per SM
+  LaunchScope ls(what, st);
+#define PCOE_FWD3(TC_)                                                                                     \
+  {                                                                                                        \
+    auto k = v3::tc3_fwd_kernel<Prod, Epi, TC_>;                                                           \
+    static bool attr = false;                                                                              \
+    if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+    k<<<grid, v3::kCtaThreads, smem, st>>>(prod, Wb, ldw, wrows, epi, M, ncols, kpad, kmma);                 \
+  }
+  if (tcols <= 128) PCOE_FWD3(128) else if (tcols == 256) PCOE_FWD3(256) else PCOE_FWD3(512)
+#undef PCOE_FWD3
+  return ls.done();
+}
+
+template <class PProd, class QProd, class Epi>
+static int launch_bwd_v2(const PProd& pp, const QProd& qp, const __nv_bfloat16* WbT, int ldw, int wrows,
+                         const Epi& epi, float* dW, int ldo, int cb_valid, int perm_d, int M, int ca, int cbk,
+                         int cdn, cudaStream_t st, const char* what) {
+  const int cbmma = ceil_div(cb_valid, 16) * 16, dnm = ceil_div(cdn, 16) * 16, mt = ceil_div(ca, 128);
+  const int wr = cdn ? min(wrows, ceil_div(dnm, 8) * 8) : 0;
+  const int tcols = pow2_cols(ceil_div(mt * cbmma, 64) * 64 + 2 * (ceil_div(cdn, 32) * 32));
+  const size_t smem = 1024 + (size_t)(ca / 64) * (128 * 128 + wr * 128) + (size_t)(cbk / 64) * 128 * 128 +
+                      4 * 256 * sizeof(float);
+  const int tiles = ceil_div(M, 128), grid = tiles < kNumSMs ? tiles : kNumSMs;
+  LaunchScope ls(what, st);
+#define PCOE_BWD3(TC_)                                                                                     \
+  {                                                                                                        \
+    auto k = v3::tc3_bwd_kernel<PProd, QProd, Epi, TC_>;                                                   \
+    static bool attr = false;                                                                              \
+    if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+    k<<<grid, v3::kCtaThreads, smem, st>>>(pp, qp, WbT, ldw, wrows, epi, dW, ldo, cb_valid, perm_d, M, ca, cbk, cbmma, cdn); \
+  }
+  if (tcols <= 128) PCOE_BWD3(128) else if (tcols == 256) PCOE_BWD3(256) else PCOE_BWD3(512)
+#undef PCOE_BWD3
+  return ls.done();
 }
 
 static int validate(const pcoe_sa_desc* d) {
@@ -267,16 +337,37 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       return launch_nt<AP, EP, false>(ap, P.W[l], Kin[l], epi, M, Cs[l], Kin[l], st, what);
   };
 
-  GatherProd gp{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, Cin};
-  PCOE_TRY(nt(gp, 0, StoreStatsEpi<TY>{y[0], sums[0], d.C1}, "sa_fwd_l1"));
-  if (train) PCOE_TRY(finalize(0));
-  BnReluProd<TY> p1{y[0], scale[0], shift[0], M, d.C1};
-  PCOE_TRY(nt(p1, 1, StoreStatsEpi<TY>{y[1], sums[1], d.C2}, "sa_fwd_l2"));
-  if (train) PCOE_TRY(finalize(1));
-  BnReluProd<TY> p2{y[1], scale[1], shift[1], M, d.C2};
-  GroupEpi<TY> ge{y[2], sums[2], ymax, ymin, amax, amin, d.C3, d.K};
-  PCOE_TRY(nt(p2, 2, ge, "sa_fwd_l3"));
-  if (train) PCOE_TRY(finalize(2));
+  bool done = false;
+  if constexpr (TC) {
+    if (L.v2) {   // persistent kernels, weights resident in smem, register epilogues
+      auto wb = [&](int l) { return (const __nv_bfloat16*)(wbase + L.wb_off[l]); };
+      v2::Gather2 gp{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, 0};
+      v2::StoreStats2 e0{}; e0.y = y[0]; e0.sums = sums[0]; e0.C = d.C1;
+      PCOE_TRY(launch_fwd_v2(gp, wb(0), L.wb_k[0], L.wb_rows[0], e0, M, d.C1, Cin, st, kname(d, kF1)));
+      if (train) PCOE_TRY(finalize(0));
+      v2::BnRelu2 p1{}; p1.y = y[0]; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.C = d.C1;
+      v2::StoreStats2 e1{}; e1.y = y[1]; e1.sums = sums[1]; e1.C = d.C2;
+      PCOE_TRY(launch_fwd_v2(p1, wb(1), L.wb_k[1], L.wb_rows[1], e1, M, d.C2, d.C1, st, kname(d, kF2)));
+      if (train) PCOE_TRY(finalize(1));
+      v2::BnRelu2 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.C = d.C2;
+      v2::Group2 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin; e2.C = d.C3;
+      PCOE_TRY(launch_fwd_v2(p2, wb(2), L.wb_k[2], L.wb_rows[2], e2, M, d.C3, d.C2, st, kname(d, kF3)));
+      if (train) PCOE_TRY(finalize(2));
+      done = true;
+    }
+  }
+  if (!done) {
+    GatherProd gp{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, Cin};
+    PCOE_TRY(nt(gp, 0, StoreStatsEpi<TY>{y[0], sums[0], d.C1}, kname(d, kF1)));
+    if (train) PCOE_TRY(finalize(0));
+    BnReluProd<TY> p1{y[0], scale[0], shift[0], M, d.C1};
+    PCOE_TRY(nt(p1, 1, StoreStatsEpi<TY>{y[1], sums[1], d.C2}, kname(d, kF2)));
+    if (train) PCOE_TRY(finalize(1));
+    BnReluProd<TY> p2{y[1], scale[1], shift[1], M, d.C2};
+    GroupEpi<TY> ge{y[2], sums[2], ymax, ymin, amax, amin, d.C3, d.K};
+    PCOE_TRY(nt(p2, 2, ge, kname(d, kF3)));
+    if (train) PCOE_TRY(finalize(2));
+  }
 
   const size_t total = (size_t)G * d.C3;
   int blocks = (int)((total + 255) / 256);
@@ -356,29 +447,60 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
     else return launch_tn(pp, qp, Gr.dW[l], Kin[l], M, Cs[l], Kin[l], st, what);
   };
 
+  if constexpr (TC) {
+    if (L.v2) {   // one fused wgrad+dgrad kernel per layer
+      auto wbt = [&](int l) { return (const __nv_bfloat16*)(sv + L.wbt_off[l]); };
+      v2::DyLast2 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2]; dy3.M = M; dy3.C = d.C3;
+      v2::BnRelu2 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.C = d.C2;
+      v2::MaskStats2 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
+      m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2;
+      PCOE_TRY(launch_bwd_v2(dy3, x2, wbt(2), L.wbt_k[2], L.wbt_rows[2], m2, Gr.dW[2], d.C2, d.C2, -1, M, d.C3, L.wb_k[2],
+                             d.C2, st, kname(d, kBL3)));
+      PCOE_TRY(consts(1));
+      v2::Dy2 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.C = d.C2;
+      v2::BnRelu2 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.C = d.C1;
+      v2::MaskStats2 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
+      m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1;
+      PCOE_TRY(launch_bwd_v2(dy2, x1, wbt(1), L.wbt_k[1], L.wbt_rows[1], m1, Gr.dW[1], d.C1, d.C1, -1, M, d.C2, L.wb_k[1],
+                             d.C1, st, kname(d, kBL2)));
+      PCOE_TRY(consts(0));
+      v2::Dy2 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.C = d.C1;
+      v2::Gather2 x0{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, 0};
+      if (d.D > 0 && grad_feats) {
+        v2::Scatter2 se{grad_feats, nbr, d.N, d.S, d.K, d.D, d.group_all};
+        PCOE_TRY(launch_bwd_v2(dy1, x0, wbt(0), L.wbt_k[0], L.wbt_rows[0], se, Gr.dW[0], Cin, Cin, d.D, M, d.C1, L.wb_k[0],
+                               d.D, st, kname(d, kBL1)));
+      } else {
+        PCOE_TRY(launch_bwd_v2(dy1, x0, wbt(0), L.wbt_k[0], L.wbt_rows[0], v2::NoEpi2{}, Gr.dW[0], Cin, Cin, d.D, M, d.C1,
+                               L.wb_k[0], 0, st, kname(d, kBL1)));
+      }
+      return PCOE_OK;
+    }
+  }
+
   // layer 3
   DyLastProd<TY> dy3{gm, slot, y[2], ca[2], cp[2], cq[2], M, d.C3, d.K};
   BnReluProd<TY> x2{y[1], scale[1], shift[1], M, d.C2};
-  PCOE_TRY(wgrad(dy3, x2, 2, "sa_bwd_wgrad3"));
+  PCOE_TRY(wgrad(dy3, x2, 2, kname(d, kWG3)));
   MaskStatsEpi<TY> me2{y[1], scale[1], shift[1], mean[1], invstd[1], dz[1], bs[1], d.C2};
-  PCOE_TRY(dgrad(dy3, 2, me2, "sa_bwd_dgrad3"));
+  PCOE_TRY(dgrad(dy3, 2, me2, kname(d, kDG3)));
   PCOE_TRY(consts(1));
 
   // layer 2
   DyProd<TY> dy2{dz[1], y[1], ca[1], cp[1], cq[1], M, d.C2};
   BnReluProd<TY> x1{y[0], scale[0], shift[0], M, d.C1};
-  PCOE_TRY(wgrad(dy2, x1, 1, "sa_bwd_wgrad2"));
+  PCOE_TRY(wgrad(dy2, x1, 1, kname(d, kWG2)));
   MaskStatsEpi<TY> me1{y[0], scale[0], shift[0], mean[0], invstd[0], dz[0], bs[0], d.C1};
-  PCOE_TRY(dgrad(dy2, 1, me1, "sa_bwd_dgrad2"));
+  PCOE_TRY(dgrad(dy2, 1, me1, kname(d, kDG2)));
   PCOE_TRY(consts(0));
 
   // layer 1
   DyProd<TY> dy1{dz[0], y[0], ca[0], cp[0], cq[0], M, d.C1};
   GatherProd x0{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, Cin};
-  PCOE_TRY(wgrad(dy1, x0, 0, "sa_bwd_wgrad1"));
+  PCOE_TRY(wgrad(dy1, x0, 0, kname(d, kWG1)));
   if (d.D > 0 && grad_feats) {
     ScatterEpi se{grad_feats, nbr, d.N, d.S, d.K, d.D, d.group_all};
-    PCOE_TRY(dgrad(dy1, 0, se, "sa_bwd_dgrad1"));
+    PCOE_TRY(dgrad(dy1, 0, se, kname(d, kDG1)));
   }
   return PCOE_OK;
 }

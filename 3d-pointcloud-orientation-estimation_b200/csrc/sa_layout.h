@@ -18,6 +18,7 @@ struct SaLayout {
   // bf16 weight copies (tensor-core path): offsets relative to `saved` (train) or `workspace` (eval)
   size_t wb_off[3], wbt_off[3];
   int wb_rows[3], wb_k[3], wbt_rows[3], wbt_k[3];
+  bool v2;         // bf16 mode and the layer fits the persistent on-chip kernels (sa_tc2.cuh)
   size_t workspace_bytes;
 };
 
@@ -36,9 +37,12 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   L.sv_ysel = take(s, sizeof(float) * (size_t)L.G * d.C3);
   const bool tc = d.precision == PCOE_PRECISION_BF16;
   const int Kin[3] = {3 + d.D, d.C1, d.C2};
+  auto kpad = [](int k) { return k <= 64 ? 64 : k <= 128 ? 128 : k <= 256 ? 256 : (int)align_up(k, 64); };
+  auto chan_ok = [](int c) { return c == 64 || c == 128 || c == 256; };
+  L.v2 = tc && d.K == 32 && chan_ok(d.C1) && chan_ok(d.C2) && chan_ok(d.C3) && (d.D % 32) == 0 && d.D + 3 <= 256;
   for (int l = 0; l < 3; ++l) {
-    L.wb_rows[l] = (int)align_up(C[l], 128);   L.wb_k[l] = (int)align_up(Kin[l], 64);
-    L.wbt_rows[l] = (int)align_up(Kin[l], 128); L.wbt_k[l] = (int)align_up(C[l], 64);
+    L.wb_rows[l] = (int)align_up(C[l], 128);   L.wb_k[l] = kpad(Kin[l]);
+    L.wbt_rows[l] = (int)align_up(Kin[l], 128); L.wbt_k[l] = kpad(C[l]);
     L.wb_off[l] = L.wbt_off[l] = 0;
   }
   if (tc && d.train)

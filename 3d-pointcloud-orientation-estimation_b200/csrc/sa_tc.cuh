@@ -28,15 +28,20 @@ constexpr size_t kTcTnSmem = 1024 + 4 * kTcTileBytes;
 // bf16 weights for the tensor-core path: Wb[rows_pad][kpad] (zero padded), row-major
 __global__ void convert_weights_kernel(const float* __restrict__ W, int Cout, int Cin,
                                        __nv_bfloat16* __restrict__ Wb, int rows_pad, int kpad,
-                                       __nv_bfloat16* __restrict__ WbT, int rows_pad_t, int kpad_t) {
+                                       __nv_bfloat16* __restrict__ WbT, int rows_pad_t, int kpad_t,
+                                       int perm_d /* >= 0: input channels reordered [feats(perm_d) | xyz(3)] */) {
   const int total = rows_pad * kpad, total_t = rows_pad_t * kpad_t;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total + total_t; e += gridDim.x * blockDim.x) {
     if (e < total) {
       const int r = e / kpad, c = e % kpad;
-      Wb[e] = __float2bfloat16_rn((r < Cout && c < Cin) ? W[(size_t)r * Cin + c] : 0.f);
+      int cs = c;   // source input channel
+      if (perm_d >= 0) cs = c < perm_d ? c + 3 : c - perm_d;
+      Wb[e] = __float2bfloat16_rn((r < Cout && c < Cin) ? W[(size_t)r * Cin + cs] : 0.f);
     } else {
       const int t = e - total, r = t / kpad_t, c = t % kpad_t;   // r over Cin, c over Cout
-      WbT[t] = __float2bfloat16_rn((r < Cin && c < Cout) ? W[(size_t)c * Cin + r] : 0.f);
+      int rs = r;
+      if (perm_d >= 0) rs = r < perm_d ? r + 3 : r - perm_d;
+      WbT[t] = __float2bfloat16_rn((r < Cin && c < Cout) ? W[(size_t)c * Cin + rs] : 0.f);
     }
   }
 }
@@ -46,7 +51,7 @@ __global__ void __launch_bounds__(256)
 tc_gemm_nt_kernel(const AProd ap, const __nv_bfloat16* __restrict__ Bw, int ldb, int brows, const Epi epi,
                   int M, int Ncols, int Kdim) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sA = smem;
   uint8_t* sB = smem + kTcTileBytes;
   float* Cs = reinterpret_cast<float*>(smem + 2 * kTcTileBytes);
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(256)
 tc_gemm_tn_kernel(const PProd pp, const QProd qp, float* __restrict__ out, int ldo, int M, int Ca, int Cb,
                   int rows_per_split) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sP = smem;                        // 2 tiles [128 rows x 64 ch]
   uint8_t* sQ = smem + 2 * kTcTileBytes;     // 2 tiles
   __shared__ uint64_t mbar;

@@ -141,7 +141,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 // One CTA per cloud: identity permutation in shared memory, S Fisher-Yates swaps by one thread
 // (the swaps are a dependent chain), the S random offsets are drawn in parallel beforehand.
 __global__ void random_subset_kernel(int N, int S, uint64_t seed, uint64_t offset,
-                                     int32_t* __restrict__ out_idx) {
+                                     const uint64_t* __restrict__ offset_dev, int32_t* __restrict__ out_idx) {
+  if (offset_dev) offset += *offset_dev;
   extern __shared__ int32_t s_perm[];
   int32_t* s_j = s_perm + N;
   const int b = blockIdx.x, t = threadIdx.x, T = blockDim.x;
@@ -198,7 +199,7 @@ extern "C" int pcoe_gather_points_f32(const float* src, int B, int N, int C, con
 }
 
 extern "C" int pcoe_random_subset(int B, int N, int S, uint64_t seed, uint64_t offset,
-                                  int32_t* out_idx, void* stream) {
+                                  const uint64_t* offset_dev, int32_t* out_idx, void* stream) {
   if (B <= 0 || N <= 0 || S <= 0 || S > N)
     return fail(PCOE_ERR_BAD_SHAPE, "random_subset: B=%d N=%d S=%d", B, N, S);
   if (!out_idx) return fail(PCOE_ERR_NULL, "random_subset: out_idx is NULL");
@@ -207,6 +208,6 @@ extern "C" int pcoe_random_subset(int B, int N, int S, uint64_t seed, uint64_t o
   if (smem > 48 * 1024)
     PCOE_CUDA(cudaFuncSetAttribute(random_subset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LaunchScope ls("random_subset_kernel", (cudaStream_t)stream);
-  random_subset_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(N, S, seed, offset, out_idx);
+  random_subset_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(N, S, seed, offset, offset_dev, out_idx);
   return ls.done();
 }

@@ -20,6 +20,12 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 16-byte store to a 32-bit shared-memory address (explicit st.shared: pointers rounded up to the
+// 1024-byte tile alignment lose their address space and would otherwise compile to generic ST)
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // byte offset of element (row, col) inside an [R x 64] bf16 SWIZZLE_128B tile
 __device__ __host__ __forceinline__ uint32_t sw128_off(int row, int col) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 3) ^ (row & 7)) & 7) << 4) + (col & 7) * 2);

@@ -1,0 +1,62 @@
+"""CUDA-graph capture of a whole training step ("CUDA-graph-captured steps").
+
+A step of the drop-in models is ~60 libpcoe launches plus ~150 small torch launches; at 64 clouds per
+GPU the CPU cannot enqueue them as fast as the B200 executes them.  ``GraphedTrainStep`` captures
+
+    zero_grad -> forward -> loss -> backward -> [gradient all-reduce] -> [clip_grad_norm_] -> optimizer.step
+
+once (after warm-up on a side stream) and replays it per batch; inputs are copied into static device
+buffers first.  Requirements: device-side sampling (``sampler="randperm_device"`` or ``"fps"`` - the
+reference's host-generator ``randperm`` cannot be captured), an optimizer constructed with
+``capturable=True``, fixed batch shape.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, loss_fn, optimizer, example_xyz: torch.Tensor, example_targets: tuple,
+                 clip_norm: float | None = None, engine=None, warmup: int = 3):
+        self.model, self.loss_fn, self.opt, self.clip, self.engine = model, loss_fn, optimizer, clip_norm, engine
+        for m in model.modules():
+            if getattr(m, "sampler", None) == "randperm_host" and not getattr(m, "group_all", False):
+                raise ValueError("GraphedTrainStep needs a device-side sampler (randperm_device or fps)")
+        self.xyz = example_xyz.clone()
+        self.targets = tuple(t.clone() for t in example_targets)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.loss = None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+
+    def _step(self):
+        if self.engine is not None:
+            self.engine.zero_grad()
+        else:
+            self.opt.zero_grad(set_to_none=False)
+        out = self.model(self.xyz)
+        loss = self.loss_fn(out, *self.targets)
+        loss.backward()
+        if self.engine is not None:
+            self.engine.allreduce_grads()
+        if self.clip is not None:
+            torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, xyz: torch.Tensor, *targets: torch.Tensor) -> torch.Tensor:
+        """Copies the batch into the static buffers (H2D if `xyz` is a pinned host tensor), replays the
+        step, returns the (static) loss tensor."""
+        self.xyz.copy_(xyz, non_blocking=True)
+        for dst, src in zip(self.targets, targets):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -65,10 +65,12 @@ def gather_points(points: torch.Tensor, idx32: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def random_subset(B: int, N: int, S: int, seed: int, offset: int, device) -> torch.Tensor:
-    """(B,S) int32 uniform subset without replacement, drawn on the device."""
+def random_subset(B: int, N: int, S: int, seed: int, offset: int, device,
+                  counter: torch.Tensor | None = None) -> torch.Tensor:
+    """(B,S) int32 uniform subset without replacement, drawn on the device.  ``counter`` (1-element
+    int64 CUDA tensor) is added to ``offset`` on the device (CUDA-graph friendly)."""
     out = torch.empty(B, S, dtype=torch.int32, device=device)
-    _lib.check(_lib.load().pcoe_random_subset(B, N, S, seed & (2**64 - 1), offset & (2**64 - 1),
+    _lib.check(_lib.load().pcoe_random_subset(B, N, S, seed & (2**64 - 1), offset & (2**64 - 1), _ptr(counter),
                                               out.data_ptr(), _stream()))
     return out
 

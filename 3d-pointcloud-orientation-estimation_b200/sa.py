@@ -167,7 +167,7 @@ class PointNetSetAbstraction(nn.Module):
         self.group_all = group_all
         self.sampler, self.grouper, self.radius = sampler, grouper, radius
         self._precision = precision
-        self._calls = 0
+        self._rng_counter = None
         self.last_fps_idx = None
         self.last_group_idx = None
 
@@ -189,8 +189,12 @@ class PointNetSetAbstraction(nn.Module):
             idx = torch.stack([torch.randperm(N)[:self.npoint] for _ in range(B)])
             return idx.to(torch.int32).to(xyz.device, non_blocking=True)
         if self.sampler == "randperm_device":
-            self._calls += 1
-            return ops.random_subset(B, N, self.npoint, torch.initial_seed(), (id(self) << 20) ^ self._calls, xyz.device)
+            # the call counter lives on the device so that a CUDA-graph replay draws new subsets
+            if self._rng_counter is None or self._rng_counter.device != xyz.device:
+                self._rng_counter = torch.zeros(1, dtype=torch.int64, device=xyz.device)
+            self._rng_counter.add_(1)
+            return ops.random_subset(B, N, self.npoint, torch.initial_seed(), (id(self) & 0xFFFFFF) << 32, xyz.device,
+                                     self._rng_counter)
         return ops.farthest_point_sample(xyz, self.npoint).to(torch.int32)
 
     def forward(self, xyz, points, fps_idx=None):

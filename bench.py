@@ -103,14 +103,17 @@ def kernel_work(B: int, N: int) -> dict:
     """Algorithmic work per STEP of every libpcoe kernel name (DESIGN.md 'Kernels'): FLOPs for the
     GEMM kernels (2*M*Cin*Cout, no padding/recompute), bytes for the sampling/grouping kernels."""
     sh = sa_shapes(B, N)
-    f = lambda a, b: float(sum(2.0 * s[0] * s[a] * s[b] for s in sh))
-    w = {
-        "sa_fwd_l1": ("tensor", f(1, 2)), "sa_fwd_l2": ("tensor", f(2, 3)), "sa_fwd_l3": ("tensor", f(3, 4)),
-        "sa_bwd_wgrad3": ("tensor", f(3, 4)), "sa_bwd_dgrad3": ("tensor", f(3, 4)),
-        "sa_bwd_wgrad2": ("tensor", f(2, 3)), "sa_bwd_dgrad2": ("tensor", f(2, 3)),
-        "sa_bwd_wgrad1": ("tensor", f(1, 2)),
-        "sa_bwd_dgrad1": ("tensor", float(sum(2.0 * s[0] * (s[1] - 3) * s[2] for s in sh[1:]))),
-    }
+    w = {}
+    for li, s in enumerate(sh):
+        M, c = s[0], s[1:5]
+        g = lambda a, b: 2.0 * M * c[a] * c[b]
+        t = f"sa{li + 1}_"
+        dg1 = 2.0 * M * (c[0] - 3) * c[1]                        # no data gradient into xyz
+        w.update({t + "fwd_l1": g(0, 1), t + "fwd_l2": g(1, 2), t + "fwd_l3": g(2, 3),
+                  t + "bwd_wgrad3": g(2, 3), t + "bwd_dgrad3": g(2, 3), t + "bwd_wgrad2": g(1, 2),
+                  t + "bwd_dgrad2": g(1, 2), t + "bwd_wgrad1": g(0, 1), t + "bwd_dgrad1": dg1,
+                  t + "bwd_l3": 2 * g(2, 3), t + "bwd_l2": 2 * g(1, 2), t + "bwd_l1": g(0, 1) + dg1})
+    w = {k: ("tensor", float(v)) for k, v in w.items()}
     grp = float(sum(B * (12 * s[5] + 12 * s[6] + 4 * s[6] * s[7]) for s in sh[:2]))
     smp = float(sum(B * (12 * s[5] + 4 * s[6] + 12 * s[6]) for s in sh[:2]))
     w["knn_kernel"] = ("hbm", grp)
@@ -202,7 +205,7 @@ def run_ours(args):
     torch.manual_seed(1000)
     model = getattr(pcoe, cls)(sampler="randperm_device").to(dev).train()
     engine = pcoe.dp.DataParallel(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=not args.no_graph)
     params = [p for p in model.parameters()]
     NB = 8                                               # distinct synthetic batches, rotated
     host = [(pcoe.synthetic.clouds(1, B, N, rank * NB + i).pin_memory(),
@@ -228,8 +231,18 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timed region ---------------------------------------------------------
+    # the whole step is captured in a CUDA graph (pcoe.GraphedTrainStep) and replayed per batch
     for i in range(args.warmup):
         step(*resident[i % NB])
+    graphed, cap_launches = None, None
+    if not args.no_graph:
+        l0 = pcoe._lib.launch_count()
+        graphed = pcoe.GraphedTrainStep(model, lambda res, *tg: loss_of(kind, res, tg, pcoe), opt, resident[0][0],
+                                        resident[0][1], clip_norm=1.0 if kind == "mvm" else None, engine=engine, warmup=1)
+        cap_launches = (pcoe._lib.launch_count() - l0) // 2          # 1 warm-up + 1 captured step
+        for i in range(2):
+            graphed(*([resident[i][0]] + list(resident[i][1])))
+    run = (lambda x, tg: graphed(x, *tg)) if graphed is not None else step
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -238,11 +251,13 @@ def run_ours(args):
     for i in range(args.steps):
         flush.zero_()                                     # L2 flush, outside the event pair
         ev[i][0].record()
-        step(*resident[i % NB])
+        run(*resident[i % NB])
         ev[i][1].record()
     barrier()
     t_wall1 = time.time()
     launches = pcoe._lib.launch_count() - launches0
+    if graphed is not None:
+        launches = cap_launches * args.steps              # replayed from the graph, not re-enqueued
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -258,26 +273,35 @@ def run_ours(args):
         return
 
     # ---- end-to-end through the public API with host buffers ------------------------------------
-    for m in (model.sa1, model.sa2):
-        m.sampler = "randperm_host"                       # the reference's host-generator sampling (index-exact)
-    h2d = host[0][0].numel() * 4 + sum(t.numel() * t.element_size() for t in host[0][1]) + B * (128 + 32) * 4
+    # (a) the graphed step fed from pinned host memory: H2D of xyz + targets, replay, loss D2H
+    h2d = host[0][0].numel() * 4 + sum(t.numel() * t.element_size() for t in host[0][1])
     e2e_steps = max(3, min(args.steps, 20))
-    for i in range(2):
-        float(step(host[i][0].to(dev, non_blocking=True), tuple(t.to(dev, non_blocking=True) for t in host[i][1])))
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        x, tg = host[i % NB]
-        loss = step(x.to(dev, non_blocking=True), tuple(t.to(dev, non_blocking=True) for t in tg))
-        float(loss)                                       # D2H read of the step's result
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(t.item())
+
+    def timed_e2e(fn):
+        for i in range(2):
+            float(fn(i))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            float(fn(i))                                  # D2H read of the step's result
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * B * e2e_steps / float(tt.item())
+
+    e2e_value = None
+    if graphed is not None:
+        e2e_value = timed_e2e(lambda i: graphed(host[i % NB][0], *host[i % NB][1]))
+    # (b) the eager drop-in call with the reference's host-generator sampling (index-exact mode)
+    for m in (model.sa1, model.sa2):
+        m.sampler = "randperm_host"
+    e2e_eager = timed_e2e(lambda i: step(host[i % NB][0].to(dev, non_blocking=True),
+                                         tuple(t.to(dev, non_blocking=True) for t in host[i % NB][1])).detach())
     for m in (model.sa1, model.sa2):
         m.sampler = "randperm_device"
+    if e2e_value is None:
+        e2e_value = e2e_eager
 
     # ---- per-kernel CUDA-event profile of the same step (rank 0) -> roofline ---------------------
     roofline, kernels = None, {}
@@ -341,7 +365,9 @@ def run_ours(args):
                        "l2": "512 MiB buffer written between timed steps (flush outside the event pair)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "mode": "CUDA-graph step fed from pinned host buffers" if graphed else "eager",
+                    "eager_host_sampler_value": e2e_eager},
+            "cuda_graph": graphed is not None,
             "gpu_launches": int(launches),
             "gpu_launches_per_step": launches / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
@@ -361,8 +387,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
-    ap.add_argument("--precision", choices=["fp32", "bf16"], default=os.environ.get("PCOE_PRECISION", "fp32"))
+    ap.add_argument("--precision", choices=["fp32", "bf16"], default=os.environ.get("PCOE_PRECISION", "bf16"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")
     ap.add_argument("--timed-only", action="store_true",
                     help="warm-up + timed region only (for ncu captures): no e2e / per-kernel / CPU legs")
     args = ap.parse_args()

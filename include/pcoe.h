@@ -78,9 +78,11 @@ int pcoe_gather_points_f32(const float* src, int B, int N, int C, const int32_t*
  * torch.randperm(N)[:S] (models/pointnet_pp_8dir.py:28; the on-device variant is
  * models/pointnet_pp_Fwd.py:44-47) but a different random stream: use the host-replayed
  * permutation (Python layer, sampler="randperm_host") when index parity with a seeded reference
- * run is required.   out_idx [B,S] i32. */
-int pcoe_random_subset(int B, int N, int S, uint64_t seed, uint64_t offset, int32_t* out_idx,
-                       void* stream);
+ * run is required.   out_idx [B,S] i32.  `offset_dev` (device pointer, may be NULL) is added to
+ * `offset` on the device, so that a step captured in a CUDA graph draws fresh subsets on every
+ * replay (the caller increments the counter with an ordinary captured kernel). */
+int pcoe_random_subset(int B, int N, int S, uint64_t seed, uint64_t offset,
+                       const uint64_t* offset_dev, int32_t* out_idx, void* stream);
 
 /* --------------------------------------------------------------------------------------------
  * Grouping
@@ -90,8 +92,8 @@ int pcoe_random_subset(int B, int N, int S, uint64_t seed, uint64_t offset, int3
  * square_distance + topk(largest=False, sorted=False), models/base.py:20-35.
  *   xyz [B,N,3] f32, new_xyz [B,S,3] f32 -> out_idx [B,S,K] i32.
  * The reference's order inside a row is unspecified (sorted=False); this kernel writes ascending
- * distance, ties by ascending index.  Distances are the direct sum of squared differences in
- * fp32.  Requires 1 <= K <= min(N, 128). */
+ * point index; among points at exactly the K-th distance the lowest indices are kept.  Distances
+ * are the direct sum of squared differences in fp32.  Requires 1 <= K <= min(N, 128). */
 int pcoe_knn_f32(const float* xyz, const float* new_xyz, int B, int N, int S, int K,
                  int32_t* out_idx, void* stream);
 

@@ -90,11 +90,9 @@ def test_knn_matches_oracle_sets(pcoe, cuda, N, S, K):
     n, eq, tie, bad = sampling.knn_rows_match(got, want, margin)
     assert bad == 0, f"{bad} rows differ beyond fp32 near-ties"
     assert tie <= max(1, n // 1000)
-    # properties: the centroid itself is a member; row is sorted by distance (this kernel's order)
+    # properties: the centroid itself is a member; rows come out in ascending point index (this kernel's order)
     assert (got == perm.numpy()[..., None]).any(-1).all()
-    d = ((torch.gather(xyz, 1, torch.from_numpy(got).reshape(B, -1, 1).expand(-1, -1, 3)).view(B, S, K, 3)
-          - new_xyz.unsqueeze(2)) ** 2).sum(-1)
-    assert (d[..., 1:] >= d[..., :-1] - 1e-6).all()
+    assert (got[..., 1:] > got[..., :-1]).all()
 
 
 def test_gather_points_and_index_points_3d(pcoe, cuda):
