@@ -9,8 +9,7 @@
 // per-channel constant exactly; they only shift running_mean (and enter eval mode).
 #include "sa_common.cuh"
 #include "sa_tc.cuh"
-#include "sa_tc2.cuh"
-#include "sa_tc3.cuh"
+#include "sa_tc4.cuh"
 #include "sa_layout.h"
 #include <type_traits>
 
@@ -218,57 +217,60 @@ static int convert_weights(const pcoe_sa_desc& d, const SaLayout& L, const pcoe_
   return PCOE_OK;
 }
 
-// ---- v2 (persistent, register-epilogue) launchers ------------------------------------------------
-static int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
-
-static int v2_grid(int M, size_t smem, int tcols) {
-  int occ = (int)((size_t)227 * 1024 / (smem + 1024));
-  occ = occ > 512 / tcols ? 512 / tcols : occ;
-  occ = occ > 2 ? 2 : (occ < 1 ? 1 : occ);
-  const int tiles = ceil_div(M, 128);
-  return tiles < kNumSMs * occ ? tiles : kNumSMs * occ;
+// ---- v4 (channel-on-lane, persistent, warp-specialised) launchers --------------------------------
+template <class Prod>
+static size_t tile_bytes4(const Prod& p) {   // host mirror of v4::prod_tile_bytes, rounded to 1 KB
+  size_t b = Prod::kChMajor ? (size_t)2 * p.rows() * 128 : (size_t)((p.kext() + 63) / 64) * v4::kPts * 128;
+  return align_up(b, 1024);
 }
+constexpr size_t kSmemBudget4 = 200 * 1024;
 
 template <class Prod, class Epi>
-static int launch_fwd_v2(const Prod& prod, const __nv_bfloat16* Wb, int ldw, int wrows, const Epi& epi, int M,
-                         int ncols, int kin, cudaStream_t st, const char* what) {
-  const int kpad = ldw, kmma = ceil_div(kin, 16) * 16, nmma = ceil_div(ncols, 16) * 16;
-  const int wr = min(wrows, ceil_div(nmma, 8) * 8), tcols = pow2_cols(2 * (ceil_div(ncols, 32) * 32));
-  const size_t smem = 1024 + (size_t)(kpad / 64) * (128 * 128 + wr * 128) + 4 * 256 * sizeof(float);
-  const int tiles = ceil_div(M, 128), grid = tiles < kNumSMs ? tiles : kNumSMs;   // one persistent CTA per SM
+static int launch_fwd4(const Prod& prod, const __nv_bfloat16* Wb, int Rp, int Kp, const Epi& epi, int M,
+                       cudaStream_t st, const char* what) {
+  const size_t wbytes = (size_t)Rp * Kp * 2, tb = tile_bytes4(prod);
+  const size_t cbytes = sizeof(float) * (size_t)(prod.nconst() + epi.nconst()) + 256;
+  int stages = (int)((kSmemBudget4 - 1024 - wbytes - cbytes) / tb);
+  stages = stages > v4::kMaxStages ? v4::kMaxStages : stages;
+  if (stages < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  const size_t smem = 1024 + wbytes + (size_t)stages * tb + cbytes;
+  const int tiles = ceil_div(M, v4::kPts), grid = tiles < kNumSMs ? tiles : kNumSMs;   // one persistent CTA per SM
+  auto k = v4::tc4_fwd_kernel<Prod, Epi, 512>;
+  static bool attr = false;
+  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget4)); attr = true; }
   LaunchScope ls(what, st);
-#define PCOE_FWD3(TC_)                                                                                     \
-  {                                                                                                        \
-    auto k = v3::tc3_fwd_kernel<Prod, Epi, TC_>;                                                           \
-    static bool attr = false;                                                                              \
-    if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
-    k<<<grid, v3::kCtaThreads, smem, st>>>(prod, Wb, ldw, wrows, epi, M, ncols, kpad, kmma);                 \
-  }
-  if (tcols <= 128) PCOE_FWD3(128) else if (tcols == 256) PCOE_FWD3(256) else PCOE_FWD3(512)
-#undef PCOE_FWD3
+  k<<<grid, v4::kThreads, smem, st>>>(prod, Wb, Rp, Kp, epi, M, stages);
   return ls.done();
 }
 
-template <class PProd, class QProd, class Epi>
-static int launch_bwd_v2(const PProd& pp, const QProd& qp, const __nv_bfloat16* WbT, int ldw, int wrows,
-                         const Epi& epi, float* dW, int ldo, int cb_valid, int perm_d, int M, int ca, int cbk,
-                         int cdn, cudaStream_t st, const char* what) {
-  const int cbmma = ceil_div(cb_valid, 16) * 16, dnm = ceil_div(cdn, 16) * 16, mt = ceil_div(ca, 128);
-  const int wr = cdn ? min(wrows, ceil_div(dnm, 8) * 8) : 0;
-  const int tcols = pow2_cols(ceil_div(mt * cbmma, 64) * 64 + 2 * (ceil_div(cdn, 32) * 32));
-  const size_t smem = 1024 + (size_t)(ca / 64) * (128 * 128 + wr * 128) + (size_t)(cbk / 64) * 128 * 128 +
-                      4 * 256 * sizeof(float);
-  const int tiles = ceil_div(M, 128), grid = tiles < kNumSMs ? tiles : kNumSMs;
+template <int DGRAD, class PProd, class QProd, class Epi>
+static int launch_bwd4(const PProd& pp, const QProd& qp, const __nv_bfloat16* Wb, int Rp, int Kp, const Epi& epi,
+                       float* dW, int ldo, int cq_valid, int perm_d, int M, int cprev, cudaStream_t st,
+                       const char* what) {
+  const size_t wbytes = DGRAD ? (size_t)Rp * Kp * 2 : 0;
+  const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + qp.nconst() + epi.nconst()) + 256;
+  const size_t smem = 1024 + wbytes + tile_bytes4(pp) + tile_bytes4(qp) + cbytes;
+  if (smem > kSmemBudget4) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  const int tiles = ceil_div(M, v4::kPts), grid = tiles < kNumSMs ? tiles : kNumSMs;
+  auto k = v4::tc4_bwd_kernel<PProd, QProd, Epi, DGRAD, 512>;
+  static bool attr = false;
+  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget4)); attr = true; }
   LaunchScope ls(what, st);
-#define PCOE_BWD3(TC_)                                                                                     \
-  {                                                                                                        \
-    auto k = v3::tc3_bwd_kernel<PProd, QProd, Epi, TC_>;                                                   \
-    static bool attr = false;                                                                              \
-    if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
-    k<<<grid, v3::kCtaThreads, smem, st>>>(pp, qp, WbT, ldw, wrows, epi, dW, ldo, cb_valid, perm_d, M, ca, cbk, cbmma, cdn); \
+  k<<<grid, v4::kThreads, smem, st>>>(pp, qp, Wb, Rp, Kp, epi, dW, ldo, cq_valid, perm_d, M, cprev);
+  return ls.done();
+}
+
+static int convert_weights4(const pcoe_sa_desc& d, const SaLayout& L, const pcoe_sa_params& P, char* base,
+                            cudaStream_t st) {
+  const int Cs[3] = {d.C1, d.C2, d.C3}, Kin[3] = {3 + d.D, d.C1, d.C2};
+  v4::ConvW4 w[3];
+  int total = 0;
+  for (int l = 0; l < 3; ++l) {
+    w[l] = v4::ConvW4{P.W[l], (__nv_bfloat16*)(base + L.wb_off[l]), Cs[l], Kin[l], L.w4_rp[l], L.w4_kp[l], l == 0 ? d.D : -1};
+    total += L.w4_rp[l] * L.w4_kp[l];
   }
-  if (tcols <= 128) PCOE_BWD3(128) else if (tcols == 256) PCOE_BWD3(256) else PCOE_BWD3(512)
-#undef PCOE_BWD3
+  LaunchScope ls("convert_weights_kernel", st);
+  v4::convert_weights4_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(w[0], w[1], w[2]);
   return ls.done();
 }
 
@@ -326,7 +328,9 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
 
   const int Kin[3] = {Cin, d.C1, d.C2};
   char* wbase = train ? sv : ws;   // bf16 weight copies live with the saved state in train mode
-  if (TC) PCOE_TRY(convert_weights(d, L, P, wbase, st));
+  bool use4 = false;
+  if constexpr (TC) use4 = L.v2;
+  if (TC && !use4) PCOE_TRY(convert_weights(d, L, P, wbase, st));
   auto nt = [&](const auto& ap, int l, const auto& epi, const char* what) -> int {
     using AP = std::decay_t<decltype(ap)>;
     using EP = std::decay_t<decltype(epi)>;
@@ -339,19 +343,27 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
 
   bool done = false;
   if constexpr (TC) {
-    if (L.v2) {   // persistent kernels, weights resident in smem, register epilogues
+    if (use4) {   // channel-on-lane persistent kernels, activations channel-major [C][Mld]
+      PCOE_TRY(convert_weights4(d, L, P, wbase, st));
       auto wb = [&](int l) { return (const __nv_bfloat16*)(wbase + L.wb_off[l]); };
-      v2::Gather2 gp{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, 0};
-      v2::StoreStats2 e0{}; e0.y = y[0]; e0.sums = sums[0]; e0.C = d.C1;
-      PCOE_TRY(launch_fwd_v2(gp, wb(0), L.wb_k[0], L.wb_rows[0], e0, M, d.C1, Cin, st, kname(d, kF1)));
+      const int Mld = L.Mld;
+      v4::StoreStats4 e0{}; e0.y = y[0]; e0.sums = sums[0]; e0.C = d.C1; e0.Mld = Mld;
+      if (d.D == 0) {
+        v4::GatherXyz4 gp{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M};
+        PCOE_TRY(launch_fwd4(gp, wb(0), L.w4_rp[0], L.w4_kp[0], e0, M, st, kname(d, kF1)));
+      } else {
+        v4::GatherFeat4 gp{xyz, new_xyz, nbr, feats, d.N, d.S, d.D, d.group_all, M};
+        PCOE_TRY(launch_fwd4(gp, wb(0), L.w4_rp[0], L.w4_kp[0], e0, M, st, kname(d, kF1)));
+      }
       if (train) PCOE_TRY(finalize(0));
-      v2::BnRelu2 p1{}; p1.y = y[0]; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.C = d.C1;
-      v2::StoreStats2 e1{}; e1.y = y[1]; e1.sums = sums[1]; e1.C = d.C2;
-      PCOE_TRY(launch_fwd_v2(p1, wb(1), L.wb_k[1], L.wb_rows[1], e1, M, d.C2, d.C1, st, kname(d, kF2)));
+      v4::BnRelu4 p1{}; p1.y = y[0]; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.Mld = Mld; p1.C = d.C1;
+      v4::StoreStats4 e1{}; e1.y = y[1]; e1.sums = sums[1]; e1.C = d.C2; e1.Mld = Mld;
+      PCOE_TRY(launch_fwd4(p1, wb(1), L.w4_rp[1], L.w4_kp[1], e1, M, st, kname(d, kF2)));
       if (train) PCOE_TRY(finalize(1));
-      v2::BnRelu2 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.C = d.C2;
-      v2::Group2 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin; e2.C = d.C3;
-      PCOE_TRY(launch_fwd_v2(p2, wb(2), L.wb_k[2], L.wb_rows[2], e2, M, d.C3, d.C2, st, kname(d, kF3)));
+      v4::BnRelu4 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.Mld = Mld; p2.C = d.C2;
+      v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
+      e2.C = d.C3; e2.Mld = Mld;
+      PCOE_TRY(launch_fwd4(p2, wb(2), L.w4_rp[2], L.w4_kp[2], e2, M, st, kname(d, kF3)));
       if (train) PCOE_TRY(finalize(2));
       done = true;
     }
@@ -448,31 +460,34 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   };
 
   if constexpr (TC) {
-    if (L.v2) {   // one fused wgrad+dgrad kernel per layer
-      auto wbt = [&](int l) { return (const __nv_bfloat16*)(sv + L.wbt_off[l]); };
-      v2::DyLast2 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2]; dy3.M = M; dy3.C = d.C3;
-      v2::BnRelu2 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.C = d.C2;
-      v2::MaskStats2 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
-      m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2;
-      PCOE_TRY(launch_bwd_v2(dy3, x2, wbt(2), L.wbt_k[2], L.wbt_rows[2], m2, Gr.dW[2], d.C2, d.C2, -1, M, d.C3, L.wb_k[2],
-                             d.C2, st, kname(d, kBL3)));
+    if (L.v2) {   // one fused wgrad+dgrad kernel per layer (sa_tc4.cuh)
+      auto wb = [&](int l) { return (const __nv_bfloat16*)(sv + L.wb_off[l]); };
+      const int Mld = L.Mld;
+      v4::DyLast4 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
+      dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3;
+      v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2;
+      v4::MaskStats4 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
+      m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2; m2.Mld = Mld;
+      PCOE_TRY(launch_bwd4<1>(dy3, x2, wb(2), L.w4_rp[2], L.w4_kp[2], m2, Gr.dW[2], d.C2, d.C2, -1, M, d.C2, st, kname(d, kBL3)));
       PCOE_TRY(consts(1));
-      v2::Dy2 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.C = d.C2;
-      v2::BnRelu2 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.C = d.C1;
-      v2::MaskStats2 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
-      m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1;
-      PCOE_TRY(launch_bwd_v2(dy2, x1, wbt(1), L.wbt_k[1], L.wbt_rows[1], m1, Gr.dW[1], d.C1, d.C1, -1, M, d.C2, L.wb_k[1],
-                             d.C1, st, kname(d, kBL2)));
+      v4::Dy4 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.Mld = Mld; dy2.C = d.C2;
+      v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1;
+      v4::MaskStats4 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
+      m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1; m1.Mld = Mld;
+      PCOE_TRY(launch_bwd4<1>(dy2, x1, wb(1), L.w4_rp[1], L.w4_kp[1], m1, Gr.dW[1], d.C1, d.C1, -1, M, d.C1, st, kname(d, kBL2)));
       PCOE_TRY(consts(0));
-      v2::Dy2 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.C = d.C1;
-      v2::Gather2 x0{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, 0};
-      if (d.D > 0 && grad_feats) {
-        v2::Scatter2 se{grad_feats, nbr, d.N, d.S, d.K, d.D, d.group_all};
-        PCOE_TRY(launch_bwd_v2(dy1, x0, wbt(0), L.wbt_k[0], L.wbt_rows[0], se, Gr.dW[0], Cin, Cin, d.D, M, d.C1, L.wb_k[0],
-                               d.D, st, kname(d, kBL1)));
+      v4::Dy4 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.Mld = Mld; dy1.C = d.C1;
+      if (d.D == 0) {
+        v4::GatherXyz4 x0{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M};
+        PCOE_TRY(launch_bwd4<0>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], v4::NoEpi4{}, Gr.dW[0], Cin, Cin, 0, M, 0, st, kname(d, kBL1)));
       } else {
-        PCOE_TRY(launch_bwd_v2(dy1, x0, wbt(0), L.wbt_k[0], L.wbt_rows[0], v2::NoEpi2{}, Gr.dW[0], Cin, Cin, d.D, M, d.C1,
-                               L.wb_k[0], 0, st, kname(d, kBL1)));
+        v4::GatherFeat4 x0{xyz, new_xyz, nbr, feats, d.N, d.S, d.D, d.group_all, M};
+        if (grad_feats) {
+          v4::Scatter4 se{grad_feats, nbr, d.N, d.S, d.D, d.group_all};
+          PCOE_TRY(launch_bwd4<2>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], se, Gr.dW[0], Cin, Cin, d.D, M, d.D, st, kname(d, kBL1)));
+        } else {
+          PCOE_TRY(launch_bwd4<0>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], v4::NoEpi4{}, Gr.dW[0], Cin, Cin, d.D, M, 0, st, kname(d, kBL1)));
+        }
       }
       return PCOE_OK;
     }

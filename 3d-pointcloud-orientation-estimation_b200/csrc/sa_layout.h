@@ -18,7 +18,10 @@ struct SaLayout {
   // bf16 weight copies (tensor-core path): offsets relative to `saved` (train) or `workspace` (eval)
   size_t wb_off[3], wbt_off[3];
   int wb_rows[3], wb_k[3], wbt_rows[3], wbt_k[3];
-  bool v2;         // bf16 mode and the layer fits the persistent on-chip kernels (sa_tc2.cuh)
+  bool v2;         // bf16 mode and the layer fits the persistent channel-on-lane kernels (sa_tc4.cuh):
+                   // activations are then stored channel-major [C][Mld], one weight image [Rp][Kp] per layer
+  int Mld;         // rows rounded up to 128 (v2 only)
+  int w4_rp[3], w4_kp[3];
   size_t workspace_bytes;
 };
 
@@ -30,16 +33,23 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   const int C[3] = {d.C1, d.C2, d.C3};
   auto take = [](size_t& cur, size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
 
+  const bool tc = d.precision == PCOE_PRECISION_BF16;
+  const int Kin[3] = {3 + d.D, d.C1, d.C2};
+  auto chan_ok = [](int c) { return c == 64 || c == 128 || c == 256; };
+  L.v2 = tc && d.K == 32 && chan_ok(d.C1) && chan_ok(d.C2) && chan_ok(d.C3) && (d.D % 32) == 0 && d.D + 3 <= 192;
+  L.Mld = (int)align_up(L.M, 128);
+  const size_t rows_ld = L.v2 ? (size_t)L.Mld : (size_t)L.M;
+  for (int l = 0; l < 3; ++l) {
+    L.w4_rp[l] = (int)align_up(C[l], 128);
+    L.w4_kp[l] = (int)align_up(l == 0 ? (Kin[0] + 15) / 16 * 16 : Kin[l], 128);
+  }
+
   size_t s = 0;
-  for (int l = 0; l < 3; ++l) L.sv_y[l] = take(s, (size_t)L.M * C[l] * L.esz);
+  for (int l = 0; l < 3; ++l) L.sv_y[l] = take(s, rows_ld * C[l] * L.esz);
   for (int l = 0; l < 3; ++l) L.sv_stat[l] = take(s, sizeof(float) * 4 * C[l]);
   L.sv_slot = take(s, (size_t)L.G * d.C3);
   L.sv_ysel = take(s, sizeof(float) * (size_t)L.G * d.C3);
-  const bool tc = d.precision == PCOE_PRECISION_BF16;
-  const int Kin[3] = {3 + d.D, d.C1, d.C2};
   auto kpad = [](int k) { return k <= 64 ? 64 : k <= 128 ? 128 : k <= 256 ? 256 : (int)align_up(k, 64); };
-  auto chan_ok = [](int c) { return c == 64 || c == 128 || c == 256; };
-  L.v2 = tc && d.K == 32 && chan_ok(d.C1) && chan_ok(d.C2) && chan_ok(d.C3) && (d.D % 32) == 0 && d.D + 3 <= 256;
   for (int l = 0; l < 3; ++l) {
     L.wb_rows[l] = (int)align_up(C[l], 128);   L.wb_k[l] = kpad(Kin[l]);
     L.wbt_rows[l] = (int)align_up(Kin[l], 128); L.wbt_k[l] = kpad(C[l]);
@@ -47,6 +57,7 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   }
   if (tc && d.train)
     for (int l = 0; l < 3; ++l) {
+      if (L.v2) { L.wb_off[l] = take(s, (size_t)2 * L.w4_rp[l] * L.w4_kp[l]); continue; }
       L.wb_off[l] = take(s, (size_t)2 * L.wb_rows[l] * L.wb_k[l]);
       L.wbt_off[l] = take(s, (size_t)2 * L.wbt_rows[l] * L.wbt_k[l]);
     }
@@ -62,9 +73,10 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   for (int l = 0; l < 3; ++l) L.ws_stat[l] = take(f, sizeof(float) * 4 * C[l]);
   L.ws_y[0] = L.ws_y[1] = 0;
   if (!d.train) {
-    for (int l = 0; l < 2; ++l) L.ws_y[l] = take(f, (size_t)L.M * C[l] * L.esz);
+    for (int l = 0; l < 2; ++l) L.ws_y[l] = take(f, rows_ld * C[l] * L.esz);
     if (tc)
       for (int l = 0; l < 3; ++l) {
+        if (L.v2) { L.wb_off[l] = take(f, (size_t)2 * L.w4_rp[l] * L.w4_kp[l]); continue; }
         L.wb_off[l] = take(f, (size_t)2 * L.wb_rows[l] * L.wb_k[l]);
         L.wbt_off[l] = take(f, (size_t)2 * L.wbt_rows[l] * L.wbt_k[l]);
       }
@@ -75,7 +87,7 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   L.wb_sums_bytes = b - L.wb_sums[0];
   for (int l = 0; l < 3; ++l) L.wb_consts[l] = take(b, sizeof(float) * 3 * C[l]);
   L.wb_gm = take(b, sizeof(float) * (size_t)L.G * d.C3);
-  for (int l = 0; l < 2; ++l) L.wb_dz[l] = take(b, (size_t)L.M * C[l] * L.esz);
+  for (int l = 0; l < 2; ++l) L.wb_dz[l] = take(b, rows_ld * C[l] * L.esz);
   if (!d.train) b = 0;
 
   L.workspace_bytes = f > b ? f : b;
