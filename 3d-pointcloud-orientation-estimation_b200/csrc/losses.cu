@@ -2,7 +2,8 @@
 //   pcoe_vm_kl_fwd_bwd      train_single_peak_vonMises_KL.py:23-28 / train_multi_peaks_vonMises_KL.py:38-52
 //   pcoe_mvm_match_fwd_bwd  train_multi_peaks_vonMises_KL.py:54-81 (+ scipy linear_sum_assignment)
 //   pcoe_soft_ce_fwd_bwd    train_8dir_KL.py:60-68
-// The tensors are tiny (B x <=16 values): one thread per sample, arithmetic in fp64 so the result
+// The tensors are tiny (B x <=16 values): one thread (one warp for the matched loss) per sample,
+// arithmetic in fp64 so the result
 // is at least as accurate as the reference's fp32 Cephes evaluation; the fp32 overflow behaviour
 // of torch.special.i0/i1 (exp(x) = inf for x > log(FLT_MAX)) is reproduced explicitly.
 #include "common.cuh"
@@ -125,84 +126,95 @@ __global__ void vm_kl_kernel(const float* __restrict__ mu_p, const float* __rest
   if (dkappa) dkappa[i] = (float)gk;
 }
 
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  return __hiloint2double(__shfl_sync(0xFFFFFFFFu, __double2hiint(v), src), __shfl_sync(0xFFFFFFFFu, __double2loint(v), src));
+}
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+  return __hiloint2double(__shfl_xor_sync(0xFFFFFFFFu, __double2hiint(v), m), __shfl_xor_sync(0xFFFFFFFFu, __double2loint(v), m));
+}
+
+// One warp per sample: lane 4*i + j (< 16) evaluates the cost of matching predicted component i to
+// ground-truth component j (two Bessel evaluations and one KL per lane instead of 8 + 16 per
+// thread), the <= 256 assignment codes are scored 32 at a time with warp shuffles.
 __global__ void mvm_match_kernel(const float* __restrict__ mu, const float* __restrict__ kappa,
                                  const float* __restrict__ w, const float* __restrict__ gt,
                                  int gt_stride, const int32_t* __restrict__ K_gt, int B, int Kmax,
                                  float* __restrict__ loss, float* __restrict__ dmu,
                                  float* __restrict__ dkappa, float* __restrict__ dw,
                                  int32_t* __restrict__ perm) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;                       // whole warps only
   int K = K_gt[b];
   K = K > Kmax ? Kmax : K;
-  for (int i = 0; i < Kmax; ++i) {
-    if (dmu) dmu[b * Kmax + i] = 0.f;
-    if (dkappa) dkappa[b * Kmax + i] = 0.f;
-    if (dw) dw[b * Kmax + i] = 0.f;
-    if (perm) perm[b * Kmax + i] = -1;
-  }
-  if (K <= 0) { loss[b] = 0.f; return; }
-
-  VmTerm tp[4], tq[4];
-  for (int i = 0; i < K; ++i) {
-    tp[i] = vm_term(kappa[b * Kmax + i], true);
-    tq[i] = vm_term(gt[((size_t)b * Kmax + i) * gt_stride + 1], true);
-  }
-  double cost[4][4], gmu[4][4], gk[4][4];
-  for (int i = 0; i < K; ++i)
-    for (int j = 0; j < K; ++j) {
-      double kl, a, c;
-      vm_kl_pair(mu[b * Kmax + i], tp[i], gt[((size_t)b * Kmax + j) * gt_stride], tq[j], true,
-                 0.f, &kl, &a, &c);
-      float klf = (float)kl;  // the reference stores the cost matrix in fp32 before nan_to_num
-      if (isnan(klf) || isinf(klf)) {
-        // nan_to_num(1e6): autograd multiplies the (non-finite) local derivatives by 0, which is
-        // NaN wherever fp32 I0 overflowed - reproduced so that gradients match the reference.
-        kl = 1e6;
-        a = isinf(tp[i].logi0) ? NAN : 0.0;
-        c = NAN;
-      }
-      cost[i][j] = kl; gmu[i][j] = a; gk[i][j] = c;
+  if (K <= 0) {
+    if (lane < Kmax) {
+      if (dmu) dmu[b * Kmax + lane] = 0.f;
+      if (dkappa) dkappa[b * Kmax + lane] = 0.f;
+      if (dw) dw[b * Kmax + lane] = 0.f;
+      if (perm) perm[b * Kmax + lane] = -1;
     }
-  // minimum-cost assignment: brute force over the K! permutations (K <= 4)
-  // (codes are base-4 digit strings, element 0 most significant: lexicographic order; the first
-  //  minimum wins)
-  int best_p[4] = {0, 1, 2, 3};
-  double best_cost = INFINITY;
+    if (lane == 0) loss[b] = 0.f;
+    return;
+  }
+
+  const int ci = (lane >> 2) & 3, cj = lane & 3;
+  double kl = 0.0, ga = 0.0, gc = 0.0;
+  if (lane < 16 && ci < K && cj < K) {
+    const VmTerm tp = vm_term(kappa[b * Kmax + ci], true);
+    const VmTerm tq = vm_term(gt[((size_t)b * Kmax + cj) * gt_stride + 1], true);
+    vm_kl_pair(mu[b * Kmax + ci], tp, gt[((size_t)b * Kmax + cj) * gt_stride], tq, true, 0.f, &kl, &ga, &gc);
+    const float klf = (float)kl;  // the reference stores the cost matrix in fp32 before nan_to_num
+    if (isnan(klf) || isinf(klf)) {
+      // nan_to_num(1e6): autograd multiplies the (non-finite) local derivatives by 0, which is
+      // NaN wherever fp32 I0 overflowed - reproduced so that gradients match the reference.
+      kl = 1e6;
+      ga = isinf(tp.logi0) ? NAN : 0.0;
+      gc = NAN;
+    }
+  }
+  // minimum-cost assignment: brute force over the K! permutations (K <= 4).  Codes are base-4
+  // digit strings, element 0 most significant (lexicographic order); the lowest code among the
+  // minima wins, as in a sequential first-minimum scan.
+  double best = INFINITY;
+  int best_code = 0x7FFFFFFF;
   const int ncode = 1 << (2 * K);
-  for (int code = 0; code < ncode; ++code) {
-    int pj[4], used = 0;
-    bool ok = true;
+  for (int base = 0; base < ncode; base += 32) {
+    const int code = base + lane;
+    int pj[4] = {0, 0, 0, 0}, used = 0;
+    bool ok = code < ncode;
     for (int i = 0; i < K; ++i) {
       const int j = (code >> (2 * (K - 1 - i))) & 3;
       pj[i] = j;
       ok = ok && j < K && !((used >> j) & 1);
       used |= 1 << j;
     }
-    if (!ok) continue;
     double tot = 0.0;
-    for (int i = 0; i < K; ++i) tot += cost[i][pj[i]];
-    if (tot < best_cost) {
-      best_cost = tot;
-      for (int i = 0; i < K; ++i) best_p[i] = pj[i];
-    }
+    for (int i = 0; i < K; ++i) tot += shfl_d(kl, i * 4 + (ok ? pj[i] : 0));
+    if (ok && tot < best) { best = tot; best_code = code; }
   }
-  double wsum = 0.0, num = 0.0;
-  for (int i = 0; i < K; ++i) {
-    const int j = best_p[i];
-    wsum += (double)w[b * Kmax + i];
-    num += (double)w[b * Kmax + i] * cost[i][j];
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const double ob = shfl_xor_d(best, m);
+    const int oc = __shfl_xor_sync(0xFFFFFFFFu, best_code, m);
+    if (ob < best || (ob == best && oc < best_code)) { best = ob; best_code = oc; }
   }
+  // lane i < K: predicted component i is matched to ground-truth component j
+  const bool mine = lane < K;
+  const int j = mine ? (best_code >> (2 * (K - 1 - lane))) & 3 : 0;
+  const int src = mine ? lane * 4 + j : 0;
+  const double cs = shfl_d(kl, src), gms = shfl_d(ga, src), gks = shfl_d(gc, src);
+  const double wi = mine ? (double)w[b * Kmax + lane] : 0.0;
+  double wsum = wi, num = mine ? wi * cs : 0.0;
+#pragma unroll
+  for (int m = 2; m >= 1; m >>= 1) { wsum += shfl_xor_d(wsum, m); num += shfl_xor_d(num, m); }   // lanes 0..3
   const double W = wsum + 1e-8;
   const double L = num / W;
-  loss[b] = (float)L;
-  for (int i = 0; i < K; ++i) {
-    const int j = best_p[i];
-    const double wi = (double)w[b * Kmax + i];
-    if (dmu) dmu[b * Kmax + i] = (float)(wi / W * gmu[i][j]);
-    if (dkappa) dkappa[b * Kmax + i] = (float)(wi / W * gk[i][j]);
-    if (dw) dw[b * Kmax + i] = (float)((cost[i][j] - L) / W);
-    if (perm) perm[b * Kmax + i] = j;
+  if (lane == 0) loss[b] = (float)L;
+  if (lane < Kmax) {
+    if (dmu) dmu[b * Kmax + lane] = mine ? (float)(wi / W * gms) : 0.f;
+    if (dkappa) dkappa[b * Kmax + lane] = mine ? (float)(wi / W * gks) : 0.f;
+    if (dw) dw[b * Kmax + lane] = mine ? (float)((cs - L) / W) : 0.f;
+    if (perm) perm[b * Kmax + lane] = mine ? j : -1;
   }
 }
 
@@ -253,7 +265,7 @@ extern "C" int pcoe_mvm_match_fwd_bwd(const float* mu, const float* kappa, const
   if (B == 0) return PCOE_OK;
   if (!mu || !kappa || !w || !gt || !K_gt || !loss) return fail(PCOE_ERR_NULL, "mvm_match: NULL pointer");
   LaunchScope ls("mvm_match_kernel", (cudaStream_t)stream);
-  mvm_match_kernel<<<ceil_div(B, 64), 64, 0, (cudaStream_t)stream>>>(mu, kappa, w, gt, gt_stride, K_gt,
+  mvm_match_kernel<<<ceil_div(B, 4), 128, 0, (cudaStream_t)stream>>>(mu, kappa, w, gt, gt_stride, K_gt,
                                                                      B, Kmax, loss, dmu, dkappa, dw, perm);
   return ls.done();
 }

@@ -223,23 +223,26 @@ static size_t tile_bytes4(const Prod& p) {   // host mirror of v4::prod_tile_byt
   size_t b = Prod::kChMajor ? (size_t)2 * p.rows() * 128 : (size_t)((p.kext() + 63) / 64) * v4::kPts * 128;
   return align_up(b, 1024);
 }
-constexpr size_t kSmemBudget4 = 200 * 1024;
+constexpr size_t kSmemBudget4 = 224 * 1024;
 
 template <class Prod, class Epi>
 static int launch_fwd4(const Prod& prod, const __nv_bfloat16* Wb, int Rp, int Kp, const Epi& epi, int M,
                        cudaStream_t st, const char* what) {
   const size_t wbytes = (size_t)Rp * Kp * 2, tb = tile_bytes4(prod);
-  const size_t cbytes = sizeof(float) * (size_t)(prod.nconst() + epi.nconst()) + 256;
-  int stages = (int)((kSmemBudget4 - 1024 - wbytes - cbytes) / tb);
+  const size_t cbytes = sizeof(float) * (size_t)(prod.nconst() + epi.nconst()) + 512, sb = (size_t)epi.stage_bytes();
+  const size_t avail = kSmemBudget4 - 1024 - wbytes - cbytes;
+  // prefer two operand stages, then a double-buffered output staging tile, then more operand stages
+  int nstg = (sb && avail >= 2 * sb + 2 * tb) ? 2 : 1;
+  if (avail < nstg * sb + tb) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  int stages = (int)((avail - nstg * sb) / tb);
   stages = stages > v4::kMaxStages ? v4::kMaxStages : stages;
-  if (stages < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
-  const size_t smem = 1024 + wbytes + (size_t)stages * tb + cbytes;
+  const size_t smem = 1024 + wbytes + (size_t)stages * tb + cbytes + nstg * sb;
   const int tiles = ceil_div(M, v4::kPts), grid = tiles < kNumSMs ? tiles : kNumSMs;   // one persistent CTA per SM
   auto k = v4::tc4_fwd_kernel<Prod, Epi, 512>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget4)); attr = true; }
   LaunchScope ls(what, st);
-  k<<<grid, v4::kThreads, smem, st>>>(prod, Wb, Rp, Kp, epi, M, stages);
+  k<<<grid, v4::kThreads, smem, st>>>(prod, Wb, Rp, Kp, epi, M, stages, nstg);
   return ls.done();
 }
 
@@ -248,15 +251,17 @@ static int launch_bwd4(const PProd& pp, const QProd& qp, const __nv_bfloat16* Wb
                        float* dW, int ldo, int cq_valid, int perm_d, int M, int cprev, cudaStream_t st,
                        const char* what) {
   const size_t wbytes = DGRAD ? (size_t)Rp * Kp * 2 : 0;
-  const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + qp.nconst() + epi.nconst()) + 256;
-  const size_t smem = 1024 + wbytes + tile_bytes4(pp) + tile_bytes4(qp) + cbytes;
+  const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + qp.nconst() + epi.nconst()) + 512, sb = (size_t)epi.stage_bytes();
+  const size_t base = 1024 + wbytes + tile_bytes4(pp) + tile_bytes4(qp) + cbytes;
+  const int nstg = (sb && base + 2 * sb <= kSmemBudget4) ? 2 : 1;
+  const size_t smem = base + nstg * sb;
   if (smem > kSmemBudget4) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
   const int tiles = ceil_div(M, v4::kPts), grid = tiles < kNumSMs ? tiles : kNumSMs;
   auto k = v4::tc4_bwd_kernel<PProd, QProd, Epi, DGRAD, 512>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget4)); attr = true; }
   LaunchScope ls(what, st);
-  k<<<grid, v4::kThreads, smem, st>>>(pp, qp, Wb, Rp, Kp, epi, dW, ldo, cq_valid, perm_d, M, cprev);
+  k<<<grid, v4::kThreads, smem, st>>>(pp, qp, Wb, Rp, Kp, epi, dW, ldo, cq_valid, perm_d, M, cprev, nstg);
   return ls.done();
 }
 
@@ -349,10 +354,10 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       const int Mld = L.Mld;
       v4::StoreStats4 e0{}; e0.y = y[0]; e0.sums = sums[0]; e0.C = d.C1; e0.Mld = Mld;
       if (d.D == 0) {
-        v4::GatherXyz4 gp{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M};
+        v4::GatherXyz4 gp{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}};
         PCOE_TRY(launch_fwd4(gp, wb(0), L.w4_rp[0], L.w4_kp[0], e0, M, st, kname(d, kF1)));
       } else {
-        v4::GatherFeat4 gp{xyz, new_xyz, nbr, feats, d.N, d.S, d.D, d.group_all, M};
+        v4::GatherFeat4 gp{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
         PCOE_TRY(launch_fwd4(gp, wb(0), L.w4_rp[0], L.w4_kp[0], e0, M, st, kname(d, kF1)));
       }
       if (train) PCOE_TRY(finalize(0));
@@ -478,10 +483,10 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       PCOE_TRY(consts(0));
       v4::Dy4 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.Mld = Mld; dy1.C = d.C1;
       if (d.D == 0) {
-        v4::GatherXyz4 x0{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M};
+        v4::GatherXyz4 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}};
         PCOE_TRY(launch_bwd4<0>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], v4::NoEpi4{}, Gr.dW[0], Cin, Cin, 0, M, 0, st, kname(d, kBL1)));
       } else {
-        v4::GatherFeat4 x0{xyz, new_xyz, nbr, feats, d.N, d.S, d.D, d.group_all, M};
+        v4::GatherFeat4 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
         if (grad_feats) {
           v4::Scatter4 se{grad_feats, nbr, d.N, d.S, d.D, d.group_all};
           PCOE_TRY(launch_bwd4<2>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], se, Gr.dW[0], Cin, Cin, d.D, M, d.D, st, kname(d, kBL1)));
@@ -523,6 +528,20 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
 }  // namespace pcoe
 
 using namespace pcoe;
+
+#ifdef PCOE_TC4_TRACE
+// debug build only: copy out / reset the in-kernel clock trace of CTA 0 (tag, index, clock64 triples)
+extern "C" int pcoe_debug_trace(long long* host_buf, int cap_triples, int reset) {
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, v4::g_trace_n, sizeof(int));
+  if (n > 2700) n = 2700;
+  if (n > cap_triples) n = cap_triples;
+  if (host_buf && n > 0) cudaMemcpyFromSymbol(host_buf, v4::g_trace, sizeof(long long) * 3 * n);
+  if (reset) { int z = 0; cudaMemcpyToSymbol(v4::g_trace_n, &z, sizeof(int)); }
+  return n;
+}
+#endif
 
 extern "C" size_t pcoe_sa_saved_bytes(const pcoe_sa_desc* desc) {
   if (validate(desc) != PCOE_OK) return 0;

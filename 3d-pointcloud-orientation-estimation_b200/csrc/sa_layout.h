@@ -36,7 +36,7 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   const bool tc = d.precision == PCOE_PRECISION_BF16;
   const int Kin[3] = {3 + d.D, d.C1, d.C2};
   auto chan_ok = [](int c) { return c == 64 || c == 128 || c == 256; };
-  L.v2 = tc && d.K == 32 && chan_ok(d.C1) && chan_ok(d.C2) && chan_ok(d.C3) && (d.D % 32) == 0 && d.D + 3 <= 192;
+  L.v2 = tc && d.K == 32 && chan_ok(d.C1) && chan_ok(d.C2) && chan_ok(d.C3) && (d.D == 0 || d.D == 32 || d.D == 64 || d.D == 128);
   L.Mld = (int)align_up(L.M, 128);
   const size_t rows_ld = L.v2 ? (size_t)L.Mld : (size_t)L.M;
   for (int l = 0; l < 3; ++l) {

@@ -8,8 +8,12 @@
 // so BatchNorm batch statistics, the BatchNorm-backward sums and the max / arg-max over a group of
 // K = 32 neighbours (= one 32-column tcgen05.ld) are plain per-thread register reductions - no warp
 // shuffles - and BatchNorm's scale/shift are per-thread constants.  Activations live in HBM
-// channel-major: y^T [C][Mld] bf16 (Mld = rows rounded up to 128), so a thread's 32 points are 64
-// contiguous bytes and a tile row is 256 contiguous bytes.
+// channel-major and TILE-BLOCKED: y^T as [tile][C][128 points] bf16 with the eight-point (16-byte)
+// chunks of a row XOR-swizzled by the channel: element (t, c, p) sits at byte
+//     (t*C + c)*256 + (((p>>3) ^ (c&15)) << 4) + (p&7)*2 .
+// A tile is one contiguous C*256-byte block: the epilogue stages it in shared memory in exactly this
+// image (the swizzle makes the one-row-per-thread 16-byte stores bank-conflict free) and ONE bulk
+// async copy per tile writes it out; consumers read 256-byte rows with coalesced 16-byte loads.
 //
 // Shared-memory operand images (all SWIZZLE_128B, 8-row / 1024-byte atoms, see tc_common.cuh):
 //   activation tile, channel-major  [C rows][128 points] = 2 blocks (64 points = 128 B per row) of
@@ -21,10 +25,11 @@
 //       Used K-major (forward A) and MN-major (dgrad A: M = input channels, K = C_out rows;
 //       layer-1 dgrad B: N = input channels).  One bf16 copy per layer serves every GEMM.
 //
-// CTA = 13 warps, persistent over 128-point tiles, one CTA per SM:
-//   warps 0-3   epilogue   (warp w owns TMEM lanes 32w..32w+31)
-//   warps 4-11  producers  (global -> BN/ReLU or BN-backward transform -> bf16 -> swizzled smem)
-//   warp  12    MMA issue  (one elected thread)
+// CTA = 17 warps, persistent over 128-point tiles, one CTA per SM:
+//   warps 0-7   epilogue   (warp w owns TMEM lanes 32(w%4)..+31 = one channel per thread and half of
+//                           the tile's 32-column blocks, (w/4))
+//   warps 8-15  producers  (global -> BN/ReLU or BN-backward transform -> bf16 -> swizzled smem)
+//   warp  16    MMA issue  (one elected thread)
 // Pipelines: smem stage ring (full/empty mbarriers), double-buffered TMEM accumulators
 // (tmem_full/tmem_empty); dW accumulates in TMEM over the CTA's whole tile range.
 #pragma once
@@ -34,18 +39,57 @@
 namespace pcoe {
 namespace v4 {
 
+#ifdef PCOE_TC4_TRACE
+// debug build: low-overhead clock trace of CTA 0.  Each traced thread records (tag, index, clock64)
+// into a local array and dumps it when it leaves the kernel.
+__device__ long long g_trace[8192];
+__device__ int g_trace_n;
+struct Tracer {
+  long long buf[3 * 80];
+  int n = 0;
+  __device__ __forceinline__ void rec(int tag, int idx) {
+    if (blockIdx.x == 0 && n < 80) { buf[3 * n] = tag; buf[3 * n + 1] = idx; buf[3 * n + 2] = clock64(); ++n; }
+  }
+  __device__ void dump() {
+    if (blockIdx.x != 0 || n == 0) return;
+    const int k = atomicAdd(&g_trace_n, n);
+    for (int i = 0; i < n && k + i < 2700; ++i)
+      for (int j = 0; j < 3; ++j) g_trace[3 * (k + i) + j] = buf[3 * i + j];
+  }
+};
+#define TC4_TRACER Tracer tracer_
+#define TC4_TRACE(tag, idx) tracer_.rec((tag), (idx))
+#define TC4_TRACE_DUMP() tracer_.dump()
+#else
+#define TC4_TRACER do {} while (0)
+#define TC4_TRACE(tag, idx) do {} while (0)
+#define TC4_TRACE_DUMP() do {} while (0)
+#endif
+
 constexpr int kPts = 128;
-constexpr int kEpiThreads = 128, kProdThreads = 256, kThreads = kEpiThreads + kProdThreads + 32;
+constexpr int kEpiThreads = 256, kProdThreads = 256, kThreads = kEpiThreads + kProdThreads + 32;
 constexpr int kMaxStages = 3;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(mbar)) : "memory");
+}
+// arrive without release semantics: the epilogue's TMEM reads are already complete (tcgen05.wait::ld)
+// and its global stores need no ordering against the barrier - a releasing arrive would wait for
+// every outstanding global store of the thread to be acknowledged by L2
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(mbar)) : "memory");
 }
 
 // byte offset of the 16-byte chunk (8 points) `chunk` (0..15) of channel row c in a channel-major tile
 __device__ __forceinline__ uint32_t cm_off(int crows, int c, int chunk) {
   return (uint32_t)((chunk >> 3) * crows * 128 + (c >> 3) * 1024 + (c & 7) * 128 + ((((chunk & 7) ^ (c & 7))) << 4));
 }
+
+// 16-byte chunk `chunk` (points 8*chunk..+7) of channel c in tile `tile` of a tile-blocked activation
+__device__ __forceinline__ const uint4* tb_chunk(const __nv_bfloat16* y, int C, int tile, int c, int chunk) {
+  return reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(y) + ((size_t)tile * C + c) * 256 + ((chunk ^ (c & 15)) << 4));
+}
+__device__ __forceinline__ uint32_t tb_stage_off(int c, int chunk) { return (uint32_t)(c * 256 + ((chunk ^ (c & 15)) << 4)); }
 
 __device__ __forceinline__ void unpack8(const uint4& a, float (&v)[8]) {
   const uint32_t w[4] = {a.x, a.y, a.z, a.w};
@@ -61,16 +105,32 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Producers.  kChMajor: tile image (see header).  rows(): rows of the image (channel rows for a
-// channel-major tile).  tile_bytes(): smem bytes of one stage.  nconst(): floats of per-channel
-// constants cached in shared memory.  produce(ptid, m0, saddr): write the tile of points
-// [m0, m0+128); every element of the K extent that the MMAs read must be written (or stay zero
-// from the one-time clear of the stage buffers).
+// Producers.  A producer group of G threads builds one operand tile per 128 points in `nbatches(G)`
+// batches of kBatch 16-byte units per thread, as a three-stage software pipeline so that global
+// loads of the next batch (possibly of the next tile) are in flight while the current batch is
+// transformed and stored:
+//     load_idx(g, G, m0, b, Idx&)        neighbour indices of the batch (gather producers only)
+//     load(g, G, m0, b, Idx, Raw&)       raw global loads into registers, no dependent arithmetic
+//     store(g, G, m0, b, Raw, saddr)     transform -> bf16 -> swizzled shared memory
+// kChMajor: tile image (see header).  rows(): rows of the image.  kext(): channel extent the MMAs
+// read (multiple of 16).  nconst(): floats of per-channel constants cached in shared memory.
+// Elements inside the K extent that are never written stay zero from the one-time clear.
 // ---------------------------------------------------------------------------------------------
+constexpr int kBatch = 4;
+struct NoIdx {};
+
+// channel-major mapping: thread g -> 16-byte chunk (8 points) g&15 of channel rows (g>>4) + j*(G/16)
+#define PCOE_CM_MAP                                                        \
+  const int chunk = g & 15, r0 = g >> 4, rstep = G >> 4;                   \
+  const int m = m0 + chunk * 8;                                            \
+  const bool ok = m < M;                                                   \
+  (void)r0; (void)rstep; (void)ok;
 
 // relu(scale * y + shift) of the previous layer's pre-activations y^T [C][Mld]
 struct BnRelu4 {
   static constexpr bool kChMajor = true;
+  using Idx = NoIdx;
+  struct Raw { uint4 a[kBatch]; };
   const __nv_bfloat16* __restrict__ y;
   const float* __restrict__ scale;
   const float* __restrict__ shift;
@@ -79,24 +139,33 @@ struct BnRelu4 {
   __host__ __device__ __forceinline__ int rows() const { return C; }
   __host__ __device__ __forceinline__ int kext() const { return C; }
   __host__ __device__ __forceinline__ int nconst() const { return 2 * C; }
+  __device__ __forceinline__ int nbatches(int G) const { return (C / (G >> 4) + kBatch - 1) / kBatch; }
   __device__ __forceinline__ void init(float* csm, int tid, int nthr) {
     for (int c = tid; c < C; c += nthr) { csm[c] = scale[c]; csm[C + c] = shift[c]; }
     cs = csm;
   }
-  __device__ __forceinline__ void produce(int ptid, int m0, uint32_t saddr) const {
-    const int chunk = ptid & 15, r0 = ptid >> 4, crows = rows();
-    const bool ok = m0 + chunk * 8 < M;
-    const __nv_bfloat16* src = y + (size_t)m0 + chunk * 8;
-#pragma unroll 4
-    for (int c = r0; c < C; c += 16) {
-      uint4 raw = make_uint4(0, 0, 0, 0);
-      if (ok) raw = __ldg(reinterpret_cast<const uint4*>(src + (size_t)c * Mld));
+  __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
+  __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx&, Raw& r) const {
+    PCOE_CM_MAP
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int c = r0 + (b * kBatch + i) * rstep;
+      r.a[i] = make_uint4(0, 0, 0, 0);
+      if (ok && c < C) r.a[i] = __ldg(tb_chunk(y, C, m0 >> 7, c, chunk));
+    }
+  }
+  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr) const {
+    PCOE_CM_MAP
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int c = r0 + (b * kBatch + i) * rstep;
+      if (c >= C) continue;
       float v[8];
-      unpack8(raw, v);
+      unpack8(r.a[i], v);
       const float sc = cs[c], sh = cs[C + c];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = ok ? fmaxf(fmaf(v[u], sc, sh), 0.f) : 0.f;
-      tc::sts128(saddr + cm_off(crows, c, chunk), tc::pack8_bf16(v));
+      tc::sts128(saddr + cm_off(C, c, chunk), tc::pack8_bf16(v));
     }
   }
 };
@@ -104,6 +173,8 @@ struct BnRelu4 {
 // dy^T = a*dz^T + p*y^T + q  (BatchNorm backward folded into per-channel constants), dense dz
 struct Dy4 {
   static constexpr bool kChMajor = true;
+  using Idx = NoIdx;
+  struct Raw { uint4 d[kBatch], y[kBatch]; };
   const __nv_bfloat16* __restrict__ dz;
   const __nv_bfloat16* __restrict__ y;
   const float* __restrict__ a;
@@ -111,27 +182,37 @@ struct Dy4 {
   const float* __restrict__ q;
   int M, Mld, C;
   const float* cs;
-  __host__ __device__ __forceinline__ int rows() const { return C < 128 ? 128 : C; }
+  __host__ __device__ __forceinline__ int rows() const { return C < 128 ? 128 : C; }   // also an M operand: 128 rows
   __host__ __device__ __forceinline__ int kext() const { return C; }
   __host__ __device__ __forceinline__ int nconst() const { return 3 * C; }
+  __device__ __forceinline__ int nbatches(int G) const { return (C / (G >> 4) + kBatch - 1) / kBatch; }
   __device__ __forceinline__ void init(float* csm, int tid, int nthr) {
     for (int c = tid; c < C; c += nthr) { csm[c] = a[c]; csm[C + c] = p[c]; csm[2 * C + c] = q[c]; }
     cs = csm;
   }
-  __device__ __forceinline__ void produce(int ptid, int m0, uint32_t saddr) const {
-    const int chunk = ptid & 15, r0 = ptid >> 4, crows = rows();
-    const bool ok = m0 + chunk * 8 < M;
-    const size_t col = (size_t)m0 + chunk * 8;
-#pragma unroll 4
-    for (int c = r0; c < C; c += 16) {
-      uint4 rd = make_uint4(0, 0, 0, 0), ry = rd;
-      if (ok) {
-        rd = __ldg(reinterpret_cast<const uint4*>(dz + (size_t)c * Mld + col));
-        ry = __ldg(reinterpret_cast<const uint4*>(y + (size_t)c * Mld + col));
+  __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
+  __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx&, Raw& r) const {
+    PCOE_CM_MAP
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int c = r0 + (b * kBatch + i) * rstep;
+      r.d[i] = r.y[i] = make_uint4(0, 0, 0, 0);
+      if (ok && c < C) {
+        r.d[i] = __ldg(tb_chunk(dz, C, m0 >> 7, c, chunk));
+        r.y[i] = __ldg(tb_chunk(y, C, m0 >> 7, c, chunk));
       }
+    }
+  }
+  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr) const {
+    PCOE_CM_MAP
+    const int crows = rows();
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int c = r0 + (b * kBatch + i) * rstep;
+      if (c >= C) continue;
       float d[8], yy[8], v[8];
-      unpack8(rd, d);
-      unpack8(ry, yy);
+      unpack8(r.d[i], d);
+      unpack8(r.y[i], yy);
       const float ca = cs[c], cp = cs[C + c], cq = cs[2 * C + c];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = ok ? fmaf(ca, d[u], fmaf(cp, yy[u], cq)) : 0.f;
@@ -143,6 +224,8 @@ struct Dy4 {
 // last layer: the upstream gradient is the max-pool routing of gm[G,C] to the saved arg slot (K == 32)
 struct DyLast4 {
   static constexpr bool kChMajor = true;
+  using Idx = NoIdx;
+  struct Raw { uint4 y[kBatch]; float gv[kBatch]; int sl[kBatch]; };
   const float* __restrict__ gm;       // [G,C]
   const uint8_t* __restrict__ slot;   // [G,C]
   const __nv_bfloat16* __restrict__ y;
@@ -154,28 +237,37 @@ struct DyLast4 {
   __host__ __device__ __forceinline__ int rows() const { return C < 128 ? 128 : C; }
   __host__ __device__ __forceinline__ int kext() const { return C; }
   __host__ __device__ __forceinline__ int nconst() const { return 3 * C; }
+  __device__ __forceinline__ int nbatches(int G) const { return (C / (G >> 4) + kBatch - 1) / kBatch; }
   __device__ __forceinline__ void init(float* csm, int tid, int nthr) {
     for (int c = tid; c < C; c += nthr) { csm[c] = a[c]; csm[C + c] = p[c]; csm[2 * C + c] = q[c]; }
     cs = csm;
   }
-  __device__ __forceinline__ void produce(int ptid, int m0, uint32_t saddr) const {
-    const int chunk = ptid & 15, r0 = ptid >> 4, crows = rows();
-    const int m = m0 + chunk * 8;
-    const bool ok = m < M;
-    const int g = min(m, M - 1) >> 5, j0 = m & 31;
-#pragma unroll 4
-    for (int c = r0; c < C; c += 16) {
-      uint4 ry = make_uint4(0, 0, 0, 0);
-      float gv = 0.f;
-      int sl = -1;
-      if (ok) {
-        ry = __ldg(reinterpret_cast<const uint4*>(y + (size_t)c * Mld + m));
-        gv = __ldg(gm + (size_t)g * C + c);
-        sl = (int)__ldg(slot + (size_t)g * C + c) - j0;
+  __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
+  __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx&, Raw& r) const {
+    PCOE_CM_MAP
+    const int grp = min(m, M - 1) >> 5, j0 = m & 31;
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int c = r0 + (b * kBatch + i) * rstep;
+      r.y[i] = make_uint4(0, 0, 0, 0); r.gv[i] = 0.f; r.sl[i] = -1;
+      if (ok && c < C) {
+        r.y[i] = __ldg(tb_chunk(y, C, m0 >> 7, c, chunk));
+        r.gv[i] = __ldg(gm + (size_t)grp * C + c);
+        r.sl[i] = (int)__ldg(slot + (size_t)grp * C + c) - j0;
       }
+    }
+  }
+  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr) const {
+    PCOE_CM_MAP
+    const int crows = rows();
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int c = r0 + (b * kBatch + i) * rstep;
+      if (c >= C) continue;
       float yy[8], v[8];
-      unpack8(ry, yy);
-      const float ca = cs[c] * gv, cp = cs[C + c], cq = cs[2 * C + c];
+      unpack8(r.y[i], yy);
+      const float ca = cs[c] * r.gv[i], cp = cs[C + c], cq = cs[2 * C + c];
+      const int sl = r.sl[i];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = ok ? fmaf(cp, yy[u], cq) + (u == sl ? ca : 0.f) : 0.f;
       tc::sts128(saddr + cm_off(crows, c, chunk), tc::pack8_bf16(v));
@@ -183,99 +275,155 @@ struct DyLast4 {
   }
 };
 
-// layer-1 input without features (SA1): [xyz[nbr] - centroid] as a channel-major tile of 16 rows
-// (rows 3..15 stay zero from the one-time clear)
-struct GatherXyz4 {
-  static constexpr bool kChMajor = true;
+// shared by the gather producers: flat point index of neighbour row `row`
+struct GatherBase {
   const float* __restrict__ xyz;
   const float* __restrict__ new_xyz;
   const int32_t* __restrict__ nbr;
   int N, S, group_all, M;
+  __device__ __forceinline__ int point_of(int row) const {   // row < M
+    if (group_all) return row;
+    int i = __ldg(nbr + row);
+    i = min(max(i, 0), N - 1);
+    return ((row >> 5) / S) * N + i;
+  }
+  __device__ __forceinline__ void load_xyz(int row, int pt, float (&v)[3]) const {
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      float x = __ldg(xyz + (size_t)pt * 3 + u);
+      if (!group_all) x = __fsub_rn(x, __ldg(new_xyz + (size_t)(row >> 5) * 3 + u));
+      v[u] = x;
+    }
+  }
+};
+
+// layer-1 input without features (SA1): [xyz[nbr] - centroid] as a channel-major tile of 16 rows
+// (rows 3..15 stay zero from the one-time clear).  Thread g < 128 owns point m0 + g.
+struct GatherXyz4 {
+  static constexpr bool kChMajor = true;
+  struct Idx { int pt; };
+  struct Raw { float v[3]; };
+  GatherBase gb;
   __host__ __device__ __forceinline__ int rows() const { return 16; }
   __host__ __device__ __forceinline__ int kext() const { return 16; }
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
+  __device__ __forceinline__ int nbatches(int) const { return 1; }
   __device__ __forceinline__ void init(float*, int, int) {}
-  __device__ __forceinline__ void produce(int ptid, int m0, uint32_t saddr) const {
-    if (ptid >= kPts) return;
-    const int row = m0 + ptid;
-    float v[3] = {0.f, 0.f, 0.f};
-    if (row < M) {
-      const int g = row >> 5;
-      int pt = row;
-      if (!group_all) {
-        int i = __ldg(nbr + row);
-        i = min(max(i, 0), N - 1);
-        pt = (g / S) * N + i;
-      }
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        float x = __ldg(xyz + (size_t)pt * 3 + u);
-        if (!group_all) x = __fsub_rn(x, __ldg(new_xyz + (size_t)g * 3 + u));
-        v[u] = x;
-      }
-    }
-    const uint32_t base = saddr + (uint32_t)((ptid >> 6) * 16 * 128) + (uint32_t)((ptid & 7) * 2);
-    const int ch = (ptid & 63) >> 3;
+  __device__ __forceinline__ void load_idx(int g, int, int m0, int, Idx& ix) const {
+    ix.pt = -1;
+    if (g < kPts && m0 + g < gb.M) ix.pt = gb.point_of(m0 + g);
+  }
+  __device__ __forceinline__ void load(int g, int, int m0, int, const Idx& ix, Raw& r) const {
+    r.v[0] = r.v[1] = r.v[2] = 0.f;
+    if (ix.pt >= 0) gb.load_xyz(m0 + g, ix.pt, r.v);
+  }
+  __device__ __forceinline__ void store(int g, int, int, int, const Raw& r, uint32_t saddr) const {
+    if (g >= kPts) return;
+    const uint32_t base = saddr + (uint32_t)((g >> 6) * 16 * 128) + (uint32_t)((g & 7) * 2);
+    const int ch = (g & 63) >> 3;
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
-      const uint16_t h = __bfloat16_as_ushort(__float2bfloat16_rn(v[u]));
+      const uint16_t h = __bfloat16_as_ushort(__float2bfloat16_rn(r.v[u]));
       asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + (uint32_t)(u * 128 + ((ch ^ u) << 4))), "h"(h) : "memory");
     }
   }
 };
 
-// layer-1 input with features (SA2, SA3): point-major tile [128 points][kq channels],
-// channel order [feats(D) | xyz - centroid (3) | zeros], D % 8 == 0
+// layer-1 input with features (SA2, SA3): point-major tile [128 points][kext channels],
+// channel order [feats(D) | xyz - centroid (3) | zeros], D in {32, 64, 128, 256}.
+// Thread g owns feature unit (g % fu) (8 channels, 32 bytes of fp32) of rows (g / fu) + j*(G / fu);
+// in batch 0 thread g < 128 additionally owns the xyz unit of row g.
 struct GatherFeat4 {
   static constexpr bool kChMajor = false;
-  const float* __restrict__ xyz;
-  const float* __restrict__ new_xyz;
-  const int32_t* __restrict__ nbr;
+  struct Idx { int pt[kBatch]; int ptx; };
+  struct Raw { float4 a[kBatch], b[kBatch]; float xv[3]; };
+  GatherBase gb;
   const float* __restrict__ feats;
-  int N, S, D, group_all, M;
+  int D;
   __host__ __device__ __forceinline__ int kext() const { return (D + 3 + 15) / 16 * 16; }
   __host__ __device__ __forceinline__ int rows() const { return kPts; }
-  __host__ __device__ __forceinline__ int nblocks() const { return (kext() + 63) / 64; }
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
+  __device__ __forceinline__ int nbatches(int G) const { return (kPts / (G / (D >> 3)) + kBatch - 1) / kBatch; }
   __device__ __forceinline__ void init(float*, int, int) {}
-  __device__ __forceinline__ void produce(int ptid, int m0, uint32_t saddr) const {
-    const int upr = kext() / 8;   // 16-byte units per point row
-    for (int e = ptid; e < kPts * upr; e += kProdThreads) {
-      const int r = e / upr, j = e - r * upr, c0 = j * 8;
-      const int row = m0 + r;
-      float v[8];
+  __device__ __forceinline__ void load_idx(int g, int G, int m0, int b, Idx& ix) const {
+    const int fu = D >> 3, rstep = G / fu, r0 = g / fu;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = 0.f;
-      if (row < M && c0 < D + 3) {
-        const int g = row >> 5;
-        int pt = row;
-        if (!group_all) {
-          int i = __ldg(nbr + row);
-          i = min(max(i, 0), N - 1);
-          pt = (g / S) * N + i;
-        }
-        if (c0 < D) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(feats + (size_t)pt * D + c0));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(feats + (size_t)pt * D + c0) + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+    for (int i = 0; i < kBatch; ++i) {
+      const int r = r0 + (b * kBatch + i) * rstep;
+      ix.pt[i] = (r < kPts && m0 + r < gb.M) ? gb.point_of(m0 + r) : -1;
+    }
+    ix.ptx = (b == 0 && g < kPts && m0 + g < gb.M) ? gb.point_of(m0 + g) : -1;
+  }
+  __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx& ix, Raw& r) const {
+    const int fu = D >> 3, j = g % fu;
 #pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            float x = __ldg(xyz + (size_t)pt * 3 + u);
-            if (!group_all) x = __fsub_rn(x, __ldg(new_xyz + (size_t)g * 3 + u));
-            v[u] = x;
-          }
-        }
+    for (int i = 0; i < kBatch; ++i) {
+      r.a[i] = r.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ix.pt[i] >= 0) {
+        const float4* src = reinterpret_cast<const float4*>(feats + (size_t)ix.pt[i] * D + j * 8);
+        r.a[i] = __ldg(src);
+        r.b[i] = __ldg(src + 1);
       }
-      tc::sts128(saddr + (uint32_t)(j >> 3) * (kPts * 128) + tc::sw128_off(r, (j & 7) * 8), tc::pack8_bf16(v));
+    }
+    r.xv[0] = r.xv[1] = r.xv[2] = 0.f;
+    if (b == 0 && ix.ptx >= 0) gb.load_xyz(m0 + g, ix.ptx, r.xv);
+  }
+  __device__ __forceinline__ void store(int g, int G, int, int b, const Raw& r, uint32_t saddr) const {
+    const int fu = D >> 3, rstep = G / fu, r0 = g / fu, j = g % fu;
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int row = r0 + (b * kBatch + i) * rstep;
+      if (row >= kPts) continue;
+      const float v[8] = {r.a[i].x, r.a[i].y, r.a[i].z, r.a[i].w, r.b[i].x, r.b[i].y, r.b[i].z, r.b[i].w};
+      tc::sts128(saddr + (uint32_t)(j >> 3) * (kPts * 128) + tc::sw128_off(row, (j & 7) * 8), tc::pack8_bf16(v));
+    }
+    if (b == 0 && g < kPts) {
+      const float v[8] = {r.xv[0], r.xv[1], r.xv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+      tc::sts128(saddr + (uint32_t)(fu >> 3) * (kPts * 128) + tc::sw128_off(g, (fu & 7) * 8), tc::pack8_bf16(v));
     }
   }
 };
 
+// The producer pipeline of one group (G threads, group-local id g) over the CTA's tiles.
+// arrive(): `full` arrival after the last batch of a tile; wait_empty(t): the tile's stage is free.
+template <class Prod, class WaitEmpty, class StageAddr, class Arrive>
+__device__ __forceinline__ void producer_pipeline(const Prod& prod, int g, int G, int ntiles, WaitEmpty wait_empty,
+                                                  StageAddr stage_addr, Arrive arrive) {
+  int my_tiles = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
+  const int nb = prod.nbatches(G), W = my_tiles * nb;
+  if (W == 0) return;
+  TC4_TRACER;
+  auto m0_of = [&](int w) { return (int)((blockIdx.x + (w / nb) * gridDim.x) * kPts); };
+  typename Prod::Idx ix;
+  typename Prod::Raw ra, rb;
+  prod.load_idx(g, G, m0_of(0), 0, ix);
+  prod.load(g, G, m0_of(0), 0, ix, ra);
+  if (W > 1) prod.load_idx(g, G, m0_of(1), 1 % nb, ix);
+  auto step = [&](int w, typename Prod::Raw& cur, typename Prod::Raw& nxt) {
+    if (w + 1 < W) prod.load(g, G, m0_of(w + 1), (w + 1) % nb, ix, nxt);
+    if (w + 2 < W) prod.load_idx(g, G, m0_of(w + 2), (w + 2) % nb, ix);
+    const int t = w / nb, b = w - t * nb;
+    if (g == 0) TC4_TRACE(12, w);
+    if (b == 0) wait_empty(t);
+    if (g == 0) TC4_TRACE(10, w);
+    prod.store(g, G, m0_of(w), b, cur, stage_addr(t));
+    if (b == nb - 1) { tc::fence_proxy_async(); arrive(t); }
+    if (g == 0) TC4_TRACE(11, w);
+  };
+  for (int w = 0; w < W; w += 2) {
+    step(w, ra, rb);
+    if (w + 1 < W) step(w + 1, rb, ra);
+  }
+  if (g == 0) TC4_TRACE_DUMP();
+}
+
 // ---------------------------------------------------------------------------------------------
-// Epilogues.  Thread = channel (TMEM lane), v = 32 consecutive points.
-//   block(v, c, m, valid, mi): channel c (may be >= C: padding lane), points m..m+31, mi = M tile
-//   finish(): flush per-thread running sums
+// Epilogues.  Thread = one channel (TMEM lane) for the whole kernel; v = 32 consecutive points.
+//   init(csm, c): c = this thread's channel (may be >= C: padding lane -> the thread does nothing)
+//   block(v, m, valid): points m..m+31      finish(): flush the per-thread running sums
+// Reductions are written as 4-way / tree reductions: one epilogue warp per scheduler has to cover
+// its own ALU latency.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store32_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
 #pragma unroll
@@ -285,117 +433,157 @@ __device__ __forceinline__ void store32_bf16(__nv_bfloat16* dst, const float (&v
   }
 }
 
+// Epilogues with kStage write their output tile into a shared-memory staging image (the tile-blocked
+// HBM layout, see header); the kernel copies it out with one bulk async copy per tile.
+__device__ __forceinline__ void stage32_bf16(uint32_t stg, int c, int j, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float t[8] = {v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3], v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]};
+    tc::sts128(stg + tb_stage_off(c, j * 4 + q), tc::pack8_bf16(t));
+  }
+}
+
+__device__ __forceinline__ void sum_sumsq32(const float (&v)[32], float& s, float& ss) {
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a[k] += v[i + k]; b[k] = fmaf(v[i + k], v[i + k], b[k]); }
+  }
+  s += (a[0] + a[1]) + (a[2] + a[3]);
+  ss += (b[0] + b[1]) + (b[2] + b[3]);
+}
+
+// first arg-max (MAX) / arg-min of 32 values by a pairwise tree (depth 5); ties keep the lower index
+template <bool MAX>
+__device__ __forceinline__ void argext32(const float (&v)[32], float& val, int& arg) {
+  float mv[16];
+  int ix[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool r = MAX ? v[2 * i + 1] > v[2 * i] : v[2 * i + 1] < v[2 * i];
+    mv[i] = r ? v[2 * i + 1] : v[2 * i];
+    ix[i] = r ? 2 * i + 1 : 2 * i;
+  }
+#pragma unroll
+  for (int n = 8; n >= 1; n >>= 1) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const bool r = MAX ? mv[2 * i + 1] > mv[2 * i] : mv[2 * i + 1] < mv[2 * i];
+      const float nv = r ? mv[2 * i + 1] : mv[2 * i];
+      const int ni = r ? ix[2 * i + 1] : ix[2 * i];
+      mv[i] = nv;
+      ix[i] = ni;
+    }
+  }
+  val = mv[0];
+  arg = ix[0];
+}
+
 struct StoreStats4 {
-  __nv_bfloat16* __restrict__ y;   // [C][Mld]
+  __nv_bfloat16* __restrict__ y;   // tile-blocked [tile][C][128]
   double* __restrict__ sums;       // [2,C] or nullptr (eval)
   int C, Mld;
-  float s0[2], s1[2];
+  int c;
+  float s0, s1;
+  static constexpr bool kStage = true;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
-  __device__ __forceinline__ void init(float*, int, int) { s0[0] = s0[1] = s1[0] = s1[1] = 0.f; }
-  __device__ __forceinline__ void block(float (&v)[32], int c, int m, bool valid, int mi) {
+  __host__ __device__ __forceinline__ int stage_bytes() const { return C * 256; }
+  __device__ __forceinline__ char* tile_dst(int tile) const { return y ? reinterpret_cast<char*>(y) + (size_t)tile * C * 256 : nullptr; }
+  __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; }
+  __device__ __forceinline__ void block(float (&v)[32], int, int j, bool valid, uint32_t stg) {
     if (c >= C || !valid) return;
-    store32_bf16(y + (size_t)c * Mld + m, v);
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { a += v[i]; b = fmaf(v[i], v[i], b); }
-    if (mi == 0) { s0[0] += a; s1[0] += b; } else { s0[1] += a; s1[1] += b; }
+    stage32_bf16(stg, c, j, v);
+    sum_sumsq32(v, s0, s1);
   }
-  __device__ __forceinline__ void finish(int lane128) {
-    if (!sums) return;
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-      const int c = mi * 128 + lane128;
-      if (c < C) { atomicAdd(sums + c, (double)s0[mi]); atomicAdd(sums + C + c, (double)s1[mi]); }
-    }
+  __device__ __forceinline__ void finish() {
+    if (!sums || c >= C) return;
+    atomicAdd(sums + c, (double)s0);
+    atomicAdd(sums + C + c, (double)s1);
   }
 };
 
 struct Group4 {   // last layer, K == 32: the 32 columns of a block are one group
-  __nv_bfloat16* __restrict__ y;   // [C][Mld] or nullptr (eval)
+  __nv_bfloat16* __restrict__ y;   // tile-blocked, or nullptr (eval)
   double* __restrict__ sums;       // or nullptr
   float* __restrict__ ymax;        // [G,C]
   float* __restrict__ ymin;
   uint8_t* __restrict__ amax;
   uint8_t* __restrict__ amin;
   int C, Mld;
-  float s0[2], s1[2];
+  int c;
+  float s0, s1;
+  static constexpr bool kStage = true;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
-  __device__ __forceinline__ void init(float*, int, int) { s0[0] = s0[1] = s1[0] = s1[1] = 0.f; }
-  __device__ __forceinline__ void block(float (&v)[32], int c, int m, bool valid, int mi) {
+  __host__ __device__ __forceinline__ int stage_bytes() const { return C * 256; }
+  __device__ __forceinline__ char* tile_dst(int tile) const { return y ? reinterpret_cast<char*>(y) + (size_t)tile * C * 256 : nullptr; }
+  __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; }
+  __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid, uint32_t stg) {
     if (c >= C || !valid) return;
-    if (y) store32_bf16(y + (size_t)c * Mld + m, v);
-    float a = 0.f, b = 0.f, mx = v[0], mn = v[0];
-    int ax = 0, an = 0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      a += v[i];
-      b = fmaf(v[i], v[i], b);
-      if (v[i] > mx) { mx = v[i]; ax = i; }     // strict: first arg-max / arg-min
-      if (v[i] < mn) { mn = v[i]; an = i; }
-    }
-    if (mi == 0) { s0[0] += a; s1[0] += b; } else { s0[1] += a; s1[1] += b; }
-    const size_t o = (size_t)(m >> 5) * C + c;
+    if (y) stage32_bf16(stg, c, j, v);
+    sum_sumsq32(v, s0, s1);
+    float mx, mn;
+    int ax, an;
+    argext32<true>(v, mx, ax);
+    argext32<false>(v, mn, an);
+    const size_t o = (size_t)(tile * 4 + j) * C + c;
     ymax[o] = mx; ymin[o] = mn; amax[o] = (uint8_t)ax; amin[o] = (uint8_t)an;
   }
-  __device__ __forceinline__ void finish(int lane128) {
-    if (!sums) return;
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-      const int c = mi * 128 + lane128;
-      if (c < C) { atomicAdd(sums + c, (double)s0[mi]); atomicAdd(sums + C + c, (double)s1[mi]); }
-    }
+  __device__ __forceinline__ void finish() {
+    if (!sums || c >= C) return;
+    atomicAdd(sums + c, (double)s0);
+    atomicAdd(sums + C + c, (double)s1);
   }
 };
 
 // dz_prev^T = dx^T * [z_prev > 0]; sums of dz_prev and dz_prev * xhat_prev per channel
 struct MaskStats4 {
-  const __nv_bfloat16* __restrict__ yprev;   // [C][Mld]
+  const __nv_bfloat16* __restrict__ yprev;   // tile-blocked
   const float* __restrict__ scale;
   const float* __restrict__ shift;
   const float* __restrict__ mean;
   const float* __restrict__ invstd;
-  __nv_bfloat16* __restrict__ dz;            // [C][Mld]
+  __nv_bfloat16* __restrict__ dz;            // tile-blocked
   double* __restrict__ sums;
   int C, Mld;
-  float s0[2], s1[2];
-  float sc[2], sh[2], mu[2], is[2];
+  int c;
+  float s0, s1, sc, sh, mu, is;
+  static constexpr bool kStage = true;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
-  __device__ __forceinline__ void init(float*, int tid, int) {
-    s0[0] = s0[1] = s1[0] = s1[1] = 0.f;
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-      const int c = mi * 128 + (tid & 127);
-      const bool ok = c < C;
-      sc[mi] = ok ? scale[c] : 0.f; sh[mi] = ok ? shift[c] : 0.f; mu[mi] = ok ? mean[c] : 0.f; is[mi] = ok ? invstd[c] : 0.f;
-    }
+  __host__ __device__ __forceinline__ int stage_bytes() const { return C * 256; }
+  __device__ __forceinline__ char* tile_dst(int tile) const { return reinterpret_cast<char*>(dz) + (size_t)tile * C * 256; }
+  __device__ __forceinline__ void init(float*, int ch) {
+    c = ch; s0 = s1 = 0.f;
+    const bool ok = c < C;
+    sc = ok ? scale[c] : 0.f; sh = ok ? shift[c] : 0.f; mu = ok ? mean[c] : 0.f; is = ok ? invstd[c] : 0.f;
   }
-  __device__ __forceinline__ void block(float (&v)[32], int c, int m, bool valid, int mi) {
+  __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid, uint32_t stg) {
     if (c >= C || !valid) return;
-    const float ksc = mi ? sc[1] : sc[0], ksh = mi ? sh[1] : sh[0], kmu = mi ? mu[1] : mu[0], kis = mi ? is[1] : is[0];
-    const __nv_bfloat16* src = yprev + (size_t)c * Mld + m;
-    float a = 0.f, b = 0.f;
+    uint4 raw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) raw[q] = __ldg(tb_chunk(yprev, C, tile, c, j * 4 + q));
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float yy[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(src) + q), yy);
+      unpack8(raw[q], yy);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const bool on = fmaf(yy[u], ksc, ksh) > 0.f;
+        const bool on = fmaf(yy[u], sc, sh) > 0.f;
         const float d = on ? v[8 * q + u] : 0.f;
         v[8 * q + u] = d;
-        a += d;
-        b = fmaf(d, (yy[u] - kmu) * kis, b);
+        a[u & 3] += d;
+        b[u & 3] = fmaf(d, (yy[u] - mu) * is, b[u & 3]);
       }
     }
-    store32_bf16(dz + (size_t)c * Mld + m, v);
-    if (mi == 0) { s0[0] += a; s1[0] += b; } else { s0[1] += a; s1[1] += b; }
+    stage32_bf16(stg, c, j, v);
+    s0 += (a[0] + a[1]) + (a[2] + a[3]);
+    s1 += (b[0] + b[1]) + (b[2] + b[3]);
   }
-  __device__ __forceinline__ void finish(int lane128) {
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-      const int c = mi * 128 + lane128;
-      if (c < C) { atomicAdd(sums + c, (double)s0[mi]); atomicAdd(sums + C + c, (double)s1[mi]); }
-    }
+  __device__ __forceinline__ void finish() {
+    if (c >= C) return;
+    atomicAdd(sums + c, (double)s0);
+    atomicAdd(sums + C + c, (double)s1);
   }
 };
 
@@ -404,9 +592,12 @@ struct Scatter4 {
   float* __restrict__ grad_feats;
   const int32_t* __restrict__ nbr;
   int N, S, D, group_all;
+  static constexpr bool kStage = false;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
-  __device__ __forceinline__ void init(float*, int, int) {}
-  // here c = first feature channel of the block, m = the thread's point row
+  __host__ __device__ __forceinline__ int stage_bytes() const { return 0; }
+  __device__ __forceinline__ char* tile_dst(int) const { return nullptr; }
+  __device__ __forceinline__ void init(float*, int) {}
+  // cb = first feature channel of the block, row = the thread's point row
   __device__ __forceinline__ void block_pt(float (&v)[32], int cb, int row, bool valid) {
     if (!valid || cb >= D) return;
     int pt = row;
@@ -419,13 +610,16 @@ struct Scatter4 {
 #pragma unroll
     for (int q = 0; q < 8; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
-  __device__ __forceinline__ void finish(int) {}
+  __device__ __forceinline__ void finish() {}
 };
 
 struct NoEpi4 {
+  static constexpr bool kStage = false;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
-  __device__ __forceinline__ void init(float*, int, int) {}
-  __device__ __forceinline__ void finish(int) {}
+  __host__ __device__ __forceinline__ int stage_bytes() const { return 0; }
+  __device__ __forceinline__ char* tile_dst(int) const { return nullptr; }
+  __device__ __forceinline__ void init(float*, int) {}
+  __device__ __forceinline__ void finish() {}
 };
 
 struct Barriers4 {
@@ -464,13 +658,29 @@ __device__ __forceinline__ uint64_t act_desc_chan_k(const Prod& p, uint32_t sadd
   else return tc::make_desc_sw128(saddr + (uint32_t)(k >> 6) * (kPts * 128) + (uint32_t)((k & 63) * 2), 16, 1024);      // K-major
 }
 
+// Copy-out of a staged output tile, executed by all 256 epilogue threads after their last block():
+// one elected thread issues the bulk async copy.  nstg == 2: the staging buffer alternates and the
+// elected thread only waits (before the barrier) for the copy of the PREVIOUS tile to have read its
+// buffer; nstg == 1: everybody waits for this tile's copy before the buffer is reused.
+__device__ __forceinline__ void stage_copy_out(char* dst, uint32_t stg, int bytes, int nstg, bool elected) {
+  if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  tc::fence_proxy_async();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (elected) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(stg), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (nstg == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  if (nstg == 1) asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward layer:  Y^T[C_out x 128] = W * X^T per tile;  TMEM: 2 buffers x mt x 128 columns
 // smem: [W image][stages x tile][constants]
 // ---------------------------------------------------------------------------------------------
 template <class Prod, class Epi, int TCOLS>
 __global__ void __launch_bounds__(kThreads, 1)
-tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, Epi epi, int M, int nstages) {
+tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, Epi epi, int M, int nstages, int nstg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem0 - tc::smem_u32(smem_raw));
@@ -483,6 +693,8 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
   const uint32_t sW = smem0, sT = smem0 + wbytes;
   float* csm = reinterpret_cast<float*>(smem_gen + wbytes + (size_t)nstages * tbytes);
 
+  TC4_TRACER;
+  if (tid == 0) TC4_TRACE(0, 0);
   if (warp == 0) tc::tmem_alloc<TCOLS>(&tmem_base);
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) { tc::mbar_init(&bar.full[s], kProdThreads); tc::mbar_init(&bar.empty[s], 1); }
@@ -491,43 +703,56 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
   load_wimage(Wb, Rp, Kp, sW, tid, kThreads);
   zero_smem(sT, (uint32_t)nstages * tbytes, tid, kThreads);
   prod.init(csm, tid, kThreads);
-  epi.init(csm + prod.nconst(), tid, kThreads);
+  // epilogue work split: warp w -> TMEM lane quadrant w&3, items [eh*mt*2, (eh+1)*mt*2) of the mt*4
+  // (M tile, 32-column block) pairs of a tile; all of one thread's items share one M tile
+  const int eq = warp & 3, eh = (warp >> 2) & 1, lane = tid & 31;
+  const int emi = (eh * mt) >> 1;
+  // staging tiles (tile-blocked output image) follow the constants
+  const uint32_t stg0 = (sT + (uint32_t)nstages * tbytes + (uint32_t)(prod.nconst() + epi.nconst()) * 4u + 127u) & ~127u;
+  const uint32_t stg_bytes = (uint32_t)epi.stage_bytes();
+  epi.init(csm + prod.nconst(), emi * 128 + eq * 32 + lane);
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_base;
   const int ntiles = (M + kPts - 1) / kPts;
+  if (tid == 0) TC4_TRACE(1, 0);
 
-  if (warp < 4) {
-    // ---- epilogue: thread = TMEM lane = channel (mi*128 + tid) ----
+  if (warp < 8) {
+    // ---- epilogue ----
     int i = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
       const int b = i & 1, u = i >> 1, m0 = tile * kPts;
       tc::mbar_wait(&bar.tmem_full[b], (uint32_t)(u & 1));
+      if (tid == 0) TC4_TRACE(30, i);
       tc::fence_after_sync();
-      for (int mi = 0; mi < mt; ++mi)
+      const uint32_t stg = stg0 + (uint32_t)(i % nstg) * stg_bytes;
+      const int it0 = eh * mt * 2;
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          float v[32];
-          tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * mt * kPts + mi * kPts + j * 32), v);
-          epi.block(v, mi * 128 + tid, m0 + j * 32, m0 + j * 32 < M, mi);
-        }
+      for (int it = it0; it < it0 + mt * 2; ++it) {
+        const int j = it & 3;
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(b * mt * kPts + emi * kPts + j * 32), v);
+        if (tid == 0) TC4_TRACE(33, it);
+        epi.block(v, tile, j, m0 + j * 32 < M, stg);
+        if (tid == 0) TC4_TRACE(34, it);
+      }
       tc::fence_before_sync();
-      mbar_arrive(&bar.tmem_empty[b]);
+      mbar_arrive_relaxed(&bar.tmem_empty[b]);
+      if (tid == 0) TC4_TRACE(35, i);
+      if (Epi::kStage && epi.tile_dst(0) != nullptr) stage_copy_out(epi.tile_dst(tile), stg, (int)stg_bytes, nstg, tid == 0);
+      if (tid == 0) TC4_TRACE(31, i);
     }
-    epi.finish(tid);
-  } else if (warp < 12) {
+    if (Epi::kStage && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    epi.finish();
+    if (tid == 0) TC4_TRACE(32, 0);
+  } else if (warp < 16) {
     // ---- producers ----
-    const int ptid = tid - kEpiThreads;
-    int i = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
-      const int s = i % nstages, n = i / nstages;
-      if (n > 0) tc::mbar_wait(&bar.empty[s], (uint32_t)((n - 1) & 1));
-      prod.produce(ptid, tile * kPts, sT + (uint32_t)s * tbytes);
-      tc::fence_proxy_async();
-      mbar_arrive(&bar.full[s]);
-    }
+    producer_pipeline(prod, tid - kEpiThreads, kProdThreads, ntiles,
+                      [&](int t) { const int n = t / nstages; if (n > 0) tc::mbar_wait(&bar.empty[t % nstages], (uint32_t)((n - 1) & 1)); },
+                      [&](int t) { return sT + (uint32_t)(t % nstages) * tbytes; },
+                      [&](int t) { mbar_arrive(&bar.full[t % nstages]); });
   } else if (tid == kEpiThreads + kProdThreads) {
     // ---- MMA issue ----
     const uint32_t idesc = tc::make_idesc_bf16(128, kPts, false, Prod::kChMajor);
@@ -536,8 +761,10 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
       const int s = i % nstages, n = i / nstages, b = i & 1, u = i >> 1;
       tc::mbar_wait(&bar.full[s], (uint32_t)(n & 1));
+      TC4_TRACE(20, i);
       if (u > 0) tc::mbar_wait(&bar.tmem_empty[b], (uint32_t)((u - 1) & 1));
       tc::fence_after_sync();
+      TC4_TRACE(21, i);
       const uint32_t st = sT + (uint32_t)s * tbytes;
       for (int mi = 0; mi < mt; ++mi)
         for (int k = 0; k < kext; k += 16)
@@ -546,10 +773,13 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
                        act_desc_chan_k(prod, st, k), idesc, k > 0);
       tc::mma_commit(&bar.empty[s]);
       tc::mma_commit(&bar.tmem_full[b]);
+      TC4_TRACE(22, i);
     }
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (tid == 0) TC4_TRACE(2, 0);
+  if (tid == 0 || tid == kEpiThreads + kProdThreads) TC4_TRACE_DUMP();
   if (warp == 0) tc::tmem_dealloc<TCOLS>(tmem);
 }
 
@@ -564,7 +794,7 @@ template <class PProd, class QProd, class Epi, int DGRAD, int TCOLS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, Epi epi,
                float* __restrict__ dW, int ldo, int cq_valid, int perm_d /* >=0: layer-1 [feats|xyz] column order */,
-               int M, int cprev /* dgrad output channels */) {
+               int M, int cprev /* dgrad output channels */, int nstg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem0 - tc::smem_u32(smem_raw));
@@ -590,7 +820,12 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
   zero_smem(sP, pbytes + qbytes, tid, kThreads);
   pp.init(csm, tid, kThreads);
   qp.init(csm + pp.nconst(), tid, kThreads);
-  epi.init(csm + pp.nconst() + qp.nconst(), tid, kThreads);
+  // epilogue split as in the forward kernel (DGRAD == 1: mtp*4 items; DGRAD == 2: column blocks)
+  const int eq = warp & 3, eh = (warp >> 2) & 1, lane = tid & 31;
+  const int emi = (eh * mtp) >> 1;
+  const uint32_t stg0 = (sQ + qbytes + (uint32_t)(pp.nconst() + qp.nconst() + epi.nconst()) * 4u + 127u) & ~127u;
+  const uint32_t stg_bytes = (uint32_t)epi.stage_bytes();
+  epi.init(csm + pp.nconst() + qp.nconst(), emi * 128 + eq * 32 + lane);
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
@@ -600,41 +835,50 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
   int my_tiles = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
 
-  if (warp < 4) {
+  if (warp < 8) {
     int i = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
       const int b = i & 1, u = i >> 1, m0 = tile * kPts;
       tc::mbar_wait(&bar.tmem_full[b], (uint32_t)(u & 1));
       tc::fence_after_sync();
+      const uint32_t stg = stg0 + (uint32_t)(i % nstg) * stg_bytes;
       if constexpr (DGRAD == 1) {
-        for (int mi = 0; mi < mtp; ++mi)
+        const int it0 = eh * mtp * 2;
 #pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            float v[32];
-            tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + dx_col + (uint32_t)b * dx_cols + (uint32_t)(mi * kPts + j * 32), v);
-            epi.block(v, mi * 128 + tid, m0 + j * 32, m0 + j * 32 < M, mi);
-          }
-      } else if constexpr (DGRAD == 2) {
-#pragma unroll 1
-        for (int cb = 0; cb < cprev; cb += 32) {
+        for (int it = it0; it < it0 + mtp * 2; ++it) {
+          const int j = it & 3;
           float v[32];
-          tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + dx_col + (uint32_t)b * dx_cols + (uint32_t)cb, v);
-          epi.block_pt(v, cb, m0 + tid, m0 + tid < M);
+          tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + dx_col + (uint32_t)b * dx_cols + (uint32_t)(emi * kPts + j * 32), v);
+          epi.block(v, tile, j, m0 + j * 32 < M, stg);
+        }
+      } else if constexpr (DGRAD == 2) {
+        const int row = m0 + eq * 32 + lane;
+#pragma unroll 1
+        for (int cb = eh * 32; cb < cprev; cb += 64) {
+          float v[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + dx_col + (uint32_t)b * dx_cols + (uint32_t)cb, v);
+          epi.block_pt(v, cb, row, row < M);
         }
       }
       tc::fence_before_sync();
-      mbar_arrive(&bar.tmem_empty[b]);
+      mbar_arrive_relaxed(&bar.tmem_empty[b]);
+      if constexpr (DGRAD == 1) stage_copy_out(epi.tile_dst(tile), stg, (int)stg_bytes, nstg, tid == 0);
     }
-    epi.finish(tid);
-    // flush dW (complete: the last tmem_full commit covers every earlier MMA): thread = row of dW
+    if (DGRAD == 1 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    epi.finish();
+    // flush dW (complete: the last tmem_full commit covers every earlier MMA): thread = row of dW.
+    // Column blocks are visited in a per-CTA rotated order so that the CTAs, which all finish at about
+    // the same time, do not hammer the same L2 atomic units simultaneously.
     if (my_tiles > 0) {
       tc::fence_after_sync();
+      const int nblk = (nw + 31) / 32;
       for (int mi = 0; mi < mtl; ++mi) {
-        const int crow = mi * 128 + tid;
+        const int crow = mi * 128 + eq * 32 + lane;
 #pragma unroll 1
-        for (int cb = 0; cb < nw; cb += 32) {
+        for (int k = eh; k < nblk; k += 2) {
+          const int cb = ((k + (int)blockIdx.x) % nblk) * 32;
           float v[32];
-          tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mi * nw + cb), v);   // may read past nw: unused columns
+          tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(mi * nw + cb), v);   // may read past nw: unused columns
           if (crow < cl) {
             float* dst = dW + (size_t)crow * ldo;
             if (perm_d < 0 && (ldo & 3) == 0 && cb + 32 <= cq_valid) {
@@ -642,27 +886,23 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
               for (int q = 0; q < 8; ++q) red_add_v4(dst + cb + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             } else {
 #pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                int c = cb + k;
+              for (int e = 0; e < 32; ++e) {
+                int c = cb + e;
                 if (c >= cq_valid) continue;
                 if (perm_d >= 0) c = c < perm_d ? c + 3 : c - perm_d;   // [feats | xyz] -> [xyz | feats]
-                atomicAdd(dst + c, v[k]);
+                atomicAdd(dst + c, v[e]);
               }
             }
           }
         }
       }
     }
-  } else if (warp < 12) {
-    const int ptid = tid - kEpiThreads;
-    int i = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
-      if (i > 0) tc::mbar_wait(&bar.empty[0], (uint32_t)((i - 1) & 1));
-      pp.produce(ptid, tile * kPts, sP);
-      qp.produce(ptid, tile * kPts, sQ);
-      tc::fence_proxy_async();
-      mbar_arrive(&bar.full[0]);
-    }
+  } else if (warp < 16) {
+    // ---- producers: warps 8-11 build P (dy^T), warps 12-15 build Q (x_prev); one shared stage ----
+    auto wait_empty = [&](int t) { if (t > 0) tc::mbar_wait(&bar.empty[0], (uint32_t)((t - 1) & 1)); };
+    auto arrive = [&](int) { mbar_arrive(&bar.full[0]); };
+    if (warp < 12) producer_pipeline(pp, tid - kEpiThreads, kProdThreads / 2, ntiles, wait_empty, [&](int) { return sP; }, arrive);
+    else producer_pipeline(qp, tid - kEpiThreads - kProdThreads / 2, kProdThreads / 2, ntiles, wait_empty, [&](int) { return sQ; }, arrive);
   } else if (tid == kEpiThreads + kProdThreads) {
     const uint32_t idesc_w = tc::make_idesc_bf16(128, nw, false, !QProd::kChMajor);
     const uint32_t idesc_d = DGRAD == 1 ? tc::make_idesc_bf16(128, kPts, true, true)
