@@ -31,7 +31,7 @@ class SAParams(C.Structure):
 
 class SAGrads(C.Structure):
     """pcoe_sa_grads"""
-    _fields_ = [(n, C.c_void_p * 3) for n in ("dW", "dbias", "dgamma", "dbeta")]
+    _fields_ = [(n, C.c_void_p * 3) for n in ("dW", "dbias", "dgamma", "dbeta")] + [("accumulate", C.c_int32)]
 
 
 _P, _I, _F, _D, _U64, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_uint64, C.c_size_t
@@ -57,6 +57,8 @@ SIGNATURES = {
     "pcoe_vm_kl_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "pcoe_mvm_match_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pcoe_soft_ce_fwd_bwd": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "pcoe_adam_workspace_bytes": (_SZ, []),
+    "pcoe_adam_step": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

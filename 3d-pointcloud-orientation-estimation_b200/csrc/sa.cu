@@ -94,7 +94,7 @@ __global__ void bn_bwd_consts_kernel(const double* __restrict__ sums, double cou
                                      const float* __restrict__ invstd, float* __restrict__ a,
                                      float* __restrict__ p, float* __restrict__ q,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     float* __restrict__ dbias) {
+                                     float* __restrict__ dbias, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double s0 = sums[c], s1 = sums[C + c];
@@ -104,9 +104,9 @@ __global__ void bn_bwd_consts_kernel(const double* __restrict__ sums, double cou
   a[c] = (float)av;
   p[c] = (float)pv;
   q[c] = (float)(-av * m1 - pv * (double)mean[c]);
-  if (dgamma) dgamma[c] = (float)s1;
-  if (dbeta) dbeta[c] = (float)s0;
-  if (dbias) dbias[c] = 0.f;  // exactly cancelled by the batch-mean subtraction
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
+  if (dbias && !accumulate) dbias[c] = 0.f;  // exactly cancelled by the batch-mean subtraction
 }
 
 // per-layer kernel names for the profile report: sa1 = no input features, sa3 = group-all, sa2 = the rest
@@ -428,15 +428,16 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   TY* dz[2] = {(TY*)(ws + L.wb_dz[0]), (TY*)(ws + L.wb_dz[1])};
 
   PCOE_CUDA(cudaMemsetAsync(ws + L.wb_sums[0], 0, L.wb_sums_bytes, st));
-  for (int l = 0; l < 3; ++l)
-    PCOE_CUDA(cudaMemsetAsync(Gr.dW[l], 0, sizeof(float) * (size_t)Cs[l] * Kin[l], st));
+  if (!Gr.accumulate)
+    for (int l = 0; l < 3; ++l)
+      PCOE_CUDA(cudaMemsetAsync(Gr.dW[l], 0, sizeof(float) * (size_t)Cs[l] * Kin[l], st));
   if (d.D > 0 && grad_feats)
     PCOE_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)d.B * d.N * d.D, st));
 
   auto consts = [&](int l) -> int {
     LaunchScope ls("bn_bwd_consts_kernel", st);
     bn_bwd_consts_kernel<<<ceil_div(Cs[l], 128), 128, 0, st>>>(bs[l], (double)M, Cs[l], scale[l], mean[l],
-        invstd[l], ca[l], cp[l], cq[l], Gr.dgamma[l], Gr.dbeta[l], Gr.dbias[l]);
+        invstd[l], ca[l], cp[l], cq[l], Gr.dgamma[l], Gr.dbeta[l], Gr.dbias[l], Gr.accumulate);
     return ls.done();
   };
 

@@ -30,6 +30,11 @@ class FlatGradBuffer:
                 raise ValueError("FlatGradBuffer expects fp32 parameters on one device")
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        # set-abstraction layers add their parameter gradients into these views inside pcoe_sa_backward
+        # (pcoe_sa_grads.accumulate) instead of returning fresh tensors for autograd to add
+        for m in module.modules():
+            if hasattr(m, "direct_grad_accumulation"):
+                m.direct_grad_accumulation = True
 
     def zero_(self) -> None:
         self.flat.zero_()

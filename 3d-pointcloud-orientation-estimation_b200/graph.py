@@ -38,7 +38,9 @@ class GraphedTrainStep:
             self.loss = self._step()
 
     def _step(self):
-        if self.engine is not None:
+        if getattr(self.opt, "zero_grad_in_step", False):
+            pass                                   # pcoe.optim.FusedAdam clears the gradients as it consumes them
+        elif self.engine is not None:
             self.engine.zero_grad()
         else:
             self.opt.zero_grad(set_to_none=False)
@@ -47,7 +49,7 @@ class GraphedTrainStep:
         loss.backward()
         if self.engine is not None:
             self.engine.allreduce_grads()
-        if self.clip is not None:
+        if self.clip is not None and not getattr(self.opt, "fused_clip", False):
             torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
         self.opt.step()
         return loss.detach()

@@ -110,6 +110,7 @@ class _SAFunction(torch.autograd.Function):
                 if bn.num_batches_tracked is not None:
                     bn.num_batches_tracked.add_(1)
         ctx.desc, ctx.P, ctx.train = desc, P, train
+        ctx.params = params if module.direct_grad_accumulation else None
         ctx.has_feats = feats is not None
         ctx.param_shapes = [p.shape for p in params]
         ctx.save_for_backward(xyz, new_xyz, nbr, feats, out, saved, *Ws)
@@ -125,8 +126,17 @@ class _SAFunction(torch.autograd.Function):
         xyz, new_xyz, nbr, feats, out, saved, W1, W2, W3 = ctx.saved_tensors
         desc, P = ctx.desc, ctx.P
         dev = xyz.device
-        grads = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.param_shapes]
         G = _lib.SAGrads()
+        # direct accumulation (pcoe.dp.FlatGradBuffer): the kernels add into the p.grad views of the flat
+        # gradient buffer and autograd receives None - no per-parameter `grad += g` kernel
+        direct = ctx.params is not None and all(
+            p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.device == dev
+            for p in ctx.params)
+        if direct:
+            grads = [p.grad for p in ctx.params]
+            G.accumulate = 1
+        else:
+            grads = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.param_shapes]
         _fill3(G.dW, grads[0::4]); _fill3(G.dbias, grads[1::4]); _fill3(G.dgamma, grads[2::4]); _fill3(G.dbeta, grads[3::4])
         gfeats = torch.empty_like(feats) if (ctx.has_feats and ctx.needs_input_grad[3]) else None
         ws = _workspace(dev, lib.pcoe_sa_workspace_bytes(C.byref(desc)))
@@ -135,6 +145,8 @@ class _SAFunction(torch.autograd.Function):
                                         grad_out.contiguous().data_ptr(), saved.data_ptr(), saved.numel(),
                                         ops._ptr(gfeats), C.byref(G), ws.data_ptr(), ws.numel(),
                                         torch.cuda.current_stream().cuda_stream))
+        if direct:
+            return (None, None, None, gfeats, None) + (None,) * len(grads)
         return (None, None, None, gfeats, None, *grads)
 
 
@@ -168,6 +180,8 @@ class PointNetSetAbstraction(nn.Module):
         self.sampler, self.grouper, self.radius = sampler, grouper, radius
         self._precision = precision
         self._rng_counter = None
+        # set by pcoe.dp.FlatGradBuffer: backward adds parameter gradients straight into p.grad
+        self.direct_grad_accumulation = False
         self.last_fps_idx = None
         self.last_group_idx = None
 

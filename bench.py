@@ -205,7 +205,11 @@ def run_ours(args):
     torch.manual_seed(1000)
     model = getattr(pcoe, cls)(sampler="randperm_device").to(dev).train()
     engine = pcoe.dp.DataParallel(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=not args.no_graph)
+    clip = 1.0 if kind == "mvm" else None                # train_multi_peaks_vonMises_KL.py:235
+    if args.torch_optimizer:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=not args.no_graph)
+    else:                                                # clip + Adam + zero_grad as two libpcoe launches
+        opt = pcoe.optim.FusedAdam(engine, lr=1e-3, max_grad_norm=clip, zero_grad_in_step=True)
     params = [p for p in model.parameters()]
     NB = 8                                               # distinct synthetic batches, rotated
     host = [(pcoe.synthetic.clouds(1, B, N, rank * NB + i).pin_memory(),
@@ -214,13 +218,14 @@ def run_ours(args):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step(xyz, tg):
-        engine.zero_grad()
+        if args.torch_optimizer:
+            engine.zero_grad()
         res = model(xyz)
         loss = loss_of(kind, res, tg, pcoe)
         loss.backward()
         engine.allreduce_grads()
-        if kind == "mvm":
-            torch.nn.utils.clip_grad_norm_(params, 1.0, foreach=True)
+        if clip is not None and args.torch_optimizer:
+            torch.nn.utils.clip_grad_norm_(params, clip, foreach=True)
         opt.step()
         return loss
 
@@ -238,7 +243,7 @@ def run_ours(args):
     if not args.no_graph:
         l0 = pcoe._lib.launch_count()
         graphed = pcoe.GraphedTrainStep(model, lambda res, *tg: loss_of(kind, res, tg, pcoe), opt, resident[0][0],
-                                        resident[0][1], clip_norm=1.0 if kind == "mvm" else None, engine=engine, warmup=1)
+                                        resident[0][1], clip_norm=clip, engine=engine, warmup=1)
         cap_launches = (pcoe._lib.launch_count() - l0) // 2          # 1 warm-up + 1 captured step
         for i in range(2):
             graphed(*([resident[i][0]] + list(resident[i][1])))
@@ -360,7 +365,9 @@ def run_ours(args):
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAMES[args.config], "clouds_per_gpu": B, "points": N,
                        "global_clouds_per_step": B * world, "parallelism": f"dp{world}",
-                       "step": "zero_grad+fwd+loss+bwd+allreduce+clip+Adam", "sampler_value": "randperm_device",
+                       "step": "zero_grad+fwd+loss+bwd+allreduce+clip+Adam",
+                       "optimizer": "torch.optim.Adam(fused)+clip_grad_norm_" if args.torch_optimizer
+                       else "pcoe.optim.FusedAdam (clip+Adam+zero_grad, 2 launches)", "sampler_value": "randperm_device",
                        "sampler_e2e": "randperm_host (reference-faithful)", "precision": args.precision,
                        "l2": "512 MiB buffer written between timed steps (flush outside the event pair)"},
             "clocks": clocks,
@@ -390,6 +397,8 @@ def main():
     ap.add_argument("--precision", choices=["fp32", "bf16"], default=os.environ.get("PCOE_PRECISION", "bf16"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")
+    ap.add_argument("--torch-optimizer", action="store_true",
+                    help="torch.optim.Adam(fused) + clip_grad_norm_ instead of pcoe.optim.FusedAdam")
     ap.add_argument("--timed-only", action="store_true",
                     help="warm-up + timed region only (for ncu captures): no e2e / per-kernel / CPU legs")
     args = ap.parse_args()

@@ -139,12 +139,16 @@ typedef struct pcoe_sa_params {
   float* running_var[3];
 } pcoe_sa_params;
 
-/* Gradients written by pcoe_sa_backward (all overwritten, not accumulated), same layouts. */
+/* Gradients written by pcoe_sa_backward, same layouts.  accumulate == 0: every array is
+ * overwritten.  accumulate != 0: the gradient is ADDED to what the arrays hold (autograd's
+ * `p.grad += g`): the Python layer points these at slices of the flat gradient buffer that the
+ * data-parallel all-reduce and the fused optimizer work on, so no per-parameter add kernel runs. */
 typedef struct pcoe_sa_grads {
   float* dW[3];
   float* dbias[3];
   float* dgamma[3];
   float* dbeta[3];
+  int32_t accumulate;
 } pcoe_sa_grads;
 
 /* Bytes of the `saved` buffer (forward -> backward state: pre-BN activations, batch statistics,
@@ -204,6 +208,29 @@ int pcoe_mvm_match_fwd_bwd(const float* mu, const float* kappa, const float* w, 
  * kl_loss_per_sample_from_logits, train_8dir_KL.py:60-68.  logits,p [B,C] f32, C <= 64. */
 int pcoe_soft_ce_fwd_bwd(const float* logits, const float* p, int B, int C, float* loss,
                          float* dlogits, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Optimizer step over flat buffers: gradient-norm clipping + Adam (+ zero_grad)
+ * Replaces torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.Adam.step()
+ * (+ optimizer.zero_grad()), train_multi_peaks_vonMises_KL.py:182,221,235-236,
+ * train_single_peak_vonMises_KL.py:68,81,90, train_8dir_KL.py:72,93,97.
+ *   param, grad, exp_avg, exp_avg_sq   [n] f32, 16-byte aligned flat buffers (all parameters
+ *                                      concatenated; the drop-in modules' p.data / p.grad are views)
+ *   max_grad_norm  > 0: grad *= min(1, max_grad_norm / (||grad||_2 + 1e-6)) first; <= 0: no clipping
+ *   zero_grad      != 0: grad is cleared after use; == 0: grad holds the clipped gradient on return
+ *   step_dev       [1] i64 device step counter, incremented by this call (bias correction uses
+ *                  the incremented value, as torch does); lives on the device so that a step captured
+ *                  in a CUDA graph keeps counting on replay
+ *   grad_norm_dev  [1] f32 out: ||grad||_2 before clipping (clip_grad_norm_'s return value)
+ *   workspace      pcoe_adam_workspace_bytes() bytes, ZEROED ONCE by the caller before the first call
+ *                  (the library leaves it zeroed)
+ * Update rule (torch.optim.Adam, amsgrad=False, maximize=False; weight_decay is L2 as in Adam):
+ *   m = m + (g-m)(1-b1); v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) */
+size_t pcoe_adam_workspace_bytes(void);
+int pcoe_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                   int zero_grad, int64_t* step_dev, float* grad_norm_dev, void* workspace,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,125 @@
+"""pcoe.optim.FusedAdam (pcoe_adam_step) vs torch.optim.Adam + clip_grad_norm_, and direct gradient
+accumulation of the set-abstraction backward into the flat gradient buffer vs the autograd path."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class _Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(37, 53)          # odd sizes: flat offsets that are not multiples of 4
+        self.b = torch.nn.Linear(53, 7)
+        self.c = torch.nn.Parameter(torch.randn(3))
+
+    def forward(self, x):
+        return self.b(torch.tanh(self.a(x))) * self.c.sum()
+
+
+@pytest.mark.parametrize("max_norm,wd", [(None, 0.0), (1.0, 0.0), (0.05, 0.0), (1.0, 0.01)])
+def test_fused_adam_matches_torch(pcoe, cuda, max_norm, wd):
+    torch.manual_seed(3)
+    ref = _Net().to(cuda)
+    ours = copy.deepcopy(ref)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=wd)
+    opt = pcoe.optim.FusedAdam(ours, lr=1e-3, weight_decay=wd, max_grad_norm=max_norm)
+    for it in range(6):
+        x = torch.randn(16, 37, device=cuda) * (1 + 3 * it)
+        opt_ref.zero_grad()
+        opt.zero_grad()
+        ref(x).square().mean().backward()
+        ours(x).square().mean().backward()
+        want_norm = None
+        if max_norm is not None:
+            want_norm = torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm)
+        opt_ref.step()
+        opt.step()
+        if want_norm is not None:
+            assert torch.allclose(opt.grad_norm[0], want_norm, rtol=1e-5)
+            for p, q in zip(ours.parameters(), ref.parameters()):       # grads hold the clipped gradient
+                assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-7)
+        for (n, p), q in zip(ours.named_parameters(), ref.parameters()):
+            assert torch.allclose(p, q, rtol=1e-4, atol=2e-6), (it, n, float((p - q).abs().max()))   # 2e-6 = 0.2 % of one lr step
+    assert int(opt.step_dev) == 6
+    # state_dict in torch.optim.Adam's layout; loads into a torch optimizer and back
+    sd = opt.state_dict()
+    sd_ref = opt_ref.state_dict()
+    assert sd["state"].keys() == sd_ref["state"].keys()
+    for i in sd["state"]:
+        assert float(sd["state"][i]["step"]) == float(sd_ref["state"][i]["step"])
+        assert torch.allclose(sd["state"][i]["exp_avg"], sd_ref["state"][i]["exp_avg"], rtol=1e-4, atol=1e-8)
+        assert torch.allclose(sd["state"][i]["exp_avg_sq"], sd_ref["state"][i]["exp_avg_sq"], rtol=1e-4, atol=1e-12)
+    opt2 = pcoe.optim.FusedAdam(copy.deepcopy(ref), lr=5e-4)
+    opt2.load_state_dict(sd_ref)
+    assert int(opt2.step_dev) == 6 and opt2.defaults["lr"] == 1e-3
+    assert torch.allclose(opt2.exp_avg, opt.exp_avg, rtol=1e-4, atol=1e-8)
+
+
+def test_fused_adam_zero_grad_in_step_and_graph(pcoe, cuda):
+    """The step is capturable: the counter and the norm live on the device; gradients are cleared in the step."""
+    torch.manual_seed(4)
+    ref = _Net().to(cuda)
+    ours = copy.deepcopy(ref)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    opt = pcoe.optim.FusedAdam(ours, lr=1e-3, max_grad_norm=1.0, zero_grad_in_step=True)
+    x = torch.randn(16, 37, device=cuda)
+    xs = x.clone()
+
+    def step():
+        ours(xs).square().mean().backward()
+        opt.step()
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert int(opt.step_dev) == 4
+    assert float(opt.grads.flat.abs().max()) == 0.0
+    for _ in range(4):
+        opt_ref.zero_grad()
+        ref(x).square().mean().backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        opt_ref.step()
+    for p, q in zip(ours.parameters(), ref.parameters()):
+        assert torch.allclose(p, q, rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_direct_grad_accumulation_equals_autograd_path(pcoe, cuda, precision):
+    """FlatGradBuffer makes pcoe_sa_backward add into p.grad (pcoe_sa_grads.accumulate): same gradients
+    as returning them to autograd, and a second backward accumulates (p.grad += g)."""
+    torch.manual_seed(11)
+    B, N, D = 4, 256, 32
+    xyz = pcoe.synthetic.clouds(1, B, N, 0).to(cuda)
+    feats = torch.randn(B, N, D, device=cuda)
+    idx = torch.stack([torch.randperm(N)[:32] for _ in range(B)]).to(cuda)
+
+    def run(direct):
+        torch.manual_seed(12)
+        layer = pcoe.PointNetSetAbstraction(32, 32, D, [64, 64, 128], precision=precision).to(cuda).train()
+        if direct:
+            buf = pcoe.dp.FlatGradBuffer(layer)
+            assert layer.direct_grad_accumulation
+        f = feats.clone().requires_grad_(True)
+        for _ in range(2):                                   # two backward passes: accumulation semantics
+            _, out = layer(xyz, f, fps_idx=idx)
+            (out * torch.linspace(-1, 1, out.size(-1), device=cuda)).sum().backward()
+        return [p.grad.clone() for p in layer.parameters()], f.grad.clone()
+
+    ga, fa = run(False)
+    gb, fb = run(True)
+    tol = dict(rtol=1e-4, atol=1e-5) if precision == "fp32" else dict(rtol=2e-3, atol=2e-3)   # atomics order only
+    assert torch.allclose(fa, fb, **tol)
+    for a, b in zip(ga, gb):
+        assert torch.allclose(a, b, **tol), float((a - b).abs().max())
