@@ -10,6 +10,7 @@
 #include "sa_common.cuh"
 #include "sa_tc.cuh"
 #include "sa_tc4.cuh"
+#include "sa_tc5.cuh"
 #include "sa_layout.h"
 #include <type_traits>
 
@@ -265,6 +266,64 @@ static int launch_bwd4(const PProd& pp, const QProd& qp, const __nv_bfloat16* Wb
   return ls.done();
 }
 
+// ---- v5 (K-chunk-streamed, (tile x channel-block) grid) launchers ----------------------------------
+constexpr size_t kSmemBudget5 = 224 * 1024;
+static int stages5(int want, size_t stage_bytes, size_t cbytes) {
+  int n = (int)((kSmemBudget5 - 1024 - cbytes) / stage_bytes);
+  n = n > v5::kMaxStages5 ? v5::kMaxStages5 : n;
+  return want < n ? want : n;
+}
+
+template <class Prod, class Epi>
+static int launch_fwd5(const Prod& prod, const __nv_bfloat16* Wb, int Kp, const Epi& epi, int M, int Cout, int nk,
+                       cudaStream_t st, const char* what) {
+  const size_t cbytes = sizeof(float) * (size_t)(prod.nconst() + epi.nconst()) + 512;
+  const int nst = stages5(nk, 32768, cbytes);
+  if (nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  const size_t smem = 1024 + (size_t)nst * 32768 + cbytes;
+  auto k = v5::tc5_fwd_kernel<Prod, Epi>;
+  static bool attr = false;
+  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget5)); attr = true; }
+  LaunchScope ls(what, st);
+  k<<<dim3(ceil_div(M, v4::kPts), Cout / 128), v4::kThreads, smem, st>>>(prod, Wb, Kp, epi, M, nst);
+  return ls.done();
+}
+
+template <bool PT, class PProd, class Epi>
+static int launch_dgrad5(const PProd& pp, const __nv_bfloat16* Wb, int Kp, const Epi& epi, int M, int Cprev,
+                         cudaStream_t st, const char* what) {
+  const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + epi.nconst()) + 512;
+  const int nst = stages5(pp.C / 64, 32768, cbytes);
+  if (nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  const size_t smem = 1024 + (size_t)nst * 32768 + cbytes;
+  auto k = v5::tc5_dgrad_kernel<PProd, Epi, PT>;
+  static bool attr = false;
+  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget5)); attr = true; }
+  LaunchScope ls(what, st);
+  k<<<dim3(ceil_div(M, v4::kPts), Cprev / 128), v4::kThreads, smem, st>>>(pp, Wb, Kp, epi, M, nst);
+  return ls.done();
+}
+
+template <class PProd, class QProd>
+static int launch_wgrad5(const PProd& pp, const QProd& qp, float* dW, int ldo, int cq_valid, int perm_d, int M, int nqb,
+                         cudaStream_t st, const char* what) {
+  const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + qp.nconst()) + 512;
+  const int ntiles = ceil_div(M, v4::kPts), items = (pp.C / 128) * nqb;
+  int splits = kNumSMs / items;
+  splits = splits < 1 ? 1 : (splits > ntiles ? ntiles : splits);
+  const int tps = ceil_div(ntiles, splits);
+  splits = ceil_div(ntiles, tps);
+  const int nst = stages5(tps, 65536, cbytes);
+  if (nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  const size_t smem = 1024 + (size_t)nst * 65536 + cbytes;
+  auto k = v5::tc5_wgrad_kernel<PProd, QProd>;
+  static bool attr = false;
+  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget5)); attr = true; }
+  LaunchScope ls(what, st);
+  k<<<dim3(pp.C / 128, nqb, splits), v4::kThreads, smem, st>>>(pp, qp, dW, ldo, cq_valid, perm_d, M, tps, nst);
+  return ls.done();
+}
+
 static int convert_weights4(const pcoe_sa_desc& d, const SaLayout& L, const pcoe_sa_params& P, char* base,
                             cudaStream_t st) {
   const int Cs[3] = {d.C1, d.C2, d.C3}, Kin[3] = {3 + d.D, d.C1, d.C2};
@@ -333,9 +392,9 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
 
   const int Kin[3] = {Cin, d.C1, d.C2};
   char* wbase = train ? sv : ws;   // bf16 weight copies live with the saved state in train mode
-  bool use4 = false;
-  if constexpr (TC) use4 = L.v2;
-  if (TC && !use4) PCOE_TRY(convert_weights(d, L, P, wbase, st));
+  bool use4 = false, use5 = false;
+  if constexpr (TC) { use4 = L.v2; use5 = L.v5; }
+  if (TC && !use4 && !use5) PCOE_TRY(convert_weights(d, L, P, wbase, st));
   auto nt = [&](const auto& ap, int l, const auto& epi, const char* what) -> int {
     using AP = std::decay_t<decltype(ap)>;
     using EP = std::decay_t<decltype(epi)>;
@@ -369,6 +428,25 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
       e2.C = d.C3; e2.Mld = Mld;
       PCOE_TRY(launch_fwd4(p2, wb(2), L.w4_rp[2], L.w4_kp[2], e2, M, st, kname(d, kF3)));
+      if (train) PCOE_TRY(finalize(2));
+      done = true;
+    }
+    if (use5) {   // wide layers: (tile x 128-channel block) grid, K streamed in 64-channel chunks
+      PCOE_TRY(convert_weights4(d, L, P, wbase, st));
+      auto wb = [&](int l) { return (const __nv_bfloat16*)(wbase + L.wb_off[l]); };
+      const int Mld = L.Mld;
+      v4::StoreStats4 e0{}; e0.y = y[0]; e0.sums = sums[0]; e0.C = d.C1; e0.Mld = Mld;
+      v5::GatherFeat5 gp{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
+      PCOE_TRY(launch_fwd5(gp, wb(0), L.w4_kp[0], e0, M, d.C1, gp.nblocks(), st, kname(d, kF1)));
+      if (train) PCOE_TRY(finalize(0));
+      v4::BnRelu4 p1{}; p1.y = y[0]; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.Mld = Mld; p1.C = d.C1;
+      v4::StoreStats4 e1{}; e1.y = y[1]; e1.sums = sums[1]; e1.C = d.C2; e1.Mld = Mld;
+      PCOE_TRY(launch_fwd5(p1, wb(1), L.w4_kp[1], e1, M, d.C2, d.C1 / 64, st, kname(d, kF2)));
+      if (train) PCOE_TRY(finalize(1));
+      v4::BnRelu4 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.Mld = Mld; p2.C = d.C2;
+      v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
+      e2.C = d.C3; e2.Mld = Mld;
+      PCOE_TRY(launch_fwd5(p2, wb(2), L.w4_kp[2], e2, M, d.C3, d.C2 / 64, st, kname(d, kF3)));
       if (train) PCOE_TRY(finalize(2));
       done = true;
     }
@@ -494,6 +572,36 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
         } else {
           PCOE_TRY(launch_bwd4<0>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], v4::NoEpi4{}, Gr.dW[0], Cin, Cin, d.D, M, 0, st, kname(d, kBL1)));
         }
+      }
+      return PCOE_OK;
+    }
+  }
+
+  if constexpr (TC) {
+    if (L.v5) {   // wide layers: separate streamed wgrad / dgrad kernels (sa_tc5.cuh)
+      auto wb = [&](int l) { return (const __nv_bfloat16*)(sv + L.wb_off[l]); };
+      const int Mld = L.Mld;
+      v4::DyLast4 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
+      dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3;
+      v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2;
+      v4::MaskStats4 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
+      m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2; m2.Mld = Mld;
+      PCOE_TRY(launch_wgrad5(dy3, x2, Gr.dW[2], d.C2, d.C2, -1, M, d.C2 / 128, st, kname(d, kWG3)));
+      PCOE_TRY(launch_dgrad5<false>(dy3, wb(2), L.w4_kp[2], m2, M, d.C2, st, kname(d, kDG3)));
+      PCOE_TRY(consts(1));
+      v4::Dy4 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.Mld = Mld; dy2.C = d.C2;
+      v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1;
+      v4::MaskStats4 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
+      m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1; m1.Mld = Mld;
+      PCOE_TRY(launch_wgrad5(dy2, x1, Gr.dW[1], d.C1, d.C1, -1, M, d.C1 / 128, st, kname(d, kWG2)));
+      PCOE_TRY(launch_dgrad5<false>(dy2, wb(1), L.w4_kp[1], m1, M, d.C1, st, kname(d, kDG2)));
+      PCOE_TRY(consts(0));
+      v4::Dy4 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.Mld = Mld; dy1.C = d.C1;
+      v5::GatherFeat5 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
+      PCOE_TRY(launch_wgrad5(dy1, x0, Gr.dW[0], Cin, Cin, d.D, M, ceil_div(x0.nblocks(), 2), st, kname(d, kWG1)));
+      if (grad_feats) {
+        v4::Scatter4 se{grad_feats, nbr, d.N, d.S, d.D, d.group_all};
+        PCOE_TRY(launch_dgrad5<true>(dy1, wb(0), L.w4_kp[0], se, M, d.D, st, kname(d, kDG1)));
       }
       return PCOE_OK;
     }

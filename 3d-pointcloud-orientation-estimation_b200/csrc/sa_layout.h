@@ -20,7 +20,9 @@ struct SaLayout {
   int wb_rows[3], wb_k[3], wbt_rows[3], wbt_k[3];
   bool v2;         // bf16 mode and the layer fits the persistent channel-on-lane kernels (sa_tc4.cuh):
                    // activations are then stored channel-major [C][Mld], one weight image [Rp][Kp] per layer
-  int Mld;         // rows rounded up to 128 (v2 only)
+  bool v5;         // bf16 mode, wide layers that do not fit v4 (SA3): K-chunk-streamed kernels (sa_tc5.cuh), same
+                   // HBM layouts as v2
+  int Mld;         // rows rounded up to 128 (v2 / v5)
   int w4_rp[3], w4_kp[3];
   size_t workspace_bytes;
 };
@@ -37,8 +39,10 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   const int Kin[3] = {3 + d.D, d.C1, d.C2};
   auto chan_ok = [](int c) { return c == 64 || c == 128 || c == 256; };
   L.v2 = tc && d.K == 32 && chan_ok(d.C1) && chan_ok(d.C2) && chan_ok(d.C3) && (d.D == 0 || d.D == 32 || d.D == 64 || d.D == 128);
+  L.v5 = tc && !L.v2 && d.K == 32 && d.C1 % 128 == 0 && d.C2 % 128 == 0 && d.C3 % 128 == 0 && d.D > 0 && d.D % 128 == 0;
+  const bool cm = L.v2 || L.v5;   // tile-blocked channel-major activations + one weight image per layer
   L.Mld = (int)align_up(L.M, 128);
-  const size_t rows_ld = L.v2 ? (size_t)L.Mld : (size_t)L.M;
+  const size_t rows_ld = cm ? (size_t)L.Mld : (size_t)L.M;
   for (int l = 0; l < 3; ++l) {
     L.w4_rp[l] = (int)align_up(C[l], 128);
     L.w4_kp[l] = (int)align_up(l == 0 ? (Kin[0] + 15) / 16 * 16 : Kin[l], 128);
@@ -57,7 +61,7 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   }
   if (tc && d.train)
     for (int l = 0; l < 3; ++l) {
-      if (L.v2) { L.wb_off[l] = take(s, (size_t)2 * L.w4_rp[l] * L.w4_kp[l]); continue; }
+      if (cm) { L.wb_off[l] = take(s, (size_t)2 * L.w4_rp[l] * L.w4_kp[l]); continue; }
       L.wb_off[l] = take(s, (size_t)2 * L.wb_rows[l] * L.wb_k[l]);
       L.wbt_off[l] = take(s, (size_t)2 * L.wbt_rows[l] * L.wbt_k[l]);
     }
@@ -76,7 +80,7 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
     for (int l = 0; l < 2; ++l) L.ws_y[l] = take(f, rows_ld * C[l] * L.esz);
     if (tc)
       for (int l = 0; l < 3; ++l) {
-        if (L.v2) { L.wb_off[l] = take(f, (size_t)2 * L.w4_rp[l] * L.w4_kp[l]); continue; }
+        if (cm) { L.wb_off[l] = take(f, (size_t)2 * L.w4_rp[l] * L.w4_kp[l]); continue; }
         L.wb_off[l] = take(f, (size_t)2 * L.wb_rows[l] * L.wb_k[l]);
         L.wbt_off[l] = take(f, (size_t)2 * L.wbt_rows[l] * L.wbt_k[l]);
       }

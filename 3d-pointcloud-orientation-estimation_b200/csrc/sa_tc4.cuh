@@ -154,8 +154,11 @@ struct BnRelu4 {
       if (ok && c < C) r.a[i] = __ldg(tb_chunk(y, C, m0 >> 7, c, chunk));
     }
   }
-  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr) const {
+  // lrows / rshift (v5 chunk streaming): the image has lrows rows and channel c goes to row c + rshift
+  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr, int lrows = 0,
+                                        int rshift = 0) const {
     PCOE_CM_MAP
+    const int crows = lrows ? lrows : C;
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
       const int c = r0 + (b * kBatch + i) * rstep;
@@ -165,7 +168,7 @@ struct BnRelu4 {
       const float sc = cs[c], sh = cs[C + c];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = ok ? fmaxf(fmaf(v[u], sc, sh), 0.f) : 0.f;
-      tc::sts128(saddr + cm_off(C, c, chunk), tc::pack8_bf16(v));
+      tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16(v));
     }
   }
 };
@@ -203,9 +206,10 @@ struct Dy4 {
       }
     }
   }
-  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr) const {
+  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr, int lrows = 0,
+                                        int rshift = 0) const {
     PCOE_CM_MAP
-    const int crows = rows();
+    const int crows = lrows ? lrows : rows();
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
       const int c = r0 + (b * kBatch + i) * rstep;
@@ -216,7 +220,7 @@ struct Dy4 {
       const float ca = cs[c], cp = cs[C + c], cq = cs[2 * C + c];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = ok ? fmaf(ca, d[u], fmaf(cp, yy[u], cq)) : 0.f;
-      tc::sts128(saddr + cm_off(crows, c, chunk), tc::pack8_bf16(v));
+      tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16(v));
     }
   }
 };
@@ -257,9 +261,10 @@ struct DyLast4 {
       }
     }
   }
-  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr) const {
+  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr, int lrows = 0,
+                                        int rshift = 0) const {
     PCOE_CM_MAP
-    const int crows = rows();
+    const int crows = lrows ? lrows : rows();
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
       const int c = r0 + (b * kBatch + i) * rstep;
@@ -270,7 +275,7 @@ struct DyLast4 {
       const int sl = r.sl[i];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = ok ? fmaf(cp, yy[u], cq) + (u == sl ? ca : 0.f) : 0.f;
-      tc::sts128(saddr + cm_off(crows, c, chunk), tc::pack8_bf16(v));
+      tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16(v));
     }
   }
 };

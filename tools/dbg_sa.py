@@ -9,7 +9,7 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 shapes = sys.argv[1:] or ["sa1", "sa2"]
 for shape in shapes:
-    B = 8
+    B = int(os.environ.get("DBG_B", "8"))
     N, S, K, D, mlp, ga = dict(sa1=(1024, 128, 32, 0, [64, 64, 128], False), sa2=(128, 32, 32, 128, [128, 128, 256], False),
                                sa3=(32, None, None, 256, [256, 512, 1024], True))[shape]
     layer = pcoe.PointNetSetAbstraction(S, K, D, mlp, group_all=ga, precision="bf16").to(cuda).train()
