@@ -167,8 +167,8 @@ struct BnRelu4 {
       unpack8(r.a[i], v);
       const float sc = cs[c], sh = cs[C + c];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = ok ? fmaxf(fmaf(v[u], sc, sh), 0.f) : 0.f;
-      tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16(v));
+      for (int u = 0; u < 8; ++u) v[u] = ok ? fmaf(v[u], sc, sh) : 0.f;
+      tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16_relu(v));
     }
   }
 };
@@ -249,7 +249,7 @@ struct DyLast4 {
   __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
   __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx&, Raw& r) const {
     PCOE_CM_MAP
-    const int grp = min(m, M - 1) >> 5, j0 = m & 31;
+    const int grp = min(m, M - 1) >> 5;
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
       const int c = r0 + (b * kBatch + i) * rstep;
@@ -257,7 +257,7 @@ struct DyLast4 {
       if (ok && c < C) {
         r.y[i] = __ldg(tb_chunk(y, C, m0 >> 7, c, chunk));
         r.gv[i] = __ldg(gm + (size_t)grp * C + c);
-        r.sl[i] = (int)__ldg(slot + (size_t)grp * C + c) - j0;
+        r.sl[i] = (int)__ldg(slot + (size_t)grp * C + c);   // raw: no arithmetic on loaded values in load()
       }
     }
   }
@@ -272,7 +272,7 @@ struct DyLast4 {
       float yy[8], v[8];
       unpack8(r.y[i], yy);
       const float ca = cs[c] * r.gv[i], cp = cs[C + c], cq = cs[2 * C + c];
-      const int sl = r.sl[i];
+      const int sl = r.sl[i] - (m & 31);     // slot relative to this 8-point chunk (-1 - j0 < 0 never matches)
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = ok ? fmaf(cp, yy[u], cq) + (u == sl ? ca : 0.f) : 0.f;
       tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16(v));
@@ -292,14 +292,16 @@ struct GatherBase {
     i = min(max(i, 0), N - 1);
     return ((row >> 5) / S) * N + i;
   }
-  __device__ __forceinline__ void load_xyz(int row, int pt, float (&v)[3]) const {
+  // raw loads only (the subtraction happens in the producers' store(): no arithmetic on loaded values
+  // in load(), otherwise the load stage of the software pipeline stalls on its own loads)
+  __device__ __forceinline__ void load_xyz_raw(int row, int pt, float (&x)[3], float (&c)[3]) const {
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
-      float x = __ldg(xyz + (size_t)pt * 3 + u);
-      if (!group_all) x = __fsub_rn(x, __ldg(new_xyz + (size_t)(row >> 5) * 3 + u));
-      v[u] = x;
+      x[u] = __ldg(xyz + (size_t)pt * 3 + u);
+      c[u] = group_all ? 0.f : __ldg(new_xyz + (size_t)(row >> 5) * 3 + u);
     }
   }
+  __device__ __forceinline__ float centred(float x, float c) const { return group_all ? x : __fsub_rn(x, c); }
 };
 
 // layer-1 input without features (SA1): [xyz[nbr] - centroid] as a channel-major tile of 16 rows
@@ -307,7 +309,7 @@ struct GatherBase {
 struct GatherXyz4 {
   static constexpr bool kChMajor = true;
   struct Idx { int pt; };
-  struct Raw { float v[3]; };
+  struct Raw { float v[3], c[3]; };
   GatherBase gb;
   __host__ __device__ __forceinline__ int rows() const { return 16; }
   __host__ __device__ __forceinline__ int kext() const { return 16; }
@@ -319,8 +321,8 @@ struct GatherXyz4 {
     if (g < kPts && m0 + g < gb.M) ix.pt = gb.point_of(m0 + g);
   }
   __device__ __forceinline__ void load(int g, int, int m0, int, const Idx& ix, Raw& r) const {
-    r.v[0] = r.v[1] = r.v[2] = 0.f;
-    if (ix.pt >= 0) gb.load_xyz(m0 + g, ix.pt, r.v);
+    r.v[0] = r.v[1] = r.v[2] = r.c[0] = r.c[1] = r.c[2] = 0.f;
+    if (ix.pt >= 0) gb.load_xyz_raw(m0 + g, ix.pt, r.v, r.c);
   }
   __device__ __forceinline__ void store(int g, int, int, int, const Raw& r, uint32_t saddr) const {
     if (g >= kPts) return;
@@ -328,7 +330,7 @@ struct GatherXyz4 {
     const int ch = (g & 63) >> 3;
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
-      const uint16_t h = __bfloat16_as_ushort(__float2bfloat16_rn(r.v[u]));
+      const uint16_t h = __bfloat16_as_ushort(__float2bfloat16_rn(gb.centred(r.v[u], r.c[u])));
       asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + (uint32_t)(u * 128 + ((ch ^ u) << 4))), "h"(h) : "memory");
     }
   }
@@ -341,7 +343,7 @@ struct GatherXyz4 {
 struct GatherFeat4 {
   static constexpr bool kChMajor = false;
   struct Idx { int pt[kBatch]; int ptx; };
-  struct Raw { float4 a[kBatch], b[kBatch]; float xv[3]; };
+  struct Raw { float4 a[kBatch], b[kBatch]; float xv[3], xc[3]; };
   GatherBase gb;
   const float* __restrict__ feats;
   int D;
@@ -370,8 +372,8 @@ struct GatherFeat4 {
         r.b[i] = __ldg(src + 1);
       }
     }
-    r.xv[0] = r.xv[1] = r.xv[2] = 0.f;
-    if (b == 0 && ix.ptx >= 0) gb.load_xyz(m0 + g, ix.ptx, r.xv);
+    r.xv[0] = r.xv[1] = r.xv[2] = r.xc[0] = r.xc[1] = r.xc[2] = 0.f;
+    if (b == 0 && ix.ptx >= 0) gb.load_xyz_raw(m0 + g, ix.ptx, r.xv, r.xc);
   }
   __device__ __forceinline__ void store(int g, int G, int, int b, const Raw& r, uint32_t saddr) const {
     const int fu = D >> 3, rstep = G / fu, r0 = g / fu, j = g % fu;
@@ -383,7 +385,8 @@ struct GatherFeat4 {
       tc::sts128(saddr + (uint32_t)(j >> 3) * (kPts * 128) + tc::sw128_off(row, (j & 7) * 8), tc::pack8_bf16(v));
     }
     if (b == 0 && g < kPts) {
-      const float v[8] = {r.xv[0], r.xv[1], r.xv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float v[8] = {gb.centred(r.xv[0], r.xc[0]), gb.centred(r.xv[1], r.xc[1]), gb.centred(r.xv[2], r.xc[2]),
+                          0.f, 0.f, 0.f, 0.f, 0.f};
       tc::sts128(saddr + (uint32_t)(fu >> 3) * (kPts * 128) + tc::sw128_off(g, (fu & 7) * 8), tc::pack8_bf16(v));
     }
   }
@@ -758,7 +761,8 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
                       [&](int t) { const int n = t / nstages; if (n > 0) tc::mbar_wait(&bar.empty[t % nstages], (uint32_t)((n - 1) & 1)); },
                       [&](int t) { return sT + (uint32_t)(t % nstages) * tbytes; },
                       [&](int t) { mbar_arrive(&bar.full[t % nstages]); });
-  } else if (tid == kEpiThreads + kProdThreads) {
+  } else {   // warp 16: MMA issue, warp-uniform loop, one elected lane issues
+    const uint32_t tmem = tc::uniform_u32(tmem_base);
     // ---- MMA issue ----
     const uint32_t idesc = tc::make_idesc_bf16(128, kPts, false, Prod::kChMajor);
     const int kext = prod.kext();
@@ -766,19 +770,19 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
       const int s = i % nstages, n = i / nstages, b = i & 1, u = i >> 1;
       tc::mbar_wait(&bar.full[s], (uint32_t)(n & 1));
-      TC4_TRACE(20, i);
+      if ((tid & 31) == 0) TC4_TRACE(20, i);
       if (u > 0) tc::mbar_wait(&bar.tmem_empty[b], (uint32_t)((u - 1) & 1));
       tc::fence_after_sync();
-      TC4_TRACE(21, i);
+      if ((tid & 31) == 0) TC4_TRACE(21, i);
       const uint32_t st = sT + (uint32_t)s * tbytes;
       for (int mi = 0; mi < mt; ++mi)
         for (int k = 0; k < kext; k += 16)
-          tc::mma_bf16(tmem + (uint32_t)(b * mt * kPts + mi * kPts),
+          tc::mma_bf16_warp(tmem + (uint32_t)(b * mt * kPts + mi * kPts),
                        tc::make_desc_sw128(sW + (uint32_t)(k >> 6) * (uint32_t)(Rp * 128) + (uint32_t)(mi * 128 * 128) + (uint32_t)((k & 63) * 2), 16, 1024),
                        act_desc_chan_k(prod, st, k), idesc, k > 0);
-      tc::mma_commit(&bar.empty[s]);
-      tc::mma_commit(&bar.tmem_full[b]);
-      TC4_TRACE(22, i);
+      tc::mma_commit_warp(&bar.empty[s]);
+      tc::mma_commit_warp(&bar.tmem_full[b]);
+      if ((tid & 31) == 0) TC4_TRACE(22, i);
     }
   }
   tc::fence_before_sync();
@@ -840,11 +844,14 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
   int my_tiles = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
 
+  TC4_TRACER;
+  if (tid == 0) { TC4_TRACE(0, 0); TC4_TRACE(1, 0); }
   if (warp < 8) {
     int i = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
       const int b = i & 1, u = i >> 1, m0 = tile * kPts;
       tc::mbar_wait(&bar.tmem_full[b], (uint32_t)(u & 1));
+      if (tid == 0) TC4_TRACE(30, i);
       tc::fence_after_sync();
       const uint32_t stg = stg0 + (uint32_t)(i % nstg) * stg_bytes;
       if constexpr (DGRAD == 1) {
@@ -867,15 +874,19 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
       }
       tc::fence_before_sync();
       mbar_arrive_relaxed(&bar.tmem_empty[b]);
+      if (tid == 0) TC4_TRACE(35, i);
       if constexpr (DGRAD == 1) stage_copy_out(epi.tile_dst(tile), stg, (int)stg_bytes, nstg, tid == 0);
+      if (tid == 0) TC4_TRACE(31, i);
     }
     if (DGRAD == 1 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     epi.finish();
+    if (tid == 0) TC4_TRACE(32, 0);
     // flush dW (complete: the last tmem_full commit covers every earlier MMA): thread = row of dW.
     // Column blocks are visited in a per-CTA rotated order so that the CTAs, which all finish at about
     // the same time, do not hammer the same L2 atomic units simultaneously.
     if (my_tiles > 0) {
       tc::fence_after_sync();
+      if (tid == 0) TC4_TRACE(36, 0);
       const int nblk = (nw + 31) / 32;
       for (int mi = 0; mi < mtl; ++mi) {
         const int crow = mi * 128 + eq * 32 + lane;
@@ -903,12 +914,48 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
       }
     }
   } else if (warp < 16) {
-    // ---- producers: warps 8-11 build P (dy^T), warps 12-15 build Q (x_prev); one shared stage ----
-    auto wait_empty = [&](int t) { if (t > 0) tc::mbar_wait(&bar.empty[0], (uint32_t)((t - 1) & 1)); };
-    auto arrive = [&](int) { mbar_arrive(&bar.full[0]); };
-    if (warp < 12) producer_pipeline(pp, tid - kEpiThreads, kProdThreads / 2, ntiles, wait_empty, [&](int) { return sP; }, arrive);
-    else producer_pipeline(qp, tid - kEpiThreads - kProdThreads / 2, kProdThreads / 2, ntiles, wait_empty, [&](int) { return sQ; }, arrive);
-  } else if (tid == kEpiThreads + kProdThreads) {
+    // ---- producers: all 8 warps build P (dy^T) and then Q (x_prev) of a tile, batch by batch, as one
+    // three-stage software pipeline (indices two units ahead, global loads one unit ahead); one shared stage ----
+    const int g = tid - kEpiThreads;
+    const int nbp = pp.nbatches(kProdThreads), nbq = qp.nbatches(kProdThreads), upt = nbp + nbq;
+    const int W = my_tiles * upt;
+    union RawU { typename PProd::Raw p; typename QProd::Raw q; __device__ RawU() {} };
+    typename QProd::Idx ix;   // the dy producers have no index stage
+    auto m0_of = [&](int w) { return (int)((blockIdx.x + (w / upt) * gridDim.x) * kPts); };
+    auto do_idx = [&](int w) {
+      const int u = w % upt;
+      if (u >= nbp) qp.load_idx(g, kProdThreads, m0_of(w), u - nbp, ix);
+    };
+    auto do_load = [&](int w, RawU& r) {
+      const int u = w % upt;
+      if (u < nbp) pp.load(g, kProdThreads, m0_of(w), u, NoIdx{}, r.p);
+      else qp.load(g, kProdThreads, m0_of(w), u - nbp, ix, r.q);
+    };
+    auto step = [&](int w, RawU& cur, RawU& nxt) {
+      if (w + 1 < W) do_load(w + 1, nxt);
+      if (w + 2 < W) do_idx(w + 2);
+      const int t = w / upt, u = w - t * upt;
+      if (g == 0) TC4_TRACE(12, w);
+      if (u == 0 && t > 0) tc::mbar_wait(&bar.empty[0], (uint32_t)((t - 1) & 1));
+      if (g == 0) TC4_TRACE(10, w);
+      if (u < nbp) pp.store(g, kProdThreads, m0_of(w), u, cur.p, sP);
+      else qp.store(g, kProdThreads, m0_of(w), u - nbp, cur.q, sQ);
+      if (u == upt - 1) { tc::fence_proxy_async(); mbar_arrive(&bar.full[0]); }
+      if (g == 0) TC4_TRACE(11, w);
+    };
+    if (W > 0) {
+      RawU ra, rb;
+      do_idx(0);
+      do_load(0, ra);
+      if (W > 1) do_idx(1);
+      for (int w = 0; w < W; w += 2) {
+        step(w, ra, rb);
+        if (w + 1 < W) step(w + 1, rb, ra);
+      }
+    }
+    if (g == 0) TC4_TRACE_DUMP();
+  } else {   // warp 16: MMA issue, warp-uniform loop, one elected lane issues
+    const uint32_t tmem = tc::uniform_u32(tmem_base);
     const uint32_t idesc_w = tc::make_idesc_bf16(128, nw, false, !QProd::kChMajor);
     const uint32_t idesc_d = DGRAD == 1 ? tc::make_idesc_bf16(128, kPts, true, true)
                                         : tc::make_idesc_bf16(128, (cprev + 15) / 16 * 16, true, true);
@@ -917,8 +964,10 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
       const int b = i & 1, u = i >> 1;
       tc::mbar_wait(&bar.full[0], (uint32_t)(i & 1));
+      if ((tid & 31) == 0) TC4_TRACE(20, i);
       if (DGRAD && u > 0) tc::mbar_wait(&bar.tmem_empty[b], (uint32_t)((u - 1) & 1));
       tc::fence_after_sync();
+      if ((tid & 31) == 0) TC4_TRACE(21, i);
       // dW += P Q^T: contraction over the 128 points, 16 per MMA
       for (int mi = 0; mi < mtl; ++mi)
         for (int ks = 0; ks < 8; ++ks) {
@@ -926,26 +975,29 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
           const uint64_t bd = QProd::kChMajor
               ? tc::make_desc_sw128(sQ + (uint32_t)(ks >> 2) * (uint32_t)(qp.rows() * 128) + (uint32_t)((ks & 3) * 32), 16, 1024)
               : tc::make_desc_sw128(sQ + (uint32_t)ks * 2048, kPts * 128, 1024);
-          tc::mma_bf16(tmem + (uint32_t)(mi * nw), ad, bd, idesc_w, i > 0 || ks > 0);
+          tc::mma_bf16_warp(tmem + (uint32_t)(mi * nw), ad, bd, idesc_w, i > 0 || ks > 0);
         }
       if constexpr (DGRAD == 1) {
         for (int mj = 0; mj < mtp; ++mj)
           for (int k = 0; k < cl; k += 16)
-            tc::mma_bf16(tmem + dx_col + (uint32_t)b * dx_cols + (uint32_t)(mj * kPts),
+            tc::mma_bf16_warp(tmem + dx_col + (uint32_t)b * dx_cols + (uint32_t)(mj * kPts),
                          tc::make_desc_sw128(sW + (uint32_t)(2 * mj) * (uint32_t)(Rp * 128) + (uint32_t)(k >> 4) * 2048, (uint32_t)Rp * 128, 1024),
                          tc::make_desc_sw128(sP + (uint32_t)(k >> 4) * 2048, (uint32_t)prow * 128, 1024), idesc_d, k > 0);
       } else if constexpr (DGRAD == 2) {
         for (int k = 0; k < cl; k += 16)
-          tc::mma_bf16(tmem + dx_col + (uint32_t)b * dx_cols,
+          tc::mma_bf16_warp(tmem + dx_col + (uint32_t)b * dx_cols,
                        tc::make_desc_sw128(sP + (uint32_t)(k >> 4) * 2048, (uint32_t)prow * 128, 1024),
                        tc::make_desc_sw128(sW + (uint32_t)(k >> 4) * 2048, (uint32_t)Rp * 128, 1024), idesc_d, k > 0);
       }
-      tc::mma_commit(&bar.empty[0]);
-      tc::mma_commit(&bar.tmem_full[b]);
+      tc::mma_commit_warp(&bar.empty[0]);
+      tc::mma_commit_warp(&bar.tmem_full[b]);
+      if ((tid & 31) == 0) TC4_TRACE(22, i);
     }
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (tid == 0) TC4_TRACE(2, 0);
+  if (tid == 0 || tid == kEpiThreads + kProdThreads) TC4_TRACE_DUMP();
   if (warp == 0) tc::tmem_dealloc<TCOLS>(tmem);
 }
 

@@ -56,9 +56,10 @@ struct GatherFeat5 {
         }
       }
     } else {
-      float v[3] = {0.f, 0.f, 0.f};
-      if (g < kPts && m0 + g < gb.M) gb.load_xyz(m0 + g, gb.point_of(m0 + g), v);
+      float v[3] = {0.f, 0.f, 0.f}, c[3] = {0.f, 0.f, 0.f};
+      if (g < kPts && m0 + g < gb.M) gb.load_xyz_raw(m0 + g, gb.point_of(m0 + g), v, c);
       r.a[0] = make_float4(v[0], v[1], v[2], 0.f);
+      r.b[0] = make_float4(c[0], c[1], c[2], 0.f);
     }
   }
   __device__ __forceinline__ void store64(int g, int kb, const Raw& r, uint32_t saddr) const {
@@ -70,7 +71,8 @@ struct GatherFeat5 {
         tc::sts128(saddr + tc::sw128_off((g >> 3) + 32 * i, j * 8), tc::pack8_bf16(v));
       }
     } else if (g < kPts) {
-      const float v[8] = {r.a[0].x, r.a[0].y, r.a[0].z, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float v[8] = {gb.centred(r.a[0].x, r.b[0].x), gb.centred(r.a[0].y, r.b[0].y), gb.centred(r.a[0].z, r.b[0].z),
+                          0.f, 0.f, 0.f, 0.f, 0.f};
       tc::sts128(saddr + tc::sw128_off(g, 0), tc::pack8_bf16(v));
       tc::sts128(saddr + tc::sw128_off(g, 8), make_uint4(0u, 0u, 0u, 0u));
     }
@@ -195,7 +197,8 @@ tc5_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Kp, Epi epi,
             mbar_arrive(&bar.full[s]);
           }
         });
-  } else if (tid == kEpiThreads + kProdThreads) {
+  } else {   // warp 16: MMA issue, warp-uniform loop, one elected lane issues
+    const uint32_t tmem = tc::uniform_u32(tmem_base);
     const uint32_t idesc = tc::make_idesc_bf16(128, kPts, false, Prod::kChMajor);
     for (int k = 0; k < nk; ++k) {
       const int s = k % nst;
@@ -205,13 +208,13 @@ tc5_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Kp, Epi epi,
       int kk = 64;
       if constexpr (!Prod::kChMajor) kk = prod.block_k(k);
       for (int q = 0; q < kk / 16; ++q)
-        tc::mma_bf16(tmem, tc::make_desc_sw128(sA + (uint32_t)q * 32, 16, 1024),
+        tc::mma_bf16_warp(tmem, tc::make_desc_sw128(sA + (uint32_t)q * 32, 16, 1024),
                      Prod::kChMajor ? tc::make_desc_sw128(sB + (uint32_t)q * 2048, 8192, 1024)
                                     : tc::make_desc_sw128(sB + (uint32_t)q * 32, 16, 1024),
                      idesc, k > 0 || q > 0);
-      tc::mma_commit(&bar.empty[s]);
+      tc::mma_commit_warp(&bar.empty[s]);
     }
-    tc::mma_commit(&bar.tmem_full);
+    tc::mma_commit_warp(&bar.tmem_full);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -285,7 +288,8 @@ tc5_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wb, int Kp, Epi epi
             mbar_arrive(&bar.full[s]);
           }
         });
-  } else if (tid == kEpiThreads + kProdThreads) {
+  } else {   // warp 16: MMA issue, warp-uniform loop, one elected lane issues
+    const uint32_t tmem = tc::uniform_u32(tmem_base);
     const uint32_t idesc = tc::make_idesc_bf16(128, 128, true, true);
     for (int k = 0; k < nk; ++k) {
       const int s = k % nst;
@@ -295,11 +299,11 @@ tc5_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wb, int Kp, Epi epi
       for (int q = 0; q < 4; ++q) {
         const uint64_t dw = tc::make_desc_sw128(sWp + (uint32_t)q * 2048, 8192, 1024);
         const uint64_t dp = tc::make_desc_sw128(sPp + (uint32_t)q * 2048, 8192, 1024);
-        tc::mma_bf16(tmem, PT ? dp : dw, PT ? dw : dp, idesc, k > 0 || q > 0);
+        tc::mma_bf16_warp(tmem, PT ? dp : dw, PT ? dw : dp, idesc, k > 0 || q > 0);
       }
-      tc::mma_commit(&bar.empty[s]);
+      tc::mma_commit_warp(&bar.empty[s]);
     }
-    tc::mma_commit(&bar.tmem_full);
+    tc::mma_commit_warp(&bar.tmem_full);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -381,7 +385,8 @@ tc5_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_val
           else qp.store64(g, 2 * qb + (u - 2), r.q, st + 2 * kPart + (uint32_t)(u - 2) * kPart);
           if (u == upt - 1) { tc::fence_proxy_async(); mbar_arrive(&bar.full[s]); }
         });
-  } else if (tid == kEpiThreads + kProdThreads) {
+  } else {   // warp 16: MMA issue, warp-uniform loop, one elected lane issues
+    const uint32_t tmem = tc::uniform_u32(tmem_base);
     const uint32_t idesc = tc::make_idesc_bf16(128, nq, false, !QProd::kChMajor);
     for (int i = 0; i < nt; ++i) {
       const int s = i % nst;
@@ -393,11 +398,11 @@ tc5_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_val
         const uint64_t bd = QProd::kChMajor
             ? tc::make_desc_sw128(sQ + (uint32_t)(ks >> 2) * kPart + (uint32_t)((ks & 3) * 32), 16, 1024)
             : tc::make_desc_sw128(sQ + (uint32_t)ks * 2048, kPart, 1024);
-        tc::mma_bf16(tmem, ad, bd, idesc, i > 0 || ks > 0);
+        tc::mma_bf16_warp(tmem, ad, bd, idesc, i > 0 || ks > 0);
       }
-      tc::mma_commit(&bar.empty[s]);
+      tc::mma_commit_warp(&bar.empty[s]);
     }
-    if (nt > 0) tc::mma_commit(&bar.tmem_full);
+    if (nt > 0) tc::mma_commit_warp(&bar.tmem_full);
   }
   tc::fence_before_sync();
   __syncthreads();

@@ -81,6 +81,28 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// Warp-wide variants: the WHOLE warp executes the call (convergent, warp-uniform operands) and one
+// elected lane issues the instruction.  Keeping the issue loop warp-uniform lets the compiler hold
+// descriptors, TMEM addresses and loop state in uniform registers; a loop run by a single thread of a
+// divergent branch instead pays a vector->uniform register broadcast (R2UR + ELECT loop, ~100+ cycles)
+// per tcgen05.mma.  elect.sync picks the same lane for the same member mask, so the commit below
+// tracks the MMAs issued here.
+__device__ __forceinline__ void mma_bf16_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_warp(uint64_t* mbar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(mbar)) : "memory");
+}
+// broadcast of a value every lane already holds: tells the compiler it is warp-uniform
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xFFFFFFFFu, v, 0); }
+
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
@@ -127,6 +149,20 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
   uint4 r;
   r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
   r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+
+// pack 8 floats to 8 bf16 with ReLU folded into the conversion (cvt.rn.relu: max(x, 0) then round;
+// identical to rounding relu(x) because rounding preserves sign and zero)
+__device__ __forceinline__ uint32_t pack2_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint4 pack8_bf16_relu(const float (&v)[8]) {
+  uint4 r;
+  r.x = pack2_bf16_relu(v[0], v[1]); r.y = pack2_bf16_relu(v[2], v[3]);
+  r.z = pack2_bf16_relu(v[4], v[5]); r.w = pack2_bf16_relu(v[6], v[7]);
   return r;
 }
 
