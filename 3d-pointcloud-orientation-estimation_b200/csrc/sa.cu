@@ -53,11 +53,21 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 }
 
 // out = relu(a * (a >= 0 ? ymax : ymin) + b), slot = the matching arg, ysel = the selected y
+// fin.sums != nullptr (v4/v5 train mode): the last layer's batch statistics are finalised here, per block,
+// into a shared-memory table (block 0 writes the saved statistics / running buffers).
 __global__ void sa_out_finalize_kernel(const float* __restrict__ ymax, const float* __restrict__ ymin,
                                        const uint8_t* __restrict__ amax, const uint8_t* __restrict__ amin,
                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                        size_t total, int C, float* __restrict__ out,
-                                       uint8_t* __restrict__ slot, float* __restrict__ ysel) {
+                                       uint8_t* __restrict__ slot, float* __restrict__ ysel, v4::BnFin fin) {
+  extern __shared__ float fin_tab[];   // [2,C] when fused
+  if (fin.sums) {
+    const bool w = blockIdx.x == 0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) fin.eval(c, C, w, fin_tab[c], fin_tab[C + c]);
+    __syncthreads();
+    scale = fin_tab;
+    shift = fin_tab + C;
+  }
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(e % C);
     const float a = scale[c];
@@ -389,6 +399,17 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
     return ls.done();
   };
   if (!train) for (int l = 0; l < 3; ++l) PCOE_TRY(finalize(l));
+  // v4 / v5 train mode: the statistics of layer l are finalised inline by the kernel that consumes them
+  auto mkfin = [&](int l) {
+    v4::BnFin f{};
+    if (train) {
+      f.sums = sums[l]; f.count = (double)M; f.gamma = P.gamma[l]; f.beta = P.beta[l]; f.bias = P.bias[l];
+      f.running_mean = P.running_mean[l]; f.running_var = P.running_var[l]; f.eps = d.eps; f.momentum = d.momentum;
+      f.scale = scale[l]; f.shift = shift[l]; f.mean = mean[l]; f.invstd = invstd[l];
+    }
+    return f;
+  };
+  v4::BnFin fin_out{};
 
   const int Kin[3] = {Cin, d.C1, d.C2};
   char* wbase = train ? sv : ws;   // bf16 weight copies live with the saved state in train mode
@@ -419,16 +440,16 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
         v4::GatherFeat4 gp{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
         PCOE_TRY(launch_fwd4(gp, wb(0), L.w4_rp[0], L.w4_kp[0], e0, M, st, kname(d, kF1)));
       }
-      if (train) PCOE_TRY(finalize(0));
       v4::BnRelu4 p1{}; p1.y = y[0]; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.Mld = Mld; p1.C = d.C1;
+      p1.fin = mkfin(0);
       v4::StoreStats4 e1{}; e1.y = y[1]; e1.sums = sums[1]; e1.C = d.C2; e1.Mld = Mld;
       PCOE_TRY(launch_fwd4(p1, wb(1), L.w4_rp[1], L.w4_kp[1], e1, M, st, kname(d, kF2)));
-      if (train) PCOE_TRY(finalize(1));
       v4::BnRelu4 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.Mld = Mld; p2.C = d.C2;
+      p2.fin = mkfin(1);
       v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
       e2.C = d.C3; e2.Mld = Mld;
       PCOE_TRY(launch_fwd4(p2, wb(2), L.w4_rp[2], L.w4_kp[2], e2, M, st, kname(d, kF3)));
-      if (train) PCOE_TRY(finalize(2));
+      fin_out = mkfin(2);
       done = true;
     }
     if (use5) {   // wide layers: (tile x 128-channel block) grid, K streamed in 64-channel chunks
@@ -438,16 +459,16 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       v4::StoreStats4 e0{}; e0.y = y[0]; e0.sums = sums[0]; e0.C = d.C1; e0.Mld = Mld;
       v5::GatherFeat5 gp{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
       PCOE_TRY(launch_fwd5(gp, wb(0), L.w4_kp[0], e0, M, d.C1, gp.nblocks(), st, kname(d, kF1)));
-      if (train) PCOE_TRY(finalize(0));
       v4::BnRelu4 p1{}; p1.y = y[0]; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.Mld = Mld; p1.C = d.C1;
+      p1.fin = mkfin(0);
       v4::StoreStats4 e1{}; e1.y = y[1]; e1.sums = sums[1]; e1.C = d.C2; e1.Mld = Mld;
       PCOE_TRY(launch_fwd5(p1, wb(1), L.w4_kp[1], e1, M, d.C2, d.C1 / 64, st, kname(d, kF2)));
-      if (train) PCOE_TRY(finalize(1));
       v4::BnRelu4 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.Mld = Mld; p2.C = d.C2;
+      p2.fin = mkfin(1);
       v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
       e2.C = d.C3; e2.Mld = Mld;
       PCOE_TRY(launch_fwd5(p2, wb(2), L.w4_kp[2], e2, M, d.C3, d.C2 / 64, st, kname(d, kF3)));
-      if (train) PCOE_TRY(finalize(2));
+      fin_out = mkfin(2);
       done = true;
     }
   }
@@ -468,9 +489,9 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
   int blocks = (int)((total + 255) / 256);
   blocks = blocks > kNumSMs * 8 ? kNumSMs * 8 : blocks;
   LaunchScope ls("sa_out_finalize_kernel", st);
-  sa_out_finalize_kernel<<<blocks, 256, 0, st>>>(ymax, ymin, amax, amin, scale[2], shift[2], total, d.C3, out,
-                                                train ? (uint8_t*)(sv + L.sv_slot) : nullptr,
-                                                train ? (float*)(sv + L.sv_ysel) : nullptr);
+  sa_out_finalize_kernel<<<blocks, 256, fin_out.sums ? sizeof(float) * 2 * d.C3 : 0, st>>>(
+      ymax, ymin, amax, amin, scale[2], shift[2], total, d.C3, out, train ? (uint8_t*)(sv + L.sv_slot) : nullptr,
+      train ? (float*)(sv + L.sv_ysel) : nullptr, fin_out);
   return ls.done();
 }
 
@@ -519,6 +540,16 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
     return ls.done();
   };
 
+  // v4 / v5: the BatchNorm-backward constants of layer l are derived inline by the kernels that consume them
+  auto mkbfin = [&](int l, int write) {
+    v4::BnBwdFin f{};
+    f.sums = bs[l]; f.count = (double)M; f.scale = scale[l]; f.mean = mean[l]; f.invstd = invstd[l];
+    f.dgamma = Gr.dgamma[l]; f.dbeta = Gr.dbeta[l]; f.dbias = Gr.dbias[l]; f.accumulate = Gr.accumulate; f.write = write;
+    return f;
+  };
+  bool fused_consts = false;
+  if constexpr (TC) fused_consts = L.v2 || L.v5;
+
   {
     const int gpb = ceil_div(G, kNumSMs * 2);
     LaunchScope ls("bwd_last_reduce_kernel", st);
@@ -526,7 +557,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
                                                             gpb, gm, bs[2]);
     PCOE_TRY(ls.done());
   }
-  PCOE_TRY(consts(2));
+  if (!fused_consts) PCOE_TRY(consts(2));
 
   // dgrad: dx_prev[M x Kin[l]] = dy_l[M x Cs[l]] * W_l ;  wgrad: dW_l[Cs[l] x Kin[l]] = dy_l^T x_prev
   auto dgrad = [&](const auto& ap, int l, const auto& epi, const char* what) -> int {
@@ -548,19 +579,19 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       auto wb = [&](int l) { return (const __nv_bfloat16*)(sv + L.wb_off[l]); };
       const int Mld = L.Mld;
       v4::DyLast4 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
-      dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3;
+      dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3; dy3.fin = mkbfin(2, 1);
       v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2;
       v4::MaskStats4 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
       m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2; m2.Mld = Mld;
       PCOE_TRY(launch_bwd4<1>(dy3, x2, wb(2), L.w4_rp[2], L.w4_kp[2], m2, Gr.dW[2], d.C2, d.C2, -1, M, d.C2, st, kname(d, kBL3)));
-      PCOE_TRY(consts(1));
       v4::Dy4 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.Mld = Mld; dy2.C = d.C2;
+      dy2.fin = mkbfin(1, 1);
       v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1;
       v4::MaskStats4 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
       m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1; m1.Mld = Mld;
       PCOE_TRY(launch_bwd4<1>(dy2, x1, wb(1), L.w4_rp[1], L.w4_kp[1], m1, Gr.dW[1], d.C1, d.C1, -1, M, d.C1, st, kname(d, kBL2)));
-      PCOE_TRY(consts(0));
       v4::Dy4 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.Mld = Mld; dy1.C = d.C1;
+      dy1.fin = mkbfin(0, 1);
       if (d.D == 0) {
         v4::GatherXyz4 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}};
         PCOE_TRY(launch_bwd4<0>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], v4::NoEpi4{}, Gr.dW[0], Cin, Cin, 0, M, 0, st, kname(d, kBL1)));
@@ -582,23 +613,26 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       auto wb = [&](int l) { return (const __nv_bfloat16*)(sv + L.wb_off[l]); };
       const int Mld = L.Mld;
       v4::DyLast4 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
-      dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3;
+      dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3; dy3.fin = mkbfin(2, 1);   // wgrad owns the parameter-gradient outputs
       v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2;
       v4::MaskStats4 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
       m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2; m2.Mld = Mld;
       PCOE_TRY(launch_wgrad5(dy3, x2, Gr.dW[2], d.C2, d.C2, -1, M, d.C2 / 128, st, kname(d, kWG3)));
+      dy3.fin.write = 0;
       PCOE_TRY(launch_dgrad5<false>(dy3, wb(2), L.w4_kp[2], m2, M, d.C2, st, kname(d, kDG3)));
-      PCOE_TRY(consts(1));
       v4::Dy4 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.Mld = Mld; dy2.C = d.C2;
+      dy2.fin = mkbfin(1, 1);
       v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1;
       v4::MaskStats4 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
       m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1; m1.Mld = Mld;
       PCOE_TRY(launch_wgrad5(dy2, x1, Gr.dW[1], d.C1, d.C1, -1, M, d.C1 / 128, st, kname(d, kWG2)));
+      dy2.fin.write = 0;
       PCOE_TRY(launch_dgrad5<false>(dy2, wb(1), L.w4_kp[1], m1, M, d.C1, st, kname(d, kDG2)));
-      PCOE_TRY(consts(0));
       v4::Dy4 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.Mld = Mld; dy1.C = d.C1;
+      dy1.fin = mkbfin(0, 1);
       v5::GatherFeat5 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
       PCOE_TRY(launch_wgrad5(dy1, x0, Gr.dW[0], Cin, Cin, d.D, M, ceil_div(x0.nblocks(), 2), st, kname(d, kWG1)));
+      dy1.fin.write = 0;
       if (grad_feats) {
         v4::Scatter4 se{grad_feats, nbr, d.N, d.S, d.D, d.group_all};
         PCOE_TRY(launch_dgrad5<true>(dy1, wb(0), L.w4_kp[0], se, M, d.D, st, kname(d, kDG1)));

@@ -104,6 +104,60 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Train-mode BatchNorm finalisation evaluated INLINE by the kernel that consumes it (instead of a
+// per-channel kernel between two layers): every CTA derives (scale, shift) of the channels it needs
+// from the fp64 batch sums the previous kernel accumulated; block (0,0,0) also writes the saved
+// statistics for backward and updates the running buffers (bn_finalize_kernel's arithmetic, sa.cu).
+struct BnFin {
+  const double* sums;            // [2,C] sum, sum of squares; nullptr = not fused (read scale/shift arrays)
+  double count;
+  const float* gamma;
+  const float* beta;
+  const float* bias;             // conv bias: only shifts running_mean (cancelled by the batch-mean subtraction)
+  float* running_mean;           // may be nullptr
+  float* running_var;
+  float eps, momentum;
+  float* scale; float* shift; float* mean; float* invstd;   // saved for backward (written by one block)
+  __device__ __forceinline__ void eval(int c, int C, bool write, float& sc, float& sh) const {
+    const double mu = sums[c] / count;
+    double var = sums[C + c] / count - mu * mu;   // biased, as BatchNorm normalises
+    var = var < 0.0 ? 0.0 : var;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    sc = gamma[c] * is;
+    sh = beta[c] - (float)mu * sc;
+    if (write) {
+      scale[c] = sc; shift[c] = sh; mean[c] = (float)mu; invstd[c] = is;
+      if (running_mean) {
+        const float b = bias ? bias[c] : 0.f;
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)(mu + (double)b);
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    }
+  }
+};
+// BatchNorm-backward constants (a, p, q) + parameter gradients, inline (bn_bwd_consts_kernel's arithmetic)
+struct BnBwdFin {
+  const double* sums;            // [2,C] sum dz, sum dz*xhat; nullptr = not fused (read a/p/q arrays)
+  double count;
+  const float* scale; const float* mean; const float* invstd;
+  float* dgamma; float* dbeta; float* dbias;
+  int accumulate, write;         // write: this launch owns the parameter-gradient outputs
+  __device__ __forceinline__ void eval(int c, int C, bool first_block, float& a, float& p, float& q) const {
+    const double s0 = sums[c], s1 = sums[C + c];
+    const double m1 = s0 / count, m2 = s1 / count;
+    const double av = scale[c];
+    const double pv = -av * (double)invstd[c] * m2;
+    a = (float)av; p = (float)pv; q = (float)(-av * m1 - pv * (double)mean[c]);
+    if (write && first_block) {
+      if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;
+      if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
+      if (dbias && !accumulate) dbias[c] = 0.f;
+    }
+  }
+};
+__device__ __forceinline__ bool first_block() { return (blockIdx.x | blockIdx.y | blockIdx.z) == 0; }
+
 // ---------------------------------------------------------------------------------------------
 // Producers.  A producer group of G threads builds one operand tile per 128 points in `nbatches(G)`
 // batches of kBatch 16-byte units per thread, as a three-stage software pipeline so that global
@@ -136,12 +190,18 @@ struct BnRelu4 {
   const float* __restrict__ shift;
   int M, Mld, C;
   const float* cs;
+  BnFin fin;     // fin.sums != nullptr: forward of a train-mode layer, statistics finalised here
   __host__ __device__ __forceinline__ int rows() const { return C; }
   __host__ __device__ __forceinline__ int kext() const { return C; }
   __host__ __device__ __forceinline__ int nconst() const { return 2 * C; }
   __device__ __forceinline__ int nbatches(int G) const { return (C / (G >> 4) + kBatch - 1) / kBatch; }
   __device__ __forceinline__ void init(float* csm, int tid, int nthr) {
-    for (int c = tid; c < C; c += nthr) { csm[c] = scale[c]; csm[C + c] = shift[c]; }
+    if (fin.sums) {
+      const bool w = first_block();
+      for (int c = tid; c < C; c += nthr) fin.eval(c, C, w, csm[c], csm[C + c]);
+    } else {
+      for (int c = tid; c < C; c += nthr) { csm[c] = scale[c]; csm[C + c] = shift[c]; }
+    }
     cs = csm;
   }
   __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
@@ -185,12 +245,18 @@ struct Dy4 {
   const float* __restrict__ q;
   int M, Mld, C;
   const float* cs;
+  BnBwdFin fin;  // fin.sums != nullptr: BatchNorm-backward constants derived here from the batch sums
   __host__ __device__ __forceinline__ int rows() const { return C < 128 ? 128 : C; }   // also an M operand: 128 rows
   __host__ __device__ __forceinline__ int kext() const { return C; }
   __host__ __device__ __forceinline__ int nconst() const { return 3 * C; }
   __device__ __forceinline__ int nbatches(int G) const { return (C / (G >> 4) + kBatch - 1) / kBatch; }
   __device__ __forceinline__ void init(float* csm, int tid, int nthr) {
-    for (int c = tid; c < C; c += nthr) { csm[c] = a[c]; csm[C + c] = p[c]; csm[2 * C + c] = q[c]; }
+    if (fin.sums) {
+      const bool w = first_block();
+      for (int c = tid; c < C; c += nthr) fin.eval(c, C, w, csm[c], csm[C + c], csm[2 * C + c]);
+    } else {
+      for (int c = tid; c < C; c += nthr) { csm[c] = a[c]; csm[C + c] = p[c]; csm[2 * C + c] = q[c]; }
+    }
     cs = csm;
   }
   __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
@@ -238,12 +304,18 @@ struct DyLast4 {
   const float* __restrict__ q;
   int M, Mld, C;
   const float* cs;
+  BnBwdFin fin;
   __host__ __device__ __forceinline__ int rows() const { return C < 128 ? 128 : C; }
   __host__ __device__ __forceinline__ int kext() const { return C; }
   __host__ __device__ __forceinline__ int nconst() const { return 3 * C; }
   __device__ __forceinline__ int nbatches(int G) const { return (C / (G >> 4) + kBatch - 1) / kBatch; }
   __device__ __forceinline__ void init(float* csm, int tid, int nthr) {
-    for (int c = tid; c < C; c += nthr) { csm[c] = a[c]; csm[C + c] = p[c]; csm[2 * C + c] = q[c]; }
+    if (fin.sums) {
+      const bool w = first_block();
+      for (int c = tid; c < C; c += nthr) fin.eval(c, C, w, csm[c], csm[C + c], csm[2 * C + c]);
+    } else {
+      for (int c = tid; c < C; c += nthr) { csm[c] = a[c]; csm[C + c] = p[c]; csm[2 * C + c] = q[c]; }
+    }
     cs = csm;
   }
   __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
