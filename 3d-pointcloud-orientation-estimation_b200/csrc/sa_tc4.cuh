@@ -223,11 +223,12 @@ struct BnRelu4 {
     for (int i = 0; i < kBatch; ++i) {
       const int c = r0 + (b * kBatch + i) * rstep;
       if (c >= C) continue;
+      if (!ok) { tc::sts128(saddr + cm_off(crows, c + rshift, chunk), make_uint4(0u, 0u, 0u, 0u)); continue; }   // tail tile
       float v[8];
       unpack8(r.a[i], v);
       const float sc = cs[c], sh = cs[C + c];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = ok ? fmaf(v[u], sc, sh) : 0.f;
+      for (int u = 0; u < 8; ++u) v[u] = fmaf(v[u], sc, sh);
       tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16_relu(v));
     }
   }
@@ -280,12 +281,13 @@ struct Dy4 {
     for (int i = 0; i < kBatch; ++i) {
       const int c = r0 + (b * kBatch + i) * rstep;
       if (c >= C) continue;
+      if (!ok) { tc::sts128(saddr + cm_off(crows, c + rshift, chunk), make_uint4(0u, 0u, 0u, 0u)); continue; }   // tail tile
       float d[8], yy[8], v[8];
       unpack8(r.d[i], d);
       unpack8(r.y[i], yy);
       const float ca = cs[c], cp = cs[C + c], cq = cs[2 * C + c];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = ok ? fmaf(ca, d[u], fmaf(cp, yy[u], cq)) : 0.f;
+      for (int u = 0; u < 8; ++u) v[u] = fmaf(ca, d[u], fmaf(cp, yy[u], cq));
       tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16(v));
     }
   }
@@ -341,12 +343,16 @@ struct DyLast4 {
     for (int i = 0; i < kBatch; ++i) {
       const int c = r0 + (b * kBatch + i) * rstep;
       if (c >= C) continue;
+      if (!ok) { tc::sts128(saddr + cm_off(crows, c + rshift, chunk), make_uint4(0u, 0u, 0u, 0u)); continue; }   // tail tile
       float yy[8], v[8];
       unpack8(r.y[i], yy);
       const float ca = cs[c] * r.gv[i], cp = cs[C + c], cq = cs[2 * C + c];
       const int sl = r.sl[i] - (m & 31);     // slot relative to this 8-point chunk (-1 - j0 < 0 never matches)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = ok ? fmaf(cp, yy[u], cq) + (u == sl ? ca : 0.f) : 0.f;
+      for (int u = 0; u < 8; ++u) {
+        v[u] = fmaf(cp, yy[u], cq);
+        if (u == sl) v[u] += ca;             // the max-pool gradient lands on one point of the group
+      }
       tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16(v));
     }
   }
@@ -474,22 +480,27 @@ __device__ __forceinline__ void producer_pipeline(const Prod& prod, int g, int G
   const int nb = prod.nbatches(G), W = my_tiles * nb;
   if (W == 0) return;
   TC4_TRACER;
-  auto m0_of = [&](int w) { return (int)((blockIdx.x + (w / nb) * gridDim.x) * kPts); };
+  // cursors (tile ordinal t, batch b, first row m0) of the index / load / store stages, advanced
+  // incrementally: no integer division in the steady state
+  struct Cur { int t, b, m0; };
+  const int mstep = (int)gridDim.x * kPts;
+  auto adv = [&](Cur& c) { if (++c.b == nb) { c.b = 0; ++c.t; c.m0 += mstep; } };
+  Cur ci{0, 0, (int)blockIdx.x * kPts}, cl = ci, cst = ci;
   typename Prod::Idx ix;
   typename Prod::Raw ra, rb;
-  prod.load_idx(g, G, m0_of(0), 0, ix);
-  prod.load(g, G, m0_of(0), 0, ix, ra);
-  if (W > 1) prod.load_idx(g, G, m0_of(1), 1 % nb, ix);
+  prod.load_idx(g, G, ci.m0, ci.b, ix); adv(ci);
+  prod.load(g, G, cl.m0, cl.b, ix, ra); adv(cl);
+  if (W > 1) { prod.load_idx(g, G, ci.m0, ci.b, ix); adv(ci); }
   auto step = [&](int w, typename Prod::Raw& cur, typename Prod::Raw& nxt) {
-    if (w + 1 < W) prod.load(g, G, m0_of(w + 1), (w + 1) % nb, ix, nxt);
-    if (w + 2 < W) prod.load_idx(g, G, m0_of(w + 2), (w + 2) % nb, ix);
-    const int t = w / nb, b = w - t * nb;
+    if (w + 1 < W) { prod.load(g, G, cl.m0, cl.b, ix, nxt); adv(cl); }
+    if (w + 2 < W) { prod.load_idx(g, G, ci.m0, ci.b, ix); adv(ci); }
     if (g == 0) TC4_TRACE(12, w);
-    if (b == 0) wait_empty(t);
+    if (cst.b == 0) wait_empty(cst.t);
     if (g == 0) TC4_TRACE(10, w);
-    prod.store(g, G, m0_of(w), b, cur, stage_addr(t));
-    if (b == nb - 1) { tc::fence_proxy_async(); arrive(t); }
+    prod.store(g, G, cst.m0, cst.b, cur, stage_addr(cst.t));
+    if (cst.b == nb - 1) { tc::fence_proxy_async(); arrive(cst.t); }
     if (g == 0) TC4_TRACE(11, w);
+    adv(cst);
   };
   for (int w = 0; w < W; w += 2) {
     step(w, ra, rb);
@@ -627,7 +638,7 @@ struct MaskStats4 {
   double* __restrict__ sums;
   int C, Mld;
   int c;
-  float s0, s1, sc, sh, mu, is;
+  float s0, s1, sc, sh, is, nmi;   // nmi = -mean * invstd: xhat = y * invstd + nmi
   static constexpr bool kStage = true;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return C * 256; }
@@ -635,7 +646,7 @@ struct MaskStats4 {
   __device__ __forceinline__ void init(float*, int ch) {
     c = ch; s0 = s1 = 0.f;
     const bool ok = c < C;
-    sc = ok ? scale[c] : 0.f; sh = ok ? shift[c] : 0.f; mu = ok ? mean[c] : 0.f; is = ok ? invstd[c] : 0.f;
+    sc = ok ? scale[c] : 0.f; sh = ok ? shift[c] : 0.f; is = ok ? invstd[c] : 0.f; nmi = ok ? -mean[c] * is : 0.f;
   }
   __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid, uint32_t stg) {
     if (c >= C || !valid) return;
@@ -653,7 +664,7 @@ struct MaskStats4 {
         const float d = on ? v[8 * q + u] : 0.f;
         v[8 * q + u] = d;
         a[u & 3] += d;
-        b[u & 3] = fmaf(d, (yy[u] - mu) * is, b[u & 3]);
+        b[u & 3] = fmaf(d, fmaf(yy[u], is, nmi), b[u & 3]);
       }
     }
     stage32_bf16(stg, c, j, v);
@@ -829,10 +840,11 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
     if (tid == 0) TC4_TRACE(32, 0);
   } else if (warp < 16) {
     // ---- producers ----
+    int ring_s = 0, ring_n = 0;   // stage slot / round of the tile being stored (tiles are stored in order)
     producer_pipeline(prod, tid - kEpiThreads, kProdThreads, ntiles,
-                      [&](int t) { const int n = t / nstages; if (n > 0) tc::mbar_wait(&bar.empty[t % nstages], (uint32_t)((n - 1) & 1)); },
-                      [&](int t) { return sT + (uint32_t)(t % nstages) * tbytes; },
-                      [&](int t) { mbar_arrive(&bar.full[t % nstages]); });
+                      [&](int t) { if (t >= nstages) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_n - 1) & 1)); },
+                      [&](int) { return sT + (uint32_t)ring_s * tbytes; },
+                      [&](int) { mbar_arrive(&bar.full[ring_s]); if (++ring_s == nstages) { ring_s = 0; ++ring_n; } });
   } else {   // warp 16: MMA issue, warp-uniform loop, one elected lane issues
     const uint32_t tmem = tc::uniform_u32(tmem_base);
     // ---- MMA issue ----
@@ -993,33 +1005,36 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
     const int W = my_tiles * upt;
     union RawU { typename PProd::Raw p; typename QProd::Raw q; __device__ RawU() {} };
     typename QProd::Idx ix;   // the dy producers have no index stage
-    auto m0_of = [&](int w) { return (int)((blockIdx.x + (w / upt) * gridDim.x) * kPts); };
-    auto do_idx = [&](int w) {
-      const int u = w % upt;
-      if (u >= nbp) qp.load_idx(g, kProdThreads, m0_of(w), u - nbp, ix);
+    struct Cur { int t, u, m0; };   // tile ordinal, unit within the tile, first row: advanced incrementally (no division)
+    const int mstep = (int)gridDim.x * kPts;
+    auto adv = [&](Cur& c) { if (++c.u == upt) { c.u = 0; ++c.t; c.m0 += mstep; } };
+    Cur ci{0, 0, (int)blockIdx.x * kPts}, cl = ci, cst = ci;
+    auto do_idx = [&]() {
+      if (ci.u >= nbp) qp.load_idx(g, kProdThreads, ci.m0, ci.u - nbp, ix);
+      adv(ci);
     };
-    auto do_load = [&](int w, RawU& r) {
-      const int u = w % upt;
-      if (u < nbp) pp.load(g, kProdThreads, m0_of(w), u, NoIdx{}, r.p);
-      else qp.load(g, kProdThreads, m0_of(w), u - nbp, ix, r.q);
+    auto do_load = [&](RawU& r) {
+      if (cl.u < nbp) pp.load(g, kProdThreads, cl.m0, cl.u, NoIdx{}, r.p);
+      else qp.load(g, kProdThreads, cl.m0, cl.u - nbp, ix, r.q);
+      adv(cl);
     };
     auto step = [&](int w, RawU& cur, RawU& nxt) {
-      if (w + 1 < W) do_load(w + 1, nxt);
-      if (w + 2 < W) do_idx(w + 2);
-      const int t = w / upt, u = w - t * upt;
+      if (w + 1 < W) do_load(nxt);
+      if (w + 2 < W) do_idx();
       if (g == 0) TC4_TRACE(12, w);
-      if (u == 0 && t > 0) tc::mbar_wait(&bar.empty[0], (uint32_t)((t - 1) & 1));
+      if (cst.u == 0 && cst.t > 0) tc::mbar_wait(&bar.empty[0], (uint32_t)((cst.t - 1) & 1));
       if (g == 0) TC4_TRACE(10, w);
-      if (u < nbp) pp.store(g, kProdThreads, m0_of(w), u, cur.p, sP);
-      else qp.store(g, kProdThreads, m0_of(w), u - nbp, cur.q, sQ);
-      if (u == upt - 1) { tc::fence_proxy_async(); mbar_arrive(&bar.full[0]); }
+      if (cst.u < nbp) pp.store(g, kProdThreads, cst.m0, cst.u, cur.p, sP);
+      else qp.store(g, kProdThreads, cst.m0, cst.u - nbp, cur.q, sQ);
+      if (cst.u == upt - 1) { tc::fence_proxy_async(); mbar_arrive(&bar.full[0]); }
       if (g == 0) TC4_TRACE(11, w);
+      adv(cst);
     };
     if (W > 0) {
       RawU ra, rb;
-      do_idx(0);
-      do_load(0, ra);
-      if (W > 1) do_idx(1);
+      do_idx();
+      do_load(ra);
+      if (W > 1) do_idx();
       for (int w = 0; w < W; w += 2) {
         step(w, ra, rb);
         if (w + 1 < W) step(w + 1, rb, ra);

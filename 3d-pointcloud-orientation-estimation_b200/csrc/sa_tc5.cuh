@@ -369,21 +369,31 @@ tc5_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_val
   } else if (warp < 16) {
     const int g = tid - kEpiThreads;
     union RawU { typename PProd::Raw p; typename QProd::Raw q; __device__ RawU() {} };
+    struct Cur { int i, u, m0; };   // tile ordinal, unit, first row: advanced incrementally (no division)
+    auto adv = [&](Cur& c) { if (++c.u == upt) { c.u = 0; ++c.i; c.m0 += kPts; } };
+    Cur cl{0, 0, t0 * kPts}, cst = cl;
+    int ring_s = 0, ring_n = 0;
     unit_pipeline<RawU>(nt * upt,
-        [&](int w, RawU& r) {
-          const int i = w / upt, u = w - i * upt, m0 = (t0 + i) * kPts;
+        [&](int, RawU& r) {
+          const int u = cl.u, m0 = cl.m0;
           if (u < 2) pp.load(g, kProdThreads, m0, (cl0 >> 6) + u, NoIdx{}, r.p);
           else if constexpr (QProd::kChMajor) qp.load(g, kProdThreads, m0, 2 * qb + (u - 2), NoIdx{}, r.q);
           else qp.load64(g, m0, 2 * qb + (u - 2), r.q);
+          adv(cl);
         },
-        [&](int w, const RawU& r) {
-          const int i = w / upt, u = w - i * upt, m0 = (t0 + i) * kPts, s = i % nst;
+        [&](int, const RawU& r) {
+          const int u = cst.u, m0 = cst.m0, s = ring_s;
           const uint32_t st = sS + (uint32_t)s * sbytes;
-          if (u == 0 && i >= nst) tc::mbar_wait(&bar.empty[s], (uint32_t)((i / nst - 1) & 1));
+          if (u == 0 && ring_n > 0) tc::mbar_wait(&bar.empty[s], (uint32_t)((ring_n - 1) & 1));
           if (u < 2) pp.store(g, kProdThreads, m0, (cl0 >> 6) + u, r.p, st, 128, -cl0);
           else if constexpr (QProd::kChMajor) qp.store(g, kProdThreads, m0, 2 * qb + (u - 2), r.q, st + 2 * kPart, 128, -128 * qb);
           else qp.store64(g, 2 * qb + (u - 2), r.q, st + 2 * kPart + (uint32_t)(u - 2) * kPart);
-          if (u == upt - 1) { tc::fence_proxy_async(); mbar_arrive(&bar.full[s]); }
+          if (u == upt - 1) {
+            tc::fence_proxy_async();
+            mbar_arrive(&bar.full[s]);
+            if (++ring_s == nst) { ring_s = 0; ++ring_n; }
+          }
+          adv(cst);
         });
   } else {   // warp 16: MMA issue, warp-uniform loop, one elected lane issues
     const uint32_t tmem = tc::uniform_u32(tmem_base);
