@@ -221,9 +221,10 @@ struct BnRelu4 {
     const int crows = lrows ? lrows : C;
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
+      // branch-free on purpose: the four chunks of a batch are independent and the compiler interleaves them
+      // (C is a multiple of the 64 channels a batch covers; columns of points >= M hold relu(shift): they are
+      // never read back - forward / dgrad epilogues skip them and the wgrad dy operand zeroes them)
       const int c = r0 + (b * kBatch + i) * rstep;
-      if (c >= C) continue;
-      if (!ok) { tc::sts128(saddr + cm_off(crows, c + rshift, chunk), make_uint4(0u, 0u, 0u, 0u)); continue; }   // tail tile
       float v[8];
       unpack8(r.a[i], v);
       const float sc = cs[c], sh = cs[C + c];
@@ -277,15 +278,14 @@ struct Dy4 {
                                         int rshift = 0) const {
     PCOE_CM_MAP
     const int crows = lrows ? lrows : rows();
+    const float okf = ok ? 1.f : 0.f;
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
-      const int c = r0 + (b * kBatch + i) * rstep;
-      if (c >= C) continue;
-      if (!ok) { tc::sts128(saddr + cm_off(crows, c + rshift, chunk), make_uint4(0u, 0u, 0u, 0u)); continue; }   // tail tile
+      const int c = r0 + (b * kBatch + i) * rstep;   // branch-free: see BnRelu4::store
       float d[8], yy[8], v[8];
       unpack8(r.d[i], d);
       unpack8(r.y[i], yy);
-      const float ca = cs[c], cp = cs[C + c], cq = cs[2 * C + c];
+      const float ca = cs[c] * okf, cp = cs[C + c] * okf, cq = cs[2 * C + c] * okf;   // points >= M contribute 0 to dW
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = fmaf(ca, d[u], fmaf(cp, yy[u], cq));
       tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16(v));
@@ -339,14 +339,13 @@ struct DyLast4 {
                                         int rshift = 0) const {
     PCOE_CM_MAP
     const int crows = lrows ? lrows : rows();
+    const float okf = ok ? 1.f : 0.f;
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
-      const int c = r0 + (b * kBatch + i) * rstep;
-      if (c >= C) continue;
-      if (!ok) { tc::sts128(saddr + cm_off(crows, c + rshift, chunk), make_uint4(0u, 0u, 0u, 0u)); continue; }   // tail tile
+      const int c = r0 + (b * kBatch + i) * rstep;   // branch-free: see BnRelu4::store
       float yy[8], v[8];
       unpack8(r.y[i], yy);
-      const float ca = cs[c] * r.gv[i], cp = cs[C + c], cq = cs[2 * C + c];
+      const float ca = cs[c] * r.gv[i], cp = cs[C + c] * okf, cq = cs[2 * C + c] * okf;   // gv is 0 for points >= M
       const int sl = r.sl[i] - (m & 31);     // slot relative to this 8-point chunk (-1 - j0 < 0 never matches)
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
