@@ -85,17 +85,33 @@ __global__ void bwd_last_reduce_kernel(const float* __restrict__ grad_out, const
                                        float* __restrict__ gm, double* __restrict__ sums) {
   const int g0 = blockIdx.x * groups_per_block, g1 = min(G, g0 + groups_per_block);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float mu = mean[c], is = invstd[c];
-    float s0 = 0.f, s1 = 0.f;
-    for (int g = g0; g < g1; ++g) {
+    const float is = invstd[c], nmi = -mean[c] * is;
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    int g = g0;
+    for (; g + 4 <= g1; g += 4) {          // four independent groups per iteration: the twelve loads overlap
+      float o[4], go[4], ys[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const size_t e = (size_t)(g + k) * C + c;
+        o[k] = __ldg(out + e); go[k] = __ldg(grad_out + e); ys[k] = __ldg(ysel + e);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float v = o[k] > 0.f ? go[k] : 0.f;
+        gm[(size_t)(g + k) * C + c] = v;
+        s0[k] += v;
+        s1[k] = fmaf(v, fmaf(ys[k], is, nmi), s1[k]);
+      }
+    }
+    for (; g < g1; ++g) {
       const size_t e = (size_t)g * C + c;
       const float v = out[e] > 0.f ? grad_out[e] : 0.f;
       gm[e] = v;
-      s0 += v;
-      s1 = fmaf(v, (ysel[e] - mu) * is, s1);
+      s0[0] += v;
+      s1[0] = fmaf(v, fmaf(ysel[e], is, nmi), s1[0]);
     }
-    atomicAdd(sums + c, (double)s0);
-    atomicAdd(sums + C + c, (double)s1);
+    atomicAdd(sums + c, (double)((s0[0] + s0[1]) + (s0[2] + s0[3])));
+    atomicAdd(sums + C + c, (double)((s1[0] + s1[1]) + (s1[2] + s1[3])));
   }
 }
 
@@ -263,16 +279,21 @@ static int launch_bwd4(const PProd& pp, const QProd& qp, const __nv_bfloat16* Wb
                        const char* what) {
   const size_t wbytes = DGRAD ? (size_t)Rp * Kp * 2 : 0;
   const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + qp.nconst() + epi.nconst()) + 512, sb = (size_t)epi.stage_bytes();
-  const size_t base = 1024 + wbytes + tile_bytes4(pp) + tile_bytes4(qp) + cbytes;
-  const int nstg = (sb && base + 2 * sb <= kSmemBudget4) ? 2 : 1;
-  const size_t smem = base + nstg * sb;
-  if (smem > kSmemBudget4) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  const size_t pq = tile_bytes4(pp) + tile_bytes4(qp), base = 1024 + wbytes + pq + cbytes;
+  if (base + sb > kSmemBudget4) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  // A second P/Q operand stage (producers working on tile i+1 while the MMAs of tile i run) is implemented
+  // (npq = 2) but measured SLOWER on B200 (sa1_bwd_l2 55.7 -> 63.5 us, sa2_bwd_l2 39 -> 47.5 us): the larger
+  // carve-out shrinks L1 and the producers running further ahead evict the y tile that the MaskStats epilogue
+  // re-reads.  The remaining shared memory goes to a second output staging tile instead.
+  const int npq = 1;
+  const int nstg = (sb && base + (npq - 1) * pq + 2 * sb <= kSmemBudget4) ? 2 : 1;
+  const size_t smem = base + (npq - 1) * pq + nstg * sb;
   const int tiles = ceil_div(M, v4::kPts), grid = tiles < kNumSMs ? tiles : kNumSMs;
   auto k = v4::tc4_bwd_kernel<PProd, QProd, Epi, DGRAD, 512>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget4)); attr = true; }
   LaunchScope ls(what, st);
-  k<<<grid, v4::kThreads, smem, st>>>(pp, qp, Wb, Rp, Kp, epi, dW, ldo, cq_valid, perm_d, M, cprev, nstg);
+  k<<<grid, v4::kThreads, smem, st>>>(pp, qp, Wb, Rp, Kp, epi, dW, ldo, cq_valid, perm_d, M, cprev, nstg, npq);
   return ls.done();
 }
 
@@ -551,9 +572,9 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   if constexpr (TC) fused_consts = L.v2 || L.v5;
 
   {
-    const int gpb = ceil_div(G, kNumSMs * 2);
+    const int gpb = ceil_div(G, kNumSMs * 2);   // few blocks: every block ends with 2*C3 same-address fp64 atomics
     LaunchScope ls("bwd_last_reduce_kernel", st);
-    bwd_last_reduce_kernel<<<ceil_div(G, gpb), 256, 0, st>>>(grad_out, out, ysel, mean[2], invstd[2], G, d.C3,
+    bwd_last_reduce_kernel<<<ceil_div(G, gpb), d.C3 >= 256 ? 256 : (d.C3 >= 128 ? 128 : 64), 0, st>>>(grad_out, out, ysel, mean[2], invstd[2], G, d.C3,
                                                             gpb, gm, bs[2]);
     PCOE_TRY(ls.done());
   }

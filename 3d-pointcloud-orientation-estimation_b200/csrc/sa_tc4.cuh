@@ -886,7 +886,7 @@ template <class PProd, class QProd, class Epi, int DGRAD, int TCOLS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, Epi epi,
                float* __restrict__ dW, int ldo, int cq_valid, int perm_d /* >=0: layer-1 [feats|xyz] column order */,
-               int M, int cprev /* dgrad output channels */, int nstg) {
+               int M, int cprev /* dgrad output channels */, int nstg, int npq /* P/Q operand stages: 1 or 2 */) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem0 - tc::smem_u32(smem_raw));
@@ -898,24 +898,24 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
   const int mtp = (cprev + 127) / 128;
   const uint32_t wbytes = DGRAD ? (uint32_t)Rp * (uint32_t)Kp * 2u : 0u;
   const uint32_t pbytes = (prod_tile_bytes(pp) + 1023u) & ~1023u, qbytes = (prod_tile_bytes(qp) + 1023u) & ~1023u;
-  const uint32_t sW = smem0, sP = smem0 + wbytes, sQ = sP + pbytes;
-  float* csm = reinterpret_cast<float*>(smem_gen + wbytes + pbytes + qbytes);
+  const uint32_t sW = smem0, sP0 = smem0 + wbytes, pqbytes = pbytes + qbytes;   // stage s: P at sP0 + s*pqbytes, Q behind it
+  float* csm = reinterpret_cast<float*>(smem_gen + wbytes + (size_t)npq * pqbytes);
   const uint32_t dx_col = (uint32_t)((mtl * nw + 31) / 32 * 32);
   const uint32_t dx_cols = DGRAD == 1 ? (uint32_t)(mtp * kPts) : (uint32_t)((cprev + 31) / 32 * 32);
 
   if (warp == 0) tc::tmem_alloc<TCOLS>(&tmem_base);
   if (tid == 0) {
-    tc::mbar_init(&bar.full[0], kProdThreads); tc::mbar_init(&bar.empty[0], 1);
+    for (int s = 0; s < npq; ++s) { tc::mbar_init(&bar.full[s], kProdThreads); tc::mbar_init(&bar.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar.tmem_full[b], 1); tc::mbar_init(&bar.tmem_empty[b], kEpiThreads); }
   }
   if (DGRAD) load_wimage(Wb, Rp, Kp, sW, tid, kThreads);
-  zero_smem(sP, pbytes + qbytes, tid, kThreads);
+  zero_smem(sP0, (uint32_t)npq * pqbytes, tid, kThreads);
   pp.init(csm, tid, kThreads);
   qp.init(csm + pp.nconst(), tid, kThreads);
   // epilogue split as in the forward kernel (DGRAD == 1: mtp*4 items; DGRAD == 2: column blocks)
   const int eq = warp & 3, eh = (warp >> 2) & 1, lane = tid & 31;
   const int emi = (eh * mtp) >> 1;
-  const uint32_t stg0 = (sQ + qbytes + (uint32_t)(pp.nconst() + qp.nconst() + epi.nconst()) * 4u + 127u) & ~127u;
+  const uint32_t stg0 = (sP0 + (uint32_t)npq * pqbytes + (uint32_t)(pp.nconst() + qp.nconst() + epi.nconst()) * 4u + 127u) & ~127u;
   const uint32_t stg_bytes = (uint32_t)epi.stage_bytes();
   epi.init(csm + pp.nconst() + qp.nconst(), emi * 128 + eq * 32 + lane);
   tc::fence_proxy_async();
@@ -1021,11 +1021,13 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
       if (w + 1 < W) do_load(nxt);
       if (w + 2 < W) do_idx();
       if (g == 0) TC4_TRACE(12, w);
-      if (cst.u == 0 && cst.t > 0) tc::mbar_wait(&bar.empty[0], (uint32_t)((cst.t - 1) & 1));
+      const int s = cst.t & (npq - 1), n = npq == 2 ? cst.t >> 1 : cst.t;     // stage slot, round
+      if (cst.u == 0 && n > 0) tc::mbar_wait(&bar.empty[s], (uint32_t)((n - 1) & 1));
       if (g == 0) TC4_TRACE(10, w);
+      const uint32_t sP = sP0 + (uint32_t)s * pqbytes;
       if (cst.u < nbp) pp.store(g, kProdThreads, cst.m0, cst.u, cur.p, sP);
-      else qp.store(g, kProdThreads, cst.m0, cst.u - nbp, cur.q, sQ);
-      if (cst.u == upt - 1) { tc::fence_proxy_async(); mbar_arrive(&bar.full[0]); }
+      else qp.store(g, kProdThreads, cst.m0, cst.u - nbp, cur.q, sP + pbytes);
+      if (cst.u == upt - 1) { tc::fence_proxy_async(); mbar_arrive(&bar.full[s]); }
       if (g == 0) TC4_TRACE(11, w);
       adv(cst);
     };
@@ -1049,7 +1051,9 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
     int i = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
       const int b = i & 1, u = i >> 1;
-      tc::mbar_wait(&bar.full[0], (uint32_t)(i & 1));
+      const int s = i & (npq - 1), n = npq == 2 ? i >> 1 : i;
+      const uint32_t sP = sP0 + (uint32_t)s * pqbytes, sQ = sP + pbytes;
+      tc::mbar_wait(&bar.full[s], (uint32_t)(n & 1));
       if ((tid & 31) == 0) TC4_TRACE(20, i);
       if (DGRAD && u > 0) tc::mbar_wait(&bar.tmem_empty[b], (uint32_t)((u - 1) & 1));
       tc::fence_after_sync();
@@ -1075,7 +1079,7 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
                        tc::make_desc_sw128(sP + (uint32_t)(k >> 4) * 2048, (uint32_t)prow * 128, 1024),
                        tc::make_desc_sw128(sW + (uint32_t)(k >> 4) * 2048, (uint32_t)Rp * 128, 1024), idesc_d, k > 0);
       }
-      tc::mma_commit_warp(&bar.empty[0]);
+      tc::mma_commit_warp(&bar.empty[s]);
       tc::mma_commit_warp(&bar.tmem_full[b]);
       if ((tid & 31) == 0) TC4_TRACE(22, i);
     }

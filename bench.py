@@ -51,7 +51,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -60,7 +60,7 @@ class ClockSampler:
         self.lines, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -100,28 +100,52 @@ def sa_shapes(B: int, N: int):
 
 
 def kernel_work(B: int, N: int) -> dict:
-    """Algorithmic work per STEP of every libpcoe kernel name (DESIGN.md 'Kernels'): FLOPs for the
-    GEMM kernels (2*M*Cin*Cout, no padding/recompute), bytes for the sampling/grouping kernels."""
+    """Algorithmic work per STEP of every libpcoe kernel name: name -> (FLOPs, bytes).
+    FLOPs = 2*M*Cin*Cout per GEMM (no padding / recompute).  Bytes = compulsory HBM traffic of the launch:
+    every input it must read once and every output it must write once (bf16 activations, fp32 sources,
+    int32 indices; weights and per-channel vectors are negligible and left out).  The roofline that binds
+    a kernel is whichever of FLOPs / tensor peak and bytes / HBM peak takes longer."""
     sh = sa_shapes(B, N)
     w = {}
     for li, s in enumerate(sh):
-        M, c = s[0], s[1:5]
+        M, c, Nin, S = s[0], s[1:5], s[5], s[6]
+        G = M // 32
         g = lambda a, b: 2.0 * M * c[a] * c[b]
+        act = lambda k: 2.0 * M * c[k]                                # one bf16 activation tensor [M x C_k]
+        src = 4.0 * M + 4.0 * (M // (S * 32)) * Nin * c[0]             # neighbour indices + the gathered fp32 source, once
+        pool = 10.0 * G * c[3]                                        # ymax, ymin (f32) + amax, amin (u8) per group
         t = f"sa{li + 1}_"
-        dg1 = 2.0 * M * (c[0] - 3) * c[1]                        # no data gradient into xyz
-        w.update({t + "fwd_l1": g(0, 1), t + "fwd_l2": g(1, 2), t + "fwd_l3": g(2, 3),
-                  t + "bwd_wgrad3": g(2, 3), t + "bwd_dgrad3": g(2, 3), t + "bwd_wgrad2": g(1, 2),
-                  t + "bwd_dgrad2": g(1, 2), t + "bwd_wgrad1": g(0, 1), t + "bwd_dgrad1": dg1,
-                  t + "bwd_l3": 2 * g(2, 3), t + "bwd_l2": 2 * g(1, 2), t + "bwd_l1": g(0, 1) + dg1})
-    w = {k: ("tensor", float(v)) for k, v in w.items()}
+        dg1 = 2.0 * M * (c[0] - 3) * c[1]                             # no data gradient into xyz
+        scat = 4.0 * (M // (S * 32)) * Nin * (c[0] - 3)               # grad_feats written once
+        w.update({
+            t + "fwd_l1": (g(0, 1), src + act(1)), t + "fwd_l2": (g(1, 2), act(1) + act(2)),
+            t + "fwd_l3": (g(2, 3), act(2) + act(3) + pool),
+            # v4: one fused wgrad+dgrad kernel per layer
+            t + "bwd_l3": (2 * g(2, 3), act(3) + act(2) + 5.0 * G * c[3] + act(2)),
+            t + "bwd_l2": (2 * g(1, 2), 2 * act(2) + act(1) + act(1)),
+            t + "bwd_l1": (g(0, 1) + dg1, 2 * act(1) + src + scat),
+            # v5 / first-generation path: separate kernels
+            t + "bwd_wgrad3": (g(2, 3), act(3) + act(2) + 5.0 * G * c[3]),
+            t + "bwd_dgrad3": (g(2, 3), act(3) + act(2) + 5.0 * G * c[3] + act(2)),
+            t + "bwd_wgrad2": (g(1, 2), 2 * act(2) + act(1)), t + "bwd_dgrad2": (g(1, 2), 2 * act(2) + act(1) + act(1)),
+            t + "bwd_wgrad1": (g(0, 1), 2 * act(1) + src), t + "bwd_dgrad1": (dg1, 2 * act(1) + scat)})
     grp = float(sum(B * (12 * s[5] + 12 * s[6] + 4 * s[6] * s[7]) for s in sh[:2]))
     smp = float(sum(B * (12 * s[5] + 4 * s[6] + 12 * s[6]) for s in sh[:2]))
-    w["knn_kernel"] = ("hbm", grp)
-    w["ball_query_kernel"] = ("hbm", grp)
-    w["fps_kernel"] = ("hbm", smp)
-    w["random_subset_kernel"] = ("hbm", float(sum(B * 4 * s[6] for s in sh[:2])))
-    w["gather_points_kernel"] = ("hbm", float(sum(B * (4 * s[6] + 24 * s[6]) for s in sh[:2])))
+    w["knn_kernel"] = (0.0, grp)
+    w["ball_query_kernel"] = (0.0, grp)
+    w["fps_kernel"] = (0.0, smp)
+    w["random_subset_kernel"] = (0.0, float(sum(B * 4 * s[6] for s in sh[:2])))
+    w["gather_points_kernel"] = (0.0, float(sum(B * (4 * s[6] + 24 * s[6]) for s in sh[:2])))
     return w
+
+
+def load_traffic() -> dict:
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels captured with
+    `ncu --set full`, summarised by tools/ncu_summary.py into profiles/traffic.json (kernel name -> bytes)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
 
 
 def make_targets(kind: str, B: int, pcoe, batch: int):
@@ -280,7 +304,7 @@ def run_ours(args):
     # ---- end-to-end through the public API with host buffers ------------------------------------
     # (a) the graphed step fed from pinned host memory: H2D of xyz + targets, replay, loss D2H
     h2d = host[0][0].numel() * 4 + sum(t.numel() * t.element_size() for t in host[0][1])
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 100))
 
     def timed_e2e(fn):
         for i in range(2):
@@ -327,18 +351,27 @@ def run_ours(args):
         for name, (n, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
             ent = {"launches_per_step": n / psteps, "ms_per_step": ms / psteps, "share_of_libpcoe_time": ms / tot_ms}
             if name in work:
-                bound, amount = work[name]
-                ach = amount / (ms / psteps * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+                flops, nbytes = work[name]
+                t_s = ms / psteps * 1e-3
+                t_tensor, t_hbm = flops / (peaks["tensor"] * 1e12), nbytes / (peaks["hbm"] * 1e9)
+                bound = "tensor" if t_tensor > t_hbm else "hbm"
+                ach = flops / t_s / 1e12 if bound == "tensor" else nbytes / t_s / 1e9
                 ent.update(bound=bound, achieved=ach, unit="TFLOP/s" if bound == "tensor" else "GB/s",
-                           frac=ach / peaks[bound])
+                           frac=ach / peaks[bound], tflops=flops / t_s / 1e12, gbs=nbytes / t_s / 1e9,
+                           tensor_frac=flops / t_s / 1e12 / peaks["tensor"])
             kernels[name] = ent
         top = next((n for n in kernels if "achieved" in kernels[n]), None)
         if top:
             k = kernels[top]
+            traffic = load_traffic().get(top) if (args.config == "c2" and args.precision == "bf16") else None
             roofline = {"kernel": top, "bound": k["bound"], "achieved": k["achieved"], "peak": peaks[k["bound"]],
-                        "unit": k["unit"], "frac": k["frac"], "traffic": None, "peak_source": peaks["source"],
+                        "unit": k["unit"], "frac": k["frac"], "traffic": traffic, "peak_source": peaks["source"],
                         "avg_launch_ms": k["ms_per_step"] / k["launches_per_step"],
-                        "share_of_libpcoe_time": k["share_of_libpcoe_time"]}
+                        "share_of_libpcoe_time": k["share_of_libpcoe_time"],
+                        "algorithmic_bytes": work[top][1] / k["launches_per_step"],
+                        "algorithmic_flops": work[top][0] / k["launches_per_step"],
+                        "tensor_frac": k.get("tensor_frac"),
+                        "note": "bound = the slower of FLOPs/tensor peak and compulsory bytes/HBM peak for this kernel"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
     cpu = None
@@ -390,7 +423,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")

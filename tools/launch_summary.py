@@ -10,15 +10,14 @@ import sys
 
 
 def short(name: str) -> str:
-    name = re.sub(r"\(.*$", "", name)            # drop the argument list
     name = name.replace("void ", "")
-    m = re.match(r"(pcoe::(?:v4::)?\w+)<(.*)>?$", name)
-    if m:
-        args = re.findall(r"pcoe::(?:v4::)?(\w+)", m.group(2))
-        tail = re.findall(r"\(int\)(\d+)", m.group(2))
-        return f"{m.group(1)}<{','.join(args + tail)}>"
-    name = re.sub(r"<.*$", "", name)
-    return name[:70]
+    fn = name.split("<")[0].split("(")[0]
+    if fn.startswith(("pcoe::", "v4::", "v5::")):          # ncu drops the outer namespace of nested ones
+        targs = name[len(fn):].split(">(")[0] if "<" in name else ""
+        args = re.findall(r"(?:pcoe|v4|v5)::(\w+)", targs)
+        fn = fn if fn.startswith("pcoe::") else "pcoe::" + fn
+        return f"{fn}<{','.join(args)}>" if args else fn
+    return fn[:70]
 
 
 def main():
