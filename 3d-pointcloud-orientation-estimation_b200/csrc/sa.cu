@@ -29,8 +29,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
   if (c >= C) return;
   const float b = bias ? bias[c] : 0.f;
   if (train) {
-    const double mean = sums[c] / count;
-    double var = sums[C + c] / count - mean * mean;  // biased, as BatchNorm normalises
+    double t0 = 0.0, t1 = 0.0;   // the v4 / v5 epilogues spread their atomics over kRedCopies copies
+    for (int k = 0; k < kRedCopies; ++k) { t0 += sums[(size_t)k * 2 * C + c]; t1 += sums[(size_t)k * 2 * C + C + c]; }
+    const double mean = t0 / count;
+    double var = t1 / count - mean * mean;  // biased, as BatchNorm normalises
     var = var < 0.0 ? 0.0 : var;
     const float invstd = (float)(1.0 / sqrt(var + (double)eps));
     const float sc = gamma[c] * invstd;
@@ -110,8 +112,9 @@ __global__ void bwd_last_reduce_kernel(const float* __restrict__ grad_out, const
       s0[0] += v;
       s1[0] = fmaf(v, fmaf(ysel[e], is, nmi), s1[0]);
     }
-    atomicAdd(sums + c, (double)((s0[0] + s0[1]) + (s0[2] + s0[3])));
-    atomicAdd(sums + C + c, (double)((s1[0] + s1[1]) + (s1[2] + s1[3])));
+    double* dst = sums + (size_t)(blockIdx.x % kRedCopies) * 2 * C;
+    atomicAdd(dst + c, (double)((s0[0] + s0[1]) + (s0[2] + s0[3])));
+    atomicAdd(dst + C + c, (double)((s1[0] + s1[1]) + (s1[2] + s1[3])));
   }
 }
 
@@ -124,7 +127,8 @@ __global__ void bn_bwd_consts_kernel(const double* __restrict__ sums, double cou
                                      float* __restrict__ dbias, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double s0 = sums[c], s1 = sums[C + c];
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < kRedCopies; ++k) { s0 += sums[(size_t)k * 2 * C + c]; s1 += sums[(size_t)k * 2 * C + C + c]; }
   const double m1 = s0 / count, m2 = s1 / count;
   const double av = scale[c];
   const double pv = -av * (double)invstd[c] * m2;
@@ -548,9 +552,14 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   TY* dz[2] = {(TY*)(ws + L.wb_dz[0]), (TY*)(ws + L.wb_dz[1])};
 
   PCOE_CUDA(cudaMemsetAsync(ws + L.wb_sums[0], 0, L.wb_sums_bytes, st));
-  if (!Gr.accumulate)
+  bool v4path = false;
+  if constexpr (TC) v4path = L.v2;
+  if (v4path) {   // the v4 kernels accumulate into copies; dw_combine_kernel writes / adds into dW at the end
+    PCOE_CUDA(cudaMemsetAsync(ws + L.wb_dwc[0], 0, L.wb_dwc_bytes, st));
+  } else if (!Gr.accumulate) {
     for (int l = 0; l < 3; ++l)
       PCOE_CUDA(cudaMemsetAsync(Gr.dW[l], 0, sizeof(float) * (size_t)Cs[l] * Kin[l], st));
+  }
   if (d.D > 0 && grad_feats)
     PCOE_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)d.B * d.N * d.D, st));
 
@@ -598,32 +607,44 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   if constexpr (TC) {
     if (L.v2) {   // one fused wgrad+dgrad kernel per layer (sa_tc4.cuh)
       auto wb = [&](int l) { return (const __nv_bfloat16*)(sv + L.wb_off[l]); };
+      auto dwc = [&](int l) { return (float*)(ws + L.wb_dwc[l]); };
       const int Mld = L.Mld;
       v4::DyLast4 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
       dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3; dy3.fin = mkbfin(2, 1);
       v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2;
       v4::MaskStats4 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
       m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2; m2.Mld = Mld;
-      PCOE_TRY(launch_bwd4<1>(dy3, x2, wb(2), L.w4_rp[2], L.w4_kp[2], m2, Gr.dW[2], d.C2, d.C2, -1, M, d.C2, st, kname(d, kBL3)));
+      PCOE_TRY(launch_bwd4<1>(dy3, x2, wb(2), L.w4_rp[2], L.w4_kp[2], m2, dwc(2), L.dwc_ld[2], d.C2, -1, M, d.C2, st, kname(d, kBL3)));
       v4::Dy4 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.Mld = Mld; dy2.C = d.C2;
       dy2.fin = mkbfin(1, 1);
       v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1;
       v4::MaskStats4 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
       m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1; m1.Mld = Mld;
-      PCOE_TRY(launch_bwd4<1>(dy2, x1, wb(1), L.w4_rp[1], L.w4_kp[1], m1, Gr.dW[1], d.C1, d.C1, -1, M, d.C1, st, kname(d, kBL2)));
+      PCOE_TRY(launch_bwd4<1>(dy2, x1, wb(1), L.w4_rp[1], L.w4_kp[1], m1, dwc(1), L.dwc_ld[1], d.C1, -1, M, d.C1, st, kname(d, kBL2)));
       v4::Dy4 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.Mld = Mld; dy1.C = d.C1;
       dy1.fin = mkbfin(0, 1);
       if (d.D == 0) {
         v4::GatherXyz4 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}};
-        PCOE_TRY(launch_bwd4<0>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], v4::NoEpi4{}, Gr.dW[0], Cin, Cin, 0, M, 0, st, kname(d, kBL1)));
+        PCOE_TRY(launch_bwd4<0>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], v4::NoEpi4{}, dwc(0), L.dwc_ld[0], Cin, 0, M, 0, st, kname(d, kBL1)));
       } else {
         v4::GatherFeat4 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
         if (grad_feats) {
           v4::Scatter4 se{grad_feats, nbr, d.N, d.S, d.D, d.group_all};
-          PCOE_TRY(launch_bwd4<2>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], se, Gr.dW[0], Cin, Cin, d.D, M, d.D, st, kname(d, kBL1)));
+          PCOE_TRY(launch_bwd4<2>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], se, dwc(0), L.dwc_ld[0], Cin, d.D, M, d.D, st, kname(d, kBL1)));
         } else {
-          PCOE_TRY(launch_bwd4<0>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], v4::NoEpi4{}, Gr.dW[0], Cin, Cin, d.D, M, 0, st, kname(d, kBL1)));
+          PCOE_TRY(launch_bwd4<0>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], v4::NoEpi4{}, dwc(0), L.dwc_ld[0], Cin, d.D, M, 0, st, kname(d, kBL1)));
         }
+      }
+      {   // dW_l (+)= sum of the copies
+        v4::DwComb cmb[3];
+        int total = 0;
+        for (int l = 0; l < 3; ++l) {
+          cmb[l] = v4::DwComb{dwc(l), Gr.dW[l], Cs[l], Kin[l], L.dwc_ld[l], l == 0 ? d.D : -1};
+          total += Cs[l] * Kin[l];
+        }
+        LaunchScope ls("dw_combine_kernel", st);
+        v4::dw_combine_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(cmb[0], cmb[1], cmb[2], Gr.accumulate);
+        PCOE_TRY(ls.done());
       }
       return PCOE_OK;
     }

@@ -6,6 +6,13 @@
 
 namespace pcoe {
 
+// Grid-wide reductions (BatchNorm batch sums, weight gradients) are accumulated into kRedCopies
+// interleaved copies - CTA k adds into copy k % kRedCopies - and the consumer adds the copies up.
+// All CTAs of a persistent kernel flush at the same time; atomics that land in the same 32-byte L2
+// sector are serialised, so with one copy the tail of every kernel was ~10 us of 148-deep atomic
+// chains (measured: in-kernel clock trace, profiles/README.md).
+constexpr int kRedCopies = 8;
+
 struct SaLayout {
   int M, G;        // rows = B*S*K, groups = B*S
   size_t esz;      // bytes per stored activation element (4 fp32, 2 bf16)
@@ -15,6 +22,9 @@ struct SaLayout {
   size_t ws_sums[3], ws_sums_bytes, ws_ymax, ws_ymin, ws_amax, ws_amin, ws_y[2], ws_stat[3];
   // workspace, backward
   size_t wb_sums[3], wb_sums_bytes, wb_consts[3], wb_gm, wb_dz[2];
+  // weight-gradient copies of the v4 kernels: [kRedCopies][C_l][dwc_ld[l]] fp32, layer-1 columns in [feats | xyz] order
+  size_t wb_dwc[3], wb_dwc_bytes;
+  int dwc_ld[3];
   // bf16 weight copies (tensor-core path): offsets relative to `saved` (train) or `workspace` (eval)
   size_t wb_off[3], wbt_off[3];
   int wb_rows[3], wb_k[3], wbt_rows[3], wbt_k[3];
@@ -68,7 +78,7 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   L.saved_bytes = d.train ? s : 0;
 
   size_t f = 0;
-  for (int l = 0; l < 3; ++l) L.ws_sums[l] = take(f, sizeof(double) * 2 * C[l]);
+  for (int l = 0; l < 3; ++l) L.ws_sums[l] = take(f, sizeof(double) * 2 * C[l] * kRedCopies);
   L.ws_sums_bytes = f - L.ws_sums[0];
   L.ws_ymax = take(f, sizeof(float) * (size_t)L.G * d.C3);
   L.ws_ymin = take(f, sizeof(float) * (size_t)L.G * d.C3);
@@ -87,8 +97,13 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   }
 
   size_t b = 0;
-  for (int l = 0; l < 3; ++l) L.wb_sums[l] = take(b, sizeof(double) * 2 * C[l]);
+  for (int l = 0; l < 3; ++l) L.wb_sums[l] = take(b, sizeof(double) * 2 * C[l] * kRedCopies);
   L.wb_sums_bytes = b - L.wb_sums[0];
+  for (int l = 0; l < 3; ++l) {
+    L.dwc_ld[l] = l == 0 ? (Kin[0] + 15) / 16 * 16 : Kin[l];       // = the Q operand's channel extent (multiple of 16)
+    L.wb_dwc[l] = L.v2 ? take(b, sizeof(float) * (size_t)kRedCopies * C[l] * L.dwc_ld[l]) : 0;
+  }
+  L.wb_dwc_bytes = L.v2 ? b - L.wb_dwc[0] : 0;
   for (int l = 0; l < 3; ++l) L.wb_consts[l] = take(b, sizeof(float) * 3 * C[l]);
   L.wb_gm = take(b, sizeof(float) * (size_t)L.G * d.C3);
   for (int l = 0; l < 2; ++l) L.wb_dz[l] = take(b, rows_ld * C[l] * L.esz);

@@ -34,6 +34,7 @@
 // (tmem_full/tmem_empty); dW accumulates in TMEM over the CTA's whole tile range.
 #pragma once
 #include "sa_common.cuh"
+#include "sa_layout.h"
 #include "tc_common.cuh"
 
 namespace pcoe {
@@ -119,8 +120,11 @@ struct BnFin {
   float eps, momentum;
   float* scale; float* shift; float* mean; float* invstd;   // saved for backward (written by one block)
   __device__ __forceinline__ void eval(int c, int C, bool write, float& sc, float& sh) const {
-    const double mu = sums[c] / count;
-    double var = sums[C + c] / count - mu * mu;   // biased, as BatchNorm normalises
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kRedCopies; ++k) { t0 += sums[(size_t)k * 2 * C + c]; t1 += sums[(size_t)k * 2 * C + C + c]; }
+    const double mu = t0 / count;
+    double var = t1 / count - mu * mu;   // biased, as BatchNorm normalises
     var = var < 0.0 ? 0.0 : var;
     const float is = (float)(1.0 / sqrt(var + (double)eps));
     sc = gamma[c] * is;
@@ -144,7 +148,9 @@ struct BnBwdFin {
   float* dgamma; float* dbeta; float* dbias;
   int accumulate, write;         // write: this launch owns the parameter-gradient outputs
   __device__ __forceinline__ void eval(int c, int C, bool first_block, float& a, float& p, float& q) const {
-    const double s0 = sums[c], s1 = sums[C + c];
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kRedCopies; ++k) { s0 += sums[(size_t)k * 2 * C + c]; s1 += sums[(size_t)k * 2 * C + C + c]; }
     const double m1 = s0 / count, m2 = s1 / count;
     const double av = scale[c];
     const double pv = -av * (double)invstd[c] * m2;
@@ -588,8 +594,9 @@ struct StoreStats4 {
   }
   __device__ __forceinline__ void finish() {
     if (!sums || c >= C) return;
-    atomicAdd(sums + c, (double)s0);
-    atomicAdd(sums + C + c, (double)s1);
+    double* dst = sums + (size_t)(blockIdx.x % kRedCopies) * 2 * C;
+    atomicAdd(dst + c, (double)s0);
+    atomicAdd(dst + C + c, (double)s1);
   }
 };
 
@@ -621,8 +628,9 @@ struct Group4 {   // last layer, K == 32: the 32 columns of a block are one grou
   }
   __device__ __forceinline__ void finish() {
     if (!sums || c >= C) return;
-    atomicAdd(sums + c, (double)s0);
-    atomicAdd(sums + C + c, (double)s1);
+    double* dst = sums + (size_t)(blockIdx.x % kRedCopies) * 2 * C;
+    atomicAdd(dst + c, (double)s0);
+    atomicAdd(dst + C + c, (double)s1);
   }
 };
 
@@ -672,8 +680,9 @@ struct MaskStats4 {
   }
   __device__ __forceinline__ void finish() {
     if (c >= C) return;
-    atomicAdd(sums + c, (double)s0);
-    atomicAdd(sums + C + c, (double)s1);
+    double* dst = sums + (size_t)(blockIdx.x % kRedCopies) * 2 * C;
+    atomicAdd(dst + c, (double)s0);
+    atomicAdd(dst + C + c, (double)s1);
   }
 };
 
@@ -964,13 +973,14 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
     if (DGRAD == 1 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     epi.finish();
     if (tid == 0) TC4_TRACE(32, 0);
-    // flush dW (complete: the last tmem_full commit covers every earlier MMA): thread = row of dW.
-    // Column blocks are visited in a per-CTA rotated order so that the CTAs, which all finish at about
-    // the same time, do not hammer the same L2 atomic units simultaneously.
+    // flush dW (complete: the last tmem_full commit covers every earlier MMA): thread = row of dW, into this
+    // CTA's copy dWc[blockIdx.x % kRedCopies][C_l][ldo] (ldo = nw, a multiple of 16; padding columns hold the
+    // zeros of the Q tile's unused channels).  pcoe_sa_backward adds the copies up (dw_combine_kernel).
     if (my_tiles > 0) {
       tc::fence_after_sync();
       if (tid == 0) TC4_TRACE(36, 0);
       const int nblk = (nw + 31) / 32;
+      float* base = dW + (size_t)(blockIdx.x % kRedCopies) * cl * ldo;
       for (int mi = 0; mi < mtl; ++mi) {
         const int crow = mi * 128 + eq * 32 + lane;
 #pragma unroll 1
@@ -979,19 +989,10 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
           float v[32];
           tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(mi * nw + cb), v);   // may read past nw: unused columns
           if (crow < cl) {
-            float* dst = dW + (size_t)crow * ldo;
-            if (perm_d < 0 && (ldo & 3) == 0 && cb + 32 <= cq_valid) {
+            float* dst = base + (size_t)crow * ldo + cb;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) red_add_v4(dst + cb + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                int c = cb + e;
-                if (c >= cq_valid) continue;
-                if (perm_d >= 0) c = c < perm_d ? c + 3 : c - perm_d;   // [feats | xyz] -> [xyz | feats]
-                atomicAdd(dst + c, v[e]);
-              }
-            }
+            for (int q = 0; q < 8; ++q)
+              if (cb + 4 * q < nw) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         }
       }
@@ -1089,6 +1090,26 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
   if (tid == 0) TC4_TRACE(2, 0);
   if (tid == 0 || tid == kEpiThreads + kProdThreads) TC4_TRACE_DUMP();
   if (warp == 0) tc::tmem_dealloc<TCOLS>(tmem);
+}
+
+// dW_l (+)= sum over the kRedCopies copies the v4 backward kernels accumulated; layer 1 goes back from the
+// [feats(perm_d) | xyz(3)] column order to the parameter's [xyz | feats]
+struct DwComb { const float* copies; float* dW; int rows, cin, ld, perm_d; };
+__global__ void dw_combine_kernel(DwComb a, DwComb b, DwComb c, int accumulate) {
+  const DwComb* L[3] = {&a, &b, &c};
+  const int n0 = a.rows * a.cin, n1 = b.rows * b.cin, n2 = c.rows * c.cin;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n0 + n1 + n2; e += gridDim.x * blockDim.x) {
+    const int l = e < n0 ? 0 : (e < n0 + n1 ? 1 : 2);
+    const DwComb& w = *L[l];
+    const int ee = e - (l == 0 ? 0 : (l == 1 ? n0 : n0 + n1));
+    const int r = ee / w.cin, k = ee - r * w.cin;
+    int src = k;
+    if (w.perm_d >= 0) src = k < 3 ? w.perm_d + k : k - 3;
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < kRedCopies; ++g) s += w.copies[((size_t)g * w.rows + r) * w.ld + src];
+    w.dW[ee] = accumulate ? w.dW[ee] + s : s;
+  }
 }
 
 // fp32 [C_out][C_in] -> zero-padded bf16 [Rp][Kp]; perm_d >= 0: layer-1 column order [feats(perm_d) | xyz(3)]
