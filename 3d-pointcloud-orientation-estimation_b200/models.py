@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
 from .sa import PointNetSetAbstraction
 
 # 8 horizontal directions, 45 degree steps starting from the original "forward" [0,0,-1]
@@ -141,6 +142,36 @@ def _maybe_transpose_xyz(xyz: torch.Tensor) -> torch.Tensor:
     raise ValueError(f"xyz must be (B,N,3) or (B,3,N), got {xyz.shape}")
 
 
+class _MvMHead(torch.autograd.Function):
+    """(pi, mu_raw, kappa_raw) -> (mu, kappa, weight): pcoe_mvm_head_fwd / _bwd, one launch each instead of the
+    ~20 (+ ~35 in backward) elementwise ops of models/pointnet_pp_mvM.py:91-125."""
+
+    @staticmethod
+    def forward(ctx, pi, mu_raw, kappa_raw, temp, kappa_max):
+        pi, mu_raw, kappa_raw = pi.contiguous().float(), mu_raw.contiguous().float(), kappa_raw.contiguous().float()
+        B, K = pi.shape
+        w, mu, kp = torch.empty_like(pi), torch.empty_like(pi), torch.empty_like(pi)
+        clamp = kappa_max is not None
+        _lib.check(_lib.load().pcoe_mvm_head_fwd(pi.data_ptr(), mu_raw.data_ptr(), kappa_raw.data_ptr(), B, K, float(temp),
+                                                 float(kappa_max) if clamp else 0.0, int(clamp), w.data_ptr(),
+                                                 mu.data_ptr(), kp.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        ctx.save_for_backward(pi, mu_raw, kappa_raw)
+        ctx.cfg = (float(temp), float(kappa_max) if clamp else 0.0, int(clamp))
+        return mu, kp, w
+
+    @staticmethod
+    def backward(ctx, g_mu, g_k, g_w):
+        pi, mu_raw, kappa_raw = ctx.saved_tensors
+        B, K = pi.shape
+        temp, kmax, clamp = ctx.cfg
+        d_pi, d_mu, d_k = torch.empty_like(pi), torch.empty_like(mu_raw), torch.empty_like(kappa_raw)
+        ptr = lambda t: None if t is None else t.contiguous().data_ptr()
+        _lib.check(_lib.load().pcoe_mvm_head_bwd(pi.data_ptr(), mu_raw.data_ptr(), kappa_raw.data_ptr(), B, K, temp, kmax,
+                                                 clamp, ptr(g_w), ptr(g_mu), ptr(g_k), d_pi.data_ptr(), d_mu.data_ptr(),
+                                                 d_k.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return d_pi, d_mu, d_k, None, None
+
+
 class PointNetPPMvM(_Backbone):
     """Mixture-of-von-Mises head.  The three host synchronisations of the reference forward
     (isfinite prints and the ``(norm < 1e-3).any()`` branch, :98,108,118) are removed: the fallback
@@ -169,6 +200,13 @@ class PointNetPPMvM(_Backbone):
 
     def forward(self, xyz: torch.Tensor):
         feat = self._global_feat(_maybe_transpose_xyz(xyz))
+        if self.max_K <= 8:
+            return _MvMHead.apply(self.head_pi(feat), self.head_mu(feat), self.head_kappa(feat), self.temp, self.kappa_max)
+        return self._head_torch(feat)
+
+    def _head_torch(self, feat):
+        """The head transform spelled with torch ops (the reference's formulation; used for max_K > 8 and as the
+        fp32 reference of the fused kernels in the tests)."""
         weight = F.softmax(self.head_pi(feat) / self.temp, dim=-1)
         mu_raw = self.head_mu(feat).view(-1, self.max_K, 2)
         mu_unit = F.normalize(mu_raw, dim=-1, eps=1e-4)

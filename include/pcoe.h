@@ -204,6 +204,19 @@ int pcoe_mvm_match_fwd_bwd(const float* mu, const float* kappa, const float* w, 
                            int gt_stride, const int32_t* K_gt, int B, int Kmax, float* loss,
                            float* dmu, float* dkappa, float* dw, int32_t* perm, void* stream);
 
+/* Mixture-of-von-Mises head transform of PointNetPPMvM.forward, models/pointnet_pp_mvM.py:91-125:
+ *   weight = softmax(pi / temp);  mu = atan2 of the eps-normalised (1e-4) mu_raw pair with the (1,0)
+ *   fallback for vectors shorter than 1e-3 after normalisation;  kappa = softplus(kappa_raw) + 1e-6,
+ *   clamped to kappa_max when clamp_kappa != 0.   pi, kappa_raw, outputs [B,K]; mu_raw [B,K,2]; K <= 8.
+ * The backward call recomputes the forward from the raw head outputs; g_* may be NULL (= zero). */
+int pcoe_mvm_head_fwd(const float* pi, const float* mu_raw, const float* kappa_raw, int B, int K,
+                      float temp, float kappa_max, int clamp_kappa, float* weight, float* mu,
+                      float* kappa, void* stream);
+int pcoe_mvm_head_bwd(const float* pi, const float* mu_raw, const float* kappa_raw, int B, int K,
+                      float temp, float kappa_max, int clamp_kappa, const float* g_weight,
+                      const float* g_mu, const float* g_kappa, float* d_pi, float* d_mu_raw,
+                      float* d_kappa_raw, void* stream);
+
 /* Soft-label cross entropy -(p * log_softmax(logits)).sum(1).  Replaces
  * kl_loss_per_sample_from_logits, train_8dir_KL.py:60-68.  logits,p [B,C] f32, C <= 64. */
 int pcoe_soft_ce_fwd_bwd(const float* logits, const float* p, int B, int C, float* loss,

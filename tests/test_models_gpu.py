@@ -155,3 +155,34 @@ def test_other_heads_and_samplers_run(pcoe, cuda):
     assert pcoe.DIRS_8.shape == (8, 3) and abs(float(pcoe.DIRS_8[1, 0]) - 0.7071) < 1e-6
     th, p = pcoe.mvm_density_on_grid(torch.zeros(2, 4, device=cuda), torch.ones(2, 4, device=cuda), torch.full((2, 4), 0.25, device=cuda))
     assert p.shape == (2, 359) and torch.allclose(p.sum(-1), torch.ones(2, device=cuda), atol=1e-5)
+
+
+def test_mvm_head_fused_matches_torch_formulation(pcoe, cuda):
+    """pcoe_mvm_head_fwd/_bwd vs the reference's elementwise formulation (models/pointnet_pp_mvM.py:91-125) in torch
+    fp32: values and gradients, including the zero-vector fallback, the eps branch of normalize, the softplus
+    threshold and the kappa clamp."""
+    torch.manual_seed(5)
+    model = pcoe.PointNetPPMvM().to(cuda)
+    with torch.no_grad():
+        for m in (model.head_pi, model.head_mu, model.head_kappa):
+            m.weight.normal_(0, 0.3); m.bias.normal_(0, 0.3)
+        model.head_kappa.bias[0] = 30.0           # softplus threshold (> 20) and clamp_max(80) untouched
+        model.head_kappa.bias[1] = 200.0          # clamped: zero gradient
+        model.head_mu.weight[0:2].zero_(); model.head_mu.bias[0:2].zero_()            # mu_raw == 0: fallback, no grad
+        model.head_mu.weight[2:4].mul_(1e-6); model.head_mu.bias[2:4].mul_(1e-6)      # |v| < eps: u = v / eps
+    feat = torch.randn(33, 256, device=cuda)
+    fa, fb = feat.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    got = pcoe.models._MvMHead.apply(model.head_pi(fa), model.head_mu(fa), model.head_kappa(fa), model.temp, model.kappa_max)
+    want = model._head_torch(fb)
+    for g, w, name in zip(got, want, ("mu", "kappa", "weight")):
+        assert torch.allclose(g, w, rtol=1e-5, atol=1e-6), name
+    coef = [torch.randn_like(t) for t in got]
+    sum((c * t).sum() for c, t in zip(coef, got)).backward()
+    ga = [p.grad.clone() for p in model.parameters() if p.grad is not None]
+    model.zero_grad()
+    sum((c * t).sum() for c, t in zip(coef, want)).backward()
+    gb = [p.grad.clone() for p in model.parameters() if p.grad is not None]
+    assert torch.allclose(fa.grad, fb.grad, rtol=1e-4, atol=1e-5)
+    assert len(ga) == len(gb) and len(ga) >= 6
+    for a, b in zip(ga, gb):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-4 * float(b.abs().max()) + 1e-6)
