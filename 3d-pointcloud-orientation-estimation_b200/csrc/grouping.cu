@@ -149,6 +149,162 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int
   }
 }
 
+// K <= 32: candidate pre-selection.  The maximum over the 32 lanes of each lane's smallest distance bounds the
+// K-th smallest distance of the chunk from above (32 elements are <= it), so only the ~10 % of the chunk below
+// that bound - compacted in ascending point index into a per-warp shared-memory list together with the running
+// K-best list - enter the 31-step bitwise search for the exact K-th value; the search then compares <= kCandPerLane
+// registers per lane instead of 33.  Same selection rule and output order as knn_kernel (exact, ties keep the
+// lowest indices); a chunk whose candidate set does not fit falls back to searching all 32 registers.
+constexpr int kCandPerLane = 6;                    // candidate capacity per warp = 32 * kCandPerLane
+__global__ void __launch_bounds__(1024)
+knn_k32_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S, int K,
+               int32_t* __restrict__ out_idx) {
+  extern __shared__ float smem_f[];
+  float* sx = smem_f;
+  float* sy = sx + N;
+  float* sz = sy + N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  constexpr int kCap = 32 * kCandPerLane;
+  uint32_t* cand_d = reinterpret_cast<uint32_t*>(sz + N) + warp * kCap;
+  int32_t* cand_i = reinterpret_cast<int32_t*>(sz + N + nwarps * kCap) + warp * kCap;
+  constexpr uint32_t kInf = 0x7F800000u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  const int b = blockIdx.y;
+  load_cloud_soa(xyz + (size_t)b * N * 3, N, sx, sy, sz);
+  __syncthreads();
+
+  for (int s = blockIdx.x * nwarps + warp; s < S; s += gridDim.x * nwarps) {
+    const float* c = new_xyz + ((size_t)b * S + s) * 3;
+    const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
+    uint32_t ld = kInf;        // running K-best list: one slot per lane, ascending point index
+    int32_t li = -1;
+    int list_n = 0;
+    uint32_t kth = kInf;
+
+    for (int base = 0; base < N; base += 1024) {
+      uint32_t d[32];
+      uint32_t lane_min = kInf;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int i = base + q * 32 + lane;
+        uint32_t v = kInf;
+        if (i < N) v = __float_as_uint(sqdist_rn(sx[i], sy[i], sz[i], cx, cy, cz));
+        if (v >= kth) v = kInf;      // cannot enter: not below the current K-th (ties keep the lower index)
+        d[q] = v;
+        lane_min = min(lane_min, v);
+      }
+      if (__reduce_min_sync(0xFFFFFFFFu, lane_min) == kInf) continue;   // nothing below the current K-th
+      // bound: first chunk - 32 elements are <= max(lane minima); later chunks - everything below kth is a candidate
+      const uint32_t bound = list_n < K ? __reduce_max_sync(0xFFFFFFFFu, lane_min) : kInf - 1;
+
+      // candidates in ascending index: the old list first, then the chunk
+      int cn = 0;
+      {
+        const bool in = ld != kInf;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, in);
+        if (in) { const int pos = __popc(m & lt_mask); cand_d[pos] = ld; cand_i[pos] = li; }
+        cn = __popc(m);
+      }
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const bool in = d[q] <= bound && d[q] != kInf;   // kInf = out of range or already excluded
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, in);
+        const int pos = cn + __popc(m & lt_mask);
+        if (in && pos < kCap) { cand_d[pos] = d[q]; cand_i[pos] = base + q * 32 + lane; }
+        cn += __popc(m);
+      }
+      __syncwarp();
+
+      uint32_t T = 0;
+      int need_eq;
+      if (cn <= kCap) {
+        uint32_t cd[kCandPerLane];
+#pragma unroll
+        for (int j = 0; j < kCandPerLane; ++j) cd[j] = j * 32 + lane < cn ? cand_d[j * 32 + lane] : kInf;
+#pragma unroll 1
+        for (int bit = 30; bit >= 0; --bit) {
+          const uint32_t cand = T | (1u << bit);
+          int cnt = 0;
+#pragma unroll
+          for (int j = 0; j < kCandPerLane; ++j) cnt += cd[j] < cand;
+          if (__reduce_add_sync(0xFFFFFFFFu, cnt) < K) T = cand;
+        }
+        int less = 0;
+#pragma unroll
+        for (int j = 0; j < kCandPerLane; ++j) less += cd[j] < T;
+        need_eq = K - __reduce_add_sync(0xFFFFFFFFu, less);
+        // new list = candidates below T + the lowest-index candidates equal to T
+        int out_n = 0, eq_n = 0;
+        uint32_t nd = kInf;
+        int32_t ni = -1;
+#pragma unroll
+        for (int j = 0; j < kCandPerLane; ++j) {
+          const bool eq = cd[j] == T && T != kInf;
+          const unsigned meq = __ballot_sync(0xFFFFFFFFu, eq);
+          const bool sel = cd[j] < T || (eq && eq_n + __popc(meq & lt_mask) < need_eq);
+          const unsigned msel = __ballot_sync(0xFFFFFFFFu, sel);
+          // lane `pos` of the new list receives this entry: exchange through the (now consumed) candidate slots
+          const int pos = out_n + __popc(msel & lt_mask);
+          const int32_t idx = j * 32 + lane < cn ? cand_i[j * 32 + lane] : -1;
+          __syncwarp();
+          if (sel) { cand_d[pos] = cd[j]; cand_i[pos] = idx; }
+          out_n += __popc(msel);
+          eq_n += __popc(meq);
+        }
+        __syncwarp();
+        nd = lane < out_n ? cand_d[lane] : kInf;
+        ni = lane < out_n ? cand_i[lane] : -1;
+        __syncwarp();
+        ld = nd; li = ni; list_n = out_n;
+      } else {
+        // overflow (a very clustered chunk): search all 32 registers + the list, as knn_kernel does
+#pragma unroll 1
+        for (int bit = 30; bit >= 0; --bit) {
+          const uint32_t cand = T | (1u << bit);
+          int cnt = ld < cand;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) cnt += d[q] < cand;
+          if (__reduce_add_sync(0xFFFFFFFFu, cnt) < K) T = cand;
+        }
+        int less = ld < T;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) less += d[q] < T;
+        need_eq = K - __reduce_add_sync(0xFFFFFFFFu, less);
+        int out_n = 0, eq_n = 0;
+        {
+          const bool eq = ld == T && T != kInf;
+          const unsigned meq = __ballot_sync(0xFFFFFFFFu, eq);
+          const bool sel = ld < T || (eq && __popc(meq & lt_mask) < need_eq);
+          const unsigned msel = __ballot_sync(0xFFFFFFFFu, sel);
+          if (sel) { const int pos = __popc(msel & lt_mask); cand_d[pos] = ld; cand_i[pos] = li; }
+          out_n = __popc(msel);
+          eq_n = __popc(meq);
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const bool eq = d[q] == T && T != kInf;
+          const unsigned meq = __ballot_sync(0xFFFFFFFFu, eq);
+          const bool sel = d[q] < T || (eq && eq_n + __popc(meq & lt_mask) < need_eq);
+          const unsigned msel = __ballot_sync(0xFFFFFFFFu, sel);
+          if (sel) { const int pos = out_n + __popc(msel & lt_mask); cand_d[pos] = d[q]; cand_i[pos] = base + q * 32 + lane; }
+          out_n += __popc(msel);
+          eq_n += __popc(meq);
+        }
+        __syncwarp();
+        ld = lane < out_n ? cand_d[lane] : kInf;
+        li = lane < out_n ? cand_i[lane] : -1;
+        list_n = out_n;
+        __syncwarp();
+      }
+      kth = list_n >= K ? T : kInf;
+    }
+    int32_t* o = out_idx + ((size_t)b * S + s) * K;
+    if (lane < K) o[lane] = li;
+  }
+}
+
 // Ball query: ascending-index scan, the first `nsample` hits, padded with the first hit.
 __global__ void __launch_bounds__(kGroupWarps * 32)
 ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S,
@@ -212,7 +368,16 @@ extern "C" int pcoe_knn_f32(const float* xyz, const float* new_xyz, int B, int N
     knn_kernel<KR_><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, K, out_idx); \
     return ls.done();                                                                                       \
   }
-  if (K <= 32) PCOE_KNN(1) else if (K <= 64) PCOE_KNN(2) else PCOE_KNN(4)
+  if (K <= 32) {   // candidate pre-selection kernel
+    smem = (size_t)N * 3 * sizeof(float) + (size_t)warps * 32 * kCandPerLane * 8;
+    if (smem > 200 * 1024) return fail(PCOE_ERR_UNSUPPORTED, "knn: N=%d does not fit shared memory", N);
+    if (smem > 48 * 1024)
+      PCOE_CUDA(cudaFuncSetAttribute(knn_k32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LaunchScope ls("knn_kernel", (cudaStream_t)stream);
+    knn_k32_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, K, out_idx);
+    return ls.done();
+  }
+  if (K <= 64) PCOE_KNN(2) else PCOE_KNN(4)
 #undef PCOE_KNN
 }
 

@@ -224,6 +224,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     kind, cls, B, N = CONFIGS[args.config]
     pcoe.set_default_precision(args.precision)
+    if args.trunk_tf32:                                  # the 1024-512-256 trunk + heads stay torch.nn (cuBLAS)
+        torch.backends.cuda.matmul.allow_tf32 = True
     peaks = load_peaks()
 
     torch.manual_seed(1000)
@@ -432,6 +434,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")
     ap.add_argument("--torch-optimizer", action="store_true",
                     help="torch.optim.Adam(fused) + clip_grad_norm_ instead of pcoe.optim.FusedAdam")
+    ap.add_argument("--trunk-tf32", action="store_true", help="TF32 tensor-core cuBLAS kernels for the torch.nn trunk")
     ap.add_argument("--timed-only", action="store_true",
                     help="warm-up + timed region only (for ncu captures): no e2e / per-kernel / CPU legs")
     args = ap.parse_args()

@@ -95,6 +95,24 @@ def test_knn_matches_oracle_sets(pcoe, cuda, N, S, K):
     assert (got[..., 1:] > got[..., :-1]).all()
 
 
+def test_knn_ties_duplicates_and_clustered_clouds(pcoe, cuda):
+    """Exact tie rule (lowest index among equal distances) and the candidate-overflow fallback of the K<=32
+    kernel: clouds made of a few distinct points repeated many times, so that hundreds of distances are equal."""
+    g = torch.Generator().manual_seed(9)
+    for N, K, distinct in [(1024, 32, 5), (2048, 32, 3), (300, 16, 40), (1024, 32, 600)]:
+        B, S = 3, 16
+        base = torch.randn(B, distinct, 3, generator=g)
+        pick = torch.randint(0, distinct, (B, N), generator=g)
+        xyz = torch.gather(base, 1, pick.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+        new_xyz = xyz[:, :S].contiguous()
+        got = pcoe.query_ball_point(new_xyz.to(cuda), xyz.to(cuda), K).cpu().numpy()
+        x, c = xyz.numpy(), new_xyz.numpy()
+        d = (x[:, None, :, :] - c[:, :, None, :]).astype(np.float32)
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]          # the kernel's fp32 arithmetic
+        order = np.lexsort((np.broadcast_to(np.arange(N), d2.shape), d2), axis=-1)[..., :K]   # by (distance, index)
+        assert np.array_equal(got, np.sort(order, -1)), (N, K, distinct)
+
+
 def test_gather_points_and_index_points_3d(pcoe, cuda):
     pts = torch.randn(3, 50, 7)
     idx2 = torch.randint(0, 50, (3, 9))
