@@ -362,7 +362,9 @@ def run_ours(args):
                            frac=ach / peaks[bound], tflops=flops / t_s / 1e12, gbs=nbytes / t_s / 1e9,
                            tensor_frac=flops / t_s / 1e12 / peaks["tensor"])
             kernels[name] = ent
-        top = next((n for n in kernels if "achieved" in kernels[n]), None)
+        # dominant kernel = the longest single launch among the kernels with a roofline
+        cands = [n for n in kernels if "achieved" in kernels[n]]
+        top = max(cands, key=lambda n: kernels[n]["ms_per_step"] / kernels[n]["launches_per_step"]) if cands else None
         if top:
             k = kernels[top]
             traffic = load_traffic().get(top) if (args.config == "c2" and args.precision == "bf16") else None
