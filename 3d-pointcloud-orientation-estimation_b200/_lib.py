@@ -60,7 +60,7 @@ SIGNATURES = {
     "pcoe_mvm_head_fwd": (_I, [_P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P]),
     "pcoe_mvm_head_bwd": (_I, [_P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P]),
     "pcoe_adam_workspace_bytes": (_SZ, []),
-    "pcoe_adam_step": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
+    "pcoe_adam_step": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

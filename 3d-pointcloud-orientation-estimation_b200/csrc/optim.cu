@@ -61,7 +61,7 @@ grad_sumsq_kernel(const float* __restrict__ g, size_t n, AdamWs* __restrict__ ws
 }
 
 struct AdamArgs {
-  float lr, beta1, beta2, eps, weight_decay, max_norm;
+  float lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale;
   int zero_grad;
 };
 
@@ -80,9 +80,9 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(kOptThreads)
 adam_update_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
                    AdamArgs a, const float* __restrict__ norm, const long long* __restrict__ step) {
-  const float total = *norm;
-  float coef = 1.f;
-  if (a.max_norm > 0.f) coef = fminf(a.max_norm / (total + 1e-6f), 1.f);   // clip_grad_norm_
+  const float total = *norm * a.grad_scale;                                  // norm of the scaled gradient
+  float coef = a.grad_scale;
+  if (a.max_norm > 0.f) coef *= fminf(a.max_norm / (total + 1e-6f), 1.f);    // clip_grad_norm_
   const double t = (double)*step;
   const float bc1 = (float)(1.0 - pow((double)a.beta1, t)), bc2 = (float)(1.0 - pow((double)a.beta2, t));
   const float step_size = a.lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
@@ -97,7 +97,7 @@ adam_update_kernel(float* __restrict__ p, float* __restrict__ g, float* __restri
     gg.w = adam_one(pp.w, gg.w, mm.w, vv.w, a, coef, step_size, inv_sqrt_bc2);
     p4[i] = pp; m4[i] = mm; v4[i] = vv;
     if (a.zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    else if (a.max_norm > 0.f) g4[i] = gg;     // the clipped gradient, as clip_grad_norm_ leaves it
+    else if (a.max_norm > 0.f || a.grad_scale != 1.f) g4[i] = gg;     // the scaled / clipped gradient, as clip_grad_norm_ leaves it
   }
   if (blockIdx.x == 0)
     for (size_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
@@ -114,7 +114,7 @@ extern "C" size_t pcoe_adam_workspace_bytes(void) { return align_up(sizeof(AdamW
 
 extern "C" int pcoe_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                               float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
-                              int zero_grad, int64_t* step_dev, float* grad_norm_dev, void* workspace, void* stream) {
+                              float grad_scale, int zero_grad, int64_t* step_dev, float* grad_norm_dev, void* workspace, void* stream) {
   if (n == 0) return PCOE_OK;
   if (!param || !grad || !exp_avg || !exp_avg_sq || !step_dev || !grad_norm_dev || !workspace)
     return fail(PCOE_ERR_NULL, "adam_step: NULL pointer");
@@ -129,7 +129,7 @@ extern "C" int pcoe_adam_step(float* param, float* grad, float* exp_avg, float* 
                                                          (long long*)step_dev);
     PCOE_TRY(ls.done());
   }
-  AdamArgs a{lr, beta1, beta2, eps, weight_decay, max_grad_norm, zero_grad};
+  AdamArgs a{lr, beta1, beta2, eps, weight_decay, max_grad_norm, grad_scale, zero_grad};
   LaunchScope ls("adam_update_kernel", st);
   const size_t n4 = n >> 2;
   int blocks = (int)((n4 + kOptThreads - 1) / kOptThreads);

@@ -34,8 +34,11 @@ class FusedAdam:
         """`model`: an nn.Module, a pcoe.dp.DataParallel engine or a pcoe.dp.FlatGradBuffer.
         `max_grad_norm`: fold ``clip_grad_norm_(params, max_grad_norm)`` into the step.
         `zero_grad_in_step`: clear the gradients while they are consumed (then skip ``zero_grad()``)."""
+        self.grad_scale = 1.0
         if isinstance(model, DataParallel):
             grads = model.grads
+            model.defer_scale = True               # the 1/world factor of the gradient mean is applied in the step kernel
+            self.grad_scale = 1.0 / model.world
         elif isinstance(model, FlatGradBuffer):
             grads = model
         else:
@@ -80,7 +83,8 @@ class FusedAdam:
         _lib.check(_lib.load().pcoe_adam_step(
             self.flat_p.data_ptr(), self.grads.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
             self.flat_p.numel(), d["lr"], d["betas"][0], d["betas"][1], d["eps"], d["weight_decay"],
-            float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0, int(self.zero_grad_in_step),
+            float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0, self.grad_scale,
+            int(self.zero_grad_in_step),
             self.step_dev.data_ptr(), self.grad_norm.data_ptr(), self._ws.data_ptr(),
             torch.cuda.current_stream().cuda_stream))
 

@@ -111,6 +111,7 @@ class _SAFunction(torch.autograd.Function):
                     bn.num_batches_tracked.add_(1)
         ctx.desc, ctx.P, ctx.train = desc, P, train
         ctx.params = params if module.direct_grad_accumulation else None
+        ctx.after_backward = getattr(module, "_after_backward", None)
         ctx.has_feats = feats is not None
         ctx.param_shapes = [p.shape for p in params]
         ctx.save_for_backward(xyz, new_xyz, nbr, feats, out, saved, *Ws)
@@ -146,6 +147,8 @@ class _SAFunction(torch.autograd.Function):
                                         ops._ptr(gfeats), C.byref(G), ws.data_ptr(), ws.numel(),
                                         torch.cuda.current_stream().cuda_stream))
         if direct:
+            if ctx.after_backward is not None:
+                ctx.after_backward()               # pcoe.dp.DataParallel: start the all-reduce of the finished bucket
             return (None, None, None, gfeats, None) + (None,) * len(grads)
         return (None, None, None, gfeats, None, *grads)
 
@@ -182,6 +185,7 @@ class PointNetSetAbstraction(nn.Module):
         self._rng_counter = None
         # set by pcoe.dp.FlatGradBuffer: backward adds parameter gradients straight into p.grad
         self.direct_grad_accumulation = False
+        self._after_backward = None                # pcoe.dp.DataParallel hook, called at the end of this layer's backward
         self.last_fps_idx = None
         self.last_group_idx = None
 

@@ -230,7 +230,13 @@ def run_ours(args):
 
     torch.manual_seed(1000)
     model = getattr(pcoe, cls)(sampler="randperm_device").to(dev).train()
-    engine = pcoe.dp.DataParallel(model)
+    engine = pcoe.dp.DataParallel(model, overlap=not args.no_overlap)
+    if args.skip_allreduce:                              # diagnostic only: how much of the N>1 step is the exchange
+        engine.allreduce_grads = lambda: None
+        engine._late_off = None
+        for m in model.modules():
+            if hasattr(m, "_after_backward"):
+                m._after_backward = None
     clip = 1.0 if kind == "mvm" else None                # train_multi_peaks_vonMises_KL.py:235
     if args.torch_optimizer:
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=not args.no_graph)
@@ -420,8 +426,15 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        # The NCCL communicator is referenced by the captured CUDA graph; tearing it down through
+        # destroy_process_group() was observed to hang on this stack (torch 2.11 / NCCL 2.28), so the
+        # ranks leave right after the final barrier.
+        os._exit(0)
 
 
 def main():
@@ -437,6 +450,8 @@ def main():
     ap.add_argument("--torch-optimizer", action="store_true",
                     help="torch.optim.Adam(fused) + clip_grad_norm_ instead of pcoe.optim.FusedAdam")
     ap.add_argument("--trunk-tf32", action="store_true", help="TF32 tensor-core cuBLAS kernels for the torch.nn trunk")
+    ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after backward instead of two overlapped buckets")
+    ap.add_argument("--skip-allreduce", action="store_true", help="diagnostic: N>1 without the gradient exchange (INVALID as a result)")
     ap.add_argument("--timed-only", action="store_true",
                     help="warm-up + timed region only (for ncu captures): no e2e / per-kernel / CPU legs")
     args = ap.parse_args()

@@ -229,12 +229,13 @@ int pcoe_soft_ce_fwd_bwd(const float* logits, const float* p, int B, int C, floa
  * train_single_peak_vonMises_KL.py:68,81,90, train_8dir_KL.py:72,93,97.
  *   param, grad, exp_avg, exp_avg_sq   [n] f32, 16-byte aligned flat buffers (all parameters
  *                                      concatenated; the drop-in modules' p.data / p.grad are views)
- *   max_grad_norm  > 0: grad *= min(1, max_grad_norm / (||grad||_2 + 1e-6)) first; <= 0: no clipping
+ *   grad_scale     the gradient is multiplied by this first (1/world_size after a SUM all-reduce; 1 otherwise)
+ *   max_grad_norm  > 0: grad *= min(1, max_grad_norm / (||grad||_2 + 1e-6)) next; <= 0: no clipping
  *   zero_grad      != 0: grad is cleared after use; == 0: grad holds the clipped gradient on return
  *   step_dev       [1] i64 device step counter, incremented by this call (bias correction uses
  *                  the incremented value, as torch does); lives on the device so that a step captured
  *                  in a CUDA graph keeps counting on replay
- *   grad_norm_dev  [1] f32 out: ||grad||_2 before clipping (clip_grad_norm_'s return value)
+ *   grad_norm_dev  [1] f32 out: ||grad||_2 of the UNSCALED buffer (times grad_scale = clip_grad_norm_'s return value)
  *   workspace      pcoe_adam_workspace_bytes() bytes, ZEROED ONCE by the caller before the first call
  *                  (the library leaves it zeroed)
  * Update rule (torch.optim.Adam, amsgrad=False, maximize=False; weight_decay is L2 as in Adam):
@@ -242,7 +243,7 @@ int pcoe_soft_ce_fwd_bwd(const float* logits, const float* p, int B, int C, floa
 size_t pcoe_adam_workspace_bytes(void);
 int pcoe_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
-                   int zero_grad, int64_t* step_dev, float* grad_norm_dev, void* workspace,
+                   float grad_scale, int zero_grad, int64_t* step_dev, float* grad_norm_dev, void* workspace,
                    void* stream);
 
 #ifdef __cplusplus

@@ -123,3 +123,25 @@ def test_direct_grad_accumulation_equals_autograd_path(pcoe, cuda, precision):
     assert torch.allclose(fa, fb, **tol)
     for a, b in zip(ga, gb):
         assert torch.allclose(a, b, **tol), float((a - b).abs().max())
+
+
+def test_fused_adam_grad_scale_is_the_data_parallel_mean(pcoe, cuda):
+    """grad_scale = 1/world (set when the optimizer is built on a pcoe.dp.DataParallel engine): the SUM all-reduced
+    buffer is averaged inside the step kernel, the clip threshold applies to the averaged gradient."""
+    torch.manual_seed(6)
+    ref = _Net().to(cuda)
+    ours = copy.deepcopy(ref)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    opt = pcoe.optim.FusedAdam(ours, lr=1e-3, max_grad_norm=0.5)
+    opt.grad_scale = 0.25                                   # as if 4 ranks had summed their gradients
+    for it in range(3):
+        x = torch.randn(16, 37, device=cuda)
+        opt_ref.zero_grad(); opt.zero_grad()
+        ref(x).square().mean().backward()
+        (4.0 * ours(x).square().mean()).backward()          # "sum over 4 identical ranks"
+        want_norm = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.5)
+        opt_ref.step(); opt.step()
+        assert torch.allclose(opt.grad_norm[0] * 0.25, want_norm, rtol=1e-4)
+        for p, q in zip(ours.parameters(), ref.parameters()):
+            assert torch.allclose(p, q, rtol=1e-4, atol=2e-6)
+            assert torch.allclose(p.grad, q.grad, rtol=1e-3, atol=1e-6)
