@@ -611,13 +611,13 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       const int Mld = L.Mld;
       v4::DyLast4 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
       dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3; dy3.fin = mkbfin(2, 1);
-      v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2;
+      v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2; x2.packed = 1;
       v4::MaskStats4 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
       m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2; m2.Mld = Mld;
       PCOE_TRY(launch_bwd4<1>(dy3, x2, wb(2), L.w4_rp[2], L.w4_kp[2], m2, dwc(2), L.dwc_ld[2], d.C2, -1, M, d.C2, st, kname(d, kBL3)));
       v4::Dy4 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.Mld = Mld; dy2.C = d.C2;
       dy2.fin = mkbfin(1, 1);
-      v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1;
+      v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1; x1.packed = 1;
       v4::MaskStats4 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
       m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1; m1.Mld = Mld;
       PCOE_TRY(launch_bwd4<1>(dy2, x1, wb(1), L.w4_rp[1], L.w4_kp[1], m1, dwc(1), L.dwc_ld[1], d.C1, -1, M, d.C1, st, kname(d, kBL2)));
@@ -656,7 +656,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       const int Mld = L.Mld;
       v4::DyLast4 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
       dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3; dy3.fin = mkbfin(2, 1);   // wgrad owns the parameter-gradient outputs
-      v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2;
+      v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2; x2.packed = 1;
       v4::MaskStats4 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
       m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2; m2.Mld = Mld;
       PCOE_TRY(launch_wgrad5(dy3, x2, Gr.dW[2], d.C2, d.C2, -1, M, d.C2 / 128, st, kname(d, kWG3)));
@@ -664,7 +664,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       PCOE_TRY(launch_dgrad5<false>(dy3, wb(2), L.w4_kp[2], m2, M, d.C2, st, kname(d, kDG3)));
       v4::Dy4 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.Mld = Mld; dy2.C = d.C2;
       dy2.fin = mkbfin(1, 1);
-      v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1;
+      v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1; x1.packed = 1;
       v4::MaskStats4 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
       m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1; m1.Mld = Mld;
       PCOE_TRY(launch_wgrad5(dy2, x1, Gr.dW[1], d.C1, d.C1, -1, M, d.C1 / 128, st, kname(d, kWG2)));

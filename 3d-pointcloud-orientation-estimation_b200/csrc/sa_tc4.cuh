@@ -179,12 +179,27 @@ __device__ __forceinline__ bool first_block() { return (blockIdx.x | blockIdx.y 
 constexpr int kBatch = 4;
 struct NoIdx {};
 
-// channel-major mapping: thread g -> 16-byte chunk (8 points) g&15 of channel rows (g>>4) + j*(G/16)
+// Backward operands (dy = a*dz + p*y + q, and x_prev = relu(scale*y + shift) when it is the wgrad Q operand) are
+// built with packed bf16x2 FMAs: 8 instead of ~36 arithmetic instructions per 8-element chunk - the CUDA-core
+// transform is what bounds the backward kernels.  The per-channel constants are rounded to bf16 and dy takes one
+// extra bf16 rounding (relative 2^-9 each, the size of the operand rounding the MMA needs anyway); the FORWARD
+// activations keep fp32 arithmetic.  Set to false for fp32 transforms everywhere.
+constexpr bool kPackedBwd = true;
+
+// channel-major mapping: thread g -> 16-byte chunk (8 points) g&15 of channel rows c0 + 16 i, i < kBatch, where
+// c0 = (g>>4) + 64 b for batch b (G = kProdThreads = 256 threads cover 64 channel rows per batch).  Consecutive rows
+// of a thread are 16 channels apart, so the swizzle term (c & 15) / (c & 7) is the same for all of them and every
+// address is base + i * constant: HBM tile rows +4096 B, shared-memory operand rows +2048 B, constants +16 floats.
+constexpr int kRowStep = kProdThreads >> 4;            // 16
+constexpr int kGRowBytes = kRowStep * 256;             // 4096
+constexpr uint32_t kSRowBytes = (kRowStep >> 3) * 1024;   // 2048
 #define PCOE_CM_MAP                                                        \
-  const int chunk = g & 15, r0 = g >> 4, rstep = G >> 4;                   \
+  const int chunk = g & 15, c0 = (g >> 4) + b * (kBatch * kRowStep);       \
   const int m = m0 + chunk * 8;                                            \
   const bool ok = m < M;                                                   \
-  (void)r0; (void)rstep; (void)ok;
+  (void)G; (void)ok;
+// byte offset of (channel c0, chunk) inside tile (m0 >> 7) of a tile-blocked activation with C channels
+#define PCOE_TB_OFF(C_) (((size_t)(m0 >> 7) * (C_) + c0) * 256 + ((chunk ^ (c0 & 15)) << 4))
 
 // relu(scale * y + shift) of the previous layer's pre-activations y^T [C][Mld]
 struct BnRelu4 {
@@ -197,6 +212,7 @@ struct BnRelu4 {
   int M, Mld, C;
   const float* cs;
   BnFin fin;     // fin.sums != nullptr: forward of a train-mode layer, statistics finalised here
+  int packed;    // 1: backward Q operand, packed bf16x2 arithmetic (kPackedBwd)
   __host__ __device__ __forceinline__ int rows() const { return C; }
   __host__ __device__ __forceinline__ int kext() const { return C; }
   __host__ __device__ __forceinline__ int nconst() const { return 2 * C; }
@@ -213,30 +229,39 @@ struct BnRelu4 {
   __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
   __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx&, Raw& r) const {
     PCOE_CM_MAP
+    const char* src = reinterpret_cast<const char*>(y) + PCOE_TB_OFF(C);
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) {
-      const int c = r0 + (b * kBatch + i) * rstep;
-      r.a[i] = make_uint4(0, 0, 0, 0);
-      if (ok && c < C) r.a[i] = __ldg(tb_chunk(y, C, m0 >> 7, c, chunk));
-    }
+    for (int i = 0; i < kBatch; ++i)
+      r.a[i] = ok ? __ldg(reinterpret_cast<const uint4*>(src + i * kGRowBytes)) : make_uint4(0, 0, 0, 0);
   }
   // lrows / rshift (v5 chunk streaming): the image has lrows rows and channel c goes to row c + rshift
   __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr, int lrows = 0,
                                         int rshift = 0) const {
     PCOE_CM_MAP
-    const int crows = lrows ? lrows : C;
+    const uint32_t dst = saddr + cm_off(lrows ? lrows : C, c0 + rshift, chunk);
+    const float* k0 = cs + c0;
+    if (kPackedBwd && packed) {
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        const uint32_t sc2 = tc::bf2_bcast(k0[i * kRowStep]), sh2 = tc::bf2_bcast(k0[C + i * kRowStep]);
+        uint4 o;
+        o.x = tc::bf2_fma_relu(r.a[i].x, sc2, sh2); o.y = tc::bf2_fma_relu(r.a[i].y, sc2, sh2);
+        o.z = tc::bf2_fma_relu(r.a[i].z, sc2, sh2); o.w = tc::bf2_fma_relu(r.a[i].w, sc2, sh2);
+        tc::sts128(dst + i * kSRowBytes, o);
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
       // branch-free on purpose: the four chunks of a batch are independent and the compiler interleaves them
       // (C is a multiple of the 64 channels a batch covers; columns of points >= M hold relu(shift): they are
       // never read back - forward / dgrad epilogues skip them and the wgrad dy operand zeroes them)
-      const int c = r0 + (b * kBatch + i) * rstep;
       float v[8];
       unpack8(r.a[i], v);
-      const float sc = cs[c], sh = cs[C + c];
+      const float sc = k0[i * kRowStep], sh = k0[C + i * kRowStep];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = fmaf(v[u], sc, sh);
-      tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16_relu(v));
+      tc::sts128(dst + i * kSRowBytes, tc::pack8_bf16_relu(v));
     }
   }
 };
@@ -270,31 +295,40 @@ struct Dy4 {
   __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
   __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx&, Raw& r) const {
     PCOE_CM_MAP
+    const size_t off = PCOE_TB_OFF(C);
+    const char* sd = reinterpret_cast<const char*>(dz) + off;
+    const char* sy = reinterpret_cast<const char*>(y) + off;
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
-      const int c = r0 + (b * kBatch + i) * rstep;
-      r.d[i] = r.y[i] = make_uint4(0, 0, 0, 0);
-      if (ok && c < C) {
-        r.d[i] = __ldg(tb_chunk(dz, C, m0 >> 7, c, chunk));
-        r.y[i] = __ldg(tb_chunk(y, C, m0 >> 7, c, chunk));
-      }
+      r.d[i] = ok ? __ldg(reinterpret_cast<const uint4*>(sd + i * kGRowBytes)) : make_uint4(0, 0, 0, 0);
+      r.y[i] = ok ? __ldg(reinterpret_cast<const uint4*>(sy + i * kGRowBytes)) : make_uint4(0, 0, 0, 0);
     }
   }
   __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr, int lrows = 0,
                                         int rshift = 0) const {
     PCOE_CM_MAP
-    const int crows = lrows ? lrows : rows();
+    const uint32_t dst = saddr + cm_off(lrows ? lrows : rows(), c0 + rshift, chunk);
+    const float* k0 = cs + c0;
     const float okf = ok ? 1.f : 0.f;
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) {
-      const int c = r0 + (b * kBatch + i) * rstep;   // branch-free: see BnRelu4::store
-      float d[8], yy[8], v[8];
-      unpack8(r.d[i], d);
-      unpack8(r.y[i], yy);
-      const float ca = cs[c] * okf, cp = cs[C + c] * okf, cq = cs[2 * C + c] * okf;   // points >= M contribute 0 to dW
+    for (int i = 0; i < kBatch; ++i) {                 // branch-free: see BnRelu4::store
+      const float ca = k0[i * kRowStep] * okf, cp = k0[C + i * kRowStep] * okf, cq = k0[2 * C + i * kRowStep] * okf;   // points >= M contribute 0 to dW
+      if constexpr (kPackedBwd) {
+        const uint32_t a2 = tc::bf2_bcast(ca), p2 = tc::bf2_bcast(cp), q2 = tc::bf2_bcast(cq);
+        uint4 o;
+        o.x = tc::bf2_fma(a2, r.d[i].x, tc::bf2_fma(p2, r.y[i].x, q2));
+        o.y = tc::bf2_fma(a2, r.d[i].y, tc::bf2_fma(p2, r.y[i].y, q2));
+        o.z = tc::bf2_fma(a2, r.d[i].z, tc::bf2_fma(p2, r.y[i].z, q2));
+        o.w = tc::bf2_fma(a2, r.d[i].w, tc::bf2_fma(p2, r.y[i].w, q2));
+        tc::sts128(dst + i * kSRowBytes, o);
+      } else {
+        float d[8], yy[8], v[8];
+        unpack8(r.d[i], d);
+        unpack8(r.y[i], yy);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = fmaf(ca, d[u], fmaf(cp, yy[u], cq));
-      tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16(v));
+        for (int u = 0; u < 8; ++u) v[u] = fmaf(ca, d[u], fmaf(cp, yy[u], cq));
+        tc::sts128(dst + i * kSRowBytes, tc::pack8_bf16(v));
+      }
     }
   }
 };
@@ -330,35 +364,51 @@ struct DyLast4 {
   __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx&, Raw& r) const {
     PCOE_CM_MAP
     const int grp = min(m, M - 1) >> 5;
+    const char* sy = reinterpret_cast<const char*>(y) + PCOE_TB_OFF(C);
+    const float* sg = gm + (size_t)grp * C + c0;
+    const uint8_t* ss = slot + (size_t)grp * C + c0;
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
-      const int c = r0 + (b * kBatch + i) * rstep;
-      r.y[i] = make_uint4(0, 0, 0, 0); r.gv[i] = 0.f; r.sl[i] = -1;
-      if (ok && c < C) {
-        r.y[i] = __ldg(tb_chunk(y, C, m0 >> 7, c, chunk));
-        r.gv[i] = __ldg(gm + (size_t)grp * C + c);
-        r.sl[i] = (int)__ldg(slot + (size_t)grp * C + c);   // raw: no arithmetic on loaded values in load()
-      }
+      r.y[i] = ok ? __ldg(reinterpret_cast<const uint4*>(sy + i * kGRowBytes)) : make_uint4(0, 0, 0, 0);
+      r.gv[i] = ok ? __ldg(sg + i * kRowStep) : 0.f;
+      r.sl[i] = ok ? (int)__ldg(ss + i * kRowStep) : -1;   // raw: no arithmetic on loaded values in load()
     }
   }
   __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr, int lrows = 0,
                                         int rshift = 0) const {
     PCOE_CM_MAP
-    const int crows = lrows ? lrows : rows();
+    const uint32_t dst = saddr + cm_off(lrows ? lrows : rows(), c0 + rshift, chunk);
+    const float* k0 = cs + c0;
     const float okf = ok ? 1.f : 0.f;
+    const int j0 = m & 31;
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) {
-      const int c = r0 + (b * kBatch + i) * rstep;   // branch-free: see BnRelu4::store
-      float yy[8], v[8];
-      unpack8(r.y[i], yy);
-      const float ca = cs[c] * r.gv[i], cp = cs[C + c] * okf, cq = cs[2 * C + c] * okf;   // gv is 0 for points >= M
-      const int sl = r.sl[i] - (m & 31);     // slot relative to this 8-point chunk (-1 - j0 < 0 never matches)
+    for (int i = 0; i < kBatch; ++i) {                 // branch-free: see BnRelu4::store
+      const float ca = k0[i * kRowStep] * r.gv[i], cp = k0[C + i * kRowStep] * okf, cq = k0[2 * C + i * kRowStep] * okf;   // gv is 0 for points >= M
+      const int sl = r.sl[i] - j0;           // slot relative to this 8-point chunk (-1 - j0 < 0 never matches)
+      if constexpr (kPackedBwd) {
+        const uint32_t p2 = tc::bf2_bcast(cp), q2 = tc::bf2_bcast(cq);
+        uint32_t w[4] = {tc::bf2_fma(p2, r.y[i].x, q2), tc::bf2_fma(p2, r.y[i].y, q2),
+                         tc::bf2_fma(p2, r.y[i].z, q2), tc::bf2_fma(p2, r.y[i].w, q2)};
+        // the max-pool gradient lands on one point of the group: add it in fp32 to that element only
+        const bool hit = (unsigned)sl < 8u;
+        const int wi = sl >> 1;
+        const uint32_t x = wi == 0 ? w[0] : (wi == 1 ? w[1] : (wi == 2 ? w[2] : w[3]));
+        const float f = ((sl & 1) ? __uint_as_float(x & 0xFFFF0000u) : __uint_as_float(x << 16)) + ca;
+        const uint32_t nb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
+        const uint32_t nx = (sl & 1) ? ((x & 0xFFFFu) | (nb << 16)) : ((x & 0xFFFF0000u) | nb);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        v[u] = fmaf(cp, yy[u], cq);
-        if (u == sl) v[u] += ca;             // the max-pool gradient lands on one point of the group
+        for (int k = 0; k < 4; ++k) w[k] = (hit && wi == k) ? nx : w[k];
+        tc::sts128(dst + i * kSRowBytes, make_uint4(w[0], w[1], w[2], w[3]));
+      } else {
+        float yy[8], v[8];
+        unpack8(r.y[i], yy);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          v[u] = fmaf(cp, yy[u], cq);
+          if (u == sl) v[u] += ca;           // the max-pool gradient lands on one point of the group
+        }
+        tc::sts128(dst + i * kSRowBytes, tc::pack8_bf16(v));
       }
-      tc::sts128(saddr + cm_off(crows, c + rshift, chunk), tc::pack8_bf16(v));
     }
   }
 };

@@ -152,6 +152,23 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
   return r;
 }
 
+// packed bf16x2 arithmetic (one instruction per two elements; every result is rounded to bf16 once)
+__device__ __forceinline__ uint32_t bf2_bcast(float x) {   // (bf16(x), bf16(x))
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(d) : "f"(x));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_fma_relu(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 // pack 8 floats to 8 bf16 with ReLU folded into the conversion (cvt.rn.relu: max(x, 0) then round;
 // identical to rounding relu(x) because rounding preserves sign and zero)
 __device__ __forceinline__ uint32_t pack2_bf16_relu(float lo, float hi) {
