@@ -387,18 +387,8 @@ struct DyLast4 {
       const int sl = r.sl[i] - j0;           // slot relative to this 8-point chunk (-1 - j0 < 0 never matches)
       if constexpr (kPackedBwd) {
         const uint32_t p2 = tc::bf2_bcast(cp), q2 = tc::bf2_bcast(cq);
-        uint32_t w[4] = {tc::bf2_fma(p2, r.y[i].x, q2), tc::bf2_fma(p2, r.y[i].y, q2),
-                         tc::bf2_fma(p2, r.y[i].z, q2), tc::bf2_fma(p2, r.y[i].w, q2)};
-        // the max-pool gradient lands on one point of the group: add it in fp32 to that element only
-        const bool hit = (unsigned)sl < 8u;
-        const int wi = sl >> 1;
-        const uint32_t x = wi == 0 ? w[0] : (wi == 1 ? w[1] : (wi == 2 ? w[2] : w[3]));
-        const float f = ((sl & 1) ? __uint_as_float(x & 0xFFFF0000u) : __uint_as_float(x << 16)) + ca;
-        const uint32_t nb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
-        const uint32_t nx = (sl & 1) ? ((x & 0xFFFFu) | (nb << 16)) : ((x & 0xFFFF0000u) | nb);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) w[k] = (hit && wi == k) ? nx : w[k];
-        tc::sts128(dst + i * kSRowBytes, make_uint4(w[0], w[1], w[2], w[3]));
+        tc::sts128(dst + i * kSRowBytes, make_uint4(tc::bf2_fma(p2, r.y[i].x, q2), tc::bf2_fma(p2, r.y[i].y, q2),
+                                                    tc::bf2_fma(p2, r.y[i].z, q2), tc::bf2_fma(p2, r.y[i].w, q2)));
       } else {
         float yy[8], v[8];
         unpack8(r.y[i], yy);
@@ -408,6 +398,22 @@ struct DyLast4 {
           if (u == sl) v[u] += ca;           // the max-pool gradient lands on one point of the group
         }
         tc::sts128(dst + i * kSRowBytes, tc::pack8_bf16(v));
+      }
+    }
+    if constexpr (kPackedBwd) {
+      // the max-pool gradient lands on ONE point of each 32-point group: a separate pass (the loop above stays
+      // branch-free) adds it in fp32 to that bf16 element of the chunk this thread has just written
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        const int sl = r.sl[i] - j0;
+        if ((unsigned)sl < 8u) {
+          const uint32_t addr = dst + i * kSRowBytes + (uint32_t)sl * 2u;
+          uint16_t h;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr) : "memory");
+          const float f = __uint_as_float((uint32_t)h << 16) + k0[i * kRowStep] * r.gv[i];
+          h = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
+        }
       }
     }
   }
