@@ -474,7 +474,7 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
       e2.C = d.C3; e2.Mld = Mld;
       PCOE_TRY(launch_fwd4(p2, wb(2), L.w4_rp[2], L.w4_kp[2], e2, M, st, kname(d, kF3)));
-      fin_out = mkfin(2);
+      if (train) PCOE_TRY(finalize(2));   // tiny per-channel kernel: a per-block table in sa_out_finalize cost more than this launch
       done = true;
     }
     if (use5) {   // wide layers: (tile x 128-channel block) grid, K streamed in 64-channel chunks
@@ -493,7 +493,7 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
       e2.C = d.C3; e2.Mld = Mld;
       PCOE_TRY(launch_fwd5(p2, wb(2), L.w4_kp[2], e2, M, d.C3, d.C2 / 64, st, kname(d, kF3)));
-      fin_out = mkfin(2);
+      if (train) PCOE_TRY(finalize(2));   // tiny per-channel kernel: a per-block table in sa_out_finalize cost more than this launch
       done = true;
     }
   }

@@ -431,6 +431,22 @@ struct GatherBase {
     i = min(max(i, 0), N - 1);
     return ((row >> 5) / S) * N + i;
   }
+  // The same for row m0 + r of the 128-row tile starting at m0, with ONE integer division per call site instead of
+  // one per row: (cloud0, rem0) = divmod(first group of the tile, S) is passed in, the <= 3 further groups of the
+  // tile only step the cloud index.
+  __device__ __forceinline__ void tile_origin(int m0, int& cloud0, int& rem0) const {
+    const int g0 = m0 >> 5;
+    cloud0 = group_all ? 0 : g0 / S;
+    rem0 = g0 - cloud0 * S;
+  }
+  __device__ __forceinline__ int point_of_tile(int m0, int r, int cloud0, int rem0) const {   // m0 + r < M
+    if (group_all) return m0 + r;
+    int i = __ldg(nbr + m0 + r);
+    i = min(max(i, 0), N - 1);
+    int q = rem0 + (r >> 5), cl = cloud0;
+    while (q >= S) { q -= S; ++cl; }
+    return cl * N + i;
+  }
   // raw loads only (the subtraction happens in the producers' store(): no arithmetic on loaded values
   // in load(), otherwise the load stage of the software pipeline stalls on its own loads)
   __device__ __forceinline__ void load_xyz_raw(int row, int pt, float (&x)[3], float (&c)[3]) const {
@@ -457,7 +473,7 @@ struct GatherXyz4 {
   __device__ __forceinline__ void init(float*, int, int) {}
   __device__ __forceinline__ void load_idx(int g, int, int m0, int, Idx& ix) const {
     ix.pt = -1;
-    if (g < kPts && m0 + g < gb.M) ix.pt = gb.point_of(m0 + g);
+    if (g < kPts && m0 + g < gb.M) ix.pt = gb.point_of(m0 + g);   // one row per thread: one division
   }
   __device__ __forceinline__ void load(int g, int, int m0, int, const Idx& ix, Raw& r) const {
     r.v[0] = r.v[1] = r.v[2] = r.c[0] = r.c[1] = r.c[2] = 0.f;
@@ -489,19 +505,21 @@ struct GatherFeat4 {
   __host__ __device__ __forceinline__ int kext() const { return (D + 3 + 15) / 16 * 16; }
   __host__ __device__ __forceinline__ int rows() const { return kPts; }
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
-  __device__ __forceinline__ int nbatches(int G) const { return (kPts / (G / (D >> 3)) + kBatch - 1) / kBatch; }
+  __device__ __forceinline__ int nbatches(int G) const { return (kPts / (G / (D >> 3)) + kBatch - 1) / kBatch; }   // once per kernel
   __device__ __forceinline__ void init(float*, int, int) {}
   __device__ __forceinline__ void load_idx(int g, int G, int m0, int b, Idx& ix) const {
-    const int fu = D >> 3, rstep = G / fu, r0 = g / fu;
+    const int fu = D >> 3, fs = 31 - __clz(fu), rstep = G >> fs, r0 = g >> fs;   // D in {32, 64, 128}: fu is a power of two
+    int cloud0, rem0;
+    gb.tile_origin(m0, cloud0, rem0);
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
       const int r = r0 + (b * kBatch + i) * rstep;
-      ix.pt[i] = (r < kPts && m0 + r < gb.M) ? gb.point_of(m0 + r) : -1;
+      ix.pt[i] = (r < kPts && m0 + r < gb.M) ? gb.point_of_tile(m0, r, cloud0, rem0) : -1;
     }
-    ix.ptx = (b == 0 && g < kPts && m0 + g < gb.M) ? gb.point_of(m0 + g) : -1;
+    ix.ptx = (b == 0 && g < kPts && m0 + g < gb.M) ? gb.point_of_tile(m0, g, cloud0, rem0) : -1;
   }
   __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx& ix, Raw& r) const {
-    const int fu = D >> 3, j = g % fu;
+    const int fu = D >> 3, j = g & (fu - 1);
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
       r.a[i] = r.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -515,7 +533,7 @@ struct GatherFeat4 {
     if (b == 0 && ix.ptx >= 0) gb.load_xyz_raw(m0 + g, ix.ptx, r.xv, r.xc);
   }
   __device__ __forceinline__ void store(int g, int G, int, int b, const Raw& r, uint32_t saddr) const {
-    const int fu = D >> 3, rstep = G / fu, r0 = g / fu, j = g % fu;
+    const int fu = D >> 3, fs = 31 - __clz(fu), rstep = G >> fs, r0 = g >> fs, j = g & (fu - 1);
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
       const int row = r0 + (b * kBatch + i) * rstep;
