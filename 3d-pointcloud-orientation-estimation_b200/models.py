@@ -22,6 +22,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .sa import PointNetSetAbstraction
+from .trunk import MvMTrunkHead
 
 # 8 horizontal directions, 45 degree steps starting from the original "forward" [0,0,-1]
 # (values of models/pointnet_pp_8dir.py:46-55; imported by train_8dir_KL.py:14)
@@ -191,6 +192,9 @@ class PointNetPPMvM(_Backbone):
         nn.init.zeros_(self.head_mu.weight)
         nn.init.zeros_(self.head_mu.bias)
         nn.init.constant_(self.head_kappa.bias, 0.0)
+        self.fused_trunk = True                    # False: fc1..heads as torch.nn modules (the reference's formulation)
+        self.direct_grad_accumulation = False      # set by pcoe.dp.FlatGradBuffer
+        self._drop_counter = None
 
     def _global_feat(self, xyz_bn3: torch.Tensor) -> torch.Tensor:
         x = self._sa_features(xyz_bn3)
@@ -199,10 +203,39 @@ class PointNetPPMvM(_Backbone):
         return x
 
     def forward(self, xyz: torch.Tensor):
-        feat = self._global_feat(_maybe_transpose_xyz(xyz))
+        xyz = _maybe_transpose_xyz(xyz)
+        if self.fused_trunk and self.max_K <= 8 and xyz.is_cuda:
+            return self._fused(self._sa_features(xyz))
+        feat = self._global_feat(xyz)
         if self.max_K <= 8:
             return _MvMHead.apply(self.head_pi(feat), self.head_mu(feat), self.head_kappa(feat), self.temp, self.kappa_max)
         return self._head_torch(feat)
+
+    def _fused(self, x: torch.Tensor):
+        """fc1 .. heads .. (mu, kappa, weight) as one autograd node on libpcoe's trunk kernels (pcoe.trunk)."""
+        train = self.training
+        seed, counter = 0, None
+        if train and self.drop.p > 0:
+            if torch.cuda.is_current_stream_capturing():
+                # CUDA-graph capture: the call counter lives on the device so that every replay draws fresh masks
+                if self._drop_counter is None or self._drop_counter.device != x.device:
+                    raise RuntimeError("pcoe: run one eager training step before capturing (allocates the dropout counter)")
+                self._drop_counter.add_(1)
+                seed, counter = torch.initial_seed(), self._drop_counter
+            else:
+                # eager: consume torch's CUDA generator like nn.Dropout would (reproducible under torch.manual_seed)
+                if self._drop_counter is None or self._drop_counter.device != x.device:
+                    self._drop_counter = torch.zeros(1, dtype=torch.int64, device=x.device)
+                gen = torch.cuda.default_generators[x.device.index]
+                off = gen.get_offset()
+                gen.set_offset(off + 4)
+                seed = gen.initial_seed() + 0x9E3779B97F4A7C15 * (off // 4 + 1)
+        cfg = (train, float(self.drop.p), seed & 0x7FFFFFFFFFFFFFFF, counter,
+               self.ln1.eps, self.ln2.eps, self.temp, self.kappa_max, self.direct_grad_accumulation)
+        return MvMTrunkHead.apply(x, cfg, self.fc1.weight, self.fc1.bias, self.ln1.weight, self.ln1.bias,
+                                  self.fc2.weight, self.fc2.bias, self.ln2.weight, self.ln2.bias,
+                                  self.head_pi.weight, self.head_pi.bias, self.head_mu.weight, self.head_mu.bias,
+                                  self.head_kappa.weight, self.head_kappa.bias)
 
     def _head_torch(self, feat):
         """The head transform spelled with torch ops (the reference's formulation; used for max_K > 8 and as the

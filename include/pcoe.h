@@ -217,6 +217,42 @@ int pcoe_mvm_head_bwd(const float* pi, const float* mu_raw, const float* kappa_r
                       const float* g_mu, const float* g_kappa, float* d_pi, float* d_mu_raw,
                       float* d_kappa_raw, void* stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Trunk building blocks (fp32): the 1024 -> 512 -> 256 -> heads MLP of PointNetPPMvM on B rows,
+ * models/pointnet_pp_mvM.py:56-66 (fc1, ln1, fc2, ln2, dropout, head_pi / head_mu / head_kappa) and
+ * :79-84,91-105 (their use), plus autograd.  W[i] is nn.Linear.weight [N_i, K] row-major.
+ * A call with nseg > 1 applies several linears to the same input (the three heads); its output (and the
+ * matching dy) is stored segment-major: [B x N_0][B x N_1]... so that every head's block is dense.
+ * ------------------------------------------------------------------------------------------ */
+/* y = x W^T + bias.  x [B,K], bias[i] may be NULL.  Deterministic.  max_parts <= 1 (or nparts NULL): y [B, sum N]
+ * is the final result.  max_parts > 1: the contraction may be split over *nparts <= max_parts slices for
+ * parallelism; y then holds *nparts partial results [part][B, sum N] WITHOUT the bias, to be summed (in order)
+ * by the consumer - pcoe_ln_relu_dropout_fwd does. */
+int pcoe_linear_fwd(const float* x, int B, int K, int nseg, const float* const* W,
+                    const float* const* bias, const int* N, float* y, int max_parts, int* nparts,
+                    void* stream);
+/* dx [B,K] = dy W (overwritten). */
+int pcoe_linear_bwd_dx(const float* dy, int B, int K, int nseg, const float* const* W, const int* N,
+                       float* dx, void* stream);
+/* dW[i] [N_i,K] = dy_i^T x, dbias[i] [N_i] = column sums of dy_i (dbias[i] may be NULL);
+ * accumulate != 0 adds to the arrays instead of overwriting them. */
+int pcoe_linear_bwd_dw(const float* dy, const float* x, int B, int K, int nseg, const int* N,
+                       float* const* dW, float* const* dbias, int accumulate, void* stream);
+/* out = dropout_p(relu(LayerNorm_eps(x) * gamma + beta)), one row per cloud.  train == 0: no dropout.
+ * The keep mask is drawn from Philox4x32-10 keyed by (seed, *counter_dev, row, column) - a different stream
+ * than torch's dropout, same distribution; mean / rstd [B] and mask [B,N] u8 are saved for backward
+ * (each may be NULL in inference).  x may be nparts partial sums [part][B,N] (+ xbias [N]): their ordered
+ * sum is written to h [B,N] and used as the input (h may be NULL when nparts <= 1 and xbias is NULL). */
+int pcoe_ln_relu_dropout_fwd(const float* x, int nparts, const float* xbias, float* h,
+                             const float* gamma, const float* beta, int B, int N,
+                             float eps, float p, int train, uint64_t seed,
+                             const uint64_t* counter_dev, float* out, float* mean, float* rstd,
+                             uint8_t* mask, void* stream);
+/* dx overwritten; dgamma / dbeta are ADDED to (zero them first for a plain gradient). */
+int pcoe_ln_relu_dropout_bwd(const float* dout, const float* x, const float* out, const float* gamma,
+                             const float* mean, const float* rstd, const uint8_t* mask, int B, int N,
+                             float p, int train, float* dx, float* dgamma, float* dbeta, void* stream);
+
 /* Soft-label cross entropy -(p * log_softmax(logits)).sum(1).  Replaces
  * kl_loss_per_sample_from_logits, train_8dir_KL.py:60-68.  logits,p [B,C] f32, C <= 64. */
 int pcoe_soft_ce_fwd_bwd(const float* logits, const float* p, int B, int C, float* loss,

@@ -186,3 +186,83 @@ def test_mvm_head_fused_matches_torch_formulation(pcoe, cuda):
     assert len(ga) == len(gb) and len(ga) >= 6
     for a, b in zip(ga, gb):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-4 * float(b.abs().max()) + 1e-6)
+
+
+@pytest.mark.parametrize("direct", [False, True])
+def test_mvm_fused_trunk_matches_torch_modules(pcoe, cuda, direct):
+    """pcoe.trunk.MvMTrunkHead (fc1..heads as libpcoe fp32 kernels, one autograd node) vs the same parameters run
+    through torch.nn modules (the reference's formulation, fp32): outputs and every parameter / input gradient.
+    `direct`: gradients added straight into a FlatGradBuffer (two backward passes = accumulation)."""
+    torch.manual_seed(7)
+    model = pcoe.PointNetPPMvM().to(cuda).train()
+    model.drop.p = 0.0                                    # dropout draws from different random streams
+    with torch.no_grad():
+        for m in (model.head_pi, model.head_mu, model.head_kappa):
+            m.weight.normal_(0, 0.2); m.bias.normal_(0, 0.2)
+        model.ln1.weight.uniform_(0.5, 1.5); model.ln1.bias.uniform_(-0.3, 0.3)
+    for B in (64, 5):
+        if direct:
+            buf = pcoe.dp.FlatGradBuffer(model)
+            assert model.direct_grad_accumulation
+        x = torch.randn(B, 1024, device=cuda)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        coef = [torch.randn(B, 4, device=cuda) for _ in range(3)]
+        reps = 2 if direct else 1
+        model.zero_grad(set_to_none=not direct)
+        if direct:
+            buf.zero_()
+        for _ in range(reps):
+            got = model._fused(xa)
+            sum((c * t).sum() for c, t in zip(coef, got)).backward()
+        ga = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None and not n.startswith("sa")}
+        for p in model.parameters():
+            p.grad = None
+        model.direct_grad_accumulation = False
+        for _ in range(reps):
+            feat = model.drop(torch.relu(model.ln2(model.fc2(model.drop(torch.relu(model.ln1(model.fc1(xb))))))))
+            want = model._head_torch(feat)
+            sum((c * t).sum() for c, t in zip(coef, want)).backward()
+        for g, w, name in zip(got, want, ("mu", "kappa", "weight")):
+            assert torch.allclose(g, w, rtol=1e-4, atol=1e-5), (B, name)
+        assert torch.allclose(xa.grad, xb.grad, rtol=1e-3, atol=1e-5 * float(xb.grad.abs().max()) + 1e-7), B
+        for n, p in model.named_parameters():
+            if n.startswith("sa"):
+                continue
+            assert n in ga, n
+            assert torch.allclose(ga[n], p.grad, rtol=1e-3, atol=1e-4 * float(p.grad.abs().max()) + 1e-7), (B, n)
+        for p in model.parameters():
+            p.grad = None
+
+
+def test_mvm_fused_trunk_dropout_statistics_and_eval(pcoe, cuda):
+    """Dropout inside the fused trunk: keep rate 1-p, survivors scaled by 1/(1-p), a fresh mask per call, gradients
+    only through kept units; eval mode is deterministic and equals the torch modules."""
+    torch.manual_seed(8)
+    lib = pcoe._lib.load()
+    B, N, p = 64, 512, 0.4
+    x = torch.randn(B, N, device=cuda)
+    g, b = torch.ones(N, device=cuda), torch.full((N,), 3.0, device=cuda)       # shift up: ReLU keeps everything
+    out, mask = torch.empty_like(x), torch.empty(B, N, dtype=torch.uint8, device=cuda)
+    mean, rstd = torch.empty(B, device=cuda), torch.empty(B, device=cuda)
+    cnt = torch.zeros(1, dtype=torch.int64, device=cuda)
+    masks = []
+    for it in range(2):
+        cnt.add_(1)
+        pcoe._lib.check(lib.pcoe_ln_relu_dropout_fwd(x.data_ptr(), 1, None, None, g.data_ptr(), b.data_ptr(), B, N, 1e-5, p, 1, 1234, cnt.data_ptr(),
+                                                     out.data_ptr(), mean.data_ptr(), rstd.data_ptr(), mask.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream))
+        masks.append(mask.clone())
+        keep = mask.float().mean().item()
+        assert abs(keep - (1 - p)) < 0.02
+        ref = torch.relu(torch.nn.functional.layer_norm(x, (N,), g, b, 1e-5)) / (1 - p)
+        assert torch.allclose(out[mask.bool()], ref[mask.bool()], rtol=1e-5, atol=1e-5)
+        assert float(out[~mask.bool()].abs().max()) == 0.0
+    assert (masks[0] != masks[1]).float().mean().item() > 0.3                    # a new mask per call (device counter)
+    model = pcoe.PointNetPPMvM().to(cuda).eval()
+    xin = torch.randn(16, 1024, device=cuda)
+    with torch.no_grad():
+        a = model._fused(xin)
+        bb = model._head_torch(model._global_feat.__func__(type("S", (), {"_sa_features": staticmethod(lambda z: z), "drop": model.drop,
+                               "ln1": model.ln1, "ln2": model.ln2, "fc1": model.fc1, "fc2": model.fc2})(), xin))
+    for u, v in zip(a, bb):
+        assert torch.allclose(u, v, rtol=1e-4, atol=1e-5)
