@@ -266,8 +266,13 @@ ln_relu_drop_fwd_kernel(const float* __restrict__ x, int nparts, const float* __
   if (row >= B) return;
   if (h) {
     for (int n = lane; n < N; n += 32) {
+      float v[8];
+#pragma unroll
+      for (int z = 0; z < 8; ++z) v[z] = z < nparts ? __ldg(x + ((size_t)z * B + row) * N + n) : 0.f;   // independent loads
       float t = xbias ? xbias[n] : 0.f;
-      for (int z = 0; z < nparts; ++z) t += x[((size_t)z * B + row) * N + n];
+#pragma unroll
+      for (int z = 0; z < 8; ++z) t += v[z];                 // fixed order: deterministic
+      for (int z = 8; z < nparts; ++z) t += x[((size_t)z * B + row) * N + n];
       h[(size_t)row * N + n] = t;
     }
     __syncwarp();
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(256)
 ln_relu_drop_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ out,
                         const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                         const uint8_t* __restrict__ mask, int B, int N, float p, int train, float* __restrict__ dx,
-                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxbias) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= B) return;
   const float keep_scale = (train && p > 0.f) ? 1.f / (1.f - p) : 1.f;
@@ -327,7 +332,9 @@ ln_relu_drop_bwd_kernel(const float* __restrict__ dout, const float* __restrict_
     const bool on = out[o + n] > 0.f;
     const float dz = on ? dout[o + n] * keep_scale * (mask ? (float)mask[o + n] : 1.f) : 0.f;
     const float xh = (x[o + n] - mu) * rs;
-    dx[o + n] = rs * (dz * gamma[n] - m1 - xh * m2);
+    const float g = rs * (dz * gamma[n] - m1 - xh * m2);
+    dx[o + n] = g;
+    if (dxbias) atomicAdd(dxbias + n, g);     // bias gradient of the linear layer that produced x (column sums of dx)
   }
 }
 
@@ -441,13 +448,13 @@ extern "C" int pcoe_ln_relu_dropout_fwd(const float* x, int nparts, const float*
 
 extern "C" int pcoe_ln_relu_dropout_bwd(const float* dout, const float* x, const float* out, const float* gamma,
                                         const float* mean, const float* rstd, const uint8_t* mask, int B, int N, float p,
-                                        int train, float* dx, float* dgamma, float* dbeta, void* stream) {
+                                        int train, float* dx, float* dgamma, float* dbeta, float* dxbias, void* stream) {
   if (B <= 0 || N <= 0) return fail(PCOE_ERR_BAD_SHAPE, "ln_relu_dropout_bwd: B=%d N=%d", B, N);
   if (!dout || !x || !out || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta)
     return fail(PCOE_ERR_NULL, "ln_relu_dropout_bwd: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope ls("ln_relu_drop_bwd_kernel", st);
   ln_relu_drop_bwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(dout, x, out, gamma, mean, rstd, mask, B, N, p, train, dx, dgamma,
-                                                          dbeta);
+                                                          dbeta, dxbias);
   return ls.done();
 }

@@ -122,16 +122,17 @@ class MvMTrunkHead(torch.autograd.Function):
                                          draw.data_ptr(), draw[B * K:].data_ptr(), draw[3 * B * K:].data_ptr(), st))
         da2, dh2 = torch.empty_like(a2), torch.empty_like(h2)
         _linear_bwd(lib, st, draw, a2, [piw, muw, kw], [dpw, dmw, dkw], [dpb, dmb, dkb], da2, acc)
+        # the LayerNorm backward also adds the column sums of its dx into the bias gradient of the linear below it
         _lib.check(lib.pcoe_ln_relu_dropout_bwd(da2.data_ptr(), h2.data_ptr(), a2.data_ptr(), g2.data_ptr(), st2[0].data_ptr(),
                                                 st2[1].data_ptr(), m2.data_ptr(), B, h2.size(1), p, int(train),
-                                                dh2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), st))
+                                                dh2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), d2b.data_ptr(), st))
         da1, dh1 = torch.empty_like(a1), torch.empty_like(h1)
-        _linear_bwd(lib, st, dh2, a1, [fc2w], [d2w], [d2b], da1, acc)
+        _linear_bwd(lib, st, dh2, a1, [fc2w], [d2w], [None], da1, acc)
         _lib.check(lib.pcoe_ln_relu_dropout_bwd(da1.data_ptr(), h1.data_ptr(), a1.data_ptr(), g1.data_ptr(), st1[0].data_ptr(),
                                                 st1[1].data_ptr(), m1.data_ptr(), B, h1.size(1), p, int(train),
-                                                dh1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), st))
+                                                dh1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), d1b.data_ptr(), st))
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        _linear_bwd(lib, st, dh1, x, [fc1w], [d1w], [d1b], dx, acc)
+        _linear_bwd(lib, st, dh1, x, [fc1w], [d1w], [None], dx, acc)
         if direct:
             return (dx, None) + (None,) * 14
         return (dx, None, *grads)

@@ -248,10 +248,12 @@ int pcoe_ln_relu_dropout_fwd(const float* x, int nparts, const float* xbias, flo
                              float eps, float p, int train, uint64_t seed,
                              const uint64_t* counter_dev, float* out, float* mean, float* rstd,
                              uint8_t* mask, void* stream);
-/* dx overwritten; dgamma / dbeta are ADDED to (zero them first for a plain gradient). */
+/* dx overwritten; dgamma / dbeta are ADDED to (zero them first for a plain gradient); dxbias [N], optional, also
+ * ADDED to: the column sums of dx = the bias gradient of the linear layer that produced x. */
 int pcoe_ln_relu_dropout_bwd(const float* dout, const float* x, const float* out, const float* gamma,
                              const float* mean, const float* rstd, const uint8_t* mask, int B, int N,
-                             float p, int train, float* dx, float* dgamma, float* dbeta, void* stream);
+                             float p, int train, float* dx, float* dgamma, float* dbeta, float* dxbias,
+                             void* stream);
 
 /* Soft-label cross entropy -(p * log_softmax(logits)).sum(1).  Replaces
  * kl_loss_per_sample_from_logits, train_8dir_KL.py:60-68.  logits,p [B,C] f32, C <= 64. */
