@@ -227,21 +227,22 @@ linear_gemm_fast_kernel(const float* __restrict__ PA, size_t sam, size_t sak, co
   }
 }
 
-// bias gradient: db_n (+)= sum_b dY(b, n); one thread per output
+// bias gradient: db_n (+)= sum_b dY(b, n); one warp per output
 __global__ void linear_bias_grad_kernel(const float* __restrict__ dY, int B, LinSeg s, int accumulate) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (n >= s.Ntot) return;
   int sg, ln;
   seg_of(s, n, sg, ln);
   if (!s.db[sg]) return;
   float t = 0.f;
-  for (int b = 0; b < B; ++b) t += __ldg(dY + seg_major(s, B, b, n, sg, ln));
-  s.db[sg][ln] = accumulate ? s.db[sg][ln] + t : t;
+  for (int b = lane; b < B; b += 32) t += __ldg(dY + seg_major(s, B, b, n, sg, ln));
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, m);
+  if (lane == 0) s.db[sg][ln] = accumulate ? s.db[sg][ln] + t : t;
 }
 
-// ---- LayerNorm + ReLU + dropout, one warp per row ----
+// Philox4x32-10 (Salmon et al. 2011), counter (i, j, offset), key = seed; one 32-bit output
 __device__ __forceinline__ uint32_t philox_u32(uint32_t i, uint32_t j, uint64_t seed, uint64_t offset) {
-  // Philox4x32-10 (Salmon et al. 2011), counter (i, j, offset), key = seed; one 32-bit output
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
   uint4 ctr = make_uint4(i, j, (uint32_t)offset, (uint32_t)(offset >> 32));
   uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -254,47 +255,70 @@ __device__ __forceinline__ uint32_t philox_u32(uint32_t i, uint32_t j, uint64_t 
   return ctr.x;
 }
 
+// block-wide sum of one value per thread (blockDim.x = 256), result broadcast to every thread
+__device__ __forceinline__ float block_sum256(float v, float* red) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, m);
+  __syncthreads();                       // protects `red` against the previous use
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
 // x may arrive as `nparts` partial sums [part][B x N] of a split linear_fwd plus a bias vector: they are added in a
 // fixed order (deterministic) and the sum is written to h (the pre-LayerNorm activation saved for backward).
+// One CTA (256 threads) per row, up to kLnPer elements per thread in registers (N <= 256 * kLnPer).
+constexpr int kLnPer = 4;
 __global__ void __launch_bounds__(256)
 ln_relu_drop_fwd_kernel(const float* __restrict__ x, int nparts, const float* __restrict__ xbias, float* __restrict__ h,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
                         int B, int N, float eps, float p, int train, uint64_t seed, const uint64_t* __restrict__ counter,
                         float* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd,
                         uint8_t* __restrict__ mask) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= B) return;
-  if (h) {
-    for (int n = lane; n < N; n += 32) {
-      float v[8];
-#pragma unroll
-      for (int z = 0; z < 8; ++z) v[z] = z < nparts ? __ldg(x + ((size_t)z * B + row) * N + n) : 0.f;   // independent loads
-      float t = xbias ? xbias[n] : 0.f;
-#pragma unroll
-      for (int z = 0; z < 8; ++z) t += v[z];                 // fixed order: deterministic
-      for (int z = 8; z < nparts; ++z) t += x[((size_t)z * B + row) * N + n];
-      h[(size_t)row * N + n] = t;
-    }
-    __syncwarp();
-  }
-  const float* xr = (h ? h : x) + (size_t)row * N;
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  float v[kLnPer];
   float s = 0.f;
-  for (int n = lane; n < N; n += 32) s += xr[n];
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, m);
-  const float mu = s / N;
-  float v = 0.f;
-  for (int n = lane; n < N; n += 32) { const float d = xr[n] - mu; v = fmaf(d, d, v); }
+  for (int i = 0; i < kLnPer; ++i) {
+    const int n = threadIdx.x + i * 256;
+    v[i] = 0.f;
+    if (n < N) {
+      if (h) {
+        float pv[8];
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, m);
-  const float rs = rsqrtf(v / N + eps);
-  if (lane == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
+        for (int z = 0; z < 8; ++z) pv[z] = z < nparts ? __ldg(x + ((size_t)z * B + row) * N + n) : 0.f;   // independent loads
+        float t = xbias ? xbias[n] : 0.f;
+#pragma unroll
+        for (int z = 0; z < 8; ++z) t += pv[z];                  // fixed order: deterministic
+        for (int z = 8; z < nparts; ++z) t += x[((size_t)z * B + row) * N + n];
+        h[(size_t)row * N + n] = t;
+        v[i] = t;
+      } else {
+        v[i] = x[(size_t)row * N + n];
+      }
+      s += v[i];
+    }
+  }
+  const float mu = block_sum256(s, red) / N;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnPer; ++i)
+    if (threadIdx.x + i * 256 < N) { const float d = v[i] - mu; q = fmaf(d, d, q); }
+  const float rs = rsqrtf(block_sum256(q, red) / N + eps);
+  if (threadIdx.x == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
   const bool drop = train && p > 0.f;
   const float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
   const uint32_t thr = drop ? (uint32_t)fminf(p * 4294967296.f, 4294967295.f) : 0u;
   const uint64_t off = counter ? *counter : 0ull;
-  for (int n = lane; n < N; n += 32) {
-    float y = fmaxf(fmaf((xr[n] - mu) * rs, gamma[n], beta[n]), 0.f);
+#pragma unroll
+  for (int i = 0; i < kLnPer; ++i) {
+    const int n = threadIdx.x + i * 256;
+    if (n >= N) continue;
+    const float y = fmaxf(fmaf((v[i] - mu) * rs, gamma[n], beta[n]), 0.f);
     bool keep = true;
     if (drop) keep = philox_u32((uint32_t)n, (uint32_t)row, seed, off) >= thr;
     if (mask) mask[(size_t)row * N + n] = keep ? 1 : 0;
@@ -307,32 +331,36 @@ ln_relu_drop_bwd_kernel(const float* __restrict__ dout, const float* __restrict_
                         const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                         const uint8_t* __restrict__ mask, int B, int N, float p, int train, float* __restrict__ dx,
                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxbias) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= B) return;
+  __shared__ float red[8];
+  const int row = blockIdx.x;
   const float keep_scale = (train && p > 0.f) ? 1.f / (1.f - p) : 1.f;
   const float mu = mean[row], rs = rstd[row];
   const size_t o = (size_t)row * N;
-  // dz = gradient at the LayerNorm output (after dropout and ReLU masks); s1 = sum dz*gamma, s2 = sum dz*gamma*xhat
+  // dz = gradient at the LayerNorm output (after the dropout and ReLU masks); s1 = sum dz*gamma, s2 = sum dz*gamma*xhat
+  float dzg[kLnPer], xh[kLnPer];
   float s1 = 0.f, s2 = 0.f;
-  for (int n = lane; n < N; n += 32) {
+#pragma unroll
+  for (int i = 0; i < kLnPer; ++i) {
+    const int n = threadIdx.x + i * 256;
+    dzg[i] = xh[i] = 0.f;
+    if (n >= N) continue;
     const bool on = out[o + n] > 0.f;                     // ReLU and dropout both zero the output
     const float dz = on ? dout[o + n] * keep_scale * (mask ? (float)mask[o + n] : 1.f) : 0.f;
-    const float xh = (x[o + n] - mu) * rs;
-    s1 = fmaf(dz, gamma[n], s1);
-    s2 = fmaf(dz * gamma[n], xh, s2);
+    xh[i] = (x[o + n] - mu) * rs;
+    dzg[i] = dz * gamma[n];
+    s1 += dzg[i];
+    s2 = fmaf(dzg[i], xh[i], s2);
     if (dz != 0.f) {
-      atomicAdd(dgamma + n, dz * xh);
+      atomicAdd(dgamma + n, dz * xh[i]);
       atomicAdd(dbeta + n, dz);
     }
   }
+  const float m1 = block_sum256(s1, red) / N, m2 = block_sum256(s2, red) / N;
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) { s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, m); s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, m); }
-  const float m1 = s1 / N, m2 = s2 / N;
-  for (int n = lane; n < N; n += 32) {
-    const bool on = out[o + n] > 0.f;
-    const float dz = on ? dout[o + n] * keep_scale * (mask ? (float)mask[o + n] : 1.f) : 0.f;
-    const float xh = (x[o + n] - mu) * rs;
-    const float g = rs * (dz * gamma[n] - m1 - xh * m2);
+  for (int i = 0; i < kLnPer; ++i) {
+    const int n = threadIdx.x + i * 256;
+    if (n >= N) continue;
+    const float g = rs * (dzg[i] - m1 - xh[i] * m2);
     dx[o + n] = g;
     if (dxbias) atomicAdd(dxbias + n, g);     // bias gradient of the linear layer that produced x (column sums of dx)
   }
@@ -426,7 +454,7 @@ extern "C" int pcoe_linear_bwd_dw(const float* dy, const float* x, int B, int K,
   for (int i = 0; i < nseg; ++i) any = any || (dbias && dbias[i]);
   if (any) {
     LaunchScope ls("linear_bias_grad_kernel", st);
-    linear_bias_grad_kernel<<<ceil_div(s.Ntot, 128), 128, 0, st>>>(dy, B, s, accumulate);
+    linear_bias_grad_kernel<<<ceil_div(s.Ntot * 32, 128), 128, 0, st>>>(dy, B, s, accumulate);
     PCOE_TRY(ls.done());
   }
   return PCOE_OK;
@@ -441,7 +469,8 @@ extern "C" int pcoe_ln_relu_dropout_fwd(const float* x, int nparts, const float*
   if ((nparts > 1 || xbias) && !h) return fail(PCOE_ERR_NULL, "ln_relu_dropout_fwd: partial sums / bias need the h output");
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope ls("ln_relu_drop_fwd_kernel", st);
-  ln_relu_drop_fwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(x, nparts < 1 ? 1 : nparts, xbias, h, gamma, beta, B, N, eps, p, train,
+  if (N > 256 * kLnPer) return fail(PCOE_ERR_UNSUPPORTED, "ln_relu_dropout: N=%d > %d", N, 256 * kLnPer);
+  ln_relu_drop_fwd_kernel<<<B, 256, 0, st>>>(x, nparts < 1 ? 1 : nparts, xbias, h, gamma, beta, B, N, eps, p, train,
                                                           seed, counter_dev, out, mean, rstd, mask);
   return ls.done();
 }
@@ -454,7 +483,8 @@ extern "C" int pcoe_ln_relu_dropout_bwd(const float* dout, const float* x, const
     return fail(PCOE_ERR_NULL, "ln_relu_dropout_bwd: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope ls("ln_relu_drop_bwd_kernel", st);
-  ln_relu_drop_bwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(dout, x, out, gamma, mean, rstd, mask, B, N, p, train, dx, dgamma,
+  if (N > 256 * kLnPer) return fail(PCOE_ERR_UNSUPPORTED, "ln_relu_dropout: N=%d > %d", N, 256 * kLnPer);
+  ln_relu_drop_bwd_kernel<<<B, 256, 0, st>>>(dout, x, out, gamma, mean, rstd, mask, B, N, p, train, dx, dgamma,
                                                           dbeta, dxbias);
   return ls.done();
 }
