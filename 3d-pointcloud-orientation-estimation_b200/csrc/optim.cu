@@ -29,34 +29,43 @@ grad_sumsq_kernel(const float* __restrict__ g, size_t n, AdamWs* __restrict__ ws
                   long long* __restrict__ step) {
   __shared__ double red[kOptThreads / 32];
   __shared__ bool last;
+  // fp32 partial sums of 4 squares per load, promoted to fp64 per load: ~22 bits of headroom over 1.5 M elements
   double acc = 0.0;
   const size_t n4 = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
   const float4* g4 = reinterpret_cast<const float4*>(g);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = __ldg(g4 + i);
-    acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+    acc += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
   }
   if (blockIdx.x == 0)
     for (size_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) acc += (double)g[i] * (double)g[i];
+  auto block_sum = [&](double v) -> double {      // fixed tree: deterministic
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, m);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, m);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < kOptThreads / 32; ++w) t += red[w];
+    return t;
+  };
+  const double bs = block_sum(acc);
   if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < kOptThreads / 32; ++w) s += red[w];
-    ws->partial[blockIdx.x] = s;
+    ws->partial[blockIdx.x] = bs;
     __threadfence();
     last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {                                     // the last block adds the per-block partials, all threads helping
     __threadfence();
-    double s = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += ((volatile double*)ws->partial)[b];
-    *norm_out = (float)sqrt(s);
-    *step += 1;
-    ws->ticket = 0;   // self-cleaning: ready for the next launch / graph replay
+    double v = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) v += ((volatile double*)ws->partial)[b];
+    const double tot = block_sum(v);
+    if (threadIdx.x == 0) {
+      *norm_out = (float)sqrt(tot);
+      *step += 1;
+      ws->ticket = 0;   // self-cleaning: ready for the next launch / graph replay
+    }
   }
 }
 
