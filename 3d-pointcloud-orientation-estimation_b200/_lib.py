@@ -105,8 +105,13 @@ def launch_count() -> int:
     return int(load().pcoe_launch_count())
 
 
+profiling = False      # per-kernel CUDA-event timing on: side-stream overlap is switched off (kernels timed alone)
+
+
 def profile(enable: bool) -> None:
+    global profiling
     check(load().pcoe_profile_enable(int(enable)))
+    profiling = bool(enable)
 
 
 def profile_report() -> dict:

@@ -42,6 +42,27 @@ void profile_end(int slot, cudaStream_t st) {
   if (slot >= 0 && slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].b, st);
 }
 
+bool profile_enabled() { return g_prof_on; }
+
+AuxStream* aux_stream() {
+  static AuxStream tab[64];
+  static bool made[64];
+  static std::mutex mu;
+  if (g_prof_on) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!made[dev]) {
+    AuxStream a{};
+    if (cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    for (auto& e : a.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    tab[dev] = a;
+    made[dev] = true;
+  }
+  return &tab[dev];
+}
+
 }  // namespace pcoe
 
 extern "C" int pcoe_profile_enable(int on) {

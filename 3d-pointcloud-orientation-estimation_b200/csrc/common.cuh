@@ -25,6 +25,14 @@ inline int fail(pcoe_status st, const char* fmt, ...) {
 // Optional per-kernel CUDA-event timing (pcoe_profile_enable): begin/end events around a launch.
 int profile_begin(const char* what, cudaStream_t st);   // returns slot or -1 when disabled
 void profile_end(int slot, cudaStream_t st);
+bool profile_enabled();
+
+// One auxiliary stream + a few events per device (created on first use, never destroyed): lets one C-ABI call run
+// independent kernels side by side (fork: record on the caller's stream, wait on aux; join: the reverse).  Works
+// under stream capture (the dependencies become graph edges).  Disabled while per-kernel profiling is on, so that
+// the CUDA-event timings stay those of kernels running alone.
+struct AuxStream { cudaStream_t s; cudaEvent_t ev[4]; };
+AuxStream* aux_stream();   // nullptr when unavailable / profiling
 
 // Checks the launch that was just enqueued (cudaPeekAtLastError is legal during graph capture).
 inline int check_launch(const char* what) {

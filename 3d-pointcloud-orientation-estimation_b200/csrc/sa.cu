@@ -84,10 +84,20 @@ __global__ void sa_out_finalize_kernel(const float* __restrict__ ymax, const flo
 __global__ void bwd_last_reduce_kernel(const float* __restrict__ grad_out, const float* __restrict__ out,
                                        const float* __restrict__ ysel, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, int G, int C, int groups_per_block,
-                                       float* __restrict__ gm, double* __restrict__ sums) {
+                                       float* __restrict__ gm, double* __restrict__ sums,
+                                       const float* __restrict__ prescale /* DySparse4 path: gm is stored times a = scale */,
+                                       const float* __restrict__ gram, float* __restrict__ gsum, int gram_n) {
+  // DySparse4 path: the forward's kRedCopies Gram copies are summed here (independent work, no extra launch)
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < gram_n; e += gridDim.x * blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRedCopies; ++k) s += __ldg(gram + (size_t)k * gram_n + e);
+    gsum[e] = s;
+  }
   const int g0 = blockIdx.x * groups_per_block, g1 = min(G, g0 + groups_per_block);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float is = invstd[c], nmi = -mean[c] * is;
+    const float ps = prescale ? prescale[c] : 1.f;
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
     int g = g0;
     for (; g + 4 <= g1; g += 4) {          // four independent groups per iteration: the twelve loads overlap
@@ -100,7 +110,7 @@ __global__ void bwd_last_reduce_kernel(const float* __restrict__ grad_out, const
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float v = o[k] > 0.f ? go[k] : 0.f;
-        gm[(size_t)(g + k) * C + c] = v;
+        gm[(size_t)(g + k) * C + c] = v * ps;
         s0[k] += v;
         s1[k] = fmaf(v, fmaf(ys[k], is, nmi), s1[k]);
       }
@@ -108,7 +118,7 @@ __global__ void bwd_last_reduce_kernel(const float* __restrict__ grad_out, const
     for (; g < g1; ++g) {
       const size_t e = (size_t)g * C + c;
       const float v = out[e] > 0.f ? grad_out[e] : 0.f;
-      gm[e] = v;
+      gm[e] = v * ps;
       s0[0] += v;
       s1[0] = fmaf(v, fmaf(ysel[e], is, nmi), s1[0]);
     }
@@ -256,9 +266,9 @@ static size_t tile_bytes4(const Prod& p) {   // host mirror of v4::prod_tile_byt
 }
 constexpr size_t kSmemBudget4 = 224 * 1024;
 
-template <class Prod, class Epi>
+template <int GRAM = 0, class Prod, class Epi>
 static int launch_fwd4(const Prod& prod, const __nv_bfloat16* Wb, int Rp, int Kp, const Epi& epi, int M,
-                       cudaStream_t st, const char* what) {
+                       cudaStream_t st, const char* what, float* gram = nullptr) {
   const size_t wbytes = (size_t)Rp * Kp * 2, tb = tile_bytes4(prod);
   const size_t cbytes = sizeof(float) * (size_t)(prod.nconst() + epi.nconst()) + 512, sb = (size_t)epi.stage_bytes();
   const size_t avail = kSmemBudget4 - 1024 - wbytes - cbytes;
@@ -269,22 +279,24 @@ static int launch_fwd4(const Prod& prod, const __nv_bfloat16* Wb, int Rp, int Kp
   stages = stages > v4::kMaxStages ? v4::kMaxStages : stages;
   const size_t smem = 1024 + wbytes + (size_t)stages * tb + cbytes + nstg * sb;
   const int tiles = ceil_div(M, v4::kPts), grid = tiles < kNumSMs ? tiles : kNumSMs;   // one persistent CTA per SM
-  auto k = v4::tc4_fwd_kernel<Prod, Epi, 512>;
+  // TMEM: double-buffered accumulators when they fit beside the Gram accumulator (kext + 16 columns)
+  const int nbuf = (2 * Rp + (GRAM ? prod.kext() + 16 : 0) <= 512) ? 2 : 1;
+  auto k = v4::tc4_fwd_kernel<Prod, Epi, 512, GRAM>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget4)); attr = true; }
   LaunchScope ls(what, st);
-  k<<<grid, v4::kThreads, smem, st>>>(prod, Wb, Rp, Kp, epi, M, stages, nstg);
+  k<<<grid, v4::kThreads, smem, st>>>(prod, Wb, Rp, Kp, epi, M, stages, nstg, gram, nbuf);
   return ls.done();
 }
 
-template <int DGRAD, class PProd, class QProd, class Epi>
+template <int DGRAD, int GM = 0, class PProd, class QProd, class Epi>
 static int launch_bwd4(const PProd& pp, const QProd& qp, const __nv_bfloat16* Wb, int Rp, int Kp, const Epi& epi,
                        float* dW, int ldo, int cq_valid, int perm_d, int M, int cprev, cudaStream_t st,
-                       const char* what) {
-  const size_t wbytes = DGRAD ? (size_t)Rp * Kp * 2 : 0;
+                       const char* what, const __nv_bfloat16* Gmb = nullptr, int gk = 0) {
+  const size_t wbytes = (DGRAD ? (size_t)Rp * Kp * 2 : 0) + (GM ? (size_t)2 * 128 * gk : 0);
   const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + qp.nconst() + epi.nconst()) + 512, sb = (size_t)epi.stage_bytes();
   const size_t pq = tile_bytes4(pp) + tile_bytes4(qp), base = 1024 + wbytes + pq + cbytes;
-  if (base + sb > kSmemBudget4) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  if (base + sb > kSmemMax4) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
   // A second P/Q operand stage (producers working on tile i+1 while the MMAs of tile i run) is implemented
   // (npq = 2) but measured SLOWER on B200 (sa1_bwd_l2 55.7 -> 63.5 us, sa2_bwd_l2 39 -> 47.5 us): the larger
   // carve-out shrinks L1 and the producers running further ahead evict the y tile that the MaskStats epilogue
@@ -293,11 +305,11 @@ static int launch_bwd4(const PProd& pp, const QProd& qp, const __nv_bfloat16* Wb
   const int nstg = (sb && base + (npq - 1) * pq + 2 * sb <= kSmemBudget4) ? 2 : 1;
   const size_t smem = base + (npq - 1) * pq + nstg * sb;
   const int tiles = ceil_div(M, v4::kPts), grid = tiles < kNumSMs ? tiles : kNumSMs;
-  auto k = v4::tc4_bwd_kernel<PProd, QProd, Epi, DGRAD, 512>;
+  auto k = v4::tc4_bwd_kernel<PProd, QProd, Epi, DGRAD, 512, GM>;
   static bool attr = false;
-  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget4)); attr = true; }
+  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax4)); attr = true; }
   LaunchScope ls(what, st);
-  k<<<grid, v4::kThreads, smem, st>>>(pp, qp, Wb, Rp, Kp, epi, dW, ldo, cq_valid, perm_d, M, cprev, nstg, npq);
+  k<<<grid, v4::kThreads, smem, st>>>(pp, qp, Wb, Rp, Kp, epi, dW, ldo, cq_valid, perm_d, M, cprev, nstg, npq, Gmb, gk);
   return ls.done();
 }
 
@@ -403,6 +415,7 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
   // pre-BN activations: saved for backward in train mode, transient otherwise
   TY* y[3];
   for (int l = 0; l < 3; ++l) y[l] = train ? (TY*)(sv + L.sv_y[l]) : (l < 2 ? (TY*)(ws + L.ws_y[l]) : nullptr);
+  if (L.l3s) y[2] = nullptr;
   float *scale[3], *shift[3], *mean[3], *invstd[3];
   for (int l = 0; l < 3; ++l) {
     char* base = train ? sv + L.sv_stat[l] : ws + L.ws_stat[l];
@@ -473,7 +486,15 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       p2.fin = mkfin(1);
       v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
       e2.C = d.C3; e2.Mld = Mld;
-      PCOE_TRY(launch_fwd4(p2, wb(2), L.w4_rp[2], L.w4_kp[2], e2, M, st, kname(d, kF3)));
+      if (L.l3s) {   // y3 is not stored: the kernel accumulates the Gram matrix of its input instead (DySparse4 backward)
+        float* gram = (float*)(sv + L.sv_gram);
+        PCOE_CUDA(cudaMemsetAsync(gram, 0, L.sv_gram_bytes, st));
+        e2.y = nullptr;
+        p2.prows = L.gram_ld > 128 ? L.gram_ld : 128;
+        PCOE_TRY(launch_fwd4<1>(p2, wb(2), L.w4_rp[2], L.w4_kp[2], e2, M, st, kname(d, kF3), gram));
+      } else {
+        PCOE_TRY(launch_fwd4(p2, wb(2), L.w4_rp[2], L.w4_kp[2], e2, M, st, kname(d, kF3)));
+      }
       if (train) PCOE_TRY(finalize(2));   // tiny per-channel kernel: a per-block table in sa_out_finalize cost more than this launch
       done = true;
     }
@@ -579,12 +600,17 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   };
   bool fused_consts = false;
   if constexpr (TC) fused_consts = L.v2 || L.v5;
+  bool l3s = false;
+  if constexpr (TC) l3s = L.l3s;
 
   {
     const int gpb = ceil_div(G, kNumSMs * 2);   // few blocks: every block ends with 2*C3 same-address fp64 atomics
     LaunchScope ls("bwd_last_reduce_kernel", st);
     bwd_last_reduce_kernel<<<ceil_div(G, gpb), d.C3 >= 256 ? 256 : (d.C3 >= 128 ? 128 : 64), 0, st>>>(grad_out, out, ysel, mean[2], invstd[2], G, d.C3,
-                                                            gpb, gm, bs[2]);
+                                                            gpb, gm, bs[2], l3s ? scale[2] : nullptr,
+                                                            l3s ? (const float*)(sv + L.sv_gram) : nullptr,
+                                                            l3s ? (float*)(ws + L.wb_gsum) : nullptr,
+                                                            l3s ? d.C2 * L.gram_ld : 0);
     PCOE_TRY(ls.done());
   }
   if (!fused_consts) PCOE_TRY(consts(2));
@@ -609,12 +635,36 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       auto wb = [&](int l) { return (const __nv_bfloat16*)(sv + L.wb_off[l]); };
       auto dwc = [&](int l) { return (float*)(ws + L.wb_dwc[l]); };
       const int Mld = L.Mld;
-      v4::DyLast4 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
-      dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3; dy3.fin = mkbfin(2, 1);
       v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2; x2.packed = 1;
       v4::MaskStats4 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
       m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2; m2.Mld = Mld;
-      PCOE_TRY(launch_bwd4<1>(dy3, x2, wb(2), L.w4_rp[2], L.w4_kp[2], m2, dwc(2), L.dwc_ld[2], d.C2, -1, M, d.C2, st, kname(d, kBL3)));
+      v4::DwL3 x3{};
+      if (l3s) {
+        // y3 was never stored: constants, Gm = W3^T diag(p) W3, r = W3^T q and the summed Gram matrix first, then the
+        // backward kernel with the sparse max-pool-routing operand (sa_tc4.cuh, DySparse4)
+        __nv_bfloat16* gmimg = (__nv_bfloat16*)(ws + L.wb_gmimg);
+        float* rvec = (float*)(ws + L.wb_rvec);
+        float* gsum = (float*)(ws + L.wb_gsum);
+        float* ext = (float*)(ws + L.wb_l3e);
+        {
+          const size_t sm = (size_t)2 * d.C3 * L.w4_kp[2] + sizeof(float) * (size_t)(2 * d.C3 + L.gram_ld);
+          static bool attr = false;
+          if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(v4::l3_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+          LaunchScope ls("l3_prep_kernel", st);
+          v4::l3_prep_kernel<<<128, 256, sm, st>>>(mkbfin(2, 1), d.C3, d.C2, wb(2), L.w4_kp[2], gsum, L.gram_ld,
+                                                   ca[2], cp[2], cq[2], gmimg, rvec, ext);
+          PCOE_TRY(ls.done());
+        }
+        v4::DySparse4 ds{}; ds.gm = gm; ds.slot = slot; ds.M = M; ds.Mld = Mld; ds.C = d.C3;
+        m2.addc = rvec;
+        PCOE_TRY((launch_bwd4<1, 1>(ds, x2, wb(2), L.w4_rp[2], L.w4_kp[2], m2, dwc(2), L.dwc_ld[2], d.C2, -1, M, d.C2, st,
+                                    kname(d, kBL3), gmimg, d.C2)));
+        x3 = v4::DwL3{ext};
+      } else {
+        v4::DyLast4 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
+        dy3.M = M; dy3.Mld = Mld; dy3.C = d.C3; dy3.fin = mkbfin(2, 1);
+        PCOE_TRY(launch_bwd4<1>(dy3, x2, wb(2), L.w4_rp[2], L.w4_kp[2], m2, dwc(2), L.dwc_ld[2], d.C2, -1, M, d.C2, st, kname(d, kBL3)));
+      }
       v4::Dy4 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.Mld = Mld; dy2.C = d.C2;
       dy2.fin = mkbfin(1, 1);
       v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1; x1.packed = 1;
@@ -643,7 +693,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
           total += Cs[l] * Kin[l];
         }
         LaunchScope ls("dw_combine_kernel", st);
-        v4::dw_combine_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(cmb[0], cmb[1], cmb[2], Gr.accumulate);
+        v4::dw_combine_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(cmb[0], cmb[1], cmb[2], Gr.accumulate, x3);
         PCOE_TRY(ls.done());
       }
       return PCOE_OK;
@@ -659,25 +709,42 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       v4::BnRelu4 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.Mld = Mld; x2.C = d.C2; x2.packed = 1;
       v4::MaskStats4 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
       m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2; m2.Mld = Mld;
-      PCOE_TRY(launch_wgrad5(dy3, x2, Gr.dW[2], d.C2, d.C2, -1, M, d.C2 / 128, st, kname(d, kWG3)));
+      // The weight-gradient kernels are off the critical path (only the optimizer consumes them) and none of these
+      // grids fills the GPU: they run on the auxiliary stream, each forked after the dgrad that produces its dz.
+      AuxStream* ax = aux_stream();
+      cudaStream_t sw = ax ? ax->s : st;
+      auto fork = [&](int e) -> int {
+        if (!ax) return PCOE_OK;
+        PCOE_CUDA(cudaEventRecord(ax->ev[e], st));
+        PCOE_CUDA(cudaStreamWaitEvent(sw, ax->ev[e], 0));
+        return PCOE_OK;
+      };
+      PCOE_TRY(fork(0));
+      PCOE_TRY(launch_wgrad5(dy3, x2, Gr.dW[2], d.C2, d.C2, -1, M, d.C2 / 128, sw, kname(d, kWG3)));
       dy3.fin.write = 0;
       PCOE_TRY(launch_dgrad5<false>(dy3, wb(2), L.w4_kp[2], m2, M, d.C2, st, kname(d, kDG3)));
+      PCOE_TRY(fork(1));
       v4::Dy4 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.Mld = Mld; dy2.C = d.C2;
       dy2.fin = mkbfin(1, 1);
       v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1; x1.packed = 1;
       v4::MaskStats4 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
       m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1; m1.Mld = Mld;
-      PCOE_TRY(launch_wgrad5(dy2, x1, Gr.dW[1], d.C1, d.C1, -1, M, d.C1 / 128, st, kname(d, kWG2)));
+      PCOE_TRY(launch_wgrad5(dy2, x1, Gr.dW[1], d.C1, d.C1, -1, M, d.C1 / 128, sw, kname(d, kWG2)));
       dy2.fin.write = 0;
       PCOE_TRY(launch_dgrad5<false>(dy2, wb(1), L.w4_kp[1], m1, M, d.C1, st, kname(d, kDG2)));
+      PCOE_TRY(fork(2));
       v4::Dy4 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.Mld = Mld; dy1.C = d.C1;
       dy1.fin = mkbfin(0, 1);
       v5::GatherFeat5 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
-      PCOE_TRY(launch_wgrad5(dy1, x0, Gr.dW[0], Cin, Cin, d.D, M, ceil_div(x0.nblocks(), 2), st, kname(d, kWG1)));
+      PCOE_TRY(launch_wgrad5(dy1, x0, Gr.dW[0], Cin, Cin, d.D, M, ceil_div(x0.nblocks(), 2), sw, kname(d, kWG1)));
       dy1.fin.write = 0;
       if (grad_feats) {
         v4::Scatter4 se{grad_feats, nbr, d.N, d.S, d.D, d.group_all};
         PCOE_TRY(launch_dgrad5<true>(dy1, wb(0), L.w4_kp[0], se, M, d.D, st, kname(d, kDG1)));
+      }
+      if (ax) {   // join
+        PCOE_CUDA(cudaEventRecord(ax->ev[3], sw));
+        PCOE_CUDA(cudaStreamWaitEvent(st, ax->ev[3], 0));
       }
       return PCOE_OK;
     }

@@ -3,6 +3,7 @@
 // (the regions overlap in time, not in use).
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 
 namespace pcoe {
 
@@ -12,6 +13,8 @@ namespace pcoe {
 // sector are serialised, so with one copy the tail of every kernel was ~10 us of 148-deep atomic
 // chains (measured: in-kernel clock trace, profiles/README.md).
 constexpr int kRedCopies = 8;
+// largest dynamic shared memory a v4 kernel may ask for (227 KB opt-in limit minus the kernels' static barriers)
+constexpr size_t kSmemMax4 = 232448 - 256;
 
 struct SaLayout {
   int M, G;        // rows = B*S*K, groups = B*S
@@ -34,6 +37,12 @@ struct SaLayout {
                    // HBM layouts as v2
   int Mld;         // rows rounded up to 128 (v2 / v5)
   int w4_rp[3], w4_kp[3];
+  // v2 train: the last layer's pre-activations y3 are NOT stored; the forward accumulates the Gram matrix of the
+  // layer's input instead (sa_tc4.cuh, DySparse4).  sv_gram: [kRedCopies][C2][gram_ld] fp32 in `saved`;
+  // backward workspace: Gm image bf16 [128][C2], r [C2], summed Gram [C2][gram_ld], dense weight-gradient term E [C3][C2].
+  bool l3s;
+  int gram_ld;
+  size_t sv_gram, sv_gram_bytes, wb_gmimg, wb_rvec, wb_gsum, wb_l3e;
   size_t workspace_bytes;
 };
 
@@ -58,8 +67,27 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
     L.w4_kp[l] = (int)align_up(l == 0 ? (Kin[0] + 15) / 16 * 16 : Kin[l], 128);
   }
 
+  // sparse last-layer backward: needs whole tiles (tail columns would pollute the Gram matrix), C2 <= 128 (one Gm
+  // M tile) and the backward kernel's shared memory: W3 image + Gm image + P tile + Q tile + constants + one staging tile
+  L.gram_ld = d.C2 + 16;
+  {
+    const size_t need = 1024 + (size_t)2 * L.w4_rp[2] * L.w4_kp[2] + (size_t)2 * 128 * d.C2 +
+                        (size_t)2 * (d.C3 < 128 ? 128 : d.C3) * 128 + (size_t)2 * d.C2 * 128 + (size_t)(8 * d.C2 + 512) +
+                        (size_t)d.C2 * 256;
+    // PCOE_SA_STORE_Y3=1 (debug / A-B tests): keep the older formulation that stores y3 and re-reads it in backward
+    const char* keep = getenv("PCOE_SA_STORE_Y3");
+    L.l3s = L.v2 && d.train && L.M % 128 == 0 && d.C2 <= 128 && need <= kSmemMax4 &&
+            L.w4_rp[2] + L.gram_ld <= 512 &&   // forward TMEM: one accumulator buffer (pad128(C3) columns) + Gram
+            !(keep && keep[0] == '1');
+  }
+
   size_t s = 0;
-  for (int l = 0; l < 3; ++l) L.sv_y[l] = take(s, rows_ld * C[l] * L.esz);
+  for (int l = 0; l < 3; ++l) L.sv_y[l] = (l == 2 && L.l3s) ? 0 : take(s, rows_ld * C[l] * L.esz);
+  L.sv_gram = L.sv_gram_bytes = 0;
+  if (L.l3s) {
+    L.sv_gram_bytes = sizeof(float) * (size_t)kRedCopies * d.C2 * L.gram_ld;
+    L.sv_gram = take(s, L.sv_gram_bytes);
+  }
   for (int l = 0; l < 3; ++l) L.sv_stat[l] = take(s, sizeof(float) * 4 * C[l]);
   L.sv_slot = take(s, (size_t)L.G * d.C3);
   L.sv_ysel = take(s, sizeof(float) * (size_t)L.G * d.C3);
@@ -105,6 +133,13 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   }
   L.wb_dwc_bytes = L.v2 ? b - L.wb_dwc[0] : 0;
   for (int l = 0; l < 3; ++l) L.wb_consts[l] = take(b, sizeof(float) * 3 * C[l]);
+  L.wb_gmimg = L.wb_rvec = L.wb_gsum = L.wb_l3e = 0;
+  if (L.l3s) {
+    L.wb_gmimg = take(b, (size_t)2 * 128 * d.C2);
+    L.wb_rvec = take(b, sizeof(float) * d.C2);
+    L.wb_gsum = take(b, sizeof(float) * (size_t)d.C2 * L.gram_ld);
+    L.wb_l3e = take(b, sizeof(float) * (size_t)d.C3 * d.C2);
+  }
   L.wb_gm = take(b, sizeof(float) * (size_t)L.G * d.C3);
   for (int l = 0; l < 2; ++l) L.wb_dz[l] = take(b, rows_ld * C[l] * L.esz);
   if (!d.train) b = 0;

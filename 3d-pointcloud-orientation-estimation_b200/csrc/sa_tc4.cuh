@@ -213,7 +213,8 @@ struct BnRelu4 {
   const float* cs;
   BnFin fin;     // fin.sums != nullptr: forward of a train-mode layer, statistics finalised here
   int packed;    // 1: backward Q operand, packed bf16x2 arithmetic (kPackedBwd)
-  __host__ __device__ __forceinline__ int rows() const { return C; }
+  int prows;     // rows ALLOCATED for the image (0 = C): the Gram forward appends a row of ones and pads to the MMA M
+  __host__ __device__ __forceinline__ int rows() const { return prows ? prows : C; }
   __host__ __device__ __forceinline__ int kext() const { return C; }
   __host__ __device__ __forceinline__ int nconst() const { return 2 * C; }
   __device__ __forceinline__ int nbatches(int G) const { return (C / (G >> 4) + kBatch - 1) / kBatch; }
@@ -238,7 +239,7 @@ struct BnRelu4 {
   __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr, int lrows = 0,
                                         int rshift = 0) const {
     PCOE_CM_MAP
-    const uint32_t dst = saddr + cm_off(lrows ? lrows : C, c0 + rshift, chunk);
+    const uint32_t dst = saddr + cm_off(lrows ? lrows : rows(), c0 + rshift, chunk);
     const float* k0 = cs + c0;
     if (kPackedBwd && packed) {
 #pragma unroll
@@ -415,6 +416,52 @@ struct DyLast4 {
           asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
         }
       }
+    }
+  }
+};
+
+// last layer WITHOUT the saved pre-activations y3 (v4 train path).  BatchNorm backward of the last layer is
+//     dy3 = a*g + p*y3 + q,     g = max-pool routing of gm (one non-zero per group and channel),  y3 = W3 x2
+// and its dense part is linear in x2, so it never has to be materialised:
+//     dx2 = W3^T dy3 = W3^T (a*g) + (W3^T diag(p) W3) x2 + W3^T q          (Gm image + per-channel constant r)
+//     dW3 = dy3^T x2 = (a*g)^T x2 + diag(p) W3 (x2^T x2) + q (sum x2)^T     (Gram matrix from the forward kernel)
+// This producer builds only the SPARSE operand a*g (gm arrives pre-multiplied by a = scale): a zero tile with one
+// bf16 value per (group, channel).  y3 is neither written by the forward nor read here.
+struct DySparse4 {
+  static constexpr bool kChMajor = true;
+  using Idx = NoIdx;
+  struct Raw { float gv[kBatch]; int sl[kBatch]; };
+  const float* __restrict__ gm;       // [G,C], already multiplied by a
+  const uint8_t* __restrict__ slot;   // [G,C]
+  int M, Mld, C;
+  __host__ __device__ __forceinline__ int rows() const { return C < 128 ? 128 : C; }
+  __host__ __device__ __forceinline__ int kext() const { return C; }
+  __host__ __device__ __forceinline__ int nconst() const { return 0; }
+  __device__ __forceinline__ int nbatches(int G) const { return (C / (G >> 4) + kBatch - 1) / kBatch; }
+  __device__ __forceinline__ void init(float*, int, int) {}
+  __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
+  __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx&, Raw& r) const {
+    PCOE_CM_MAP
+    const int grp = min(m, M - 1) >> 5;
+    const float* sg = gm + (size_t)grp * C + c0;
+    const uint8_t* ss = slot + (size_t)grp * C + c0;
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      r.gv[i] = ok ? __ldg(sg + i * kRowStep) : 0.f;
+      r.sl[i] = ok ? (int)__ldg(ss + i * kRowStep) : -1;
+    }
+  }
+  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr, int lrows = 0,
+                                        int rshift = 0) const {
+    PCOE_CM_MAP
+    const uint32_t dst = saddr + cm_off(lrows ? lrows : rows(), c0 + rshift, chunk);
+    const int j0 = m & 31;
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int sl = r.sl[i] - j0;          // slot relative to this 8-point chunk; outside [0,8): all zero
+      const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r.gv[i])) << ((sl & 1) * 16);
+      const int w = (unsigned)sl < 8u ? (sl >> 1) : -1;
+      tc::sts128(dst + i * kSRowBytes, make_uint4(w == 0 ? h : 0u, w == 1 ? h : 0u, w == 2 ? h : 0u, w == 3 ? h : 0u));
     }
   }
 };
@@ -686,7 +733,7 @@ struct Group4 {   // last layer, K == 32: the 32 columns of a block are one grou
   float s0, s1;
   static constexpr bool kStage = true;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
-  __host__ __device__ __forceinline__ int stage_bytes() const { return C * 256; }
+  __host__ __device__ __forceinline__ int stage_bytes() const { return y ? C * 256 : 0; }
   __device__ __forceinline__ char* tile_dst(int tile) const { return y ? reinterpret_cast<char*>(y) + (size_t)tile * C * 256 : nullptr; }
   __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; }
   __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid, uint32_t stg) {
@@ -718,8 +765,9 @@ struct MaskStats4 {
   __nv_bfloat16* __restrict__ dz;            // tile-blocked
   double* __restrict__ sums;
   int C, Mld;
+  const float* __restrict__ addc;            // optional per-channel constant added to dx before the mask (DySparse4: W^T q)
   int c;
-  float s0, s1, sc, sh, is, nmi;   // nmi = -mean * invstd: xhat = y * invstd + nmi
+  float s0, s1, sc, sh, is, nmi, ac;   // nmi = -mean * invstd: xhat = y * invstd + nmi
   static constexpr bool kStage = true;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return C * 256; }
@@ -728,6 +776,7 @@ struct MaskStats4 {
     c = ch; s0 = s1 = 0.f;
     const bool ok = c < C;
     sc = ok ? scale[c] : 0.f; sh = ok ? shift[c] : 0.f; is = ok ? invstd[c] : 0.f; nmi = ok ? -mean[c] * is : 0.f;
+    ac = (ok && addc) ? addc[c] : 0.f;
   }
   __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid, uint32_t stg) {
     if (c >= C || !valid) return;
@@ -742,7 +791,7 @@ struct MaskStats4 {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const bool on = fmaf(yy[u], sc, sh) > 0.f;
-        const float d = on ? v[8 * q + u] : 0.f;
+        const float d = on ? v[8 * q + u] + ac : 0.f;
         v[8 * q + u] = d;
         a[u & 3] += d;
         b[u & 3] = fmaf(d, fmaf(yy[u], is, nmi), b[u & 3]);
@@ -848,12 +897,17 @@ __device__ __forceinline__ void stage_copy_out(char* dst, uint32_t stg, int byte
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward layer:  Y^T[C_out x 128] = W * X^T per tile;  TMEM: 2 buffers x mt x 128 columns
+// forward layer:  Y^T[C_out x 128] = W * X^T per tile;  TMEM: nbuf buffers x mt x 128 columns
 // smem: [W image][stages x tile][constants]
+// GRAM: additionally accumulate  Gram[C_in x (C_in+16)] += X^T_ext X_ext  over the CTA's tiles in TMEM columns
+// [nbuf*mt*128, +C_in+16) (X_ext = the input tile with a row of ones appended as row C_in, so column C_in of the
+// result is sum_points x): the statistics the last layer's backward needs instead of the saved y3 (DySparse4).
+// Requires M % 128 == 0 and prod.rows() >= max(128, C_in + 16); flushed into gram[blockIdx.x % kRedCopies].
 // ---------------------------------------------------------------------------------------------
-template <class Prod, class Epi, int TCOLS>
+template <class Prod, class Epi, int TCOLS, int GRAM>
 __global__ void __launch_bounds__(kThreads, 1)
-tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, Epi epi, int M, int nstages, int nstg) {
+tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, Epi epi, int M, int nstages, int nstg,
+               float* __restrict__ gram, int nbuf) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem0 - tc::smem_u32(smem_raw));
@@ -875,7 +929,17 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
   }
   load_wimage(Wb, Rp, Kp, sW, tid, kThreads);
   zero_smem(sT, (uint32_t)nstages * tbytes, tid, kThreads);
+  if constexpr (GRAM) {   // row kext() of every stage image = ones (never touched by the producers)
+    __syncthreads();
+    const int orow = prod.kext();
+    for (int e = tid; e < nstages * 16; e += kThreads) {
+      const uint32_t a = sT + (uint32_t)(e >> 4) * tbytes + (uint32_t)((e >> 3) & 1) * (uint32_t)(prod.rows() * 128) +
+                         (uint32_t)((orow >> 3) * 1024 + (orow & 7) * 128 + (e & 7) * 16);
+      tc::sts128(a, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));
+    }
+  }
   prod.init(csm, tid, kThreads);
+  const uint32_t gcol = (uint32_t)(nbuf * mt * kPts);   // Gram accumulator columns
   // epilogue work split: warp w -> TMEM lane quadrant w&3, items [eh*mt*2, (eh+1)*mt*2) of the mt*4
   // (M tile, 32-column block) pairs of a tile; all of one thread's items share one M tile
   const int eq = warp & 3, eh = (warp >> 2) & 1, lane = tid & 31;
@@ -896,7 +960,7 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
     // ---- epilogue ----
     int i = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
-      const int b = i & 1, u = i >> 1, m0 = tile * kPts;
+      const int b = nbuf == 2 ? (i & 1) : 0, u = nbuf == 2 ? (i >> 1) : i, m0 = tile * kPts;
       tc::mbar_wait(&bar.tmem_full[b], (uint32_t)(u & 1));
       if (tid == 0) TC4_TRACE(30, i);
       tc::fence_after_sync();
@@ -920,6 +984,27 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
     if (Epi::kStage && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     epi.finish();
     if (tid == 0) TC4_TRACE(32, 0);
+    if constexpr (GRAM) {
+      // flush the Gram accumulator (complete: the last tmem_full commit covers every earlier MMA): thread = row
+      if ((int)blockIdx.x < ntiles) {
+        tc::fence_after_sync();
+        const int cin = prod.kext(), gn = cin + 16, nblk = (gn + 31) / 32;
+        float* base = gram + (size_t)(blockIdx.x % kRedCopies) * cin * gn;
+        const int row = eq * 32 + lane;
+#pragma unroll 1
+        for (int k = eh; k < nblk; k += 2) {
+          const int cb = ((k + (int)blockIdx.x) % nblk) * 32;
+          float v[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + gcol + (uint32_t)cb, v);   // may read past gn: unused columns
+          if (row < cin) {
+            float* dst = base + (size_t)row * gn + cb;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (cb + 4 * q < gn) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+      }
+    }
   } else if (warp < 16) {
     // ---- producers ----
     int ring_s = 0, ring_n = 0;   // stage slot / round of the tile being stored (tiles are stored in order)
@@ -932,9 +1017,11 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
     // ---- MMA issue ----
     const uint32_t idesc = tc::make_idesc_bf16(128, kPts, false, Prod::kChMajor);
     const int kext = prod.kext();
+    const uint32_t idesc_g = tc::make_idesc_bf16(128, kext + 16, false, false);
+    const uint32_t prow = (uint32_t)prod.rows();
     int i = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
-      const int s = i % nstages, n = i / nstages, b = i & 1, u = i >> 1;
+      const int s = i % nstages, n = i / nstages, b = nbuf == 2 ? (i & 1) : 0, u = nbuf == 2 ? (i >> 1) : i;
       tc::mbar_wait(&bar.full[s], (uint32_t)(n & 1));
       if ((tid & 31) == 0) TC4_TRACE(20, i);
       if (u > 0) tc::mbar_wait(&bar.tmem_empty[b], (uint32_t)((u - 1) & 1));
@@ -946,6 +1033,12 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
           tc::mma_bf16_warp(tmem + (uint32_t)(b * mt * kPts + mi * kPts),
                        tc::make_desc_sw128(sW + (uint32_t)(k >> 6) * (uint32_t)(Rp * 128) + (uint32_t)(mi * 128 * 128) + (uint32_t)((k & 63) * 2), 16, 1024),
                        act_desc_chan_k(prod, st, k), idesc, k > 0);
+      if constexpr (GRAM) {   // Gram += X_ext^T X_ext: contraction over the 128 points, A = rows 0..127, B = rows 0..kext+15
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t xd = tc::make_desc_sw128(st + (uint32_t)(ks >> 2) * (prow * 128u) + (uint32_t)((ks & 3) * 32), 16, 1024);
+          tc::mma_bf16_warp(tmem + gcol, xd, xd, idesc_g, i > 0 || ks > 0);
+        }
+      }
       tc::mma_commit_warp(&bar.empty[s]);
       tc::mma_commit_warp(&bar.tmem_full[b]);
       if ((tid & 31) == 0) TC4_TRACE(22, i);
@@ -963,13 +1056,16 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
 //   dW[C_l x Cq] += P * Q^T            TMEM columns [0, mtl*nw), accumulated over the CTA's tiles
 //   DGRAD == 1:  dx^T[C_prev x 128] = W^T * P    (thread = channel epilogue; 2 buffers of mtp*128 cols)
 //   DGRAD == 2:  dx[128 x D]        = P^T * W     (thread = point epilogue: layer-1 scatter; 2 buffers of D cols)
-// smem: [W image (DGRAD)][P tile][Q tile][constants]   (single stage)
+//   GM (DGRAD == 1, Q channel-major, C_prev <= 128):  dx^T += Gm * Q  with Gm a [128 x gk] bf16 image (gk = C_prev):
+//                the dense part of the last layer's BatchNorm backward folded into a matrix (see DySparse4)
+// smem: [W image (DGRAD)][Gm image (GM)][P tile][Q tile][constants]   (single stage)
 // ---------------------------------------------------------------------------------------------
-template <class PProd, class QProd, class Epi, int DGRAD, int TCOLS>
+template <class PProd, class QProd, class Epi, int DGRAD, int TCOLS, int GM>
 __global__ void __launch_bounds__(kThreads, 1)
 tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, Epi epi,
                float* __restrict__ dW, int ldo, int cq_valid, int perm_d /* >=0: layer-1 [feats|xyz] column order */,
-               int M, int cprev /* dgrad output channels */, int nstg, int npq /* P/Q operand stages: 1 or 2 */) {
+               int M, int cprev /* dgrad output channels */, int nstg, int npq /* P/Q operand stages: 1 or 2 */,
+               const __nv_bfloat16* __restrict__ Gmb, int gk) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem0 - tc::smem_u32(smem_raw));
@@ -980,9 +1076,10 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
   const int nw = qp.kext();                       // dW columns per M tile (Cq rounded up to 16)
   const int mtp = (cprev + 127) / 128;
   const uint32_t wbytes = DGRAD ? (uint32_t)Rp * (uint32_t)Kp * 2u : 0u;
+  const uint32_t gbytes = GM ? 128u * (uint32_t)gk * 2u : 0u;
   const uint32_t pbytes = (prod_tile_bytes(pp) + 1023u) & ~1023u, qbytes = (prod_tile_bytes(qp) + 1023u) & ~1023u;
-  const uint32_t sW = smem0, sP0 = smem0 + wbytes, pqbytes = pbytes + qbytes;   // stage s: P at sP0 + s*pqbytes, Q behind it
-  float* csm = reinterpret_cast<float*>(smem_gen + wbytes + (size_t)npq * pqbytes);
+  const uint32_t sW = smem0, sG = smem0 + wbytes, sP0 = sG + gbytes, pqbytes = pbytes + qbytes;   // stage s: P at sP0 + s*pqbytes, Q behind it
+  float* csm = reinterpret_cast<float*>(smem_gen + wbytes + gbytes + (size_t)npq * pqbytes);
   const uint32_t dx_col = (uint32_t)((mtl * nw + 31) / 32 * 32);
   const uint32_t dx_cols = DGRAD == 1 ? (uint32_t)(mtp * kPts) : (uint32_t)((cprev + 31) / 32 * 32);
 
@@ -992,6 +1089,7 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar.tmem_full[b], 1); tc::mbar_init(&bar.tmem_empty[b], kEpiThreads); }
   }
   if (DGRAD) load_wimage(Wb, Rp, Kp, sW, tid, kThreads);
+  if (GM) load_wimage(Gmb, 128, gk, sG, tid, kThreads);
   zero_smem(sP0, (uint32_t)npq * pqbytes, tid, kThreads);
   pp.init(csm, tid, kThreads);
   qp.init(csm + pp.nconst(), tid, kThreads);
@@ -1148,6 +1246,13 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
             tc::mma_bf16_warp(tmem + dx_col + (uint32_t)b * dx_cols + (uint32_t)(mj * kPts),
                          tc::make_desc_sw128(sW + (uint32_t)(2 * mj) * (uint32_t)(Rp * 128) + (uint32_t)(k >> 4) * 2048, (uint32_t)Rp * 128, 1024),
                          tc::make_desc_sw128(sP + (uint32_t)(k >> 4) * 2048, (uint32_t)prow * 128, 1024), idesc_d, k > 0);
+        if constexpr (GM) {   // dx^T += Gm * Q : A = Gm image K-major, B = the Q tile MN-major (N = points)
+          const uint32_t idesc_g = tc::make_idesc_bf16(128, kPts, false, true);
+          for (int k = 0; k < gk; k += 16)
+            tc::mma_bf16_warp(tmem + dx_col + (uint32_t)b * dx_cols,
+                         tc::make_desc_sw128(sG + (uint32_t)(k >> 6) * (128u * 128u) + (uint32_t)((k & 63) * 2), 16, 1024),
+                         tc::make_desc_sw128(sQ + (uint32_t)(k >> 4) * 2048, (uint32_t)qp.rows() * 128, 1024), idesc_g, true);
+        }
       } else if constexpr (DGRAD == 2) {
         for (int k = 0; k < cl; k += 16)
           tc::mma_bf16_warp(tmem + dx_col + (uint32_t)b * dx_cols,
@@ -1169,7 +1274,10 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
 // dW_l (+)= sum over the kRedCopies copies the v4 backward kernels accumulated; layer 1 goes back from the
 // [feats(perm_d) | xyz(3)] column order to the parameter's [xyz | feats]
 struct DwComb { const float* copies; float* dW; int rows, cin, ld, perm_d; };
-__global__ void dw_combine_kernel(DwComb a, DwComb b, DwComb c, int accumulate) {
+// last layer on the DySparse4 path: dW3 += E,  E[c][k] = p_c * sum_j W3[c][j] * Gram[j][k] + q_c * sum_points x2[k]
+// (l3_prep_kernel), the dense part of the BatchNorm backward
+struct DwL3 { const float* E; };
+__global__ void dw_combine_kernel(DwComb a, DwComb b, DwComb c, int accumulate, DwL3 x3) {
   const DwComb* L[3] = {&a, &b, &c};
   const int n0 = a.rows * a.cin, n1 = b.rows * b.cin, n2 = c.rows * c.cin;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n0 + n1 + n2; e += gridDim.x * blockDim.x) {
@@ -1182,7 +1290,95 @@ __global__ void dw_combine_kernel(DwComb a, DwComb b, DwComb c, int accumulate) 
     float s = 0.f;
 #pragma unroll
     for (int g = 0; g < kRedCopies; ++g) s += w.copies[((size_t)g * w.rows + r) * w.ld + src];
+    if (l == 2 && x3.E) s += x3.E[ee];
     w.dW[ee] = accumulate ? w.dW[ee] + s : s;
+  }
+}
+
+// Last layer on the DySparse4 path, after bwd_last_reduce (which also sums the forward's Gram copies into gsum):
+// BatchNorm-backward constants (a, p, q) of layer 3 and its parameter gradients, and the three small matrices the
+// rewritten backward needs, from the layer's bf16 weight image W [C3][Kp]:
+//     Gm = W^T diag(p) W          bf16 image [128][C2] (rows >= C2 zero)      block k1 -> row k1   (W staged in smem)
+//     r  = W^T q                  [C2]                                          block 0
+//     E  = diag(p) W Gram + q s^T [C3][C2] fp32 (s = column C2 of gsum)         block k1 -> column k1, thread = row c:
+//                                 Gram is symmetric, so the column is the contiguous row k1 of gsum; each thread
+//                                 dots its own W row (16-byte global loads, all in flight at once) with it
+// Grid = 128 blocks of 256 threads; dynamic smem = C3*Kp*2 + 8*C3 + 4*ld bytes.  This kernel sits on the backward's
+// critical path: every global load is issued in large independent batches (a first version that looped over global
+// memory took 70 us, staging with an unbatched copy loop 12 us).
+__global__ void __launch_bounds__(256)
+l3_prep_kernel(BnBwdFin fin, int C3, int C2, const __nv_bfloat16* __restrict__ Wb, int Kp,
+               const float* __restrict__ gsum, int ld, float* __restrict__ a_out, float* __restrict__ p_out,
+               float* __restrict__ q_out, __nv_bfloat16* __restrict__ gmimg, float* __restrict__ rvec,
+               float* __restrict__ E) {
+  extern __shared__ uint4 l3sm[];
+  const __nv_bfloat16* sW = reinterpret_cast<const __nv_bfloat16*>(l3sm);
+  const int nw4 = C3 * Kp / 8;
+  float* sp = reinterpret_cast<float*>(l3sm + nw4);
+  float* sq = sp + C3;
+  float* sg = sq + C3;   // row k1 of gsum
+  const int k1 = blockIdx.x, t = threadIdx.x, nthr = blockDim.x;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(Wb);
+    int e = t;
+    for (; e + 7 * nthr < nw4; e += 8 * nthr) {
+      uint4 r[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) r[u] = __ldg(src + e + u * nthr);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) l3sm[e + u * nthr] = r[u];
+    }
+    for (; e < nw4; e += nthr) l3sm[e] = __ldg(src + e);
+  }
+  if (k1 < C2 && t < ld) sg[t] = __ldg(gsum + (size_t)k1 * ld + t);
+  for (int c = t; c < C3; c += nthr) {
+    float a, p, q;
+    fin.eval(c, C3, k1 == 0, a, p, q);
+    sp[c] = p; sq[c] = q;
+    if (k1 == 0) { a_out[c] = a; p_out[c] = p; q_out[c] = q; }
+  }
+  __syncthreads();
+  if (t < C2) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k1 < C2) {
+#pragma unroll 4
+      for (int c = 0; c < C3; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          acc[u] = fmaf(__bfloat162float(sW[(c + u) * Kp + k1]) * sp[c + u], __bfloat162float(sW[(c + u) * Kp + t]), acc[u]);
+      }
+    }
+    gmimg[(size_t)k1 * C2 + t] = __float2bfloat16_rn((acc[0] + acc[1]) + (acc[2] + acc[3]));
+    if (k1 == 0) {
+      float r0 = 0.f, r1 = 0.f;
+      for (int c = 0; c < C3; c += 2) {
+        r0 = fmaf(__bfloat162float(sW[c * Kp + t]), sq[c], r0);
+        r1 = fmaf(__bfloat162float(sW[(c + 1) * Kp + t]), sq[c + 1], r1);
+      }
+      rvec[t] = r0 + r1;
+    }
+  }
+  if (k1 < C2) {
+    for (int c = t; c < C3; c += nthr) {
+      const uint4* wr = reinterpret_cast<const uint4*>(Wb + (size_t)c * Kp);
+      float e0 = 0.f, e1 = 0.f;
+      for (int j0 = 0; j0 < C2; j0 += 64) {   // C2 in {64, 128}
+        uint4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(wr + (j0 >> 3) + u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float v[8];
+          unpack8(w[u], v);
+#pragma unroll
+          for (int x = 0; x < 8; x += 2) {
+            e0 = fmaf(v[x], sg[j0 + u * 8 + x], e0);
+            e1 = fmaf(v[x + 1], sg[j0 + u * 8 + x + 1], e1);
+          }
+        }
+      }
+      E[(size_t)c * C2 + k1] = fmaf(sp[c], e0 + e1, sq[c] * sg[C2]);
+    }
   }
 }
 

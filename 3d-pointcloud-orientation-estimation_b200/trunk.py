@@ -47,10 +47,29 @@ def _linear_fwd(lib, st, x, Ws, bs, out, max_parts=1):
     return n.value
 
 
-def _linear_bwd(lib, st, dy, x, Ws, dWs, dbs, dx, accumulate):
+_side_streams: dict = {}
+
+
+def _side_stream(dev):
+    """Auxiliary stream for the weight-gradient kernels of the trunk backward: only the optimizer consumes them, so
+    they run beside the dx chain (forked per linear layer, joined at the end of the node).  None while per-kernel
+    profiling is on (kernels are then timed alone)."""
+    if _lib.profiling:
+        return None
+    s = _side_streams.get(dev.index)
+    if s is None:
+        s = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def _linear_bwd(lib, st, dy, x, Ws, dWs, dbs, dx, accumulate, side=None):
     Ns = _ints([w.size(0) for w in Ws])
+    st_w = st
+    if side is not None:                       # fork: dy is ready on the current stream
+        side.wait_stream(torch.cuda.current_stream())
+        st_w = side.cuda_stream
     _lib.check(lib.pcoe_linear_bwd_dw(dy.data_ptr(), x.data_ptr(), x.size(0), x.size(1), len(Ws), Ns, _ptrs(dWs),
-                                      _ptrs(dbs), int(accumulate), st))
+                                      _ptrs(dbs), int(accumulate), st_w))
     if dx is not None:
         _lib.check(lib.pcoe_linear_bwd_dx(dy.data_ptr(), x.size(0), x.size(1), len(Ws), _ptrs(Ws), Ns, dx.data_ptr(), st))
 
@@ -121,18 +140,21 @@ class MvMTrunkHead(torch.autograd.Function):
                                          float(kmax) if clamp else 0.0, int(clamp), ptr(g_w), ptr(g_mu), ptr(g_k),
                                          draw.data_ptr(), draw[B * K:].data_ptr(), draw[3 * B * K:].data_ptr(), st))
         da2, dh2 = torch.empty_like(a2), torch.empty_like(h2)
-        _linear_bwd(lib, st, draw, a2, [piw, muw, kw], [dpw, dmw, dkw], [dpb, dmb, dkb], da2, acc)
+        side = _side_stream(dev)
+        _linear_bwd(lib, st, draw, a2, [piw, muw, kw], [dpw, dmw, dkw], [dpb, dmb, dkb], da2, acc, side)
         # the LayerNorm backward also adds the column sums of its dx into the bias gradient of the linear below it
         _lib.check(lib.pcoe_ln_relu_dropout_bwd(da2.data_ptr(), h2.data_ptr(), a2.data_ptr(), g2.data_ptr(), st2[0].data_ptr(),
                                                 st2[1].data_ptr(), m2.data_ptr(), B, h2.size(1), p, int(train),
                                                 dh2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), d2b.data_ptr(), st))
         da1, dh1 = torch.empty_like(a1), torch.empty_like(h1)
-        _linear_bwd(lib, st, dh2, a1, [fc2w], [d2w], [None], da1, acc)
+        _linear_bwd(lib, st, dh2, a1, [fc2w], [d2w], [None], da1, acc, side)
         _lib.check(lib.pcoe_ln_relu_dropout_bwd(da1.data_ptr(), h1.data_ptr(), a1.data_ptr(), g1.data_ptr(), st1[0].data_ptr(),
                                                 st1[1].data_ptr(), m1.data_ptr(), B, h1.size(1), p, int(train),
                                                 dh1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), d1b.data_ptr(), st))
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        _linear_bwd(lib, st, dh1, x, [fc1w], [d1w], [None], dx, acc)
+        _linear_bwd(lib, st, dh1, x, [fc1w], [d1w], [None], dx, acc, side)
+        if side is not None:                   # join before the node returns (buffers above are freed on this stream)
+            torch.cuda.current_stream().wait_stream(side)
         if direct:
             return (dx, None) + (None,) * 14
         return (dx, None, *grads)

@@ -182,3 +182,38 @@ def test_sa_bf16_eval_matches_fp32_eval(pcoe, golden, cuda):
             _, a = l32(xyz, pts, fps_idx=fps)
             _, b = l16(xyz, pts, fps_idx=fps)
         assert _rel(b, a) < BF16_FWD, tag
+
+
+@pytest.mark.parametrize("shape", ["sa1", "sa2"])
+def test_sa_bf16_sparse_last_layer_matches_stored_y3(pcoe, cuda, shape, monkeypatch):
+    """The v4 train path does not store the last layer's pre-activations y3: its BatchNorm backward is rewritten with
+    the Gram matrix of the layer's input (sa_tc4.cuh, DySparse4).  A/B against the older formulation (y3 stored in
+    bf16 and re-read; PCOE_SA_STORE_Y3=1) on the same inputs: identical forward, gradients equal to bf16 rounding."""
+    B = 8
+    N, S, K, D, mlp = dict(sa1=(1024, 128, 32, 0, [64, 64, 128]), sa2=(128, 32, 32, 128, [128, 128, 256]))[shape]
+    g = torch.Generator().manual_seed(23)
+    xyz = torch.randn(B, N, 3, generator=g)
+    xyz = (xyz / xyz.norm(dim=-1).amax(1).view(B, 1, 1)).to(cuda)
+    pts = torch.randn(B, N, D, generator=g).to(cuda) if D else None
+    fps = torch.stack([torch.randperm(N, generator=g)[:S] for _ in range(B)]).to(cuda)
+    gout = None
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PCOE_SA_STORE_Y3", mode)
+        torch.manual_seed(5)
+        layer = pcoe.PointNetSetAbstraction(S, K, D, mlp, precision="bf16").to(cuda).train()
+        with torch.no_grad():
+            for bn in layer.bns:
+                bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.3, 0.3)
+        p = pts.clone().requires_grad_(True) if D else None
+        _, out = layer(xyz, p, fps_idx=fps)
+        if gout is None:
+            gout = torch.randn(out.shape, generator=g).to(cuda)
+        out.backward(gout)
+        res[mode] = (out.detach(), {n: q.grad.clone() for n, q in layer.named_parameters()}, p.grad.clone() if D else None)
+    assert torch.equal(res["0"][0], res["1"][0])
+    rels = {n: _rel(res["0"][1][n], res["1"][1][n]) for n in res["0"][1] if not (n.startswith("convs") and n.endswith("bias"))}
+    if D:
+        rels["grad_feats"] = _rel(res["0"][2], res["1"][2])
+    print(f"\n[bf16 sparse-l3 vs stored-y3 {shape}] " + ", ".join(f"{k}={v:.1e}" for k, v in rels.items()))
+    assert max(rels.values()) < 2e-2
