@@ -301,8 +301,11 @@ static int launch_bwd4(const PProd& pp, const QProd& qp, const __nv_bfloat16* Wb
   // (npq = 2) but measured SLOWER on B200 (sa1_bwd_l2 55.7 -> 63.5 us, sa2_bwd_l2 39 -> 47.5 us): the larger
   // carve-out shrinks L1 and the producers running further ahead evict the y tile that the MaskStats epilogue
   // re-reads.  The remaining shared memory goes to a second output staging tile instead.
-  const int npq = 1;
-  const int nstg = (sb && base + (npq - 1) * pq + 2 * sb <= kSmemBudget4) ? 2 : 1;
+  // With the sparse last-layer operand (GM) the producers are light and the single stage serialises them with the
+  // MMAs of the previous tile; PCOE_BWD_NPQ2=1 switches the second stage on where it fits (experiment switch).
+  static const bool want2 = [] { const char* e = getenv("PCOE_BWD_NPQ2"); return e && e[0] == '1'; }();
+  const int npq = (GM && want2 && base + pq + sb <= kSmemMax4) ? 2 : 1;
+  const int nstg = (sb && base + (npq - 1) * pq + 2 * sb <= (npq == 2 ? kSmemMax4 : kSmemBudget4)) ? 2 : 1;
   const size_t smem = base + (npq - 1) * pq + nstg * sb;
   const int tiles = ceil_div(M, v4::kPts), grid = tiles < kNumSMs ? tiles : kNumSMs;
   auto k = v4::tc4_bwd_kernel<PProd, QProd, Epi, DGRAD, 512, GM>;

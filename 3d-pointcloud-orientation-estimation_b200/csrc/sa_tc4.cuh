@@ -81,6 +81,15 @@ __device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(mbar)) : "memory");
 }
 
+// producers' `full` arrival (experiment switch: relaxed arrive after the proxy fence)
+__device__ __forceinline__ void mbar_arrive_full(uint64_t* mbar) {
+#ifdef PCOE_EXP_RELAXED_ARRIVE
+  mbar_arrive_relaxed(mbar);
+#else
+  mbar_arrive(mbar);
+#endif
+}
+
 // byte offset of the 16-byte chunk (8 points) `chunk` (0..15) of channel row c in a channel-major tile
 __device__ __forceinline__ uint32_t cm_off(int crows, int c, int chunk) {
   return (uint32_t)((chunk >> 3) * crows * 128 + (c >> 3) * 1024 + (c & 7) * 128 + ((((chunk & 7) ^ (c & 7))) << 4));
@@ -257,6 +266,10 @@ struct BnRelu4 {
       // branch-free on purpose: the four chunks of a batch are independent and the compiler interleaves them
       // (C is a multiple of the 64 channels a batch covers; columns of points >= M hold relu(shift): they are
       // never read back - forward / dgrad epilogues skip them and the wgrad dy operand zeroes them)
+#ifdef PCOE_EXP_NOXFORM
+      tc::sts128(dst + i * kSRowBytes, r.a[i]);
+      continue;
+#endif
       float v[8];
       unpack8(r.a[i], v);
       const float sc = k0[i * kRowStep], sh = k0[C + i * kRowStep];
@@ -596,11 +609,18 @@ struct GatherFeat4 {
   }
 };
 
+// Global loads kept in flight per producer thread, in units (batches): HBM latency x bandwidth needs ~44 KB in
+// flight per SM; one unit of 256 threads x kBatch x 16 B is 16 KB.  Two units ahead when the raw registers of a
+// unit are small (<= 16 registers), one otherwise (register budget: 120 per thread at 544 threads).
+template <class Raw>
+struct LoadDepth { static constexpr int value = sizeof(Raw) <= 64 ? 2 : 1; };
+
 // The producer pipeline of one group (G threads, group-local id g) over the CTA's tiles.
 // arrive(): `full` arrival after the last batch of a tile; wait_empty(t): the tile's stage is free.
 template <class Prod, class WaitEmpty, class StageAddr, class Arrive>
 __device__ __forceinline__ void producer_pipeline(const Prod& prod, int g, int G, int ntiles, WaitEmpty wait_empty,
                                                   StageAddr stage_addr, Arrive arrive) {
+  constexpr int D = LoadDepth<typename Prod::Raw>::value;
   int my_tiles = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
   const int nb = prod.nbatches(G), W = my_tiles * nb;
@@ -613,13 +633,16 @@ __device__ __forceinline__ void producer_pipeline(const Prod& prod, int g, int G
   auto adv = [&](Cur& c) { if (++c.b == nb) { c.b = 0; ++c.t; c.m0 += mstep; } };
   Cur ci{0, 0, (int)blockIdx.x * kPts}, cl = ci, cst = ci;
   typename Prod::Idx ix;
-  typename Prod::Raw ra, rb;
+  typename Prod::Raw r[D + 1];   // unit u lives in r[u % (D + 1)]; indices are compile-time after unrolling
   prod.load_idx(g, G, ci.m0, ci.b, ix); adv(ci);
-  prod.load(g, G, cl.m0, cl.b, ix, ra); adv(cl);
-  if (W > 1) { prod.load_idx(g, G, ci.m0, ci.b, ix); adv(ci); }
+#pragma unroll
+  for (int u = 0; u < D; ++u) {
+    if (u < W) { prod.load(g, G, cl.m0, cl.b, ix, r[u]); adv(cl); }
+    if (u + 1 < W) { prod.load_idx(g, G, ci.m0, ci.b, ix); adv(ci); }
+  }
   auto step = [&](int w, typename Prod::Raw& cur, typename Prod::Raw& nxt) {
-    if (w + 1 < W) { prod.load(g, G, cl.m0, cl.b, ix, nxt); adv(cl); }
-    if (w + 2 < W) { prod.load_idx(g, G, ci.m0, ci.b, ix); adv(ci); }
+    if (w + D < W) { prod.load(g, G, cl.m0, cl.b, ix, nxt); adv(cl); }
+    if (w + D + 1 < W) { prod.load_idx(g, G, ci.m0, ci.b, ix); adv(ci); }
     if (g == 0) TC4_TRACE(12, w);
     if (cst.b == 0) wait_empty(cst.t);
     if (g == 0) TC4_TRACE(10, w);
@@ -628,9 +651,10 @@ __device__ __forceinline__ void producer_pipeline(const Prod& prod, int g, int G
     if (g == 0) TC4_TRACE(11, w);
     adv(cst);
   };
-  for (int w = 0; w < W; w += 2) {
-    step(w, ra, rb);
-    if (w + 1 < W) step(w + 1, rb, ra);
+  for (int w = 0; w < W; w += D + 1) {
+#pragma unroll
+    for (int u = 0; u <= D; ++u)
+      if (w + u < W) step(w + u, r[u], r[(u + D) % (D + 1)]);
   }
   if (g == 0) TC4_TRACE_DUMP();
 }
@@ -710,8 +734,12 @@ struct StoreStats4 {
   __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; }
   __device__ __forceinline__ void block(float (&v)[32], int, int j, bool valid, uint32_t stg) {
     if (c >= C || !valid) return;
+#ifndef PCOE_EXP_NOSTAGE
     stage32_bf16(stg, c, j, v);
+#endif
+#ifndef PCOE_EXP_NOSUMS
     sum_sumsq32(v, s0, s1);
+#endif
   }
   __device__ __forceinline__ void finish() {
     if (!sums || c >= C) return;
@@ -739,11 +767,17 @@ struct Group4 {   // last layer, K == 32: the 32 columns of a block are one grou
   __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid, uint32_t stg) {
     if (c >= C || !valid) return;
     if (y) stage32_bf16(stg, c, j, v);
+#ifndef PCOE_EXP_NOSUMS
     sum_sumsq32(v, s0, s1);
+#endif
     float mx, mn;
     int ax, an;
+#ifndef PCOE_EXP_NOARG
     argext32<true>(v, mx, ax);
     argext32<false>(v, mn, an);
+#else
+    mx = v[0]; mn = v[1]; ax = 0; an = 1;
+#endif
     const size_t o = (size_t)(tile * 4 + j) * C + c;
     ymax[o] = mx; ymin[o] = mn; amax[o] = (uint8_t)ax; amin[o] = (uint8_t)an;
   }
@@ -1011,7 +1045,7 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
     producer_pipeline(prod, tid - kEpiThreads, kProdThreads, ntiles,
                       [&](int t) { if (t >= nstages) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_n - 1) & 1)); },
                       [&](int) { return sT + (uint32_t)ring_s * tbytes; },
-                      [&](int) { mbar_arrive(&bar.full[ring_s]); if (++ring_s == nstages) { ring_s = 0; ++ring_n; } });
+                      [&](int) { mbar_arrive_full(&bar.full[ring_s]); if (++ring_s == nstages) { ring_s = 0; ++ring_n; } });
   } else {   // warp 16: MMA issue, warp-uniform loop, one elected lane issues
     const uint32_t tmem = tc::uniform_u32(tmem_base);
     // ---- MMA issue ----
@@ -1148,7 +1182,11 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
     // flush dW (complete: the last tmem_full commit covers every earlier MMA): thread = row of dW, into this
     // CTA's copy dWc[blockIdx.x % kRedCopies][C_l][ldo] (ldo = nw, a multiple of 16; padding columns hold the
     // zeros of the Q tile's unused channels).  pcoe_sa_backward adds the copies up (dw_combine_kernel).
+#ifdef PCOE_EXP_NOFLUSH
+    if (false) {
+#else
     if (my_tiles > 0) {
+#endif
       tc::fence_after_sync();
       if (tid == 0) TC4_TRACE(36, 0);
       const int nblk = (nw + 31) / 32;
@@ -1176,6 +1214,7 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
     const int nbp = pp.nbatches(kProdThreads), nbq = qp.nbatches(kProdThreads), upt = nbp + nbq;
     const int W = my_tiles * upt;
     union RawU { typename PProd::Raw p; typename QProd::Raw q; __device__ RawU() {} };
+    constexpr int D = LoadDepth<RawU>::value;
     typename QProd::Idx ix;   // the dy producers have no index stage
     struct Cur { int t, u, m0; };   // tile ordinal, unit within the tile, first row: advanced incrementally (no division)
     const int mstep = (int)gridDim.x * kPts;
@@ -1191,8 +1230,8 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
       adv(cl);
     };
     auto step = [&](int w, RawU& cur, RawU& nxt) {
-      if (w + 1 < W) do_load(nxt);
-      if (w + 2 < W) do_idx();
+      if (w + D < W) do_load(nxt);
+      if (w + D + 1 < W) do_idx();
       if (g == 0) TC4_TRACE(12, w);
       const int s = cst.t & (npq - 1), n = npq == 2 ? cst.t >> 1 : cst.t;     // stage slot, round
       if (cst.u == 0 && n > 0) tc::mbar_wait(&bar.empty[s], (uint32_t)((n - 1) & 1));
@@ -1200,18 +1239,22 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
       const uint32_t sP = sP0 + (uint32_t)s * pqbytes;
       if (cst.u < nbp) pp.store(g, kProdThreads, cst.m0, cst.u, cur.p, sP);
       else qp.store(g, kProdThreads, cst.m0, cst.u - nbp, cur.q, sP + pbytes);
-      if (cst.u == upt - 1) { tc::fence_proxy_async(); mbar_arrive(&bar.full[s]); }
+      if (cst.u == upt - 1) { tc::fence_proxy_async(); mbar_arrive_full(&bar.full[s]); }
       if (g == 0) TC4_TRACE(11, w);
       adv(cst);
     };
     if (W > 0) {
-      RawU ra, rb;
+      RawU r[D + 1];   // unit u lives in r[u % (D + 1)]
       do_idx();
-      do_load(ra);
-      if (W > 1) do_idx();
-      for (int w = 0; w < W; w += 2) {
-        step(w, ra, rb);
-        if (w + 1 < W) step(w + 1, rb, ra);
+#pragma unroll
+      for (int u = 0; u < D; ++u) {
+        if (u < W) do_load(r[u]);
+        if (u + 1 < W) do_idx();
+      }
+      for (int w = 0; w < W; w += D + 1) {
+#pragma unroll
+        for (int u = 0; u <= D; ++u)
+          if (w + u < W) step(w + u, r[u], r[(u + D) % (D + 1)]);
       }
     }
     if (g == 0) TC4_TRACE_DUMP();

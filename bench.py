@@ -117,11 +117,15 @@ def kernel_work(B: int, N: int) -> dict:
         t = f"sa{li + 1}_"
         dg1 = 2.0 * M * (c[0] - 3) * c[1]                             # no data gradient into xyz
         scat = 4.0 * (M // (S * 32)) * Nin * (c[0] - 3)               # grad_feats written once
+        # SA1 / SA2 (v4 kernels): the last layer's pre-activations y3 are never stored - the forward accumulates the
+        # Gram matrix of its input and the backward uses the sparse max-pool routing - so
+        # act(3) is neither written by fwd_l3 nor read by bwd_l3.  SA3 (v5 kernels) still stores y3.
+        y3 = 0.0 if li < 2 else act(3)
         w.update({
             t + "fwd_l1": (g(0, 1), src + act(1)), t + "fwd_l2": (g(1, 2), act(1) + act(2)),
-            t + "fwd_l3": (g(2, 3), act(2) + act(3) + pool),
+            t + "fwd_l3": (g(2, 3), act(2) + y3 + pool),
             # v4: one fused wgrad+dgrad kernel per layer
-            t + "bwd_l3": (2 * g(2, 3), act(3) + act(2) + 5.0 * G * c[3] + act(2)),
+            t + "bwd_l3": (2 * g(2, 3), y3 + act(2) + 5.0 * G * c[3] + act(2)),
             t + "bwd_l2": (2 * g(1, 2), 2 * act(2) + act(1) + act(1)),
             t + "bwd_l1": (g(0, 1) + dg1, 2 * act(1) + src + scat),
             # v5 / first-generation path: separate kernels
