@@ -26,7 +26,7 @@ class SADesc(C.Structure):
 class SAParams(C.Structure):
     """pcoe_sa_params"""
     _fields_ = [(n, C.c_void_p * 3) for n in
-                ("W", "bias", "gamma", "beta", "running_mean", "running_var")]
+                ("W", "bias", "gamma", "beta", "running_mean", "running_var", "num_batches_tracked")]
 
 
 class SAGrads(C.Structure):

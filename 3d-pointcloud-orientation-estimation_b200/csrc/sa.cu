@@ -61,8 +61,13 @@ __global__ void sa_out_finalize_kernel(const float* __restrict__ ymax, const flo
                                        const uint8_t* __restrict__ amax, const uint8_t* __restrict__ amin,
                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                        size_t total, int C, float* __restrict__ out,
-                                       uint8_t* __restrict__ slot, float* __restrict__ ysel, v4::BnFin fin) {
+                                       uint8_t* __restrict__ slot, float* __restrict__ ysel, v4::BnFin fin,
+                                       long long* nbt0, long long* nbt1, long long* nbt2) {
   extern __shared__ float fin_tab[];   // [2,C] when fused
+  if (blockIdx.x == 0 && threadIdx.x < 3) {   // BatchNorm2d.num_batches_tracked += 1 (train mode; NULL otherwise)
+    long long* n = threadIdx.x == 0 ? nbt0 : (threadIdx.x == 1 ? nbt1 : nbt2);
+    if (n) *n += 1;
+  }
   if (fin.sums) {
     const bool w = blockIdx.x == 0;
     for (int c = threadIdx.x; c < C; c += blockDim.x) fin.eval(c, C, w, fin_tab[c], fin_tab[C + c]);
@@ -384,7 +389,7 @@ static int convert_weights4(const pcoe_sa_desc& d, const SaLayout& L, const pcoe
     total += L.w4_rp[l] * L.w4_kp[l];
   }
   LaunchScope ls("convert_weights_kernel", st);
-  v4::convert_weights4_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(w[0], w[1], w[2]);
+  v4::convert_weights4_kernel<<<min(ceil_div(total / 8, 256), kNumSMs * 4), 256, 0, st>>>(w[0], w[1], w[2]);
   return ls.done();
 }
 
@@ -540,7 +545,8 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
   LaunchScope ls("sa_out_finalize_kernel", st);
   sa_out_finalize_kernel<<<blocks, 256, fin_out.sums ? sizeof(float) * 2 * d.C3 : 0, st>>>(
       ymax, ymin, amax, amin, scale[2], shift[2], total, d.C3, out, train ? (uint8_t*)(sv + L.sv_slot) : nullptr,
-      train ? (float*)(sv + L.sv_ysel) : nullptr, fin_out);
+      train ? (float*)(sv + L.sv_ysel) : nullptr, fin_out, train ? P.num_batches_tracked[0] : nullptr,
+      train ? P.num_batches_tracked[1] : nullptr, train ? P.num_batches_tracked[2] : nullptr);
   return ls.done();
 }
 
@@ -607,9 +613,11 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   if constexpr (TC) l3s = L.l3s;
 
   {
-    const int gpb = ceil_div(G, kNumSMs * 2);   // few blocks: every block ends with 2*C3 same-address fp64 atomics
+    // every block ends with 2*C3 fp64 atomics spread over kRedCopies copies: ~8 blocks per SM keep the per-thread
+    // chain of dependent load batches short (it was 17 us at 2 blocks per SM) without long same-address queues
+    const int gpb = ceil_div(G, kNumSMs * 8);
     LaunchScope ls("bwd_last_reduce_kernel", st);
-    bwd_last_reduce_kernel<<<ceil_div(G, gpb), d.C3 >= 256 ? 256 : (d.C3 >= 128 ? 128 : 64), 0, st>>>(grad_out, out, ysel, mean[2], invstd[2], G, d.C3,
+    bwd_last_reduce_kernel<<<ceil_div(G, gpb), d.C3 >= 1024 ? 1024 : (d.C3 >= 256 ? 256 : (d.C3 >= 128 ? 128 : 64)), 0, st>>>(grad_out, out, ysel, mean[2], invstd[2], G, d.C3,
                                                             gpb, gm, bs[2], l3s ? scale[2] : nullptr,
                                                             l3s ? (const float*)(sv + L.sv_gram) : nullptr,
                                                             l3s ? (float*)(ws + L.wb_gsum) : nullptr,

@@ -1427,19 +1427,24 @@ l3_prep_kernel(BnBwdFin fin, int C3, int C2, const __nv_bfloat16* __restrict__ W
 
 // fp32 [C_out][C_in] -> zero-padded bf16 [Rp][Kp]; perm_d >= 0: layer-1 column order [feats(perm_d) | xyz(3)]
 struct ConvW4 { const float* W; __nv_bfloat16* dst; int cout, cin, Rp, Kp, perm_d; };
+// one thread = 8 consecutive image columns (Kp is a multiple of 128): one 16-byte store, one division
 __global__ void convert_weights4_kernel(ConvW4 a, ConvW4 b, ConvW4 c) {
   const ConvW4* L[3] = {&a, &b, &c};
-  const int n0 = a.Rp * a.Kp, n1 = b.Rp * b.Kp, n2 = c.Rp * c.Kp;
+  const int n0 = a.Rp * a.Kp / 8, n1 = b.Rp * b.Kp / 8, n2 = c.Rp * c.Kp / 8;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n0 + n1 + n2; e += gridDim.x * blockDim.x) {
     const int l = e < n0 ? 0 : (e < n0 + n1 ? 1 : 2);
     const ConvW4& w = *L[l];
     const int ee = e - (l == 0 ? 0 : (l == 1 ? n0 : n0 + n1));
-    const int r = ee / w.Kp, k = ee - r * w.Kp;
-    int src = k;
-    if (w.perm_d >= 0) src = k < w.perm_d ? k + 3 : (k < w.perm_d + 3 ? k - w.perm_d : w.cin);
-    float v = 0.f;
-    if (r < w.cout && src < w.cin) v = w.W[(size_t)r * w.cin + src];
-    w.dst[ee] = __float2bfloat16_rn(v);
+    const int kp8 = w.Kp >> 3, r = ee / kp8, k0 = (ee - r * kp8) * 8;
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u;
+      int src = k;
+      if (w.perm_d >= 0) src = k < w.perm_d ? k + 3 : (k < w.perm_d + 3 ? k - w.perm_d : w.cin);
+      v[u] = (r < w.cout && src < w.cin) ? __ldg(w.W + (size_t)r * w.cin + src) : 0.f;
+    }
+    reinterpret_cast<uint4*>(w.dst)[ee] = tc::pack8_bf16(v);
   }
 }
 

@@ -95,6 +95,8 @@ class _SAFunction(torch.autograd.Function):
         _fill3(P.W, Ws); _fill3(P.bias, bs); _fill3(P.gamma, gs); _fill3(P.beta, bes)
         _fill3(P.running_mean, [bn.running_mean for bn in module.bns])
         _fill3(P.running_var, [bn.running_var for bn in module.bns])
+        # incremented inside pcoe_sa_forward (one thread of its last kernel) instead of three torch add_ launches
+        _fill3(P.num_batches_tracked, [bn.num_batches_tracked if train else None for bn in module.bns])
         sv_bytes = lib.pcoe_sa_saved_bytes(C.byref(desc))
         ws_bytes = lib.pcoe_sa_workspace_bytes(C.byref(desc))
         if ws_bytes == 0:
@@ -105,10 +107,6 @@ class _SAFunction(torch.autograd.Function):
         _lib.check(lib.pcoe_sa_forward(C.byref(desc), xyz.data_ptr(), ops._ptr(new_xyz), ops._ptr(nbr),
                                        ops._ptr(feats), C.byref(P), out.data_ptr(), ops._ptr(saved), sv_bytes,
                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
-        if train:
-            for bn in module.bns:
-                if bn.num_batches_tracked is not None:
-                    bn.num_batches_tracked.add_(1)
         ctx.desc, ctx.P, ctx.train = desc, P, train
         ctx.params = params if module.direct_grad_accumulation else None
         ctx.after_backward = getattr(module, "_after_backward", None)

@@ -137,6 +137,8 @@ typedef struct pcoe_sa_params {
   const float* beta[3];
   float* running_mean[3];
   float* running_var[3];
+  long long* num_batches_tracked[3]; /* BatchNorm2d.num_batches_tracked (int64 scalars), incremented by one per
+                                        train-mode forward; entries may be NULL */
 } pcoe_sa_params;
 
 /* Gradients written by pcoe_sa_backward, same layouts.  accumulate == 0: every array is
