@@ -64,6 +64,10 @@ SIGNATURES = {
     "pcoe_linear_bwd_dw": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
     "pcoe_ln_relu_dropout_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _F, _F, _I, _U64, _P, _P, _P, _P, _P, _P]),
     "pcoe_ln_relu_dropout_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P]),
+    "pcoe_ln_relu_dropout_heads_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _F, _F, _I, _U64, _P, _P, _P, _P, _P,
+                                            _I, _P, _P, _P, _P, _I, _F, _F, _I, _P, _P, _P, _P]),
+    "pcoe_heads_ln_relu_dropout_bwd": (_I, [_P, _I, _F, _F, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P,
+                                            _I, _I, _F, _I, _P, _P, _P, _P, _P]),
     "pcoe_adam_workspace_bytes": (_SZ, []),
     "pcoe_adam_step": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
 }

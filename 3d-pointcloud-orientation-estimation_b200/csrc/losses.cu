@@ -7,6 +7,7 @@
 // is at least as accurate as the reference's fp32 Cephes evaluation; the fp32 overflow behaviour
 // of torch.special.i0/i1 (exp(x) = inf for x > log(FLT_MAX)) is reproduced explicitly.
 #include "common.cuh"
+#include "mvm_head.cuh"
 #include <math.h>
 
 namespace pcoe {
@@ -276,30 +277,14 @@ extern "C" int pcoe_mvm_match_fwd_bwd(const float* mu, const float* kappa, const
 // normalised vector is shorter than 1e-3, mu = atan2(s, c); kappa = min(softplus(kappa_raw) + 1e-6, kappa_max).
 namespace pcoe {
 
-constexpr int kHeadMaxK = 8;
-
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // torch threshold 20
-
 __global__ void mvm_head_fwd_kernel(const float* __restrict__ pi, const float* __restrict__ mu_raw,
                                     const float* __restrict__ kappa_raw, int B, int K, float temp, float kappa_max,
                                     int clamp_kappa, float* __restrict__ weight, float* __restrict__ mu,
                                     float* __restrict__ kappa) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  float z[kHeadMaxK], mx = -INFINITY, sum = 0.f;
-  for (int k = 0; k < K; ++k) { z[k] = pi[b * K + k] / temp; mx = fmaxf(mx, z[k]); }
-  for (int k = 0; k < K; ++k) { z[k] = expf(z[k] - mx); sum += z[k]; }
-  for (int k = 0; k < K; ++k) {
-    weight[b * K + k] = z[k] / sum;
-    const float vx = mu_raw[(b * K + k) * 2], vy = mu_raw[(b * K + k) * 2 + 1];
-    const float dn = fmaxf(sqrtf(vx * vx + vy * vy), 1e-4f);
-    const float c = vx / dn, s = vy / dn;
-    const bool masked = sqrtf(c * c + s * s) < 1e-3f;
-    mu[b * K + k] = masked ? 0.f : atan2f(s, c);
-    float kp = softplus_f(kappa_raw[b * K + k]) + 1e-6f;
-    if (clamp_kappa) kp = fminf(kp, kappa_max);
-    kappa[b * K + k] = kp;
-  }
+  mvm_head_fwd_row(pi + b * K, mu_raw + b * K * 2, kappa_raw + b * K, K, temp, kappa_max, clamp_kappa, weight + b * K,
+                   mu + b * K, kappa + b * K);
 }
 
 __global__ void mvm_head_bwd_kernel(const float* __restrict__ pi, const float* __restrict__ mu_raw,
@@ -309,36 +294,9 @@ __global__ void mvm_head_bwd_kernel(const float* __restrict__ pi, const float* _
                                     float* __restrict__ d_mu_raw, float* __restrict__ d_kappa_raw) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  float z[kHeadMaxK], mx = -INFINITY, sum = 0.f, dot = 0.f;
-  for (int k = 0; k < K; ++k) { z[k] = pi[b * K + k] / temp; mx = fmaxf(mx, z[k]); }
-  for (int k = 0; k < K; ++k) { z[k] = expf(z[k] - mx); sum += z[k]; }
-  for (int k = 0; k < K; ++k) { z[k] /= sum; dot += (g_w ? g_w[b * K + k] : 0.f) * z[k]; }
-  for (int k = 0; k < K; ++k) {
-    d_pi[b * K + k] = g_w ? z[k] * (g_w[b * K + k] - dot) / temp : 0.f;
-    // mu: atan2 -> where-fallback -> normalize(eps)
-    const float vx = mu_raw[(b * K + k) * 2], vy = mu_raw[(b * K + k) * 2 + 1];
-    const float n = sqrtf(vx * vx + vy * vy), dn = fmaxf(n, 1e-4f);
-    const float c = vx / dn, s = vy / dn, r2 = c * c + s * s;
-    float gx = 0.f, gy = 0.f;
-    if (g_mu && !(sqrtf(r2) < 1e-3f)) {
-      const float g = g_mu[b * K + k];
-      const float gc = -s / r2 * g, gs = c / r2 * g;           // d atan2(s, c)
-      if (n > 1e-4f) {                                         // u = v / |v|
-        const float proj = (vx * gc + vy * gs) / (n * n * n);
-        gx = gc / n - vx * proj;
-        gy = gs / n - vy * proj;
-      } else {                                                 // u = v / eps (clamp_min passes no gradient to |v|)
-        gx = gc / 1e-4f;
-        gy = gs / 1e-4f;
-      }
-    }
-    d_mu_raw[(b * K + k) * 2] = gx;
-    d_mu_raw[(b * K + k) * 2 + 1] = gy;
-    const float x = kappa_raw[b * K + k];
-    float gk = g_k ? g_k[b * K + k] : 0.f;
-    if (clamp_kappa && softplus_f(x) + 1e-6f > kappa_max) gk = 0.f;
-    d_kappa_raw[b * K + k] = gk * (x > 20.f ? 1.f : 1.f / (1.f + expf(-x)));
-  }
+  mvm_head_bwd_row(pi + b * K, mu_raw + b * K * 2, kappa_raw + b * K, K, temp, kappa_max, clamp_kappa,
+                   g_w ? g_w + b * K : nullptr, g_mu ? g_mu + b * K : nullptr, g_k ? g_k + b * K : nullptr, d_pi + b * K,
+                   d_mu_raw + b * K * 2, d_kappa_raw + b * K);
 }
 
 }  // namespace pcoe

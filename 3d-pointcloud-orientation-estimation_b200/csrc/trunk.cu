@@ -11,6 +11,7 @@
 //   ln_relu_drop_fwd  out = dropout(relu(LayerNorm(x))), saves mean / rstd / keep-mask
 //   ln_relu_drop_bwd  dx, dgamma, dbeta
 #include "common.cuh"
+#include "mvm_head.cuh"
 
 namespace pcoe {
 
@@ -272,13 +273,32 @@ __device__ __forceinline__ float block_sum256(float v, float* red) {
 // fixed order (deterministic) and the sum is written to h (the pre-LayerNorm activation saved for backward).
 // One CTA (256 threads) per row, up to kLnPer elements per thread in registers (N <= 256 * kLnPer).
 constexpr int kLnPer = 4;
+constexpr int kTailMaxOut = 64;
+// Optional tail of the row kernels (the trunk's last stage): the up-to-three small linear heads that share the row
+// (Ntot <= 64 outputs, written segment-major like linear_fwd) and, when K > 0, the mixture head transform of the
+// row (N = {K, 2K, K}: pi | mu_raw | kappa_raw).  Everything after the last LayerNorm is per-row work: fusing it
+// replaces a one-CTA GEMM launch (13 us) and the head-transform launch (7 us) by ~1 us inside this kernel.
+struct HeadTail {
+  LinSeg seg;          // W, b, N (forward) ; W, N (backward)
+  float* raw;          // forward: [B x N0][B x N1][B x N2] linear outputs ; backward: the saved outputs (read)
+  float* d_raw;        // backward: gradient w.r.t. raw (written, same layout)
+  int K;               // > 0: mixture head transform
+  float temp, kappa_max;
+  int clamp_kappa;
+  float *weight, *mu, *kappa;              // forward outputs [B,K]
+  const float *g_w, *g_mu, *g_k;           // backward upstream gradients [B,K] (may be NULL)
+};
+
+template <bool TAIL>
 __global__ void __launch_bounds__(256)
 ln_relu_drop_fwd_kernel(const float* __restrict__ x, int nparts, const float* __restrict__ xbias, float* __restrict__ h,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
                         int B, int N, float eps, float p, int train, uint64_t seed, const uint64_t* __restrict__ counter,
                         float* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd,
-                        uint8_t* __restrict__ mask) {
+                        uint8_t* __restrict__ mask, HeadTail tail) {
   __shared__ float red[8];
+  __shared__ float rowbuf[TAIL ? 256 * kLnPer : 1];
+  __shared__ float rawbuf[TAIL ? kTailMaxOut : 1];
   const int row = blockIdx.x;
   float v[kLnPer];
   float s = 0.f;
@@ -322,17 +342,74 @@ ln_relu_drop_fwd_kernel(const float* __restrict__ x, int nparts, const float* __
     bool keep = true;
     if (drop) keep = philox_u32((uint32_t)n, (uint32_t)row, seed, off) >= thr;
     if (mask) mask[(size_t)row * N + n] = keep ? 1 : 0;
-    out[(size_t)row * N + n] = keep ? y * keep_scale : 0.f;
+    const float o = keep ? y * keep_scale : 0.f;
+    out[(size_t)row * N + n] = o;
+    if constexpr (TAIL) rowbuf[n] = o;
+  }
+  if constexpr (TAIL) {
+    __syncthreads();
+    const LinSeg& sg = tail.seg;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int o = warp; o < sg.Ntot; o += 8) {          // one warp per output: coalesced reads of the weight row
+      int si, lo;
+      seg_of(sg, o, si, lo);
+      const float* w = sg.W[si] + (size_t)lo * N;
+      float a0 = 0.f, a1 = 0.f;
+      int n = lane;
+      for (; n + 32 < N; n += 64) { a0 = fmaf(rowbuf[n], __ldg(w + n), a0); a1 = fmaf(rowbuf[n + 32], __ldg(w + n + 32), a1); }
+      if (n < N) a0 = fmaf(rowbuf[n], __ldg(w + n), a0);
+      float a = a0 + a1;
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, m);
+      if (lane == 0) {
+        a += sg.b[si] ? sg.b[si][lo] : 0.f;
+        tail.raw[seg_major(sg, B, row, o, si, lo)] = a;
+        rawbuf[o] = a;
+      }
+    }
+    if (tail.K > 0) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int K = tail.K;
+        mvm_head_fwd_row(rawbuf, rawbuf + K, rawbuf + 3 * K, K, tail.temp, tail.kappa_max, tail.clamp_kappa,
+                         tail.weight + (size_t)row * K, tail.mu + (size_t)row * K, tail.kappa + (size_t)row * K);
+      }
+    }
   }
 }
 
+// TAIL: dout is not read - it is the heads' data gradient of this row, derived here from the upstream gradients of
+// the head transform:  d_raw = head_bwd(raw, g_w, g_mu, g_k)  (written for the heads' weight-gradient kernel),
+// dout[n] = sum_o d_raw[o] * W_o[n].
+template <bool TAIL>
 __global__ void __launch_bounds__(256)
 ln_relu_drop_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ out,
                         const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                         const uint8_t* __restrict__ mask, int B, int N, float p, int train, float* __restrict__ dx,
-                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxbias) {
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxbias, HeadTail tail) {
   __shared__ float red[8];
+  __shared__ float drawbuf[TAIL ? kTailMaxOut : 1];
   const int row = blockIdx.x;
+  if constexpr (TAIL) {
+    const LinSeg& sg = tail.seg;
+    const int K = tail.K;
+    if (threadIdx.x == 0) {      // K > 0 (checked on the host): raw = pi [B,K] | mu_raw [B,2K] | kappa_raw [B,K]
+      float rw[4 * kHeadMaxK];
+      const float* r0 = tail.raw;
+      for (int k = 0; k < K; ++k) rw[k] = r0[(size_t)row * K + k];
+      for (int k = 0; k < 2 * K; ++k) rw[K + k] = r0[(size_t)B * K + (size_t)row * 2 * K + k];
+      for (int k = 0; k < K; ++k) rw[3 * K + k] = r0[(size_t)B * 3 * K + (size_t)row * K + k];
+      mvm_head_bwd_row(rw, rw + K, rw + 3 * K, K, tail.temp, tail.kappa_max, tail.clamp_kappa,
+                       tail.g_w ? tail.g_w + (size_t)row * K : nullptr, tail.g_mu ? tail.g_mu + (size_t)row * K : nullptr,
+                       tail.g_k ? tail.g_k + (size_t)row * K : nullptr, drawbuf, drawbuf + K, drawbuf + 3 * K);
+      float* d0 = tail.d_raw;
+      for (int k = 0; k < K; ++k) d0[(size_t)row * K + k] = drawbuf[k];
+      for (int k = 0; k < 2 * K; ++k) d0[(size_t)B * K + (size_t)row * 2 * K + k] = drawbuf[K + k];
+      for (int k = 0; k < K; ++k) d0[(size_t)B * 3 * K + (size_t)row * K + k] = drawbuf[3 * K + k];
+    }
+    __syncthreads();
+    (void)sg;
+  }
   const float keep_scale = (train && p > 0.f) ? 1.f / (1.f - p) : 1.f;
   const float mu = mean[row], rs = rstd[row];
   const size_t o = (size_t)row * N;
@@ -345,7 +422,18 @@ ln_relu_drop_bwd_kernel(const float* __restrict__ dout, const float* __restrict_
     dzg[i] = xh[i] = 0.f;
     if (n >= N) continue;
     const bool on = out[o + n] > 0.f;                     // ReLU and dropout both zero the output
-    const float dz = on ? dout[o + n] * keep_scale * (mask ? (float)mask[o + n] : 1.f) : 0.f;
+    float dov;
+    if constexpr (TAIL) {
+      const LinSeg& sg = tail.seg;
+      float a = 0.f;
+      int oo = 0;
+      for (int si = 0; si < sg.nseg; ++si)
+        for (int lo = 0; lo < sg.N[si]; ++lo, ++oo) a = fmaf(drawbuf[oo], __ldg(sg.W[si] + (size_t)lo * N + n), a);
+      dov = a;
+    } else {
+      dov = dout[o + n];
+    }
+    const float dz = on ? dov * keep_scale * (mask ? (float)mask[o + n] : 1.f) : 0.f;
     xh[i] = (x[o + n] - mu) * rs;
     dzg[i] = dz * gamma[n];
     s1 += dzg[i];
@@ -470,8 +558,43 @@ extern "C" int pcoe_ln_relu_dropout_fwd(const float* x, int nparts, const float*
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope ls("ln_relu_drop_fwd_kernel", st);
   if (N > 256 * kLnPer) return fail(PCOE_ERR_UNSUPPORTED, "ln_relu_dropout: N=%d > %d", N, 256 * kLnPer);
-  ln_relu_drop_fwd_kernel<<<B, 256, 0, st>>>(x, nparts < 1 ? 1 : nparts, xbias, h, gamma, beta, B, N, eps, p, train,
-                                                          seed, counter_dev, out, mean, rstd, mask);
+  ln_relu_drop_fwd_kernel<false><<<B, 256, 0, st>>>(x, nparts < 1 ? 1 : nparts, xbias, h, gamma, beta, B, N, eps, p, train,
+                                                          seed, counter_dev, out, mean, rstd, mask, HeadTail{});
+  return ls.done();
+}
+
+static int check_tail(const char* what, int nseg, const int* Nout, int K) {
+  if (nseg < 1 || nseg > kMaxSeg || !Nout) return fail(PCOE_ERR_BAD_SHAPE, "%s: nseg=%d", what, nseg);
+  int tot = 0;
+  for (int i = 0; i < nseg; ++i) tot += Nout[i];
+  if (tot > kTailMaxOut) return fail(PCOE_ERR_UNSUPPORTED, "%s: %d head outputs > %d", what, tot, kTailMaxOut);
+  if (K > 0 && (K > kHeadMaxK || nseg != 3 || Nout[0] != K || Nout[1] != 2 * K || Nout[2] != K))
+    return fail(PCOE_ERR_BAD_SHAPE, "%s: the mixture head needs segments (K, 2K, K) with K <= %d", what, kHeadMaxK);
+  return PCOE_OK;
+}
+
+extern "C" int pcoe_ln_relu_dropout_heads_fwd(const float* x, int nparts, const float* xbias, float* h, const float* gamma,
+                                              const float* beta, int B, int N, float eps, float p, int train,
+                                              uint64_t seed, const uint64_t* counter_dev, float* out, float* mean,
+                                              float* rstd, uint8_t* mask, int nseg, const float* const* W,
+                                              const float* const* bias, const int* Nout, float* raw, int K, float temp,
+                                              float kappa_max, int clamp_kappa, float* weight, float* mu, float* kappa,
+                                              void* stream) {
+  if (B <= 0 || N <= 0 || !(p >= 0.f && p < 1.f)) return fail(PCOE_ERR_BAD_SHAPE, "ln_heads_fwd: B=%d N=%d p=%g", B, N, p);
+  if (!x || !gamma || !beta || !out || !W || !raw) return fail(PCOE_ERR_NULL, "ln_heads_fwd: NULL pointer");
+  if ((nparts > 1 || xbias) && !h) return fail(PCOE_ERR_NULL, "ln_heads_fwd: partial sums / bias need the h output");
+  if (N > 256 * kLnPer) return fail(PCOE_ERR_UNSUPPORTED, "ln_heads_fwd: N=%d > %d", N, 256 * kLnPer);
+  PCOE_TRY(check_tail("ln_heads_fwd", nseg, Nout, K));
+  if (K > 0 && (!(temp > 0.f) || !weight || !mu || !kappa)) return fail(PCOE_ERR_NULL, "ln_heads_fwd: head outputs / temp");
+  HeadTail t{};
+  PCOE_TRY(make_seg(t.seg, nseg, W, bias, nullptr, nullptr, Nout));
+  for (int i = 0; i < nseg; ++i) if (!W[i]) return fail(PCOE_ERR_NULL, "ln_heads_fwd: W[%d] is NULL", i);
+  t.raw = raw; t.K = K; t.temp = temp; t.kappa_max = kappa_max; t.clamp_kappa = clamp_kappa;
+  t.weight = weight; t.mu = mu; t.kappa = kappa;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope ls("ln_heads_fwd_kernel", st);
+  ln_relu_drop_fwd_kernel<true><<<B, 256, 0, st>>>(x, nparts < 1 ? 1 : nparts, xbias, h, gamma, beta, B, N, eps, p, train,
+                                                   seed, counter_dev, out, mean, rstd, mask, t);
   return ls.done();
 }
 
@@ -484,7 +607,31 @@ extern "C" int pcoe_ln_relu_dropout_bwd(const float* dout, const float* x, const
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope ls("ln_relu_drop_bwd_kernel", st);
   if (N > 256 * kLnPer) return fail(PCOE_ERR_UNSUPPORTED, "ln_relu_dropout: N=%d > %d", N, 256 * kLnPer);
-  ln_relu_drop_bwd_kernel<<<B, 256, 0, st>>>(dout, x, out, gamma, mean, rstd, mask, B, N, p, train, dx, dgamma,
-                                                          dbeta, dxbias);
+  ln_relu_drop_bwd_kernel<false><<<B, 256, 0, st>>>(dout, x, out, gamma, mean, rstd, mask, B, N, p, train, dx, dgamma,
+                                                          dbeta, dxbias, HeadTail{});
+  return ls.done();
+}
+
+extern "C" int pcoe_heads_ln_relu_dropout_bwd(const float* raw, int K, float temp, float kappa_max, int clamp_kappa,
+                                              const float* g_w, const float* g_mu, const float* g_k, float* d_raw,
+                                              int nseg, const float* const* W, const int* Nout, const float* x,
+                                              const float* out, const float* gamma, const float* mean, const float* rstd,
+                                              const uint8_t* mask, int B, int N, float p, int train, float* dx,
+                                              float* dgamma, float* dbeta, float* dxbias, void* stream) {
+  if (B <= 0 || N <= 0) return fail(PCOE_ERR_BAD_SHAPE, "heads_ln_bwd: B=%d N=%d", B, N);
+  if (!raw || !d_raw || !W || !x || !out || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta)
+    return fail(PCOE_ERR_NULL, "heads_ln_bwd: NULL pointer");
+  if (N > 256 * kLnPer) return fail(PCOE_ERR_UNSUPPORTED, "heads_ln_bwd: N=%d > %d", N, 256 * kLnPer);
+  if (K <= 0 || !(temp > 0.f)) return fail(PCOE_ERR_BAD_SHAPE, "heads_ln_bwd: K=%d temp=%g", K, temp);
+  PCOE_TRY(check_tail("heads_ln_bwd", nseg, Nout, K));
+  HeadTail t{};
+  PCOE_TRY(make_seg(t.seg, nseg, W, nullptr, nullptr, nullptr, Nout));
+  for (int i = 0; i < nseg; ++i) if (!W[i]) return fail(PCOE_ERR_NULL, "heads_ln_bwd: W[%d] is NULL", i);
+  t.raw = const_cast<float*>(raw); t.d_raw = d_raw; t.K = K; t.temp = temp; t.kappa_max = kappa_max;
+  t.clamp_kappa = clamp_kappa; t.g_w = g_w; t.g_mu = g_mu; t.g_k = g_k;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope ls("heads_ln_bwd_kernel", st);
+  ln_relu_drop_bwd_kernel<true><<<B, 256, 0, st>>>(nullptr, x, out, gamma, mean, rstd, mask, B, N, p, train, dx, dgamma,
+                                                   dbeta, dxbias, t);
   return ls.done();
 }

@@ -134,13 +134,14 @@ def mvm_match_fwd_bwd(mu, kappa, w, vm_gt, K_gt):
     if vm_gt.size(1) != Kmax:
         vm_gt = vm_gt[:, :Kmax].contiguous()
     loss = torch.empty(B, dtype=torch.float32, device=mu.device)
-    dmu = torch.empty_like(mu); dk = torch.empty_like(mu); dw = torch.empty_like(mu)
+    d3 = torch.empty(3, B, Kmax, dtype=torch.float32, device=mu.device)   # one buffer: backward scales it in one launch
+    dmu, dk, dw = d3[0], d3[1], d3[2]
     perm = torch.empty(B, Kmax, dtype=torch.int32, device=mu.device)
     _lib.check(_lib.load().pcoe_mvm_match_fwd_bwd(mu.data_ptr(), kappa.data_ptr(), w.data_ptr(),
                                                   vm_gt.data_ptr(), vm_gt.size(2), K_gt.data_ptr(), B, Kmax,
                                                   loss.data_ptr(), dmu.data_ptr(), dk.data_ptr(),
                                                   dw.data_ptr(), perm.data_ptr(), _stream()))
-    return loss, dmu, dk, dw, perm
+    return loss, d3, perm
 
 
 def soft_ce_fwd_bwd(logits, p):

@@ -100,16 +100,15 @@ class MvMTrunkHead(torch.autograd.Function):
                                                 b1.data_ptr(), B, h1.size(1), eps1, p, int(train), seed, cptr,
                                                 a1.data_ptr(), st1[0].data_ptr(), st1[1].data_ptr(), m1.data_ptr(), st))
         n2 = _linear_fwd(lib, st, a1, [fc2w], [fc2b], parts, _MAX_PARTS)
-        _lib.check(lib.pcoe_ln_relu_dropout_fwd(parts.data_ptr(), n2, fc2b.data_ptr(), h2.data_ptr(), g2.data_ptr(),
-                                                b2.data_ptr(), B, h2.size(1), eps2, p, int(train),
-                                                seed ^ 0x9E3779B97F4A7C15, cptr, a2.data_ptr(), st2[0].data_ptr(),
-                                                st2[1].data_ptr(), m2.data_ptr(), st))
-        _linear_fwd(lib, st, a2, [piw, muw, kw], [pib, mub, kb], raw)
-        pi, mur, kr = raw[:B * K], raw[B * K:3 * B * K], raw[3 * B * K:]
         clamp = kmax is not None
-        _lib.check(lib.pcoe_mvm_head_fwd(pi.data_ptr(), mur.data_ptr(), kr.data_ptr(), B, K, float(temp),
-                                         float(kmax) if clamp else 0.0, int(clamp), out[2].data_ptr(), out[0].data_ptr(),
-                                         out[1].data_ptr(), st))
+        # LayerNorm 2 + ReLU + dropout, the three heads and the head transform are all per-row work: one launch
+        heads_w, heads_b = [piw, muw, kw], [pib, mub, kb]
+        _lib.check(lib.pcoe_ln_relu_dropout_heads_fwd(
+            parts.data_ptr(), n2, fc2b.data_ptr(), h2.data_ptr(), g2.data_ptr(), b2.data_ptr(), B, h2.size(1), eps2, p,
+            int(train), seed ^ 0x9E3779B97F4A7C15, cptr, a2.data_ptr(), st2[0].data_ptr(), st2[1].data_ptr(),
+            m2.data_ptr(), 3, _ptrs(heads_w), _ptrs(heads_b), _ints([w.size(0) for w in heads_w]), raw.data_ptr(), K,
+            float(temp), float(kmax) if clamp else 0.0, int(clamp), out[2].data_ptr(), out[0].data_ptr(),
+            out[1].data_ptr(), st))
         ctx.save_for_backward(x, h1, a1, h2, a2, st1, st2, m1, m2, raw, fc1w, fc2w, piw, muw, kw, g1, g2)
         ctx.cfg = cfg
         ctx.params = (fc1w, fc1b, g1, b1, fc2w, fc2b, g2, b2, piw, pib, muw, mub, kw, kb) if direct else None
@@ -133,19 +132,20 @@ class MvMTrunkHead(torch.autograd.Function):
         d1w, d1b, dg1, db1, d2w, d2b, dg2, db2, dpw, dpb, dmw, dmb, dkw, dkb = grads
         acc = int(direct)
         ptr = lambda t: None if t is None else t.contiguous().data_ptr()
-        pi, mur, kr = raw[:B * K], raw[B * K:3 * B * K], raw[3 * B * K:]
         draw = torch.empty_like(raw)
         clamp = kmax is not None
-        _lib.check(lib.pcoe_mvm_head_bwd(pi.data_ptr(), mur.data_ptr(), kr.data_ptr(), B, K, float(temp),
-                                         float(kmax) if clamp else 0.0, int(clamp), ptr(g_w), ptr(g_mu), ptr(g_k),
-                                         draw.data_ptr(), draw[B * K:].data_ptr(), draw[3 * B * K:].data_ptr(), st))
-        da2, dh2 = torch.empty_like(a2), torch.empty_like(h2)
+        dh2 = torch.empty_like(h2)
         side = _side_stream(dev)
-        _linear_bwd(lib, st, draw, a2, [piw, muw, kw], [dpw, dmw, dkw], [dpb, dmb, dkb], da2, acc, side)
-        # the LayerNorm backward also adds the column sums of its dx into the bias gradient of the linear below it
-        _lib.check(lib.pcoe_ln_relu_dropout_bwd(da2.data_ptr(), h2.data_ptr(), a2.data_ptr(), g2.data_ptr(), st2[0].data_ptr(),
-                                                st2[1].data_ptr(), m2.data_ptr(), B, h2.size(1), p, int(train),
-                                                dh2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), d2b.data_ptr(), st))
+        heads_w = [piw, muw, kw]
+        # head-transform backward -> heads' data gradient -> LayerNorm 2 backward, per row, in one launch (the
+        # LayerNorm backward also adds the column sums of its dx into the bias gradient of the linear below it)
+        _lib.check(lib.pcoe_heads_ln_relu_dropout_bwd(
+            raw.data_ptr(), K, float(temp), float(kmax) if clamp else 0.0, int(clamp), ptr(g_w), ptr(g_mu), ptr(g_k),
+            draw.data_ptr(), 3, _ptrs(heads_w), _ints([w.size(0) for w in heads_w]), h2.data_ptr(), a2.data_ptr(),
+            g2.data_ptr(), st2[0].data_ptr(), st2[1].data_ptr(), m2.data_ptr(), B, h2.size(1), p, int(train),
+            dh2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), d2b.data_ptr(), st))
+        # the heads' weight / bias gradients (side stream)
+        _linear_bwd(lib, st, draw, a2, heads_w, [dpw, dmw, dkw], [dpb, dmb, dkb], None, acc, side)
         da1, dh1 = torch.empty_like(a1), torch.empty_like(h1)
         _linear_bwd(lib, st, dh2, a1, [fc2w], [d2w], [None], da1, acc, side)
         _lib.check(lib.pcoe_ln_relu_dropout_bwd(da1.data_ptr(), h1.data_ptr(), a1.data_ptr(), g1.data_ptr(), st1[0].data_ptr(),

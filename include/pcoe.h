@@ -257,6 +257,25 @@ int pcoe_ln_relu_dropout_bwd(const float* dout, const float* x, const float* out
                              float p, int train, float* dx, float* dgamma, float* dbeta, float* dxbias,
                              void* stream);
 
+/* The last stage of the mixture model's trunk as ONE launch per direction (models/pointnet_pp_mvM.py:84,91-125):
+ * pcoe_ln_relu_dropout_fwd followed, per row, by up to three small linear heads that share the row (nseg, W, bias,
+ * Nout as in pcoe_linear_fwd; sum(Nout) <= 64; `raw` = their outputs, segment-major) and, when K > 0, by the head
+ * transform of pcoe_mvm_head_fwd (segments must be pi (K) | mu_raw (2K) | kappa_raw (K)). */
+int pcoe_ln_relu_dropout_heads_fwd(const float* x, int nparts, const float* xbias, float* h, const float* gamma,
+                                   const float* beta, int B, int N, float eps, float p, int train, uint64_t seed,
+                                   const uint64_t* counter_dev, float* out, float* mean, float* rstd,
+                                   uint8_t* mask, int nseg, const float* const* W, const float* const* bias,
+                                   const int* Nout, float* raw, int K, float temp, float kappa_max,
+                                   int clamp_kappa, float* weight, float* mu, float* kappa, void* stream);
+/* Its backward: d_raw = pcoe_mvm_head_bwd(raw; g_w, g_mu, g_k) (written, for the heads' pcoe_linear_bwd_dw),
+ * the heads' data gradient and pcoe_ln_relu_dropout_bwd on it, per row. */
+int pcoe_heads_ln_relu_dropout_bwd(const float* raw, int K, float temp, float kappa_max, int clamp_kappa,
+                                   const float* g_w, const float* g_mu, const float* g_k, float* d_raw, int nseg,
+                                   const float* const* W, const int* Nout, const float* x, const float* out,
+                                   const float* gamma, const float* mean, const float* rstd, const uint8_t* mask,
+                                   int B, int N, float p, int train, float* dx, float* dgamma, float* dbeta,
+                                   float* dxbias, void* stream);
+
 /* Soft-label cross entropy -(p * log_softmax(logits)).sum(1).  Replaces
  * kl_loss_per_sample_from_logits, train_8dir_KL.py:60-68.  logits,p [B,C] f32, C <= 64. */
 int pcoe_soft_ce_fwd_bwd(const float* logits, const float* p, int B, int C, float* loss,
