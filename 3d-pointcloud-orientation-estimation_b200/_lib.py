@@ -46,6 +46,7 @@ SIGNATURES = {
     "pcoe_fps_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "pcoe_gather_points_f32": (_I, [_P, _I, _I, _I, _P, _I, _P, _P]),
     "pcoe_random_subset": (_I, [_I, _I, _I, _U64, _U64, _P, _P, _P]),
+    "pcoe_random_subset_xyz": (_I, [_I, _I, _I, _U64, _U64, _P, _P, _P, _P, _P]),
     "pcoe_knn_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "pcoe_ball_query_f32": (_I, [_P, _P, _I, _I, _I, _I, _D, _P, _P]),
     "pcoe_sa_saved_bytes": (_SZ, [C.POINTER(SADesc)]),

@@ -449,7 +449,7 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
   auto mkfin = [&](int l) {
     v4::BnFin f{};
     if (train) {
-      f.sums = sums[l]; f.count = (double)M; f.gamma = P.gamma[l]; f.beta = P.beta[l]; f.bias = P.bias[l];
+      f.sums = sums[l]; f.count = (double)M; f.inv_count = 1.0 / (double)M; f.gamma = P.gamma[l]; f.beta = P.beta[l]; f.bias = P.bias[l];
       f.running_mean = P.running_mean[l]; f.running_var = P.running_var[l]; f.eps = d.eps; f.momentum = d.momentum;
       f.scale = scale[l]; f.shift = shift[l]; f.mean = mean[l]; f.invstd = invstd[l];
     }
@@ -603,7 +603,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   // v4 / v5: the BatchNorm-backward constants of layer l are derived inline by the kernels that consume them
   auto mkbfin = [&](int l, int write) {
     v4::BnBwdFin f{};
-    f.sums = bs[l]; f.count = (double)M; f.scale = scale[l]; f.mean = mean[l]; f.invstd = invstd[l];
+    f.sums = bs[l]; f.count = (double)M; f.inv_count = 1.0 / (double)M; f.scale = scale[l]; f.mean = mean[l]; f.invstd = invstd[l];
     f.dgamma = Gr.dgamma[l]; f.dbeta = Gr.dbeta[l]; f.dbias = Gr.dbias[l]; f.accumulate = Gr.accumulate; f.write = write;
     return f;
   };

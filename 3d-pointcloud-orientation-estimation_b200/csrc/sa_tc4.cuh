@@ -120,7 +120,8 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 // statistics for backward and updates the running buffers (bn_finalize_kernel's arithmetic, sa.cu).
 struct BnFin {
   const double* sums;            // [2,C] sum, sum of squares; nullptr = not fused (read scale/shift arrays)
-  double count;
+  double count, inv_count;       // inv_count = 1 / count from the host: no fp64 division / square root on the device
+                                 // (every CTA evaluates this in its prologue; DDIV + DSQRT cost ~3 us per kernel)
   const float* gamma;
   const float* beta;
   const float* bias;             // conv bias: only shifts running_mean (cancelled by the batch-mean subtraction)
@@ -132,10 +133,12 @@ struct BnFin {
     double t0 = 0.0, t1 = 0.0;
 #pragma unroll
     for (int k = 0; k < kRedCopies; ++k) { t0 += sums[(size_t)k * 2 * C + c]; t1 += sums[(size_t)k * 2 * C + C + c]; }
-    const double mu = t0 / count;
-    double var = t1 / count - mu * mu;   // biased, as BatchNorm normalises
+    const double mu = t0 * inv_count;
+    double var = t1 * inv_count - mu * mu;   // biased, as BatchNorm normalises
     var = var < 0.0 ? 0.0 : var;
-    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float ve = (float)(var + (double)eps);
+    float is = rsqrtf(ve);
+    is = is * (1.5f - 0.5f * ve * is * is);  // one Newton step: fp32-exact to ~1 ulp
     sc = gamma[c] * is;
     sh = beta[c] - (float)mu * sc;
     if (write) {
@@ -152,7 +155,7 @@ struct BnFin {
 // BatchNorm-backward constants (a, p, q) + parameter gradients, inline (bn_bwd_consts_kernel's arithmetic)
 struct BnBwdFin {
   const double* sums;            // [2,C] sum dz, sum dz*xhat; nullptr = not fused (read a/p/q arrays)
-  double count;
+  double count, inv_count;
   const float* scale; const float* mean; const float* invstd;
   float* dgamma; float* dbeta; float* dbias;
   int accumulate, write;         // write: this launch owns the parameter-gradient outputs
@@ -160,7 +163,7 @@ struct BnBwdFin {
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int k = 0; k < kRedCopies; ++k) { s0 += sums[(size_t)k * 2 * C + c]; s1 += sums[(size_t)k * 2 * C + C + c]; }
-    const double m1 = s0 / count, m2 = s1 / count;
+    const double m1 = s0 * inv_count, m2 = s1 * inv_count;
     const double av = scale[c];
     const double pv = -av * (double)invstd[c] * m2;
     a = (float)av; p = (float)pv; q = (float)(-av * m1 - pv * (double)mean[c]);

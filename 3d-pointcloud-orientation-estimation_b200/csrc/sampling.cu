@@ -140,8 +140,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 
 // One CTA per cloud: identity permutation in shared memory, S Fisher-Yates swaps by one thread
 // (the swaps are a dependent chain), the S random offsets are drawn in parallel beforehand.
+// xyz != nullptr: the selected points are gathered as well (out_xyz [B,S,3]) - saves the gather launch that follows.
 __global__ void random_subset_kernel(int N, int S, uint64_t seed, uint64_t offset,
-                                     const uint64_t* __restrict__ offset_dev, int32_t* __restrict__ out_idx) {
+                                     const uint64_t* __restrict__ offset_dev, int32_t* __restrict__ out_idx,
+                                     const float* __restrict__ xyz, float* __restrict__ out_xyz) {
   if (offset_dev) offset += *offset_dev;
   extern __shared__ int32_t s_perm[];
   int32_t* s_j = s_perm + N;
@@ -163,6 +165,11 @@ __global__ void random_subset_kernel(int N, int S, uint64_t seed, uint64_t offse
   }
   __syncthreads();
   for (int i = t; i < S; i += T) out_idx[(size_t)b * S + i] = s_perm[i];
+  if (xyz)
+    for (int e = t; e < S * 3; e += T) {
+      const int i = e / 3, c = e - i * 3;
+      out_xyz[(size_t)b * S * 3 + e] = __ldg(xyz + ((size_t)b * N + s_perm[i]) * 3 + c);
+    }
 }
 
 }  // namespace pcoe
@@ -198,16 +205,24 @@ extern "C" int pcoe_gather_points_f32(const float* src, int B, int N, int C, con
   return ls.done();
 }
 
+extern "C" int pcoe_random_subset_xyz(int B, int N, int S, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                                      int32_t* out_idx, const float* xyz, float* out_xyz, void* stream);
 extern "C" int pcoe_random_subset(int B, int N, int S, uint64_t seed, uint64_t offset,
                                   const uint64_t* offset_dev, int32_t* out_idx, void* stream) {
+  return pcoe_random_subset_xyz(B, N, S, seed, offset, offset_dev, out_idx, nullptr, nullptr, stream);
+}
+
+extern "C" int pcoe_random_subset_xyz(int B, int N, int S, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                                      int32_t* out_idx, const float* xyz, float* out_xyz, void* stream) {
   if (B <= 0 || N <= 0 || S <= 0 || S > N)
     return fail(PCOE_ERR_BAD_SHAPE, "random_subset: B=%d N=%d S=%d", B, N, S);
   if (!out_idx) return fail(PCOE_ERR_NULL, "random_subset: out_idx is NULL");
+  if ((xyz == nullptr) != (out_xyz == nullptr)) return fail(PCOE_ERR_NULL, "random_subset: xyz and out_xyz go together");
   size_t smem = ((size_t)N + S) * sizeof(int32_t);
   if (smem > 200 * 1024) return fail(PCOE_ERR_UNSUPPORTED, "random_subset: N=%d too large", N);
   if (smem > 48 * 1024)
     PCOE_CUDA(cudaFuncSetAttribute(random_subset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LaunchScope ls("random_subset_kernel", (cudaStream_t)stream);
-  random_subset_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(N, S, seed, offset, offset_dev, out_idx);
+  random_subset_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(N, S, seed, offset, offset_dev, out_idx, xyz, out_xyz);
   return ls.done();
 }

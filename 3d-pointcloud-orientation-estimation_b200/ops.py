@@ -66,13 +66,20 @@ def gather_points(points: torch.Tensor, idx32: torch.Tensor) -> torch.Tensor:
 
 
 def random_subset(B: int, N: int, S: int, seed: int, offset: int, device,
-                  counter: torch.Tensor | None = None) -> torch.Tensor:
+                  counter: torch.Tensor | None = None, xyz: torch.Tensor | None = None):
     """(B,S) int32 uniform subset without replacement, drawn on the device.  ``counter`` (1-element
-    int64 CUDA tensor) is added to ``offset`` on the device (CUDA-graph friendly)."""
+    int64 CUDA tensor) is added to ``offset`` on the device (CUDA-graph friendly).  With ``xyz`` (B,N,3) the
+    selected points are gathered in the same launch and ``(idx, new_xyz)`` is returned."""
     out = torch.empty(B, S, dtype=torch.int32, device=device)
-    _lib.check(_lib.load().pcoe_random_subset(B, N, S, seed & (2**64 - 1), offset & (2**64 - 1), _ptr(counter),
-                                              out.data_ptr(), _stream()))
-    return out
+    if xyz is None:
+        _lib.check(_lib.load().pcoe_random_subset(B, N, S, seed & (2**64 - 1), offset & (2**64 - 1), _ptr(counter),
+                                                  out.data_ptr(), _stream()))
+        return out
+    xyz = _req(xyz, torch.float32, "xyz")
+    new_xyz = torch.empty(B, S, 3, dtype=torch.float32, device=device)
+    _lib.check(_lib.load().pcoe_random_subset_xyz(B, N, S, seed & (2**64 - 1), offset & (2**64 - 1), _ptr(counter),
+                                                  out.data_ptr(), xyz.data_ptr(), new_xyz.data_ptr(), _stream()))
+    return out, new_xyz
 
 
 # ------------------------------------------------------------------------------------------------

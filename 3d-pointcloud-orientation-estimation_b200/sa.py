@@ -199,19 +199,21 @@ class PointNetSetAbstraction(nn.Module):
     def precision(self) -> str:
         return self._precision or _DEFAULT_PRECISION
 
-    def _sample(self, xyz: torch.Tensor) -> torch.Tensor:
+    def _sample(self, xyz: torch.Tensor):
+        """-> (idx32 (B,S), new_xyz (B,S,3) or None when the sampler does not gather)."""
         B, N, _ = xyz.shape
         if self.sampler == "randperm_host":
             idx = torch.stack([torch.randperm(N)[:self.npoint] for _ in range(B)])
-            return idx.to(torch.int32).to(xyz.device, non_blocking=True)
+            return idx.to(torch.int32).to(xyz.device, non_blocking=True), None
         if self.sampler == "randperm_device":
             # the call counter lives on the device so that a CUDA-graph replay draws new subsets
             if self._rng_counter is None or self._rng_counter.device != xyz.device:
                 self._rng_counter = torch.zeros(1, dtype=torch.int64, device=xyz.device)
             self._rng_counter.add_(1)
             return ops.random_subset(B, N, self.npoint, torch.initial_seed(), (id(self) & 0xFFFFFF) << 32, xyz.device,
-                                     self._rng_counter)
-        return ops.farthest_point_sample(xyz, self.npoint).to(torch.int32)
+                                     self._rng_counter, xyz=xyz)
+        idx, new_xyz = ops.farthest_point_sample(xyz, self.npoint, return_xyz=True)   # the kernel gathers as it selects
+        return idx.to(torch.int32), new_xyz
 
     def forward(self, xyz, points, fps_idx=None):
         if xyz.dim() != 3 or xyz.size(-1) != 3:
@@ -228,8 +230,9 @@ class PointNetSetAbstraction(nn.Module):
             new_xyz = torch.zeros(xyz.size(0), 1, 3, device=xyz.device)
             out = _SAFunction.apply(xyz, None, None, feats, self, *params)
             return new_xyz, out
-        idx32 = self._sample(xyz) if fps_idx is None else fps_idx.to(torch.int32).to(xyz.device)
-        new_xyz = ops.gather_points(xyz, idx32)
+        idx32, new_xyz = self._sample(xyz) if fps_idx is None else (fps_idx.to(torch.int32).to(xyz.device), None)
+        if new_xyz is None:
+            new_xyz = ops.gather_points(xyz, idx32)
         if self.grouper == "knn":
             nbr = ops.knn_int32(new_xyz, xyz, self.nsample)
         else:

@@ -83,6 +83,11 @@ int pcoe_gather_points_f32(const float* src, int B, int N, int C, const int32_t*
  * replay (the caller increments the counter with an ordinary captured kernel). */
 int pcoe_random_subset(int B, int N, int S, uint64_t seed, uint64_t offset,
                        const uint64_t* offset_dev, int32_t* out_idx, void* stream);
+/* The same draw, and the selected points gathered in the same launch: out_xyz [B,S,3] = xyz[b, out_idx[b,s]]
+ * (replaces the index_points call that follows the draw, models/pointnet_pp_8dir.py:28-29). */
+int pcoe_random_subset_xyz(int B, int N, int S, uint64_t seed, uint64_t offset,
+                           const uint64_t* offset_dev, int32_t* out_idx, const float* xyz,
+                           float* out_xyz, void* stream);
 
 /* --------------------------------------------------------------------------------------------
  * Grouping

@@ -136,6 +136,11 @@ def test_random_subset_properties(pcoe, cuda):
     assert abs(hist.mean() - expect) < 1e-9 and hist.std() < 3.0 * np.sqrt(expect)   # uniform marginals
     full = pcoe.ops.random_subset(2, 37, 37, 1, 0, cuda).cpu().numpy()
     assert sorted(full[0].tolist()) == list(range(37))         # S == N is a full permutation
+    # fused gather: same draw, and new_xyz is exactly xyz[b, idx]
+    xyz = torch.randn(B, N, 3, device=cuda)
+    idx, nx = pcoe.ops.random_subset(B, N, S, 42, 1, cuda, xyz=xyz)
+    assert np.array_equal(idx.cpu().numpy(), a)
+    assert torch.equal(nx, torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)))
 
 
 def test_shape_errors_raise(pcoe, cuda):
