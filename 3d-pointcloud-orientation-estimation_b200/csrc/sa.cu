@@ -456,6 +456,7 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
     return f;
   };
   v4::BnFin fin_out{};
+  static const bool sep_fin = [] { const char* e = getenv("PCOE_SA_FINALIZE_KERNEL"); return e && e[0] == '1'; }();
 
   const int Kin[3] = {Cin, d.C1, d.C2};
   char* wbase = train ? sv : ws;   // bf16 weight copies live with the saved state in train mode
@@ -503,7 +504,9 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       } else {
         PCOE_TRY(launch_fwd4(p2, wb(2), L.w4_rp[2], L.w4_kp[2], e2, M, st, kname(d, kF3)));
       }
-      if (train) PCOE_TRY(finalize(2));   // tiny per-channel kernel: a per-block table in sa_out_finalize cost more than this launch
+      // layer 3's statistics are finalised by sa_out_finalize itself (per-block table; cheap since the inline
+      // finalisation lost its fp64 division / square root), PCOE_SA_FINALIZE_KERNEL=1 brings the separate launch back
+      if (train) { if (sep_fin) PCOE_TRY(finalize(2)); else fin_out = mkfin(2); }
       done = true;
     }
     if (use5) {   // wide layers: (tile x 128-channel block) grid, K streamed in 64-channel chunks
@@ -522,7 +525,9 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
       e2.C = d.C3; e2.Mld = Mld;
       PCOE_TRY(launch_fwd5(p2, wb(2), L.w4_kp[2], e2, M, d.C3, d.C2 / 64, st, kname(d, kF3)));
-      if (train) PCOE_TRY(finalize(2));   // tiny per-channel kernel: a per-block table in sa_out_finalize cost more than this launch
+      // layer 3's statistics are finalised by sa_out_finalize itself (per-block table; cheap since the inline
+      // finalisation lost its fp64 division / square root), PCOE_SA_FINALIZE_KERNEL=1 brings the separate launch back
+      if (train) { if (sep_fin) PCOE_TRY(finalize(2)); else fin_out = mkfin(2); }
       done = true;
     }
   }
