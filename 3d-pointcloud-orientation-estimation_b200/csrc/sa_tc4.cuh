@@ -889,13 +889,39 @@ struct Barriers4 {
 };
 
 // weight image: bf16 [Rp][Kp] row-major (zero padded) -> [Rp rows][Kp/64 blocks], SWIZZLE_128B
-__device__ __forceinline__ void load_wimage(const __nv_bfloat16* __restrict__ W, int Rp, int Kp, uint32_t saddr, int tid, int nthr) {
-  const int upr = Kp / 8;
-  for (int e = tid; e < Rp * upr; e += nthr) {
-    const int n = e / upr, j = e - n * upr;
-    const uint4 w = __ldg(reinterpret_cast<const uint4*>(W + (size_t)n * Kp + j * 8));
-    tc::sts128(saddr + (uint32_t)(j >> 3) * (uint32_t)(Rp * 128) + tc::sw128_off(n, (j & 7) * 8), w);
+// Split in two so that the kernel prologue can keep the global loads in flight while it does other work (clearing
+// the operand stages, the per-channel constants with their own L2 round trips): wimage_issue() loads the first
+// kWImgRegs 16-byte units of this thread into registers, wimage_store() stores them swizzled and loops over the rest.
+constexpr int kWImgRegs = 8;
+struct WImgRegs { uint4 w[kWImgRegs]; };
+__device__ __forceinline__ void wimage_issue(const __nv_bfloat16* __restrict__ W, int Rp, int Kp, int tid, int nthr, WImgRegs& r) {
+  const int total = Rp * (Kp / 8);            // the image is contiguous: unit e is the e-th uint4
+  const uint4* src = reinterpret_cast<const uint4*>(W);
+#pragma unroll
+  for (int u = 0; u < kWImgRegs; ++u) {
+    const int e = tid + u * nthr;
+    r.w[u] = e < total ? __ldg(src + e) : make_uint4(0, 0, 0, 0);
   }
+}
+__device__ __forceinline__ void wimage_store(const __nv_bfloat16* __restrict__ W, int Rp, int Kp, uint32_t saddr, int tid, int nthr,
+                                             const WImgRegs& r) {
+  const int upr = Kp / 8, total = Rp * upr;
+  const uint4* src = reinterpret_cast<const uint4*>(W);
+  auto put = [&](int e, const uint4& w) {
+    const int n = e / upr, j = e - n * upr;
+    tc::sts128(saddr + (uint32_t)(j >> 3) * (uint32_t)(Rp * 128) + tc::sw128_off(n, (j & 7) * 8), w);
+  };
+#pragma unroll
+  for (int u = 0; u < kWImgRegs; ++u) {
+    const int e = tid + u * nthr;
+    if (e < total) put(e, r.w[u]);
+  }
+  for (int e = tid + kWImgRegs * nthr; e < total; e += nthr) put(e, __ldg(src + e));
+}
+__device__ __forceinline__ void load_wimage(const __nv_bfloat16* __restrict__ W, int Rp, int Kp, uint32_t saddr, int tid, int nthr) {
+  WImgRegs r;
+  wimage_issue(W, Rp, Kp, tid, nthr, r);
+  wimage_store(W, Rp, Kp, saddr, tid, nthr, r);
 }
 
 __device__ __forceinline__ void zero_smem(uint32_t saddr, uint32_t bytes, int tid, int nthr) {
@@ -964,7 +990,8 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
     for (int s = 0; s < nstages; ++s) { tc::mbar_init(&bar.full[s], kProdThreads); tc::mbar_init(&bar.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar.tmem_full[b], 1); tc::mbar_init(&bar.tmem_empty[b], kEpiThreads); }
   }
-  load_wimage(Wb, Rp, Kp, sW, tid, kThreads);
+  WImgRegs wreg;
+  wimage_issue(Wb, Rp, Kp, tid, kThreads, wreg);            // in flight during the clear and the constants below
   zero_smem(sT, (uint32_t)nstages * tbytes, tid, kThreads);
   if constexpr (GRAM) {   // row kext() of every stage image = ones (never touched by the producers)
     __syncthreads();
@@ -985,6 +1012,7 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
   const uint32_t stg0 = (sT + (uint32_t)nstages * tbytes + (uint32_t)(prod.nconst() + epi.nconst()) * 4u + 127u) & ~127u;
   const uint32_t stg_bytes = (uint32_t)epi.stage_bytes();
   epi.init(csm + prod.nconst(), emi * 128 + eq * 32 + lane);
+  wimage_store(Wb, Rp, Kp, sW, tid, kThreads, wreg);
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
@@ -1125,11 +1153,14 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
     for (int s = 0; s < npq; ++s) { tc::mbar_init(&bar.full[s], kProdThreads); tc::mbar_init(&bar.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar.tmem_full[b], 1); tc::mbar_init(&bar.tmem_empty[b], kEpiThreads); }
   }
-  if (DGRAD) load_wimage(Wb, Rp, Kp, sW, tid, kThreads);
-  if (GM) load_wimage(Gmb, 128, gk, sG, tid, kThreads);
+  WImgRegs wreg, greg;
+  if (DGRAD) wimage_issue(Wb, Rp, Kp, tid, kThreads, wreg);   // in flight during the clear and the constants below
+  if (GM) wimage_issue(Gmb, 128, gk, tid, kThreads, greg);
   zero_smem(sP0, (uint32_t)npq * pqbytes, tid, kThreads);
   pp.init(csm, tid, kThreads);
   qp.init(csm + pp.nconst(), tid, kThreads);
+  if (DGRAD) wimage_store(Wb, Rp, Kp, sW, tid, kThreads, wreg);
+  if (GM) wimage_store(Gmb, 128, gk, sG, tid, kThreads, greg);
   // epilogue split as in the forward kernel (DGRAD == 1: mtp*4 items; DGRAD == 2: column blocks)
   const int eq = warp & 3, eh = (warp >> 2) & 1, lane = tid & 31;
   const int emi = (eh * mtp) >> 1;

@@ -131,6 +131,27 @@ __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+#if defined(PCOE_EXP_WAIT_HINT)
+  // experiment: explicit suspend-time hint (ns) - the waiting warp leaves the issue slots to the working warps
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(mbar)), "r"(parity), "r"((uint32_t)PCOE_EXP_WAIT_HINT)
+      : "memory");
+#elif defined(PCOE_EXP_WAIT_SLEEP)
+  // experiment: back off between polls
+  uint32_t done = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(PCOE_EXP_WAIT_SLEEP);
+  }
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
@@ -140,6 +161,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
       "DONE_%=:\n\t}"
       ::"r"(smem_u32(mbar)), "r"(parity)
       : "memory");
+#endif
 }
 
 // pack 8 floats to 8 bf16 (round to nearest even) as one 16-byte value
