@@ -586,11 +586,12 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   float* gm = (float*)(ws + L.wb_gm);
   TY* dz[2] = {(TY*)(ws + L.wb_dz[0]), (TY*)(ws + L.wb_dz[1])};
 
-  PCOE_CUDA(cudaMemsetAsync(ws + L.wb_sums[0], 0, L.wb_sums_bytes, st));
   bool v4path = false;
   if constexpr (TC) v4path = L.v2;
-  if (v4path) {   // the v4 kernels accumulate into copies; dw_combine_kernel writes / adds into dW at the end
-    PCOE_CUDA(cudaMemsetAsync(ws + L.wb_dwc[0], 0, L.wb_dwc_bytes, st));
+  // the v4 kernels accumulate dW into copies (dw_combine_kernel writes / adds into dW at the end); the copies follow
+  // the batch sums in the workspace: one memset node for both
+  PCOE_CUDA(cudaMemsetAsync(ws + L.wb_sums[0], 0, L.wb_sums_bytes + (v4path ? L.wb_dwc_bytes : 0), st));
+  if (v4path) {
   } else if (!Gr.accumulate) {
     for (int l = 0; l < 3; ++l)
       PCOE_CUDA(cudaMemsetAsync(Gr.dW[l], 0, sizeof(float) * (size_t)Cs[l] * Kin[l], st));

@@ -62,3 +62,31 @@ class GraphedTrainStep:
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+    # ---- double-buffered input feed: the H2D copy of batch i+1 overlaps step i ------------------------------
+    def prefetch(self, xyz: torch.Tensor, *targets: torch.Tensor) -> None:
+        """Start copying the NEXT batch (pinned host tensors) into staging device buffers on a copy stream; the
+        copy runs beside the step that is executing.  Consume it with ``step_prefetched()``."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = (torch.empty_like(self.xyz),) + tuple(torch.empty_like(t) for t in self.targets)
+            self._consumed = None                  # event: the staging buffers have been read by the last D2D copy
+        cs = self._copy_stream
+        if self._consumed is not None:
+            cs.wait_event(self._consumed)          # only the previous D2D copy, NOT the step that follows it
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._stage, (xyz,) + tuple(targets)):
+                dst.copy_(src, non_blocking=True)
+        self._staged = torch.cuda.Event()
+        self._staged.record(cs)
+
+    def step_prefetched(self) -> torch.Tensor:
+        """Replay the step on the batch staged by ``prefetch()`` (device-to-device copy into the static buffers)."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        for dst, src in zip((self.xyz,) + tuple(self.targets), self._stage):
+            dst.copy_(src, non_blocking=True)
+        self._consumed = torch.cuda.Event()
+        self._consumed.record(cur)
+        self.graph.replay()
+        return self.loss

@@ -145,3 +145,38 @@ def test_fused_adam_grad_scale_is_the_data_parallel_mean(pcoe, cuda):
         for p, q in zip(ours.parameters(), ref.parameters()):
             assert torch.allclose(p, q, rtol=1e-4, atol=2e-6)
             assert torch.allclose(p.grad, q.grad, rtol=1e-3, atol=1e-6)
+
+
+def test_graphed_train_step_and_prefetched_feed(pcoe, cuda):
+    """pcoe.GraphedTrainStep (the path bench.py times): the whole mvM training step captured once and replayed -
+    losses stay finite and fall on a fixed batch, parameters move, a replay launches no new libpcoe kernels from the
+    host, and the double-buffered feed (prefetch / step_prefetched) trains on exactly the staged batch."""
+    torch.manual_seed(7)
+    B, N = 8, 1024
+    model = pcoe.PointNetPPMvM(sampler="randperm_device", precision="bf16").to(cuda).train()
+    engine = pcoe.dp.DataParallel(model)
+    opt = pcoe.optim.FusedAdam(engine, lr=1e-3, max_grad_norm=1.0, zero_grad_in_step=True)
+    host = []
+    for i in range(3):
+        gt, K = pcoe.synthetic.mvm_targets(B, i)
+        host.append((pcoe.synthetic.clouds(1, B, N, i).pin_memory(), gt.pin_memory(), K.to(torch.int32).pin_memory()))
+    loss_fn = lambda res, gt, K: pcoe.match_loss(res[0], res[1], res[2], gt, None, K).mean()
+    dev0 = tuple(t.to(cuda) for t in host[0])
+    for _ in range(2):                                   # eager steps first (allocates counters, flat buffers)
+        loss_fn(model(dev0[0]), dev0[1], dev0[2]).backward()
+        opt.step()
+    g = pcoe.GraphedTrainStep(model, loss_fn, opt, dev0[0], dev0[1:], clip_norm=1.0, engine=engine, warmup=1)
+    w0 = model.fc1.weight.detach().clone()
+    n0 = pcoe._lib.launch_count()
+    losses = [float(g(*host[0])) for _ in range(30)]
+    assert pcoe._lib.launch_count() == n0                # replays enqueue nothing from libpcoe's host side
+    assert all(l == l and abs(l) < 1e4 for l in losses)
+    assert sum(losses[-5:]) < sum(losses[:5])            # same batch 30 times: the loss goes down
+    assert not torch.equal(model.fc1.weight.detach(), w0)
+    # double-buffered feed: batch 1 staged while a step on batch 0 runs, then consumed
+    g.prefetch(*host[1])
+    l1 = float(g.step_prefetched())
+    assert torch.equal(g.xyz.cpu(), host[1][0]) and torch.equal(g.targets[1].cpu(), host[1][2])
+    g.prefetch(*host[2])
+    l2 = float(g.step_prefetched())
+    assert torch.equal(g.xyz.cpu(), host[2][0]) and l1 == l1 and l2 == l2
