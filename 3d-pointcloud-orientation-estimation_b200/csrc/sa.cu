@@ -78,7 +78,7 @@ __global__ void sa_out_finalize_kernel(const float* __restrict__ ymax, const flo
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(e % C);
     const float a = scale[c];
-    const bool up = a >= 0.f;
+    const bool up = !signbit(a);   // = the sign of gamma (a = gamma * invstd), the rule the v4 / v5 epilogue uses to pick max or min
     const float ys = up ? ymax[e] : ymin[e];
     out[e] = fmaxf(fmaf(ys, a, shift[c]), 0.f);
     if (slot) { slot[e] = up ? amax[e] : amin[e]; ysel[e] = ys; }
@@ -494,7 +494,7 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       v4::BnRelu4 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.Mld = Mld; p2.C = d.C2;
       p2.fin = mkfin(1);
       v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
-      e2.C = d.C3; e2.Mld = Mld;
+      e2.C = d.C3; e2.Mld = Mld; e2.gamma = P.gamma[2];
       if (L.l3s) {   // y3 is not stored: the kernel accumulates the Gram matrix of its input instead (DySparse4 backward)
         float* gram = (float*)(sv + L.sv_gram);
         PCOE_CUDA(cudaMemsetAsync(gram, 0, L.sv_gram_bytes, st));
@@ -523,7 +523,7 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       v4::BnRelu4 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.Mld = Mld; p2.C = d.C2;
       p2.fin = mkfin(1);
       v4::Group4 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
-      e2.C = d.C3; e2.Mld = Mld;
+      e2.C = d.C3; e2.Mld = Mld; e2.gamma = P.gamma[2];
       PCOE_TRY(launch_fwd5(p2, wb(2), L.w4_kp[2], e2, M, d.C3, d.C2 / 64, st, kname(d, kF3)));
       // layer 3's statistics are finalised by sa_out_finalize itself (per-block table; cheap since the inline
       // finalisation lost its fp64 division / square root), PCOE_SA_FINALIZE_KERNEL=1 brings the separate launch back

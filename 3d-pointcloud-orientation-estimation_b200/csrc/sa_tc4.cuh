@@ -760,13 +760,16 @@ struct Group4 {   // last layer, K == 32: the 32 columns of a block are one grou
   uint8_t* __restrict__ amax;
   uint8_t* __restrict__ amin;
   int C, Mld;
+  const float* __restrict__ gamma;   // BatchNorm weight of this layer: the affine's sign is its sign, so each channel
+                                     // needs only ONE of (max, arg-max) / (min, arg-min) - the other pair is not computed
   int c;
   float s0, s1;
+  bool want_max;
   static constexpr bool kStage = true;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return y ? C * 256 : 0; }
   __device__ __forceinline__ char* tile_dst(int tile) const { return y ? reinterpret_cast<char*>(y) + (size_t)tile * C * 256 : nullptr; }
-  __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; }
+  __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; want_max = c < C ? !signbit(gamma[c]) : true; }
   __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid, uint32_t stg) {
     if (c >= C || !valid) return;
     if (y) stage32_bf16(stg, c, j, v);
@@ -775,14 +778,14 @@ struct Group4 {   // last layer, K == 32: the 32 columns of a block are one grou
 #endif
     float mx, mn;
     int ax, an;
+    const size_t o = (size_t)(tile * 4 + j) * C + c;
 #ifndef PCOE_EXP_NOARG
-    argext32<true>(v, mx, ax);
-    argext32<false>(v, mn, an);
+    if (want_max) { argext32<true>(v, mx, ax); ymax[o] = mx; amax[o] = (uint8_t)ax; }
+    else { argext32<false>(v, mn, an); ymin[o] = mn; amin[o] = (uint8_t)an; }
 #else
     mx = v[0]; mn = v[1]; ax = 0; an = 1;
-#endif
-    const size_t o = (size_t)(tile * 4 + j) * C + c;
     ymax[o] = mx; ymin[o] = mn; amax[o] = (uint8_t)ax; amin[o] = (uint8_t)an;
+#endif
   }
   __device__ __forceinline__ void finish() {
     if (!sums || c >= C) return;
