@@ -133,7 +133,9 @@ def test_sa_errors(pcoe, cuda):
 # operands are rounded to bf16 (8-bit mantissa, 3.9e-3 relative): a chain of three GEMM+BN layers
 # lands at ~1e-2 relative on the outputs and, through the discontinuous max/ReLU routing, at up to
 # ~1e-1 on the deepest weight gradients (SURVEY 7.3 measured 3.5e-3..2e-2 and 0.36..0.44 end to end).
-BF16_FWD, BF16_GRAD = 3e-2, 2e-1
+# With mixed-sign BatchNorm weights (negative channels pool through the group minimum) the worst tensor measured
+# 0.21 (SA1, first BatchNorm bias); with the default all-positive init 0.18.
+BF16_FWD, BF16_GRAD = 3e-2, 2.5e-1
 
 
 @pytest.mark.parametrize("shape", ["sa1", "sa2", "sa3"])
@@ -144,6 +146,11 @@ def test_sa_bf16_tensor_core_vs_fp64_oracle(pcoe, cuda, shape):
                                sa3=(32, None, None, 256, [256, 512, 1024], True))[shape]
     layer = pcoe.PointNetSetAbstraction(S, K, D, mlp, group_all=ga, precision="bf16").to(cuda).train()
     g = torch.Generator().manual_seed(17)
+    with torch.no_grad():       # mixed-sign BatchNorm weights: negative channels pool through the group MINIMUM
+        for bn in layer.bns:
+            sign = torch.where(torch.rand(bn.weight.shape, generator=g) < 0.3, -1.0, 1.0)
+            bn.weight.copy_((0.5 + torch.rand(bn.weight.shape, generator=g)) * sign)
+            bn.bias.copy_(torch.rand(bn.bias.shape, generator=g) * 0.4 - 0.1)
     xyz = torch.randn(B, N, 3, generator=g)
     xyz = xyz / xyz.norm(dim=-1).amax(1).view(B, 1, 1)
     pts = torch.randn(B, N, D, generator=g) if D else None
