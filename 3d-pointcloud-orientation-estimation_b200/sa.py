@@ -215,13 +215,33 @@ class PointNetSetAbstraction(nn.Module):
         idx, new_xyz = ops.farthest_point_sample(xyz, self.npoint, return_xyz=True)   # the kernel gathers as it selects
         return idx.to(torch.int32), new_xyz
 
-    def forward(self, xyz, points, fps_idx=None):
+    @staticmethod
+    def _check_xyz(xyz):
         if xyz.dim() != 3 or xyz.size(-1) != 3:
             raise ValueError(f"xyz must be (B,N,3), got {tuple(xyz.shape)}")
         if not xyz.is_cuda:
             raise RuntimeError("pcoe: PointNetSetAbstraction runs on CUDA only (no CPU fallback); move the model and "
                                "inputs to a B200")
-        xyz = xyz.contiguous().float()
+        return xyz.contiguous().float()
+
+    def sample(self, xyz, fps_idx=None):
+        """Sampling half of forward: (idx32 (B,S), new_xyz (B,S,3)).  Depends on the coordinates only, so a caller can
+        run it (and ``group``) for the NEXT layer beside this layer's MLP (pcoe.models._Backbone does)."""
+        xyz = self._check_xyz(xyz)
+        idx32, new_xyz = self._sample(xyz) if fps_idx is None else (fps_idx.to(torch.int32).to(xyz.device), None)
+        if new_xyz is None:
+            new_xyz = ops.gather_points(xyz, idx32)
+        return idx32, new_xyz
+
+    def group(self, xyz, new_xyz):
+        """Grouping half of forward: neighbour indices (B,S,nsample) int32."""
+        if self.grouper == "knn":
+            return ops.knn_int32(new_xyz, xyz, self.nsample)
+        return ops.ball_query_int32(self.radius, self.nsample, xyz, new_xyz)
+
+    def forward(self, xyz, points, fps_idx=None, pre=None):
+        """``pre`` = (idx32, new_xyz, nbr) computed earlier by ``sample`` / ``group`` (same results, other stream)."""
+        xyz = self._check_xyz(xyz)
         feats = None if points is None else points.contiguous().float()
         params = []
         for conv, bn in zip(self.convs, self.bns):
@@ -230,13 +250,11 @@ class PointNetSetAbstraction(nn.Module):
             new_xyz = torch.zeros(xyz.size(0), 1, 3, device=xyz.device)
             out = _SAFunction.apply(xyz, None, None, feats, self, *params)
             return new_xyz, out
-        idx32, new_xyz = self._sample(xyz) if fps_idx is None else (fps_idx.to(torch.int32).to(xyz.device), None)
-        if new_xyz is None:
-            new_xyz = ops.gather_points(xyz, idx32)
-        if self.grouper == "knn":
-            nbr = ops.knn_int32(new_xyz, xyz, self.nsample)
+        if pre is None:
+            idx32, new_xyz = self.sample(xyz, fps_idx)
+            nbr = self.group(xyz, new_xyz)
         else:
-            nbr = ops.ball_query_int32(self.radius, self.nsample, xyz, new_xyz)
+            idx32, new_xyz, nbr = pre
         self.last_fps_idx, self.last_group_idx = idx32, nbr
         out = _SAFunction.apply(xyz, new_xyz, nbr, feats, self, *params)
         return new_xyz, out

@@ -224,3 +224,27 @@ def test_sa_bf16_sparse_last_layer_matches_stored_y3(pcoe, cuda, shape, monkeypa
         rels["grad_feats"] = _rel(res["0"][2], res["1"][2])
     print(f"\n[bf16 sparse-l3 vs stored-y3 {shape}] " + ", ".join(f"{k}={v:.1e}" for k, v in rels.items()))
     assert max(rels.values()) < 2e-2
+
+
+def test_sa_bf16_tail_tile_falls_back_to_stored_y3(pcoe, cuda):
+    """Rows that do not fill whole 128-row tiles (B*S*K % 128 != 0): the Gram-matrix last layer needs whole tiles, so
+    the layer keeps the stored-y3 kernels - same tolerances against the fp64 oracle."""
+    torch.manual_seed(4)
+    B, N, S, K, D, mlp = 3, 200, 10, 32, 0, [64, 64, 128]            # M = 960 rows = 7.5 tiles
+    layer = pcoe.PointNetSetAbstraction(S, K, D, mlp, precision="bf16").to(cuda).train()
+    g = torch.Generator().manual_seed(19)
+    xyz = torch.randn(B, N, 3, generator=g)
+    xyz = xyz / xyz.norm(dim=-1).amax(1).view(B, 1, 1)
+    sd0 = sa_torch.clone_state({f"sa.{k}": v for k, v in layer.state_dict().items()}, dtype=torch.float64, requires_grad=True)
+    fps = torch.stack([torch.randperm(N, generator=g)[:S] for _ in range(B)])
+    _, out = layer(xyz.to(cuda), None, fps_idx=fps.to(cuda))
+    grp = layer.last_group_idx.long().cpu()
+    _, oy, _ = sa_torch.set_abstraction(sd0, "sa", xyz.double(), None, group_all=False, nsample=K, fps_idx=fps, group_idx=grp)
+    assert _rel(out, oy) < BF16_FWD
+    gout = torch.randn(out.shape, generator=g)
+    out.backward(gout.to(cuda))
+    oy.backward(gout.double())
+    rels = {n: _rel(p.grad, sd0[f"sa.{n}"].grad) for n, p in layer.named_parameters()
+            if not (n.startswith("convs") and n.endswith("bias"))}
+    print("\n[bf16 tail tile] " + ", ".join(f"{k}={v:.1e}" for k, v in rels.items()))
+    assert max(rels.values()) < BF16_GRAD
