@@ -155,8 +155,16 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int
 // K-best list - enter the 31-step bitwise search for the exact K-th value; the search then compares <= kCandPerLane
 // registers per lane instead of 33.  Same selection rule and output order as knn_kernel (exact, ties keep the
 // lowest indices); a chunk whose candidate set does not fit falls back to searching all 32 registers.
+#ifndef KNN_MINB
+#define KNN_MINB 4
+#endif
 constexpr int kCandPerLane = 6;                    // candidate capacity per warp = 32 * kCandPerLane
-__global__ void __launch_bounds__(1024)
+// WARPS = warps per CTA (8 / 16 / 32 by cloud size).  KNN_MINB = resident 8-warp CTAs per SM the register cap is set
+// for.  Measured on B200 (SA1 + SA2 grouping of the bench step): 4 CTAs (64 registers, 124 B of spills) 52.4 us,
+// 3 CTAs (80 registers, 36 B) 54.4 us, 2 CTAs (128 registers, no spills) 56.2 us - the kernel is issue-bound
+// (ncu: 76 % issue slots active) and occupancy beats spill-freedom.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? KNN_MINB : (WARPS == 16 ? 2 : 1))
 knn_k32_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S, int K,
                int32_t* __restrict__ out_idx) {
   extern __shared__ float smem_f[];
@@ -371,10 +379,15 @@ extern "C" int pcoe_knn_f32(const float* xyz, const float* new_xyz, int B, int N
   if (K <= 32) {   // candidate pre-selection kernel
     smem = (size_t)N * 3 * sizeof(float) + (size_t)warps * 32 * kCandPerLane * 8;
     if (smem > 200 * 1024) return fail(PCOE_ERR_UNSUPPORTED, "knn: N=%d does not fit shared memory", N);
-    if (smem > 48 * 1024)
-      PCOE_CUDA(cudaFuncSetAttribute(knn_k32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchScope ls("knn_kernel", (cudaStream_t)stream);
-    knn_k32_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, K, out_idx);
+#define PCOE_KNN32(W_)                                                                                              \
+    {                                                                                                               \
+      if (smem > 48 * 1024)                                                                                         \
+        PCOE_CUDA(cudaFuncSetAttribute(knn_k32_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      knn_k32_kernel<W_><<<grid, W_ * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, K, out_idx);             \
+    }
+    if (warps == 8) PCOE_KNN32(8) else if (warps == 16) PCOE_KNN32(16) else PCOE_KNN32(32)
+#undef PCOE_KNN32
     return ls.done();
   }
   if (K <= 64) PCOE_KNN(2) else PCOE_KNN(4)
