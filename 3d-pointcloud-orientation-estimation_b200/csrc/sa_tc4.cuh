@@ -446,38 +446,57 @@ struct DyLast4 {
 struct DySparse4 {
   static constexpr bool kChMajor = true;
   using Idx = NoIdx;
-  struct Raw { float gv[kBatch]; int sl[kBatch]; };
+  // ONE unit per tile: thread g owns up to two HALF rows (64 points = 2 groups of one channel): half-row index
+  // hr = g + 256 u < 2 C, half = hr / C, channel = hr % C.  It clears its 8 chunks (8 x 16-byte stores of zero, no
+  // dependence on the loads) and then drops the two max-pool gradients in (same thread: program order, no race).
+  // The dense formulation needed C / 64 units per tile, each with its own load -> wait -> store latency chain.
+  struct Raw { float gv[4]; int sl[4]; };
   const float* __restrict__ gm;       // [G,C], already multiplied by a
   const uint8_t* __restrict__ slot;   // [G,C]
   int M, Mld, C;
   __host__ __device__ __forceinline__ int rows() const { return C < 128 ? 128 : C; }
   __host__ __device__ __forceinline__ int kext() const { return C; }
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
-  __device__ __forceinline__ int nbatches(int G) const { return (C / (G >> 4) + kBatch - 1) / kBatch; }
+  __device__ __forceinline__ int nbatches(int) const { return 1; }
   __device__ __forceinline__ void init(float*, int, int) {}
   __device__ __forceinline__ void load_idx(int, int, int, int, Idx&) const {}
-  __device__ __forceinline__ void load(int g, int G, int m0, int b, const Idx&, Raw& r) const {
-    PCOE_CM_MAP
-    const int grp = min(m, M - 1) >> 5;
-    const float* sg = gm + (size_t)grp * C + c0;
-    const uint8_t* ss = slot + (size_t)grp * C + c0;
+  __device__ __forceinline__ void load(int g, int G, int m0, int, const Idx&, Raw& r) const {
+    const int g0 = m0 >> 5, ng = (M + 31) >> 5;
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) {
-      r.gv[i] = ok ? __ldg(sg + i * kRowStep) : 0.f;
-      r.sl[i] = ok ? (int)__ldg(ss + i * kRowStep) : -1;
+    for (int u = 0; u < 2; ++u) {
+      const int hr = g + u * G;
+      const bool own = hr < 2 * C;
+      const int half = hr >= C ? 1 : 0, c = hr - half * C;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int grp = g0 + 2 * half + j;
+        const bool ok = own && grp < ng;
+        const size_t o = (size_t)(ok ? grp : 0) * C + (own ? c : 0);
+        r.gv[2 * u + j] = ok ? __ldg(gm + o) : 0.f;
+        r.sl[2 * u + j] = ok ? (int)__ldg(slot + o) : -1;
+      }
     }
   }
-  __device__ __forceinline__ void store(int g, int G, int m0, int b, const Raw& r, uint32_t saddr, int lrows = 0,
-                                        int rshift = 0) const {
-    PCOE_CM_MAP
-    const uint32_t dst = saddr + cm_off(lrows ? lrows : rows(), c0 + rshift, chunk);
-    const int j0 = m & 31;
+  __device__ __forceinline__ void store(int g, int G, int, int, const Raw& r, uint32_t saddr, int = 0, int = 0) const {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) {
-      const int sl = r.sl[i] - j0;          // slot relative to this 8-point chunk; outside [0,8): all zero
-      const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r.gv[i])) << ((sl & 1) * 16);
-      const int w = (unsigned)sl < 8u ? (sl >> 1) : -1;
-      tc::sts128(dst + i * kSRowBytes, make_uint4(w == 0 ? h : 0u, w == 1 ? h : 0u, w == 2 ? h : 0u, w == 3 ? h : 0u));
+    for (int u = 0; u < 2; ++u) {
+      const int hr = g + u * G;
+      if (hr >= 2 * C) continue;
+      const int half = hr >= C ? 1 : 0, c = hr - half * C;
+      const uint32_t base = saddr + (uint32_t)half * (uint32_t)(rows() * 128) + (uint32_t)((c >> 3) * 1024 + (c & 7) * 128);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tc::sts128(base + (uint32_t)(((k + c) & 7) << 4), z);   // rotated by the row: the lanes of a
+                                                                                            // warp (rows 128 B apart) hit 8 bank groups, not one
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int sl = r.sl[2 * u + j];
+        if (sl >= 0) {
+          const int pos = j * 32 + sl;
+          const uint16_t h = __bfloat16_as_ushort(__float2bfloat16_rn(r.gv[2 * u + j]));
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + (uint32_t)((((pos >> 3) ^ (c & 7)) << 4) + (pos & 7) * 2)), "h"(h) : "memory");
+        }
+      }
     }
   }
 };
