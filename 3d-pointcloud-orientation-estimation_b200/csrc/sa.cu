@@ -687,10 +687,25 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       v4::BnRelu4 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.Mld = Mld; x1.C = d.C1; x1.packed = 1;
       v4::MaskStats4 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
       m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1; m1.Mld = Mld;
-      PCOE_TRY(launch_bwd4<1>(dy2, x1, wb(1), L.w4_rp[1], L.w4_kp[1], m1, dwc(1), L.dwc_ld[1], d.C1, -1, M, d.C1, st, kname(d, kBL2)));
+      // no input features (SA1): layer 1 only needs dW1 [C1 x 3] - accumulated by the layer-2 epilogue itself
+      // (MaskStatsW1: dz1 is never stored, the layer-1 backward kernel does not run); PCOE_SA_BWD_L1_KERNEL=1 = old path
+      const char* keep_env = getenv("PCOE_SA_BWD_L1_KERNEL");   // read per call: the A/B test flips it
+      const bool keep_l1 = keep_env && keep_env[0] == '1';
+      const bool w1_in_epi = d.D == 0 && d.C1 <= 128 && !d.group_all && !keep_l1;
+      v4::DwL1 x1c{};
+      if (w1_in_epi) {
+        v4::MaskStatsW1 mw{}; mw.yprev = y[0]; mw.scale = scale[0]; mw.shift = shift[0]; mw.mean = mean[0]; mw.invstd = invstd[0];
+        mw.sums = bs[0]; mw.C = d.C1; mw.Mld = Mld; mw.gb = v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M};
+        mw.acc = dwc(0); mw.g0 = (float*)(ws + L.wb_g0);
+        PCOE_TRY(launch_bwd4<1>(dy2, x1, wb(1), L.w4_rp[1], L.w4_kp[1], mw, dwc(1), L.dwc_ld[1], d.C1, -1, M, d.C1, st, kname(d, kBL2)));
+        x1c = v4::DwL1{dwc(0), (const float*)(ws + L.wb_g0), wb(0), L.w4_kp[0], mkbfin(0, 1)};
+      } else {
+        PCOE_TRY(launch_bwd4<1>(dy2, x1, wb(1), L.w4_rp[1], L.w4_kp[1], m1, dwc(1), L.dwc_ld[1], d.C1, -1, M, d.C1, st, kname(d, kBL2)));
+      }
       v4::Dy4 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.Mld = Mld; dy1.C = d.C1;
       dy1.fin = mkbfin(0, 1);
-      if (d.D == 0) {
+      if (w1_in_epi) {
+      } else if (d.D == 0) {
         v4::GatherXyz4 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}};
         PCOE_TRY(launch_bwd4<0>(dy1, x0, wb(0), L.w4_rp[0], L.w4_kp[0], v4::NoEpi4{}, dwc(0), L.dwc_ld[0], Cin, 0, M, 0, st, kname(d, kBL1)));
       } else {
@@ -710,7 +725,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
           total += Cs[l] * Kin[l];
         }
         LaunchScope ls("dw_combine_kernel", st);
-        v4::dw_combine_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(cmb[0], cmb[1], cmb[2], Gr.accumulate, x3);
+        v4::dw_combine_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(cmb[0], cmb[1], cmb[2], Gr.accumulate, x3, x1c);
         PCOE_TRY(ls.done());
       }
       return PCOE_OK;

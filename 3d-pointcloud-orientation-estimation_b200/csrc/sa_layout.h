@@ -27,6 +27,7 @@ struct SaLayout {
   size_t wb_sums[3], wb_sums_bytes, wb_consts[3], wb_gm, wb_dz[2];
   // weight-gradient copies of the v4 kernels: [kRedCopies][C_l][dwc_ld[l]] fp32, layer-1 columns in [feats | xyz] order
   size_t wb_dwc[3], wb_dwc_bytes;
+  size_t wb_g0;    // [kRedCopies][16] fp32: x0^T x0 and sum x0 of the MaskStatsW1 path (zeroed with the dW copies)
   int dwc_ld[3];
   // bf16 weight copies (tensor-core path): offsets relative to `saved` (train) or `workspace` (eval)
   size_t wb_off[3], wbt_off[3];
@@ -131,6 +132,7 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
     L.dwc_ld[l] = l == 0 ? (Kin[0] + 15) / 16 * 16 : Kin[l];       // = the Q operand's channel extent (multiple of 16)
     L.wb_dwc[l] = L.v2 ? take(b, sizeof(float) * (size_t)kRedCopies * C[l] * L.dwc_ld[l]) : 0;
   }
+  L.wb_g0 = L.v2 ? take(b, sizeof(float) * 16 * kRedCopies) : 0;
   L.wb_dwc_bytes = L.v2 ? b - L.wb_dwc[0] : 0;
   for (int l = 0; l < 3; ++l) L.wb_consts[l] = take(b, sizeof(float) * 3 * C[l]);
   L.wb_gmimg = L.wb_rvec = L.wb_gsum = L.wb_l3e = 0;

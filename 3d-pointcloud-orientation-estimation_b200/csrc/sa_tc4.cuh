@@ -828,6 +828,7 @@ struct MaskStats4 {
   int c;
   float s0, s1, sc, sh, is, nmi, ac;   // nmi = -mean * invstd: xhat = y * invstd + nmi
   static constexpr bool kStage = true;
+  static constexpr bool kPre = false;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return C * 256; }
   __device__ __forceinline__ char* tile_dst(int tile) const { return reinterpret_cast<char*>(dz) + (size_t)tile * C * 256; }
@@ -868,12 +869,133 @@ struct MaskStats4 {
   }
 };
 
+// SA1 (no input features, C1 <= 128): layer 1 has no data gradient, only dW1 [C1 x 3] = dy1^T x0 with
+//     dy1 = a1*dz1 + p1*y1 + q1,  y1 = W1 x0   =>   dW1 = a1 .* (dz1^T x0) + p1 .* (W1 (x0^T x0)) + q1 (sum x0)^T .
+// The layer-2 backward epilogue therefore accumulates A = dz1^T x0 itself (thread = channel: 3 floats; the 32 point
+// offsets of a block are exchanged with shuffles), one warp per block adds x0^T x0 and sum x0, and dw_combine
+// applies (a1, p1, q1) once the batch sums are complete.  dz1 is never stored and the layer-1 backward kernel
+// (35 us: a full pass over dz1 and y1 for a 64 x 3 result) does not run.  x0 is rounded to bf16 exactly as the
+// forward's MMA operand was.  The gather of x0 (nbr -> xyz, two dependent loads) is issued by pre() BEFORE the wait
+// for the accumulator, so its latency hides behind the MMAs.
+struct MaskStatsW1 {
+  const __nv_bfloat16* __restrict__ yprev;   // tile-blocked y1
+  const float* __restrict__ scale;
+  const float* __restrict__ shift;
+  const float* __restrict__ mean;
+  const float* __restrict__ invstd;
+  double* __restrict__ sums;
+  int C, Mld;
+  GatherBase gb;
+  float* __restrict__ acc;                   // [kRedCopies][C][4]: A in columns 0..2
+  float* __restrict__ g0;                    // [kRedCopies][16]: xx xy xz yy yz zz sx sy sz
+  int c, eq;
+  float s0, s1, sc, sh, is, nmi;
+  float A0, A1, A2;
+  float G[9];
+  float4* xs;                                // shared memory: [warp][2 blocks][32 points] (x, y, z, 0), written by pre()
+  static constexpr bool kStage = false;
+  static constexpr bool kPre = true;
+  __host__ __device__ __forceinline__ int nconst() const { return 8 * 2 * 32 * 4; }
+  __host__ __device__ __forceinline__ int stage_bytes() const { return 0; }
+  __device__ __forceinline__ char* tile_dst(int) const { return nullptr; }
+  __device__ __forceinline__ void init(float* csm, int ch) {
+    xs = reinterpret_cast<float4*>(csm) + (threadIdx.x >> 5) * 64;   // csm is 16-byte aligned
+    c = ch; eq = (ch >> 5) & 3; s0 = s1 = 0.f; A0 = A1 = A2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) G[i] = 0.f;
+    const bool ok = c < C;
+    sc = ok ? scale[c] : 0.f; sh = ok ? shift[c] : 0.f; is = ok ? invstd[c] : 0.f; nmi = ok ? -mean[c] * is : 0.f;
+  }
+  // Gather of the tile's point offsets, issued BEFORE the wait for the accumulator.  (A version that fetched the
+  // neighbour indices two tiles and the coordinates one tile ahead, double-buffered, measured no faster: the cost of
+  // this epilogue is its arithmetic, not the gather latency.)
+  __device__ __forceinline__ void pre(int tile, int eh, int M) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int row = tile * kPts + (2 * eh + it) * 32 + lane;
+      float o[3] = {0.f, 0.f, 0.f};
+      if (row < M) {
+        float x[3], cc[3];
+        gb.load_xyz_raw(row, gb.point_of(row), x, cc);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) o[u] = __bfloat162float(__float2bfloat16_rn(gb.centred(x[u], cc[u])));
+      }
+      xs[it * 32 + lane] = make_float4(o[0], o[1], o[2], 0.f);   // read back by this warp only (block())
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid, uint32_t) {
+    const int it = j & 1;
+    const bool act = c < C && valid;
+    if (act) {
+      uint4 raw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) raw[q] = __ldg(tb_chunk(yprev, C, tile, c, j * 4 + q));
+      float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float yy[8];
+        unpack8(raw[q], yy);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool on = fmaf(yy[u], sc, sh) > 0.f;
+          const float d = on ? v[8 * q + u] : 0.f;
+          v[8 * q + u] = d;
+          a[u & 3] += d;
+          b[u & 3] = fmaf(d, fmaf(yy[u], is, nmi), b[u & 3]);
+        }
+      }
+      s0 += (a[0] + a[1]) + (a[2] + a[3]);
+      s1 += (b[0] + b[1]) + (b[2] + b[3]);
+    }
+    // A += dz1[c, point i] * x0[point i, :]: the 32 offsets come from shared memory (one broadcast 16-byte load each)
+    const float4* xp = xs + it * 32;
+    const float4 own = xp[threadIdx.x & 31];
+    const float qx = own.x, qy = own.y, qz = own.z;
+    if (act) {
+      float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float4 o = xp[i];
+        t0[i & 3] = fmaf(v[i], o.x, t0[i & 3]); t1[i & 3] = fmaf(v[i], o.y, t1[i & 3]); t2[i & 3] = fmaf(v[i], o.z, t2[i & 3]);
+      }
+      A0 += (t0[0] + t0[1]) + (t0[2] + t0[3]); A1 += (t1[0] + t1[1]) + (t1[2] + t1[3]); A2 += (t2[0] + t2[1]) + (t2[2] + t2[3]);
+    }
+    if (eq == 3 && valid) {   // one warp per block: x0^T x0 and sum x0 of this lane's point (zero beyond M)
+      G[0] = fmaf(qx, qx, G[0]); G[1] = fmaf(qx, qy, G[1]); G[2] = fmaf(qx, qz, G[2]);
+      G[3] = fmaf(qy, qy, G[3]); G[4] = fmaf(qy, qz, G[4]); G[5] = fmaf(qz, qz, G[5]);
+      G[6] += qx; G[7] += qy; G[8] += qz;
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    const int cp = blockIdx.x % kRedCopies;
+    if (c < C) {
+      double* dst = sums + (size_t)cp * 2 * C;
+      atomicAdd(dst + c, (double)s0);
+      atomicAdd(dst + C + c, (double)s1);
+      float* ad = acc + ((size_t)cp * C + c) * 4;
+      atomicAdd(ad, A0); atomicAdd(ad + 1, A1); atomicAdd(ad + 2, A2);
+    }
+    if (eq == 3) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        float t = G[i];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, m);
+        if ((threadIdx.x & 31) == 0) atomicAdd(g0 + cp * 16 + i, t);
+      }
+    }
+  }
+};
+
 // layer-1 dgrad over the D feature columns, POINT-on-lane orientation: thread = point, v = 32 feature channels
 struct Scatter4 {
   float* __restrict__ grad_feats;
   const int32_t* __restrict__ nbr;
   int N, S, D, group_all;
   static constexpr bool kStage = false;
+  static constexpr bool kPre = false;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return 0; }
   __device__ __forceinline__ char* tile_dst(int) const { return nullptr; }
@@ -896,6 +1018,7 @@ struct Scatter4 {
 
 struct NoEpi4 {
   static constexpr bool kStage = false;
+  static constexpr bool kPre = false;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return 0; }
   __device__ __forceinline__ char* tile_dst(int) const { return nullptr; }
@@ -1204,6 +1327,7 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
     int i = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
       const int b = i & 1, u = i >> 1, m0 = tile * kPts;
+      if constexpr (Epi::kPre) epi.pre(tile, eh, M);   // loads whose latency hides behind the wait below
       tc::mbar_wait(&bar.tmem_full[b], (uint32_t)(u & 1));
       if (tid == 0) TC4_TRACE(30, i);
       tc::fence_after_sync();
@@ -1229,10 +1353,10 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
       tc::fence_before_sync();
       mbar_arrive_relaxed(&bar.tmem_empty[b]);
       if (tid == 0) TC4_TRACE(35, i);
-      if constexpr (DGRAD == 1) stage_copy_out(epi.tile_dst(tile), stg, (int)stg_bytes, nstg, tid == 0);
+      if constexpr (DGRAD == 1 && Epi::kStage) stage_copy_out(epi.tile_dst(tile), stg, (int)stg_bytes, nstg, tid == 0);
       if (tid == 0) TC4_TRACE(31, i);
     }
-    if (DGRAD == 1 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (DGRAD == 1 && Epi::kStage && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     epi.finish();
     if (tid == 0) TC4_TRACE(32, 0);
     // flush dW (complete: the last tmem_full commit covers every earlier MMA): thread = row of dW, into this
@@ -1376,7 +1500,9 @@ struct DwComb { const float* copies; float* dW; int rows, cin, ld, perm_d; };
 // last layer on the DySparse4 path: dW3 += E,  E[c][k] = p_c * sum_j W3[c][j] * Gram[j][k] + q_c * sum_points x2[k]
 // (l3_prep_kernel), the dense part of the BatchNorm backward
 struct DwL3 { const float* E; };
-__global__ void dw_combine_kernel(DwComb a, DwComb b, DwComb c, int accumulate, DwL3 x3) {
+// layer 1 on the MaskStatsW1 path (SA1): dW1[c][k] = a_c * A[c][k] + p_c * sum_j W1[c][j] G0[j][k] + q_c * s[k]
+struct DwL1 { const float* acc; const float* g0; const __nv_bfloat16* Wb; int kp; BnBwdFin fin; };
+__global__ void dw_combine_kernel(DwComb a, DwComb b, DwComb c, int accumulate, DwL3 x3, DwL1 x1) {
   const DwComb* L[3] = {&a, &b, &c};
   const int n0 = a.rows * a.cin, n1 = b.rows * b.cin, n2 = c.rows * c.cin;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n0 + n1 + n2; e += gridDim.x * blockDim.x) {
@@ -1387,6 +1513,28 @@ __global__ void dw_combine_kernel(DwComb a, DwComb b, DwComb c, int accumulate, 
     int src = k;
     if (w.perm_d >= 0) src = k < 3 ? w.perm_d + k : k - 3;
     float s = 0.f;
+    if (l == 0 && x1.acc) {          // cin == 3
+      float A = 0.f, G[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) G[i] = 0.f;
+#pragma unroll
+      for (int g = 0; g < kRedCopies; ++g) {
+        A += x1.acc[((size_t)g * w.rows + r) * 4 + k];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) G[i] += x1.g0[g * 16 + i];
+      }
+      float ca, cp, cq;
+      x1.fin.eval(r, w.rows, k == 0, ca, cp, cq);     // the k == 0 thread of a channel also writes dgamma / dbeta
+      const float w0 = __bfloat162float(x1.Wb[(size_t)r * x1.kp]), w1 = __bfloat162float(x1.Wb[(size_t)r * x1.kp + 1]),
+                  w2 = __bfloat162float(x1.Wb[(size_t)r * x1.kp + 2]);
+      // G0 rows: (xx xy xz), (xy yy yz), (xz yz zz)
+      const float gk0 = k == 0 ? G[0] : (k == 1 ? G[1] : G[2]);
+      const float gk1 = k == 0 ? G[1] : (k == 1 ? G[3] : G[4]);
+      const float gk2 = k == 0 ? G[2] : (k == 1 ? G[4] : G[5]);
+      s = ca * A + cp * (w0 * gk0 + w1 * gk1 + w2 * gk2) + cq * G[6 + k];
+      w.dW[ee] = accumulate ? w.dW[ee] + s : s;
+      continue;
+    }
 #pragma unroll
     for (int g = 0; g < kRedCopies; ++g) s += w.copies[((size_t)g * w.rows + r) * w.ld + src];
     if (l == 2 && x3.E) s += x3.E[ee];
