@@ -286,7 +286,17 @@ static int launch_fwd4(const Prod& prod, const __nv_bfloat16* Wb, int Rp, int Kp
   const int tiles = ceil_div(M, v4::kPts), grid = tiles < kNumSMs ? tiles : kNumSMs;   // one persistent CTA per SM
   // TMEM: double-buffered accumulators when they fit beside the Gram accumulator (kext + 16 columns)
   const int nbuf = (2 * Rp + (GRAM ? prod.kext() + 16 : 0) <= 512) ? 2 : 1;
-  auto k = v4::tc4_fwd_kernel<Prod, Epi, 512, GRAM>;
+  if constexpr (Epi::kHalf && GRAM == 0) {
+    if (epi.C == 64 && Rp == 128) {   // two half-block epilogue threads per channel (weight image rows duplicated)
+      auto kh = v4::tc4_fwd_kernel<Prod, Epi, 512, GRAM, true>;
+      static bool attrh = false;
+      if (!attrh) { PCOE_CUDA(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget4)); attrh = true; }
+      LaunchScope ls(what, st);
+      kh<<<grid, v4::kThreads, smem, st>>>(prod, Wb, Rp, Kp, epi, M, stages, nstg, gram, nbuf);
+      return ls.done();
+    }
+  }
+  auto k = v4::tc4_fwd_kernel<Prod, Epi, 512, GRAM, false>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget4)); attr = true; }
   LaunchScope ls(what, st);
@@ -313,7 +323,17 @@ static int launch_bwd4(const PProd& pp, const QProd& qp, const __nv_bfloat16* Wb
   const int nstg = (sb && base + (npq - 1) * pq + 2 * sb <= (npq == 2 ? kSmemMax4 : kSmemBudget4)) ? 2 : 1;
   const size_t smem = base + (npq - 1) * pq + nstg * sb;
   const int tiles = ceil_div(M, v4::kPts), grid = tiles < kNumSMs ? tiles : kNumSMs;
-  auto k = v4::tc4_bwd_kernel<PProd, QProd, Epi, DGRAD, 512, GM>;
+  if constexpr (Epi::kHalf && DGRAD == 1) {
+    if (cprev == 64) {   // two half-block epilogue threads per channel (weight image columns duplicated)
+      auto kh = v4::tc4_bwd_kernel<PProd, QProd, Epi, DGRAD, 512, GM, true>;
+      static bool attrh = false;
+      if (!attrh) { PCOE_CUDA(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax4)); attrh = true; }
+      LaunchScope ls(what, st);
+      kh<<<grid, v4::kThreads, smem, st>>>(pp, qp, Wb, Rp, Kp, epi, dW, ldo, cq_valid, perm_d, M, cprev, nstg, npq, Gmb, gk);
+      return ls.done();
+    }
+  }
+  auto k = v4::tc4_bwd_kernel<PProd, QProd, Epi, DGRAD, 512, GM, false>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax4)); attr = true; }
   LaunchScope ls(what, st);
@@ -385,7 +405,11 @@ static int convert_weights4(const pcoe_sa_desc& d, const SaLayout& L, const pcoe
   v4::ConvW4 w[3];
   int total = 0;
   for (int l = 0; l < 3; ++l) {
-    w[l] = v4::ConvW4{P.W[l], (__nv_bfloat16*)(base + L.wb_off[l]), Cs[l], Kin[l], L.w4_rp[l], L.w4_kp[l], l == 0 ? d.D : -1};
+    // 64-channel layers of the v4 kernels: rows / columns 64..127 of the image repeat 0..63 (half-block epilogues)
+    const int dup_rows = L.v2 && l < 2 && Cs[l] == 64 && L.w4_rp[l] == 128;
+    const int dup_cols = L.v2 && l >= 1 && Kin[l] == 64 && L.w4_kp[l] == 128;
+    w[l] = v4::ConvW4{P.W[l], (__nv_bfloat16*)(base + L.wb_off[l]), Cs[l], Kin[l], L.w4_rp[l], L.w4_kp[l], l == 0 ? d.D : -1,
+                      dup_rows, dup_cols};
     total += L.w4_rp[l] * L.w4_kp[l];
   }
   LaunchScope ls("convert_weights_kernel", st);

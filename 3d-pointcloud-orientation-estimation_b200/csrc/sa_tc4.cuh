@@ -743,13 +743,31 @@ __device__ __forceinline__ void argext32(const float (&v)[32], float& val, int& 
   arg = ix[0];
 }
 
+// kHalf epilogues (C == 64, weight image rows / columns duplicated): TMEM lanes 64..127 repeat channels 0..63, so the two
+// threads of a channel each take HALF of a 32-point block (16 columns): the per-tile epilogue chain - the stage that
+// bounds these kernels - is half as long, at no extra MMA cost (the MMA is M = 128 either way).
 struct StoreStats4 {
   __nv_bfloat16* __restrict__ y;   // tile-blocked [tile][C][128]
   double* __restrict__ sums;       // [2,C] or nullptr (eval)
   int C, Mld;
-  int c;
+  int c, half;
   float s0, s1;
   static constexpr bool kStage = true;
+  static constexpr bool kHalf = true;
+  __device__ __forceinline__ void init_half(float*, int ch) { c = ch & 63; half = (ch >> 6) & 1; s0 = s1 = 0.f; }
+  __device__ __forceinline__ void block16(float (&v)[16], int, int j, bool valid, uint32_t stg) {
+    if (!valid) return;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float t[8] = {v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3], v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]};
+      tc::sts128(stg + tb_stage_off(c, j * 4 + half * 2 + q), tc::pack8_bf16(t));
+    }
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a[i & 3] += v[i]; b[i & 3] = fmaf(v[i], v[i], b[i & 3]); }
+    s0 += (a[0] + a[1]) + (a[2] + a[3]);
+    s1 += (b[0] + b[1]) + (b[2] + b[3]);
+  }
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return C * 256; }
   __device__ __forceinline__ char* tile_dst(int tile) const { return y ? reinterpret_cast<char*>(y) + (size_t)tile * C * 256 : nullptr; }
@@ -785,6 +803,7 @@ struct Group4 {   // last layer, K == 32: the 32 columns of a block are one grou
   float s0, s1;
   bool want_max;
   static constexpr bool kStage = true;
+  static constexpr bool kHalf = false;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return y ? C * 256 : 0; }
   __device__ __forceinline__ char* tile_dst(int tile) const { return y ? reinterpret_cast<char*>(y) + (size_t)tile * C * 256 : nullptr; }
@@ -829,6 +848,7 @@ struct MaskStats4 {
   float s0, s1, sc, sh, is, nmi, ac;   // nmi = -mean * invstd: xhat = y * invstd + nmi
   static constexpr bool kStage = true;
   static constexpr bool kPre = false;
+  static constexpr bool kHalf = false;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return C * 256; }
   __device__ __forceinline__ char* tile_dst(int tile) const { return reinterpret_cast<char*>(dz) + (size_t)tile * C * 256; }
@@ -895,7 +915,52 @@ struct MaskStatsW1 {
   float4* xs;                                // shared memory: [warp][2 blocks][32 points] (x, y, z, 0), written by pre()
   static constexpr bool kStage = false;
   static constexpr bool kPre = true;
+  static constexpr bool kHalf = true;
+  int half;
   __host__ __device__ __forceinline__ int nconst() const { return 8 * 2 * 32 * 4; }
+  __device__ __forceinline__ void init_half(float* csm, int ch) {   // C == 64: channel ch & 63, points half*16..+15 of a block
+    init(csm, ch & 63);
+    eq = (ch >> 5) & 3;
+    half = (ch >> 6) & 1;
+  }
+  __device__ __forceinline__ void block16(float (&v)[16], int tile, int j, bool valid, uint32_t) {
+    const int it = j & 1;
+    const float4* xp = xs + it * 32;
+    if (valid) {
+      uint4 raw[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) raw[q] = __ldg(tb_chunk(yprev, C, tile, c, j * 4 + half * 2 + q));
+      float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float yy[8];
+        unpack8(raw[q], yy);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool on = fmaf(yy[u], sc, sh) > 0.f;
+          const float d = on ? v[8 * q + u] : 0.f;
+          v[8 * q + u] = d;
+          a[u & 3] += d;
+          b[u & 3] = fmaf(d, fmaf(yy[u], is, nmi), b[u & 3]);
+        }
+      }
+      s0 += (a[0] + a[1]) + (a[2] + a[3]);
+      s1 += (b[0] + b[1]) + (b[2] + b[3]);
+      float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 o = xp[half * 16 + i];
+        t0[i & 3] = fmaf(v[i], o.x, t0[i & 3]); t1[i & 3] = fmaf(v[i], o.y, t1[i & 3]); t2[i & 3] = fmaf(v[i], o.z, t2[i & 3]);
+      }
+      A0 += (t0[0] + t0[1]) + (t0[2] + t0[3]); A1 += (t1[0] + t1[1]) + (t1[2] + t1[3]); A2 += (t2[0] + t2[1]) + (t2[2] + t2[3]);
+      if (eq == 3) {   // one warp per block: x0^T x0 and sum x0 of this lane's point
+        const float4 own = xp[threadIdx.x & 31];
+        G[0] = fmaf(own.x, own.x, G[0]); G[1] = fmaf(own.x, own.y, G[1]); G[2] = fmaf(own.x, own.z, G[2]);
+        G[3] = fmaf(own.y, own.y, G[3]); G[4] = fmaf(own.y, own.z, G[4]); G[5] = fmaf(own.z, own.z, G[5]);
+        G[6] += own.x; G[7] += own.y; G[8] += own.z;
+      }
+    }
+  }
   __host__ __device__ __forceinline__ int stage_bytes() const { return 0; }
   __device__ __forceinline__ char* tile_dst(int) const { return nullptr; }
   __device__ __forceinline__ void init(float* csm, int ch) {
@@ -996,6 +1061,7 @@ struct Scatter4 {
   int N, S, D, group_all;
   static constexpr bool kStage = false;
   static constexpr bool kPre = false;
+  static constexpr bool kHalf = false;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return 0; }
   __device__ __forceinline__ char* tile_dst(int) const { return nullptr; }
@@ -1019,6 +1085,7 @@ struct Scatter4 {
 struct NoEpi4 {
   static constexpr bool kStage = false;
   static constexpr bool kPre = false;
+  static constexpr bool kHalf = false;
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return 0; }
   __device__ __forceinline__ char* tile_dst(int) const { return nullptr; }
@@ -1112,7 +1179,7 @@ __device__ __forceinline__ void stage_copy_out(char* dst, uint32_t stg, int byte
 // result is sum_points x): the statistics the last layer's backward needs instead of the saved y3 (DySparse4).
 // Requires M % 128 == 0 and prod.rows() >= max(128, C_in + 16); flushed into gram[blockIdx.x % kRedCopies].
 // ---------------------------------------------------------------------------------------------
-template <class Prod, class Epi, int TCOLS, int GRAM>
+template <class Prod, class Epi, int TCOLS, int GRAM, bool HALF>
 __global__ void __launch_bounds__(kThreads, 1)
 tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, Epi epi, int M, int nstages, int nstg,
                float* __restrict__ gram, int nbuf) {
@@ -1156,7 +1223,8 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
   // staging tiles (tile-blocked output image) follow the constants
   const uint32_t stg0 = (sT + (uint32_t)nstages * tbytes + (uint32_t)(prod.nconst() + epi.nconst()) * 4u + 127u) & ~127u;
   const uint32_t stg_bytes = (uint32_t)epi.stage_bytes();
-  epi.init(csm + prod.nconst(), emi * 128 + eq * 32 + lane);
+  if constexpr (HALF) epi.init_half(csm + prod.nconst(), emi * 128 + eq * 32 + lane);
+  else epi.init(csm + prod.nconst(), emi * 128 + eq * 32 + lane);
   wimage_store(Wb, Rp, Kp, sW, tid, kThreads, wreg);
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -1179,11 +1247,17 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
 #pragma unroll 1
       for (int it = it0; it < it0 + mt * 2; ++it) {
         const int j = it & 3;
-        float v[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(b * mt * kPts + emi * kPts + j * 32), v);
-        if (tid == 0) TC4_TRACE(33, it);
-        epi.block(v, tile, j, m0 + j * 32 < M, stg);
-        if (tid == 0) TC4_TRACE(34, it);
+        if constexpr (HALF) {   // lanes 64..127 repeat channels 0..63: this thread takes 16 of the block's 32 points
+          float v[16];
+          tc::tmem_ld16(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(b * mt * kPts + emi * kPts + j * 32 + (eq >> 1) * 16), v);
+          epi.block16(v, tile, j, m0 + j * 32 < M, stg);
+        } else {
+          float v[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(b * mt * kPts + emi * kPts + j * 32), v);
+          if (tid == 0) TC4_TRACE(33, it);
+          epi.block(v, tile, j, m0 + j * 32 < M, stg);
+          if (tid == 0) TC4_TRACE(34, it);
+        }
       }
       tc::fence_before_sync();
       mbar_arrive_relaxed(&bar.tmem_empty[b]);
@@ -1270,7 +1344,7 @@ tc4_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, 
 //                the dense part of the last layer's BatchNorm backward folded into a matrix (see DySparse4)
 // smem: [W image (DGRAD)][Gm image (GM)][P tile][Q tile][constants]   (single stage)
 // ---------------------------------------------------------------------------------------------
-template <class PProd, class QProd, class Epi, int DGRAD, int TCOLS, int GM>
+template <class PProd, class QProd, class Epi, int DGRAD, int TCOLS, int GM, bool HALF>
 __global__ void __launch_bounds__(kThreads, 1)
 tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp, int Kp, Epi epi,
                float* __restrict__ dW, int ldo, int cq_valid, int perm_d /* >=0: layer-1 [feats|xyz] column order */,
@@ -1311,7 +1385,8 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
   const int emi = (eh * mtp) >> 1;
   const uint32_t stg0 = (sP0 + (uint32_t)npq * pqbytes + (uint32_t)(pp.nconst() + qp.nconst() + epi.nconst()) * 4u + 127u) & ~127u;
   const uint32_t stg_bytes = (uint32_t)epi.stage_bytes();
-  epi.init(csm + pp.nconst() + qp.nconst(), emi * 128 + eq * 32 + lane);
+  if constexpr (HALF) epi.init_half(csm + pp.nconst() + qp.nconst(), emi * 128 + eq * 32 + lane);
+  else epi.init(csm + pp.nconst() + qp.nconst(), emi * 128 + eq * 32 + lane);
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
@@ -1337,9 +1412,15 @@ tc4_bwd_kernel(PProd pp, QProd qp, const __nv_bfloat16* __restrict__ Wb, int Rp,
 #pragma unroll 1
         for (int it = it0; it < it0 + mtp * 2; ++it) {
           const int j = it & 3;
-          float v[32];
-          tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + dx_col + (uint32_t)b * dx_cols + (uint32_t)(emi * kPts + j * 32), v);
-          epi.block(v, tile, j, m0 + j * 32 < M, stg);
+          if constexpr (HALF) {
+            float v[16];
+            tc::tmem_ld16(tmem + ((uint32_t)(eq * 32) << 16) + dx_col + (uint32_t)b * dx_cols + (uint32_t)(emi * kPts + j * 32 + (eq >> 1) * 16), v);
+            epi.block16(v, tile, j, m0 + j * 32 < M, stg);
+          } else {
+            float v[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + dx_col + (uint32_t)b * dx_cols + (uint32_t)(emi * kPts + j * 32), v);
+            epi.block(v, tile, j, m0 + j * 32 < M, stg);
+          }
         }
       } else if constexpr (DGRAD == 2) {
         const int row = m0 + eq * 32 + lane;
@@ -1630,7 +1711,9 @@ l3_prep_kernel(BnBwdFin fin, int C3, int C2, const __nv_bfloat16* __restrict__ W
 }
 
 // fp32 [C_out][C_in] -> zero-padded bf16 [Rp][Kp]; perm_d >= 0: layer-1 column order [feats(perm_d) | xyz(3)]
-struct ConvW4 { const float* W; __nv_bfloat16* dst; int cout, cin, Rp, Kp, perm_d; };
+// dup_rows / dup_cols (64-channel layers, "two half-block epilogue threads per channel", see kHalf below): image rows /
+// columns 64..127 repeat rows / columns 0..63 instead of being zero, so TMEM lanes 64..127 carry the same channels
+struct ConvW4 { const float* W; __nv_bfloat16* dst; int cout, cin, Rp, Kp, perm_d, dup_rows, dup_cols; };
 // one thread = 8 consecutive image columns (Kp is a multiple of 128): one 16-byte store, one division
 __global__ void convert_weights4_kernel(ConvW4 a, ConvW4 b, ConvW4 c) {
   const ConvW4* L[3] = {&a, &b, &c};
@@ -1639,11 +1722,12 @@ __global__ void convert_weights4_kernel(ConvW4 a, ConvW4 b, ConvW4 c) {
     const int l = e < n0 ? 0 : (e < n0 + n1 ? 1 : 2);
     const ConvW4& w = *L[l];
     const int ee = e - (l == 0 ? 0 : (l == 1 ? n0 : n0 + n1));
-    const int kp8 = w.Kp >> 3, r = ee / kp8, k0 = (ee - r * kp8) * 8;
+    const int kp8 = w.Kp >> 3, ri = ee / kp8, k0 = (ee - ri * kp8) * 8;
+    const int r = (w.dup_rows && ri < 128) ? (ri & 63) : ri;
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int k = k0 + u;
+      const int k = (w.dup_cols && k0 + u < 128) ? ((k0 + u) & 63) : k0 + u;
       int src = k;
       if (w.perm_d >= 0) src = k < w.perm_d ? k + 3 : (k < w.perm_d + 3 ? k - w.perm_d : w.cin);
       v[u] = (r < w.cout && src < w.cin) ? __ldg(w.W + (size_t)r * w.cin + src) : 0.f;
