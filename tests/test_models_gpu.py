@@ -303,6 +303,17 @@ def test_baseline_configs_c3_c4_shapes(pcoe, cuda, cls, B, N):
     rel = float((f16 - f32).norm() / f32.norm())
     print(f"\n[{cls} {B}x{N}] bf16 vs fp32 SA features rel {rel:.2e}")
     assert rel < 5e-2
+    # eval mode (running statistics, BatchNorm folded): bf16 kernels (half-block epilogues on the 64-channel layers of
+    # SA1 included) against the fp32 path, same subsets
+    m32.eval(); m16.eval()
+    with torch.no_grad():
+        torch.manual_seed(43)
+        e32 = m32._sa_features(xyz)
+        torch.manual_seed(43)
+        e16 = m16._sa_features(xyz)
+    rel_eval = float((e16 - e32).norm() / e32.norm())
+    print(f"[{cls} {B}x{N}] eval-mode bf16 vs fp32 SA features rel {rel_eval:.2e}")
+    assert rel_eval < 5e-2
     g32 = torch.cat([p.grad.flatten() for p in outs[0][1].sa1.parameters() if p.grad is not None]).norm()
     g16 = torch.cat([p.grad.flatten() for p in outs[1][1].sa1.parameters() if p.grad is not None]).norm()
     assert torch.isfinite(g16) and 0.5 < float(g16 / g32) < 2.0
