@@ -846,9 +846,34 @@ struct MaskStats4 {
   const float* __restrict__ addc;            // optional per-channel constant added to dx before the mask (DySparse4: W^T q)
   int c;
   float s0, s1, sc, sh, is, nmi, ac;   // nmi = -mean * invstd: xhat = y * invstd + nmi
+  int half;
   static constexpr bool kStage = true;
   static constexpr bool kPre = false;
-  static constexpr bool kHalf = false;
+  static constexpr bool kHalf = true;
+  __device__ __forceinline__ void init_half(float* csm, int ch) { init(csm, ch & 63); half = (ch >> 6) & 1; }
+  __device__ __forceinline__ void block16(float (&v)[16], int tile, int j, bool valid, uint32_t stg) {
+    if (!valid) return;
+    uint4 raw[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) raw[q] = __ldg(tb_chunk(yprev, C, tile, c, j * 4 + half * 2 + q));
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float yy[8], t[8];
+      unpack8(raw[q], yy);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool on = fmaf(yy[u], sc, sh) > 0.f;
+        const float d = on ? v[8 * q + u] + ac : 0.f;
+        t[u] = d;
+        a[u & 3] += d;
+        b[u & 3] = fmaf(d, fmaf(yy[u], is, nmi), b[u & 3]);
+      }
+      tc::sts128(stg + tb_stage_off(c, j * 4 + half * 2 + q), tc::pack8_bf16(t));
+    }
+    s0 += (a[0] + a[1]) + (a[2] + a[3]);
+    s1 += (b[0] + b[1]) + (b[2] + b[3]);
+  }
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
   __host__ __device__ __forceinline__ int stage_bytes() const { return C * 256; }
   __device__ __forceinline__ char* tile_dst(int tile) const { return reinterpret_cast<char*>(dz) + (size_t)tile * C * 256; }
@@ -1668,12 +1693,13 @@ l3_prep_kernel(BnBwdFin fin, int C3, int C2, const __nv_bfloat16* __restrict__ W
   __syncthreads();
   if (t < C2) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (k1 < C2) {
+    const int kr = C2 == 64 ? (k1 & 63) : k1;   // C2 == 64: rows 64..127 repeat 0..63 (half-block epilogues, kHalf)
+    if (kr < C2) {
 #pragma unroll 4
       for (int c = 0; c < C3; c += 4) {
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          acc[u] = fmaf(__bfloat162float(sW[(c + u) * Kp + k1]) * sp[c + u], __bfloat162float(sW[(c + u) * Kp + t]), acc[u]);
+          acc[u] = fmaf(__bfloat162float(sW[(c + u) * Kp + kr]) * sp[c + u], __bfloat162float(sW[(c + u) * Kp + t]), acc[u]);
       }
     }
     gmimg[(size_t)k1 * C2 + t] = __float2bfloat16_rn((acc[0] + acc[1]) + (acc[2] + acc[3]));
