@@ -44,6 +44,10 @@ void profile_end(int slot, cudaStream_t st) {
 
 bool profile_enabled() { return g_prof_on; }
 
+static std::mutex g_aux_mu;
+void aux_lock() { g_aux_mu.lock(); }
+void aux_unlock() { g_aux_mu.unlock(); }
+
 AuxStream* aux_stream() {
   static AuxStream tab[64];
   static bool made[64];

@@ -33,6 +33,18 @@ bool profile_enabled();
 // the CUDA-event timings stay those of kernels running alone.
 struct AuxStream { cudaStream_t s; cudaEvent_t ev[4]; };
 AuxStream* aux_stream();   // nullptr when unavailable / profiling
+// The auxiliary stream and its events are per-device state shared by every caller: a fork/join sequence is enqueued
+// under this lock (host-side only, microseconds), so concurrent host threads cannot interleave their event
+// record / wait pairs.
+void aux_lock();
+void aux_unlock();
+struct AuxGuard {
+  bool held;
+  explicit AuxGuard(bool take) : held(take) { if (held) aux_lock(); }
+  ~AuxGuard() { if (held) aux_unlock(); }
+  AuxGuard(const AuxGuard&) = delete;
+  AuxGuard& operator=(const AuxGuard&) = delete;
+};
 
 // Checks the launch that was just enqueued (cudaPeekAtLastError is legal during graph capture).
 inline int check_launch(const char* what) {

@@ -768,6 +768,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       // The weight-gradient kernels are off the critical path (only the optimizer consumes them) and none of these
       // grids fills the GPU: they run on the auxiliary stream, each forked after the dgrad that produces its dz.
       AuxStream* ax = aux_stream();
+      AuxGuard aux_guard(ax != nullptr);   // released when this call returns (after the join has been enqueued)
       cudaStream_t sw = ax ? ax->s : st;
       auto fork = [&](int e) -> int {
         if (!ax) return PCOE_OK;

@@ -11,7 +11,9 @@
  *   - tensors are dense, row-major, with the shapes given in the comments;
  *   - indices are int32 on this side (the Python layer widens to int64 where the reference exposes them);
  *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (no device
- *     synchronisation, no allocation, CUDA-graph capturable);
+ *     synchronisation, no allocation, CUDA-graph capturable).  pcoe_sa_backward may run independent kernels of
+ *     one call on a library-owned auxiliary stream (one per device, created on first use): it is forked from and
+ *     joined back into `stream` inside the call, under a host lock, so callers see plain stream semantics;
  *   - every call returns 0 on success or a negative pcoe_status; the message of the last failure
  *     on the calling thread is available from pcoe_last_error();
  *   - the library never keeps a caller pointer after the call returns.
