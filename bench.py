@@ -314,6 +314,13 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": dev_ms / args.steps, "gpu_launches": int(launches),
                               "precision": args.precision, "timed_only": True}), flush=True)
+        if world > 1:                                    # same clean multi-rank exit as the full run (see the end)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         return
 
     # ---- end-to-end through the public API with host buffers ------------------------------------
