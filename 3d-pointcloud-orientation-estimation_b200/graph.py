@@ -1,6 +1,6 @@
 """CUDA-graph capture of a whole training step ("CUDA-graph-captured steps").
 
-A step of the drop-in models is ~60 libpcoe launches plus ~150 small torch launches; at 64 clouds per
+A step of the drop-in models is ~50 libpcoe launches plus a handful of small torch launches; at 64 clouds per
 GPU the CPU cannot enqueue them as fast as the B200 executes them.  ``GraphedTrainStep`` captures
 
     zero_grad -> forward -> loss -> backward -> [gradient all-reduce] -> [clip_grad_norm_] -> optimizer.step

@@ -9,8 +9,9 @@ the reference, with the three set-abstraction layers running in libpcoe.
     PointNetPPXYZ_Schedmit  models/Pointnet_pp_xyz_Schedmit.py:47-92   two unit vectors (B,3)
     PointNetPPFwd           models/pointnet_pp_Fwd.py:77-98       unit vector (B,3) (device randperm)
 
-The 1024->512->256 trunk and the heads (1.3 MFLOP per cloud) stay ordinary torch modules - the
-boundary SURVEY.md draws - so optimizers, clipping and checkpoints work unchanged.
+The 1024->512->256 trunk and the heads (1.3 MFLOP per cloud) keep their torch.nn parameter modules - the
+boundary SURVEY.md draws - so optimizers, clipping and checkpoints work unchanged; PointNetPPMvM evaluates them
+with libpcoe's fused fp32 trunk kernels (pcoe.trunk), the BatchNorm1d heads with torch.
 """
 from __future__ import annotations
 
