@@ -425,6 +425,41 @@ def run_ours(args):
         cpu = {"value": B * n_cpu / dt, "unit": "clouds/s", "cores": cores, "kind": "port",
                "sample": f"{n_cpu} full steps of {B} clouds after 1 warm-up (oracle port of the reference step, torch CPU fp32)"}
 
+    # ---- the fp32 parity mode of the same step, beside the headline (rank 0, N=1) -----------------
+    # `value` is the bf16 tensor-core mode (operands rounded to bf16: loss within 1e-3 of the fp32 mode, gradients
+    # within the stated bf16 tolerance).  The mode the <= 1e-3 loss / gradient parity tests run
+    # in is fp32 (CUDA-core GEMMs); its throughput on the same workload is reported here so both are on record.
+    parity = None
+    if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_parity_leg:
+        m32 = getattr(pcoe, cls)(sampler="randperm_device", precision="fp32").to(dev).train()
+        m32.load_state_dict(model.state_dict())
+        opt32 = torch.optim.Adam(m32.parameters(), lr=1e-3, fused=True)
+        p32 = list(m32.parameters())
+
+        def step32(x, tg):
+            opt32.zero_grad(set_to_none=False)
+            l = loss_of(kind, m32(x), tg, pcoe)
+            l.backward()
+            if clip is not None:
+                torch.nn.utils.clip_grad_norm_(p32, clip, foreach=True)
+            opt32.step()
+
+        for i in range(3):
+            step32(*resident[i % NB])
+        n32 = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n32):
+            step32(*resident[i % NB])
+        e1.record()
+        torch.cuda.synchronize()
+        ms32 = e0.elapsed_time(e1) / n32
+        parity = {"precision": "fp32", "value": B / (ms32 / 1e3), "unit": "clouds/s", "ms_per_step": ms32, "steps": n32,
+                  "mode": "eager (no CUDA graph), torch.optim.Adam(fused) + clip_grad_norm_",
+                  "note": "the mode the <=1e-3 loss/gradient parity tests and smoke() run in"}
+        del m32, opt32, p32
+
     if rank == 0:
         line = {
             "metric": "train clouds/sec (1024 pts, fwd+bwd)", "value": value, "unit": "clouds/s", "n_gpus": world,
@@ -447,7 +482,7 @@ def run_ours(args):
             "cuda_graph": graphed is not None,
             "gpu_launches": int(launches),
             "gpu_launches_per_step": launches / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+            "roofline": roofline, "cpu_baseline": cpu, "fp32_parity_mode": parity, "kernels": kernels,
             "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps,
             "grad_allreduce_bytes": engine.grads.nbytes() if world > 1 else 0,
         }
@@ -473,6 +508,7 @@ def main():
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
     ap.add_argument("--precision", choices=["fp32", "bf16"], default=os.environ.get("PCOE_PRECISION", "bf16"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-leg", action="store_true", help="skip the fp32 parity-mode throughput leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: copy each batch H2D in line with its step")
     ap.add_argument("--torch-optimizer", action="store_true",
