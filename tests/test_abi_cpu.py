@@ -39,6 +39,13 @@ def test_argument_errors_without_gpu(pcoe):
     assert lib.pcoe_knn_f32(None, None, 1, 4096, 2, 256, None, None) == L.ERR_UNSUPPORTED
     assert lib.pcoe_mvm_match_fwd_bwd(None, None, None, None, 3, None, 4, 5, None, None, None, None, None, None) == L.ERR_UNSUPPORTED
     assert lib.pcoe_soft_ce_fwd_bwd(None, None, 4, 0, None, None, None) == L.ERR_BAD_SHAPE
+    # entry points added for the fused subset+gather and the trunk tail
+    assert lib.pcoe_random_subset_xyz(2, 8, 9, 1, 0, None, None, None, None, None) == L.ERR_BAD_SHAPE      # S > N
+    assert lib.pcoe_random_subset_xyz(2, 8, 4, 1, 0, None, None, None, None, None) == L.ERR_NULL
+    assert lib.pcoe_ln_relu_dropout_heads_fwd(None, 1, None, None, None, None, 0, 256, 1e-5, 0.1, 1, 0, None, None, None, None,
+                                              None, 3, None, None, None, None, 4, 0.7, 80.0, 1, None, None, None, None) == L.ERR_BAD_SHAPE
+    assert lib.pcoe_heads_ln_relu_dropout_bwd(None, 4, 0.7, 80.0, 1, None, None, None, None, 3, None, None, None, None, None,
+                                              None, None, None, 8, 256, 0.1, 1, None, None, None, None, None) == L.ERR_NULL
     with pytest.raises(ValueError):
         L.check(L.ERR_BAD_SHAPE)
     with pytest.raises(NotImplementedError):
