@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PCOE_LIB") or os.path.join(_HERE, "libpcoe.so")   # PCOE_LIB: debug builds only
 
 OK, ERR_BAD_SHAPE, ERR_UNSUPPORTED, ERR_NULL, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
-PRECISION_FP32, PRECISION_BF16 = 0, 1
+PRECISION_FP32, PRECISION_BF16, PRECISION_BF16X3 = 0, 1, 2
 VM_SINGLE, VM_MULTI = 0, 1
 
 

@@ -11,6 +11,7 @@
 #include "sa_tc.cuh"
 #include "sa_tc4.cuh"
 #include "sa_tc5.cuh"
+#include "sa_tc6.cuh"
 #include "sa_layout.h"
 #include <type_traits>
 
@@ -399,6 +400,93 @@ static int launch_wgrad5(const PProd& pp, const QProd& qp, float* dW, int ldo, i
   return ls.done();
 }
 
+
+// ---- v6 (bf16x3: split-operand, fp32-accurate) launchers ---------------------------------------------
+constexpr size_t kSmemBudget6 = 224 * 1024;
+static bool sa_x3_supported(const pcoe_sa_desc& d) {
+  return d.K == 32 && d.C1 % 64 == 0 && d.C2 % 64 == 0 && d.C3 % 64 == 0 && d.D % 64 == 0;
+}
+struct Cfg6 { int nst, wres, grid; size_t smem; };
+// persistent (tile x channel-block) kernels: CTAs per channel block, resident weights or streamed, ring depth
+static Cfg6 cfg6(int nk, int ncb, int ntiles, size_t cbytes) {
+  Cfg6 c{};
+  const int per = kNumSMs / ncb > 0 ? kNumSMs / ncb : 1;
+  const int ctas = ntiles < per ? ntiles : per;
+  c.grid = ctas * ncb;
+  const size_t avail = kSmemBudget6 - 1024 - cbytes, wb = (size_t)nk * 32768;
+  c.wres = (ntiles > ctas && wb + 2 * 32768 <= avail) ? 1 : 0;   // a CTA that sees one tile gains nothing from residency
+  const size_t ring = c.wres ? avail - wb : avail, sb = c.wres ? 32768 : 65536;
+  int n = (int)(ring / sb);
+  c.nst = n > v6::kMaxStages6 ? v6::kMaxStages6 : n;
+  c.smem = 1024 + (c.wres ? wb : 0) + (size_t)c.nst * sb + cbytes;
+  return c;
+}
+
+template <class Prod, class Epi>
+static int launch_fwd6(const Prod& prod, const __nv_bfloat16* Wh, const __nv_bfloat16* Wl, int Kp, const Epi& epi, int M,
+                       int Cout, cudaStream_t st, const char* what) {
+  const size_t cbytes = sizeof(float) * (size_t)(prod.nconst() + epi.nconst()) + 512;
+  const int ncb = ceil_div(Cout, 128);
+  const Cfg6 c = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes);
+  if (c.nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  auto k = v6::x3_fwd_kernel<Prod, Epi>;
+  static bool attr = false;
+  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
+  LaunchScope ls(what, st);
+  k<<<c.grid, v4::kThreads, c.smem, st>>>(prod, Wh, Wl, Kp, epi, M, ncb, c.nst, c.wres);
+  return ls.done();
+}
+
+template <bool PT, class PProd, class Epi>
+static int launch_dgrad6(const PProd& pp, const __nv_bfloat16* Wh, const __nv_bfloat16* Wl, int Kp, const Epi& epi, int M,
+                         int Cprev, cudaStream_t st, const char* what) {
+  const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + epi.nconst()) + 512;
+  const int ncb = ceil_div(Cprev, 128);
+  const Cfg6 c = cfg6(pp.C / 64, ncb, ceil_div(M, v4::kPts), cbytes);
+  if (c.nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  auto k = v6::x3_dgrad_kernel<PProd, Epi, PT>;
+  static bool attr = false;
+  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
+  LaunchScope ls(what, st);
+  k<<<c.grid, v4::kThreads, c.smem, st>>>(pp, Wh, Wl, Kp, epi, M, ncb, c.nst, c.wres);
+  return ls.done();
+}
+
+template <class PProd, class QProd>
+static int launch_wgrad6(const PProd& pp, const QProd& qp, float* dW, int ldo, int cq_valid, int perm_d, int M, int nqb,
+                         cudaStream_t st, const char* what) {
+  const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + qp.nconst()) + 512;
+  const int ntiles = ceil_div(M, v4::kPts), clb = ceil_div(pp.C, 128), items = clb * nqb;
+  int splits = kNumSMs / items;
+  splits = splits < 1 ? 1 : (splits > ntiles ? ntiles : splits);
+  const int tps = ceil_div(ntiles, splits);
+  splits = ceil_div(ntiles, tps);
+  int nst = (int)((kSmemBudget6 - 1024 - cbytes) / 65536);
+  nst = nst > v6::kMaxStages6 ? v6::kMaxStages6 : nst;
+  if (nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  const size_t smem = 1024 + (size_t)nst * 65536 + cbytes;
+  auto k = v6::x3_wgrad_kernel<PProd, QProd>;
+  static bool attr = false;
+  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
+  LaunchScope ls(what, st);
+  k<<<dim3(clb, nqb, splits), v4::kThreads, smem, st>>>(pp, qp, dW, ldo, cq_valid, perm_d, M, tps, nst);
+  return ls.done();
+}
+
+static int convert_weights6(const pcoe_sa_desc& d, const SaLayout& L, const pcoe_sa_params& P, char* base, cudaStream_t st) {
+  const int Cs[3] = {d.C1, d.C2, d.C3}, Kin[3] = {3 + d.D, d.C1, d.C2};
+  v6::ConvW6 w[3];
+  int total = 0;
+  for (int l = 0; l < 3; ++l) {
+    __nv_bfloat16* hi = (__nv_bfloat16*)(base + L.wb_off[l]);
+    w[l] = v6::ConvW6{P.W[l], hi, hi + (size_t)L.w4_rp[l] * L.w4_kp[l], Cs[l], Kin[l], L.w4_rp[l], L.w4_kp[l], l == 0 ? d.D : -1};
+    total += L.w4_rp[l] * L.w4_kp[l];
+  }
+  LaunchScope ls("convert_weights_kernel", st);
+  v6::convert_weights6_kernel<<<min(ceil_div(total / 8, 256), kNumSMs * 4), 256, 0, st>>>(w[0], w[1], w[2]);
+  return ls.done();
+}
+
 static int convert_weights4(const pcoe_sa_desc& d, const SaLayout& L, const pcoe_sa_params& P, char* base,
                             cudaStream_t st) {
   const int Cs[3] = {d.C1, d.C2, d.C3}, Kin[3] = {3 + d.D, d.C1, d.C2};
@@ -428,8 +516,11 @@ static int validate(const pcoe_sa_desc* d) {
     return fail(PCOE_ERR_UNSUPPORTED, "sa: K=%d must be a power of two <= 128", d->K);
   if (d->train && (long long)d->B * d->S * d->K < 2)
     return fail(PCOE_ERR_BAD_SHAPE, "sa: train-mode BatchNorm needs more than 1 value per channel");
-  if (d->precision != PCOE_PRECISION_FP32 && d->precision != PCOE_PRECISION_BF16)
+  if (d->precision != PCOE_PRECISION_FP32 && d->precision != PCOE_PRECISION_BF16 && d->precision != PCOE_PRECISION_BF16X3)
     return fail(PCOE_ERR_UNSUPPORTED, "sa: precision=%d", d->precision);
+  if (d->precision == PCOE_PRECISION_BF16X3 && !sa_x3_supported(*d))
+    return fail(PCOE_ERR_UNSUPPORTED, "sa: bf16x3 needs K == 32 and C1, C2, C3, D multiples of 64 (K=%d D=%d C=(%d,%d,%d))",
+                d->K, d->D, d->C1, d->C2, d->C3);
   return PCOE_OK;
 }
 
@@ -555,6 +646,25 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       done = true;
     }
   }
+  if constexpr (!TC) {
+    if (L.v6) {   // bf16x3: split-operand tcgen05 kernels, fp32 activations (sa_tc6.cuh)
+      PCOE_TRY(convert_weights6(d, L, P, wbase, st));
+      auto wh = [&](int l) { return (const __nv_bfloat16*)(wbase + L.wb_off[l]); };
+      auto wl = [&](int l) { return wh(l) + (size_t)L.w4_rp[l] * L.w4_kp[l]; };
+      v6::GatherFeat6 gp{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
+      v6::StoreStats6 e0{}; e0.y = y[0]; e0.sums = sums[0]; e0.C = d.C1;
+      PCOE_TRY(launch_fwd6(gp, wh(0), wl(0), L.w4_kp[0], e0, M, d.C1, st, kname(d, kF1)));
+      v6::BnRelu6 p1{}; p1.y = y[0]; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.C = d.C1; p1.fin = mkfin(0);
+      v6::StoreStats6 e1{}; e1.y = y[1]; e1.sums = sums[1]; e1.C = d.C2;
+      PCOE_TRY(launch_fwd6(p1, wh(1), wl(1), L.w4_kp[1], e1, M, d.C2, st, kname(d, kF2)));
+      v6::BnRelu6 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.C = d.C2; p2.fin = mkfin(1);
+      v6::Group6 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
+      e2.C = d.C3; e2.gamma = P.gamma[2];
+      PCOE_TRY(launch_fwd6(p2, wh(2), wl(2), L.w4_kp[2], e2, M, d.C3, st, kname(d, kF3)));
+      if (train) { if (sep_fin) PCOE_TRY(finalize(2)); else fin_out = mkfin(2); }
+      done = true;
+    }
+  }
   if (!done) {
     GatherProd gp{xyz, new_xyz, nbr, feats, d.N, d.S, d.K, d.D, d.group_all, M, Cin};
     PCOE_TRY(nt(gp, 0, StoreStatsEpi<TY>{y[0], sums[0], d.C1}, kname(d, kF1)));
@@ -637,7 +747,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
     f.dgamma = Gr.dgamma[l]; f.dbeta = Gr.dbeta[l]; f.dbias = Gr.dbias[l]; f.accumulate = Gr.accumulate; f.write = write;
     return f;
   };
-  bool fused_consts = false;
+  bool fused_consts = L.v6;
   if constexpr (TC) fused_consts = L.v2 || L.v5;
   bool l3s = false;
   if constexpr (TC) l3s = L.l3s;
@@ -802,6 +912,39 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       if (ax) {   // join
         PCOE_CUDA(cudaEventRecord(ax->ev[3], sw));
         PCOE_CUDA(cudaStreamWaitEvent(st, ax->ev[3], 0));
+      }
+      return PCOE_OK;
+    }
+  }
+
+  if constexpr (!TC) {
+    if (L.v6) {   // bf16x3: streamed wgrad / persistent dgrad kernels with split operands (sa_tc6.cuh)
+      auto wh = [&](int l) { return (const __nv_bfloat16*)(sv + L.wb_off[l]); };
+      auto wl = [&](int l) { return wh(l) + (size_t)L.w4_rp[l] * L.w4_kp[l]; };
+      v6::DyLast6 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
+      dy3.M = M; dy3.C = d.C3; dy3.fin = mkbfin(2, 1);   // the wgrad launch owns the parameter-gradient outputs
+      v6::BnRelu6 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.C = d.C2;
+      v6::MaskStats6 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];
+      m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2;
+      PCOE_TRY(launch_wgrad6(dy3, x2, Gr.dW[2], d.C2, d.C2, -1, M, ceil_div(d.C2, 128), st, kname(d, kWG3)));
+      dy3.fin.write = 0;
+      PCOE_TRY(launch_dgrad6<false>(dy3, wh(2), wl(2), L.w4_kp[2], m2, M, d.C2, st, kname(d, kDG3)));
+      v6::Dy6 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.C = d.C2;
+      dy2.fin = mkbfin(1, 1);
+      v6::BnRelu6 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.C = d.C1;
+      v6::MaskStats6 m1{}; m1.yprev = y[0]; m1.scale = scale[0]; m1.shift = shift[0]; m1.mean = mean[0]; m1.invstd = invstd[0];
+      m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1;
+      PCOE_TRY(launch_wgrad6(dy2, x1, Gr.dW[1], d.C1, d.C1, -1, M, ceil_div(d.C1, 128), st, kname(d, kWG2)));
+      dy2.fin.write = 0;
+      PCOE_TRY(launch_dgrad6<false>(dy2, wh(1), wl(1), L.w4_kp[1], m1, M, d.C1, st, kname(d, kDG2)));
+      v6::Dy6 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.C = d.C1;
+      dy1.fin = mkbfin(0, 1);
+      v6::GatherFeat6 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
+      PCOE_TRY(launch_wgrad6(dy1, x0, Gr.dW[0], Cin, Cin, d.D, M, ceil_div(x0.nchunks(), 2), st, kname(d, kWG1)));
+      dy1.fin.write = 0;
+      if (d.D > 0 && grad_feats) {
+        v4::Scatter4 se{grad_feats, nbr, d.N, d.S, d.D, d.group_all};
+        PCOE_TRY(launch_dgrad6<true>(dy1, wh(0), wl(0), L.w4_kp[0], se, M, d.D, st, kname(d, kDG1)));
       }
       return PCOE_OK;
     }

@@ -36,6 +36,8 @@ struct SaLayout {
                    // activations are then stored channel-major [C][Mld], one weight image [Rp][Kp] per layer
   bool v5;         // bf16 mode, wide layers that do not fit v4 (SA3): K-chunk-streamed kernels (sa_tc5.cuh), same
                    // HBM layouts as v2
+  bool v6;         // bf16x3 mode (sa_tc6.cuh): fp32 tile-blocked channel-major activations [tile][C][128], two bf16
+                   // planes (hi, lo) of every weight image
   int Mld;         // rows rounded up to 128 (v2 / v5)
   int w4_rp[3], w4_kp[3];
   // v2 train: the last layer's pre-activations y3 are NOT stored; the forward accumulates the Gram matrix of the
@@ -56,11 +58,13 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   auto take = [](size_t& cur, size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
 
   const bool tc = d.precision == PCOE_PRECISION_BF16;
+  const bool x3 = d.precision == PCOE_PRECISION_BF16X3;
   const int Kin[3] = {3 + d.D, d.C1, d.C2};
   auto chan_ok = [](int c) { return c == 64 || c == 128 || c == 256; };
   L.v2 = tc && d.K == 32 && chan_ok(d.C1) && chan_ok(d.C2) && chan_ok(d.C3) && (d.D == 0 || d.D == 32 || d.D == 64 || d.D == 128);
   L.v5 = tc && !L.v2 && d.K == 32 && d.C1 % 128 == 0 && d.C2 % 128 == 0 && d.C3 % 128 == 0 && d.D > 0 && d.D % 128 == 0;
-  const bool cm = L.v2 || L.v5;   // tile-blocked channel-major activations + one weight image per layer
+  L.v6 = x3;                      // shape support is checked by sa_x3_supported() (sa.cu)
+  const bool cm = L.v2 || L.v5 || L.v6;   // tile-blocked channel-major activations + one weight image per layer
   L.Mld = (int)align_up(L.M, 128);
   const size_t rows_ld = cm ? (size_t)L.Mld : (size_t)L.M;
   for (int l = 0; l < 3; ++l) {
@@ -98,9 +102,10 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
     L.wbt_rows[l] = (int)align_up(Kin[l], 128); L.wbt_k[l] = kpad(C[l]);
     L.wb_off[l] = L.wbt_off[l] = 0;
   }
-  if (tc && d.train)
+  const size_t planes = x3 ? 2 : 1;   // bf16x3: hi plane followed by lo plane
+  if ((tc || x3) && d.train)
     for (int l = 0; l < 3; ++l) {
-      if (cm) { L.wb_off[l] = take(s, (size_t)2 * L.w4_rp[l] * L.w4_kp[l]); continue; }
+      if (cm) { L.wb_off[l] = take(s, planes * 2 * L.w4_rp[l] * L.w4_kp[l]); continue; }
       L.wb_off[l] = take(s, (size_t)2 * L.wb_rows[l] * L.wb_k[l]);
       L.wbt_off[l] = take(s, (size_t)2 * L.wbt_rows[l] * L.wbt_k[l]);
     }
@@ -117,9 +122,9 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   L.ws_y[0] = L.ws_y[1] = 0;
   if (!d.train) {
     for (int l = 0; l < 2; ++l) L.ws_y[l] = take(f, rows_ld * C[l] * L.esz);
-    if (tc)
+    if (tc || x3)
       for (int l = 0; l < 3; ++l) {
-        if (cm) { L.wb_off[l] = take(f, (size_t)2 * L.w4_rp[l] * L.w4_kp[l]); continue; }
+        if (cm) { L.wb_off[l] = take(f, planes * 2 * L.w4_rp[l] * L.w4_kp[l]); continue; }
         L.wb_off[l] = take(f, (size_t)2 * L.wb_rows[l] * L.wb_k[l]);
         L.wbt_off[l] = take(f, (size_t)2 * L.wbt_rows[l] * L.wbt_k[l]);
       }

@@ -1,0 +1,873 @@
+// sa_tc6.cuh — the fp32-ACCURATE tensor-core mode of the set-abstraction MLP ("bf16x3").
+//
+// The reference computes its 1x1 convolutions in fp32 (models/pointnet_pp_8dir.py:40-41).  Plain bf16 operands
+// (sa_tc4/5.cuh) keep the loss within 1e-3 but move the max-pool / ReLU routing and with it the weight gradients by
+// tens of percent.  This mode keeps the tcgen05 pipeline and recovers fp32-class accuracy by SPLITTING
+// every operand into two bf16 planes, x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 significant bits), and
+// issuing three MMAs per step into the same fp32 TMEM accumulator:
+//        A*B  ~=  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi          (the dropped lo*lo term is 2^-16 relative)
+// Everything that is not an MMA operand stays fp32: activations live in HBM as fp32 (tile-blocked channel-major
+// [tile][C][128 points]), BatchNorm / ReLU / BatchNorm-backward transforms run in fp32 in the producers BEFORE the
+// split, batch statistics are fp64 sums of the fp32 accumulators.
+//
+// Orientation, roles and operand images are those of sa_tc5.cuh (channels on the TMEM lanes; 17 warps: 8 epilogue,
+// 8 producers, 1 MMA issue; the contraction streamed through a ring of shared-memory stages in 64-channel - or, for the
+// weight gradient, 64-point - parts of 16 KB per plane).  What is new besides the planes:
+//   * forward / dgrad kernels are PERSISTENT: CTA x owns output-channel block x % ncb and walks over the 128-point
+//     tiles x / ncb, x / ncb + gridDim.x / ncb, ... with double-buffered TMEM accumulators, so the prologue (TMEM
+//     allocation, barriers, inline BatchNorm finalisation) is paid once per SM and the epilogue of tile i overlaps the
+//     MMAs of tile i+1;
+//   * when the weight slice of the CTA's channel block fits beside the stage ring (SA1, SA2) it is loaded ONCE and stays
+//     resident (both planes); otherwise (SA3) it is streamed with the activations as in sa_tc5.cuh.
+#pragma once
+#include "sa_tc5.cuh"
+
+namespace pcoe {
+namespace v6 {
+
+using namespace v4;
+using v5::kPart;
+using v5::unit_pipeline;
+
+constexpr int kMaxStages6 = 4;
+
+// ---- operand split -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf2_pack(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// (a, b) -> packed hi plane and packed lo plane
+__device__ __forceinline__ void split2(float a, float b, uint32_t& h, uint32_t& l) {
+  h = bf2_pack(a, b);
+  l = bf2_pack(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xFFFF0000u));
+}
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& h, uint4& l) {
+  split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y);
+  split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
+}
+
+// fp32 [C_out][C_in] -> two zero-padded bf16 planes [Rp][Kp]; perm_d >= 0: layer-1 column order [feats(perm_d) | xyz(3)]
+struct ConvW6 { const float* W; __nv_bfloat16* hi; __nv_bfloat16* lo; int cout, cin, Rp, Kp, perm_d; };
+__global__ void convert_weights6_kernel(ConvW6 a, ConvW6 b, ConvW6 c) {
+  const ConvW6* L[3] = {&a, &b, &c};
+  const int n0 = a.Rp * a.Kp / 8, n1 = b.Rp * b.Kp / 8, n2 = c.Rp * c.Kp / 8;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n0 + n1 + n2; e += gridDim.x * blockDim.x) {
+    const int l = e < n0 ? 0 : (e < n0 + n1 ? 1 : 2);
+    const ConvW6& w = *L[l];
+    const int ee = e - (l == 0 ? 0 : (l == 1 ? n0 : n0 + n1));
+    const int kp8 = w.Kp >> 3, r = ee / kp8, k0 = (ee - r * kp8) * 8;
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u;
+      int src = k;
+      if (w.perm_d >= 0) src = k < w.perm_d ? k + 3 : (k < w.perm_d + 3 ? k - w.perm_d : w.cin);
+      v[u] = (r < w.cout && src < w.cin) ? __ldg(w.W + (size_t)r * w.cin + src) : 0.f;
+    }
+    uint4 h, lo;
+    split8(v, h, lo);
+    reinterpret_cast<uint4*>(w.hi)[ee] = h;
+    reinterpret_cast<uint4*>(w.lo)[ee] = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Channel-major producers.  One UNIT of the 256 producer threads covers PTS points x (kRstep * kUR) channel rows:
+// thread g owns the 8-point chunk g % (PTS/8) of rows r0 + i*kRstep, r0 = g / (PTS/8), i < kUR.
+//   PTS = 128 (forward / dgrad operand: 64-channel x 128-point part), kRstep = 16
+//   PTS = 64  (weight-gradient operand: 128-channel x 64-point part), kRstep = 32
+// load():  raw fp32 global loads only.   store(): fp32 transform -> split -> two swizzled 16-byte stores.
+// `m0` = first point row of the unit, `crow` = first channel, `lrow` = image row of `crow`, `lrows` = image rows.
+// ---------------------------------------------------------------------------------------------------------------
+template <int PTS>
+struct CM {
+  static constexpr int kCpr = PTS / 8;
+  static constexpr int kRstep = kProdThreads / kCpr;
+};
+
+// relu(scale * y + shift) of the previous layer's pre-activations
+struct BnRelu6 {
+  static constexpr bool kChMajor = true;
+  static constexpr int kUR = 4;
+  struct Raw { float4 a[kUR][2]; };
+  const float* __restrict__ y;        // tile-blocked fp32 [tile][C][128]
+  const float* __restrict__ scale;
+  const float* __restrict__ shift;
+  int M, C;
+  const float* cs;
+  BnFin fin;                          // fin.sums != nullptr: train-mode forward, statistics finalised here
+  __host__ __device__ __forceinline__ int nconst() const { return 2 * C; }
+  __host__ __device__ __forceinline__ int nchunks() const { return C / 64; }
+  __host__ __device__ __forceinline__ int chunk_k(int) const { return 64; }
+  __device__ __forceinline__ void init(float* csm, int tid, int nthr) {
+    if (fin.sums) {
+      const bool w = first_block();
+      for (int c = tid; c < C; c += nthr) fin.eval(c, C, w, csm[c], csm[C + c]);
+    } else {
+      for (int c = tid; c < C; c += nthr) { csm[c] = scale[c]; csm[C + c] = shift[c]; }
+    }
+    cs = csm;
+  }
+  template <int PTS>
+  __device__ __forceinline__ void load(int g, int m0, int crow, Raw& r) const {
+    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
+    const int m = m0 + chunk * 8;
+    const bool ok = m < M;
+    const float* src = y + ((size_t)(m >> 7) * C + crow + r0) * 128 + (m & 127);
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      const bool rok = ok && crow + r0 + i * CM<PTS>::kRstep < C;
+      const float4* p = reinterpret_cast<const float4*>(src + (size_t)i * CM<PTS>::kRstep * 128);
+      r.a[i][0] = rok ? __ldg(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      r.a[i][1] = rok ? __ldg(p + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  template <int PTS>
+  __device__ __forceinline__ void store(int g, int, int crow, int lrow, int lrows, const Raw& r, uint32_t shi, uint32_t slo) const {
+    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      const int c = crow + r0 + i * CM<PTS>::kRstep;
+      if (c >= C) continue;                       // rows beyond C stay zero from the one-time clear
+      const float sc = cs[c], sh = cs[C + c];
+      const float x[8] = {r.a[i][0].x, r.a[i][0].y, r.a[i][0].z, r.a[i][0].w, r.a[i][1].x, r.a[i][1].y, r.a[i][1].z, r.a[i][1].w};
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = fmaxf(fmaf(x[u], sc, sh), 0.f);
+      uint4 h, l;
+      split8(v, h, l);
+      const uint32_t off = cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk);
+      tc::sts128(shi + off, h);
+      tc::sts128(slo + off, l);
+    }
+  }
+};
+
+// dy^T = a*dz^T + p*y^T + q (BatchNorm backward folded into per-channel constants), dense dz
+struct Dy6 {
+  static constexpr bool kChMajor = true;
+  static constexpr int kUR = 2;
+  struct Raw { float4 d[kUR][2], y[kUR][2]; };
+  const float* __restrict__ dz;
+  const float* __restrict__ y;
+  const float* __restrict__ a;
+  const float* __restrict__ p;
+  const float* __restrict__ q;
+  int M, C;
+  const float* cs;
+  BnBwdFin fin;
+  __host__ __device__ __forceinline__ int nconst() const { return 3 * C; }
+  __device__ __forceinline__ void init(float* csm, int tid, int nthr) {
+    if (fin.sums) {
+      const bool w = first_block();
+      for (int c = tid; c < C; c += nthr) fin.eval(c, C, w, csm[c], csm[C + c], csm[2 * C + c]);
+    } else {
+      for (int c = tid; c < C; c += nthr) { csm[c] = a[c]; csm[C + c] = p[c]; csm[2 * C + c] = q[c]; }
+    }
+    cs = csm;
+  }
+  template <int PTS>
+  __device__ __forceinline__ void load(int g, int m0, int crow, Raw& r) const {
+    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
+    const int m = m0 + chunk * 8;
+    const bool ok = m < M;
+    const size_t off = ((size_t)(m >> 7) * C + crow + r0) * 128 + (m & 127);
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      const bool rok = ok && crow + r0 + i * CM<PTS>::kRstep < C;
+      const float4* pd = reinterpret_cast<const float4*>(dz + off + (size_t)i * CM<PTS>::kRstep * 128);
+      const float4* py = reinterpret_cast<const float4*>(y + off + (size_t)i * CM<PTS>::kRstep * 128);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      r.d[i][0] = rok ? __ldg(pd) : z; r.d[i][1] = rok ? __ldg(pd + 1) : z;
+      r.y[i][0] = rok ? __ldg(py) : z; r.y[i][1] = rok ? __ldg(py + 1) : z;
+    }
+  }
+  template <int PTS>
+  __device__ __forceinline__ void store(int g, int m0, int crow, int lrow, int lrows, const Raw& r, uint32_t shi, uint32_t slo) const {
+    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
+    const float okf = m0 + chunk * 8 < M ? 1.f : 0.f;     // points >= M contribute 0 to dW
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      const int c = crow + r0 + i * CM<PTS>::kRstep;
+      if (c >= C) continue;
+      const float ca = cs[c] * okf, cp = cs[C + c] * okf, cq = cs[2 * C + c] * okf;
+      const float d[8] = {r.d[i][0].x, r.d[i][0].y, r.d[i][0].z, r.d[i][0].w, r.d[i][1].x, r.d[i][1].y, r.d[i][1].z, r.d[i][1].w};
+      const float yy[8] = {r.y[i][0].x, r.y[i][0].y, r.y[i][0].z, r.y[i][0].w, r.y[i][1].x, r.y[i][1].y, r.y[i][1].z, r.y[i][1].w};
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = fmaf(ca, d[u], fmaf(cp, yy[u], cq));
+      uint4 h, l;
+      split8(v, h, l);
+      const uint32_t off = cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk);
+      tc::sts128(shi + off, h);
+      tc::sts128(slo + off, l);
+    }
+  }
+};
+
+// last layer: dy3 = p*y3 + q + a * (max-pool routing of gm[G,C] to the saved arg slot), groups of K == 32 points
+struct DyLast6 {
+  static constexpr bool kChMajor = true;
+  static constexpr int kUR = 4;
+  struct Raw { float4 y[kUR][2]; float gv[kUR]; int sl[kUR]; };
+  const float* __restrict__ gm;       // [G,C]
+  const uint8_t* __restrict__ slot;   // [G,C]
+  const float* __restrict__ y;
+  const float* __restrict__ a;
+  const float* __restrict__ p;
+  const float* __restrict__ q;
+  int M, C;
+  const float* cs;
+  BnBwdFin fin;
+  __host__ __device__ __forceinline__ int nconst() const { return 3 * C; }
+  __device__ __forceinline__ void init(float* csm, int tid, int nthr) {
+    if (fin.sums) {
+      const bool w = first_block();
+      for (int c = tid; c < C; c += nthr) fin.eval(c, C, w, csm[c], csm[C + c], csm[2 * C + c]);
+    } else {
+      for (int c = tid; c < C; c += nthr) { csm[c] = a[c]; csm[C + c] = p[c]; csm[2 * C + c] = q[c]; }
+    }
+    cs = csm;
+  }
+  template <int PTS>
+  __device__ __forceinline__ void load(int g, int m0, int crow, Raw& r) const {
+    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
+    const int m = m0 + chunk * 8;
+    const bool ok = m < M;
+    const int grp = (ok ? m : 0) >> 5;
+    const float* sy = y + ((size_t)(m >> 7) * C + crow + r0) * 128 + (m & 127);
+    const size_t go = (size_t)grp * C + crow + r0;
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      const bool rok = ok && crow + r0 + i * CM<PTS>::kRstep < C;
+      const float4* py = reinterpret_cast<const float4*>(sy + (size_t)i * CM<PTS>::kRstep * 128);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      r.y[i][0] = rok ? __ldg(py) : z; r.y[i][1] = rok ? __ldg(py + 1) : z;
+      r.gv[i] = rok ? __ldg(gm + go + i * CM<PTS>::kRstep) : 0.f;
+      r.sl[i] = rok ? (int)__ldg(slot + go + i * CM<PTS>::kRstep) : -1;
+    }
+  }
+  template <int PTS>
+  __device__ __forceinline__ void store(int g, int m0, int crow, int lrow, int lrows, const Raw& r, uint32_t shi, uint32_t slo) const {
+    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
+    const int m = m0 + chunk * 8;
+    const float okf = m < M ? 1.f : 0.f;
+    const int j0 = m & 31;
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      const int c = crow + r0 + i * CM<PTS>::kRstep;
+      if (c >= C) continue;
+      const float add = cs[c] * r.gv[i], cp = cs[C + c] * okf, cq = cs[2 * C + c] * okf;   // gv is 0 for points >= M
+      const int sl = r.sl[i] - j0;                // slot relative to this 8-point chunk
+      const float yy[8] = {r.y[i][0].x, r.y[i][0].y, r.y[i][0].z, r.y[i][0].w, r.y[i][1].x, r.y[i][1].y, r.y[i][1].z, r.y[i][1].w};
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = fmaf(cp, yy[u], cq) + (u == sl ? add : 0.f);
+      uint4 h, l;
+      split8(v, h, l);
+      const uint32_t off = cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk);
+      tc::sts128(shi + off, h);
+      tc::sts128(slo + off, l);
+    }
+  }
+};
+
+// layer-1 input, point-major, streamed in 64-channel blocks: block kb < D/64 holds feats[:, 64kb .. +63], block D/64
+// holds [xyz - centroid (3) | zeros (13)] (channel order [feats | xyz], as the layer-1 weight images).  D % 64 == 0,
+// D == 0 (SA1) is the xyz block alone.  Thread g owns the 8-channel unit g & 7 of rows (g >> 3) + 32 i, i < PTS/32.
+struct GatherFeat6 {
+  static constexpr bool kChMajor = false;
+  static constexpr int kUR = 4;       // unused (point-major): one unit per 64-channel block
+  struct Raw { float4 a[4], b[4]; };
+  GatherBase gb;
+  const float* __restrict__ feats;
+  int D;
+  __host__ __device__ __forceinline__ int nconst() const { return 0; }
+  __host__ __device__ __forceinline__ int nchunks() const { return D / 64 + 1; }
+  __host__ __device__ __forceinline__ int chunk_k(int kb) const { return kb < D / 64 ? 64 : 16; }
+  __device__ __forceinline__ void init(float*, int, int) {}
+  template <int PTS>
+  __device__ __forceinline__ void load(int g, int m0, int kb, Raw& r) const {
+    if (kb < D / 64) {
+      const int j = g & 7;
+#pragma unroll
+      for (int i = 0; i < PTS / 32; ++i) {
+        const int row = m0 + (g >> 3) + 32 * i;
+        r.a[i] = r.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < gb.M) {
+          const float4* src = reinterpret_cast<const float4*>(feats + (size_t)gb.point_of(row) * D + kb * 64 + j * 8);
+          r.a[i] = __ldg(src);
+          r.b[i] = __ldg(src + 1);
+        }
+      }
+    } else {
+      float v[3] = {0.f, 0.f, 0.f}, c[3] = {0.f, 0.f, 0.f};
+      if (g < PTS && m0 + g < gb.M) gb.load_xyz_raw(m0 + g, gb.point_of(m0 + g), v, c);
+      r.a[0] = make_float4(v[0], v[1], v[2], 0.f);
+      r.b[0] = make_float4(c[0], c[1], c[2], 0.f);
+    }
+  }
+  template <int PTS>
+  __device__ __forceinline__ void store(int g, int kb, const Raw& r, uint32_t shi, uint32_t slo) const {
+    if (kb < D / 64) {
+      const int j = g & 7;
+#pragma unroll
+      for (int i = 0; i < PTS / 32; ++i) {
+        const float v[8] = {r.a[i].x, r.a[i].y, r.a[i].z, r.a[i].w, r.b[i].x, r.b[i].y, r.b[i].z, r.b[i].w};
+        uint4 h, l;
+        split8(v, h, l);
+        const uint32_t off = tc::sw128_off((g >> 3) + 32 * i, j * 8);
+        tc::sts128(shi + off, h);
+        tc::sts128(slo + off, l);
+      }
+    } else if (g < PTS) {
+      const float v[8] = {gb.centred(r.a[0].x, r.b[0].x), gb.centred(r.a[0].y, r.b[0].y), gb.centred(r.a[0].z, r.b[0].z),
+                          0.f, 0.f, 0.f, 0.f, 0.f};
+      uint4 h, l;
+      split8(v, h, l);
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      tc::sts128(shi + tc::sw128_off(g, 0), h); tc::sts128(shi + tc::sw128_off(g, 8), z);
+      tc::sts128(slo + tc::sw128_off(g, 0), l); tc::sts128(slo + tc::sw128_off(g, 8), z);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogues: thread = one channel (TMEM lane), v = 32 consecutive points (block j of the tile), fp32 outputs written
+// straight to the tile-blocked activation (128 contiguous bytes per thread and block).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store32_f32(float* dst, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+struct StoreStats6 {
+  float* __restrict__ y;           // tile-blocked fp32
+  double* __restrict__ sums;       // [kRedCopies][2,C] or nullptr (eval)
+  int C;
+  int c;
+  float s0, s1;
+  __host__ __device__ __forceinline__ int nconst() const { return 0; }
+  __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; }
+  __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid) {
+    if (c >= C || !valid) return;
+    store32_f32(y + ((size_t)tile * C + c) * 128 + j * 32, v);
+    sum_sumsq32(v, s0, s1);
+  }
+  __device__ __forceinline__ void finish() {
+    if (!sums || c >= C) return;
+    double* dst = sums + (size_t)(blockIdx.x % kRedCopies) * 2 * C;
+    atomicAdd(dst + c, (double)s0);
+    atomicAdd(dst + C + c, (double)s1);
+  }
+};
+
+struct Group6 {   // last layer, K == 32: the 32 columns of a block are one group
+  float* __restrict__ y;           // tile-blocked fp32, or nullptr (eval)
+  double* __restrict__ sums;
+  float* __restrict__ ymax;        // [G,C]
+  float* __restrict__ ymin;
+  uint8_t* __restrict__ amax;
+  uint8_t* __restrict__ amin;
+  int C;
+  const float* __restrict__ gamma; // the affine's sign is gamma's sign: each channel needs only one of (max, min)
+  int c;
+  float s0, s1;
+  bool want_max;
+  __host__ __device__ __forceinline__ int nconst() const { return 0; }
+  __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; want_max = c < C ? !signbit(gamma[c]) : true; }
+  __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid) {
+    if (c >= C || !valid) return;
+    if (y) store32_f32(y + ((size_t)tile * C + c) * 128 + j * 32, v);
+    sum_sumsq32(v, s0, s1);
+    float ext;
+    int arg;
+    const size_t o = (size_t)(tile * 4 + j) * C + c;
+    if (want_max) { argext32<true>(v, ext, arg); ymax[o] = ext; amax[o] = (uint8_t)arg; }
+    else { argext32<false>(v, ext, arg); ymin[o] = ext; amin[o] = (uint8_t)arg; }
+  }
+  __device__ __forceinline__ void finish() {
+    if (!sums || c >= C) return;
+    double* dst = sums + (size_t)(blockIdx.x % kRedCopies) * 2 * C;
+    atomicAdd(dst + c, (double)s0);
+    atomicAdd(dst + C + c, (double)s1);
+  }
+};
+
+// dz_prev^T = dx^T * [z_prev > 0]; sums of dz_prev and dz_prev * xhat_prev per channel
+struct MaskStats6 {
+  const float* __restrict__ yprev;   // tile-blocked fp32
+  const float* __restrict__ scale;
+  const float* __restrict__ shift;
+  const float* __restrict__ mean;
+  const float* __restrict__ invstd;
+  float* __restrict__ dz;            // tile-blocked fp32
+  double* __restrict__ sums;
+  int C;
+  int c;
+  float s0, s1, sc, sh, is, nmi;
+  __host__ __device__ __forceinline__ int nconst() const { return 0; }
+  __device__ __forceinline__ void init(float*, int ch) {
+    c = ch; s0 = s1 = 0.f;
+    const bool ok = c < C;
+    sc = ok ? scale[c] : 0.f; sh = ok ? shift[c] : 0.f; is = ok ? invstd[c] : 0.f; nmi = ok ? -mean[c] * is : 0.f;
+  }
+  __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid) {
+    if (c >= C || !valid) return;
+    const size_t o = ((size_t)tile * C + c) * 128 + j * 32;
+    const float4* py = reinterpret_cast<const float4*>(yprev + o);
+    float4* pd = reinterpret_cast<float4*>(dz + o);
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                 // two halves of 16 points: bounds the registers held by the y loads
+      float4 yv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) yv[q] = __ldg(py + 4 * h + q);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float yy[4] = {yv[q].x, yv[q].y, yv[q].z, yv[q].w};
+        float d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool on = fmaf(yy[u], sc, sh) > 0.f;
+          d[u] = on ? v[16 * h + 4 * q + u] : 0.f;
+          a[u] += d[u];
+          b[u] = fmaf(d[u], fmaf(yy[u], is, nmi), b[u]);
+        }
+        pd[4 * h + q] = make_float4(d[0], d[1], d[2], d[3]);
+      }
+    }
+    s0 += (a[0] + a[1]) + (a[2] + a[3]);
+    s1 += (b[0] + b[1]) + (b[2] + b[3]);
+  }
+  __device__ __forceinline__ void finish() {
+    if (c >= C) return;
+    double* dst = sums + (size_t)(blockIdx.x % kRedCopies) * 2 * C;
+    atomicAdd(dst + c, (double)s0);
+    atomicAdd(dst + C + c, (double)s1);
+  }
+};
+
+// ---- weight-slice loads (both planes at once: 8 x 16 bytes per thread) -----------------------------------------
+// K-major slice [128 rows x 64 k] (forward A operand)
+__device__ __forceinline__ void wload_k2(const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat16* __restrict__ Wl, int Kp, int row0,
+                                         int k0, int g, uint4* w) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const size_t o = (size_t)(row0 + (g >> 3) + 32 * i) * Kp + k0 + (g & 7) * 8;
+    w[i] = __ldg(reinterpret_cast<const uint4*>(Wh + o));
+    w[4 + i] = __ldg(reinterpret_cast<const uint4*>(Wl + o));
+  }
+}
+__device__ __forceinline__ void wstore_k2(uint32_t shi, uint32_t slo, int g, const uint4* w) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t off = tc::sw128_off((g >> 3) + 32 * i, (g & 7) * 8);
+    tc::sts128(shi + off, w[i]);
+    tc::sts128(slo + off, w[4 + i]);
+  }
+}
+// MN-major slice [64 k rows x 128 columns] = 2 blocks of [64 rows x 64 columns] (dgrad A operand)
+__device__ __forceinline__ void wload_mn2(const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat16* __restrict__ Wl, int Kp, int row0,
+                                          int col0, int g, uint4* w) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const size_t o = (size_t)(row0 + (g >> 4) + 16 * i) * Kp + col0 + (g & 15) * 8;
+    w[i] = __ldg(reinterpret_cast<const uint4*>(Wh + o));
+    w[4 + i] = __ldg(reinterpret_cast<const uint4*>(Wl + o));
+  }
+}
+__device__ __forceinline__ void wstore_mn2(uint32_t shi, uint32_t slo, int g, const uint4* w) {
+  const int j = g & 15;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t off = (uint32_t)(j >> 3) * 8192u + tc::sw128_off((g >> 4) + 16 * i, (j & 7) * 8);
+    tc::sts128(shi + off, w[i]);
+    tc::sts128(slo + off, w[4 + i]);
+  }
+}
+
+struct Barriers6 {
+  uint64_t full[kMaxStages6];
+  uint64_t empty[kMaxStages6];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+};
+
+#define PCOE_V6_PROLOGUE(TCOLS)                                                                    \
+  extern __shared__ uint8_t smem_raw[];                                                            \
+  const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;                                \
+  uint8_t* smem_gen = smem_raw + (smem0 - tc::smem_u32(smem_raw));                                 \
+  __shared__ Barriers6 bar;                                                                        \
+  __shared__ uint32_t tmem_base;                                                                   \
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                                   \
+  if (warp == 0) tc::tmem_alloc<TCOLS>(&tmem_base);                                                \
+  if (tid == 0) {                                                                                  \
+    for (int s = 0; s < kMaxStages6; ++s) { tc::mbar_init(&bar.full[s], kProdThreads); tc::mbar_init(&bar.empty[s], 1); } \
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar.tmem_full[b], 1); tc::mbar_init(&bar.tmem_empty[b], kEpiThreads); } \
+  }
+
+// the three split products of one 16-deep MMA step (small terms first)
+__device__ __forceinline__ void mma3(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc, bool acc) {
+  tc::mma_bf16_warp(d, al, bh, idesc, acc);
+  tc::mma_bf16_warp(d, ah, bl, idesc, true);
+  tc::mma_bf16_warp(d, ah, bh, idesc, true);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward: Y^T[128 ch x 128 pts] = W[128 x Cin] * X^T[Cin x 128] per (tile, channel block).
+// smem: wres ? [W: nk x (hi 16K | lo 16K)][ring: nst x (X hi | X lo)] : [ring: nst x (W hi | W lo | X hi | X lo)]
+// ---------------------------------------------------------------------------------------------------------------
+template <class Prod, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat16* __restrict__ Wl, int Kp, Epi epi, int M,
+              int ncb, int nst, int wres) {
+  PCOE_V6_PROLOGUE(256)
+  const int nk = prod.nchunks();
+  const uint32_t sWres = smem0, wres_bytes = wres ? (uint32_t)nk * 2u * kPart : 0u;
+  const uint32_t sS = smem0 + wres_bytes, sbytes = wres ? 2u * kPart : 4u * kPart, xoff = wres ? 0u : 2u * kPart;
+  float* csm = reinterpret_cast<float*>(smem_gen + wres_bytes + (size_t)nst * sbytes);
+  const int cb = blockIdx.x % ncb, t0 = blockIdx.x / ncb, tstep = gridDim.x / ncb;
+  const int ntiles = (M + kPts - 1) / kPts;
+  const int my_items = t0 < ntiles ? (ntiles - t0 + tstep - 1) / tstep : 0;
+  zero_smem(sS, (uint32_t)nst * sbytes, tid, kThreads);
+  prod.init(csm, tid, kThreads);
+  const int eq = warp & 3, eh = (warp >> 2) & 1;
+  epi.init(csm + prod.nconst(), cb * 128 + eq * 32 + lane);
+  if (wres && tid < kProdThreads) {
+    for (int k = 0; k < nk; ++k) {
+      uint4 w[8];
+      wload_k2(Wh, Wl, Kp, cb * 128, k * 64, tid, w);
+      wstore_k2(sWres + (uint32_t)k * 2u * kPart, sWres + (uint32_t)k * 2u * kPart + kPart, tid, w);
+    }
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base;
+
+  if (warp < 8) {
+    int i = 0;
+    for (int tile = t0; tile < ntiles; tile += tstep, ++i) {
+      const int b = i & 1, u = i >> 1, m0 = tile * kPts;
+      tc::mbar_wait(&bar.tmem_full[b], (uint32_t)(u & 1));
+      tc::fence_after_sync();
+#pragma unroll 1
+      for (int j = eh * 2; j < eh * 2 + 2; ++j) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(b * kPts + j * 32), v);
+        epi.block(v, tile, j, m0 + j * 32 < M);
+      }
+      tc::fence_before_sync();
+      mbar_arrive_relaxed(&bar.tmem_empty[b]);
+    }
+    epi.finish();
+  } else if (warp < 16) {
+    const int g = tid - kEpiThreads;
+    constexpr int kXU = Prod::kChMajor ? 4 / Prod::kUR : 1;   // activation units per 64-channel chunk
+    const int wu = wres ? 0 : 1, upc = kXU + wu;
+    union RawU { typename Prod::Raw x; uint4 w[8]; __device__ RawU() {} };
+    struct Cur { int tile, k, u; };
+    auto adv = [&](Cur& c) { if (++c.u == upc) { c.u = 0; if (++c.k == nk) { c.k = 0; c.tile += tstep; } } };
+    Cur cl{t0, 0, 0}, cst = cl;
+    int ring_s = 0, ring_r = 0;
+    unit_pipeline<RawU>(my_items * nk * upc,
+        [&](int, RawU& r) {
+          const int xu = cl.u - wu;
+          if (xu < 0) wload_k2(Wh, Wl, Kp, cb * 128, cl.k * 64, g, r.w);
+          else if constexpr (Prod::kChMajor) prod.template load<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * Prod::kUR, r.x);
+          else prod.template load<128>(g, cl.tile * kPts, cl.k, r.x);
+          adv(cl);
+        },
+        [&](int, const RawU& r) {
+          const uint32_t st = sS + (uint32_t)ring_s * sbytes;
+          if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
+          const int xu = cst.u - wu;
+          if (xu < 0) wstore_k2(st, st + kPart, g, r.w);
+          else if constexpr (Prod::kChMajor)
+            prod.template store<128>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * Prod::kUR, xu * 16 * Prod::kUR, 64, r.x, st + xoff, st + xoff + kPart);
+          else prod.template store<128>(g, cst.k, r.x, st + xoff, st + xoff + kPart);
+          if (cst.u == upc - 1) {
+            tc::fence_proxy_async();
+            mbar_arrive(&bar.full[ring_s]);
+            if (++ring_s == nst) { ring_s = 0; ++ring_r; }
+          }
+          adv(cst);
+        });
+  } else {   // warp 16: MMA issue, warp-uniform loop, one elected lane issues
+    const uint32_t tm = tc::uniform_u32(tmem_base);
+    const uint32_t idesc = tc::make_idesc_bf16(128, kPts, false, Prod::kChMajor);
+    int ring_s = 0, ring_r = 0, i = 0;
+    for (int tile = t0; tile < ntiles; tile += tstep, ++i) {
+      const int b = i & 1, u = i >> 1;
+      for (int k = 0; k < nk; ++k) {
+        tc::mbar_wait(&bar.full[ring_s], (uint32_t)(ring_r & 1));
+        if (k == 0 && u > 0) tc::mbar_wait(&bar.tmem_empty[b], (uint32_t)((u - 1) & 1));
+        tc::fence_after_sync();
+        const uint32_t st = sS + (uint32_t)ring_s * sbytes;
+        const uint32_t sAh = wres ? sWres + (uint32_t)k * 2u * kPart : st, sAl = sAh + kPart;
+        const uint32_t sBh = st + xoff, sBl = sBh + kPart;
+        const int kk = prod.chunk_k(k);
+        for (int q = 0; q < kk / 16; ++q) {
+          const uint64_t ah = tc::make_desc_sw128(sAh + (uint32_t)q * 32, 16, 1024), al = tc::make_desc_sw128(sAl + (uint32_t)q * 32, 16, 1024);
+          const uint64_t bh = Prod::kChMajor ? tc::make_desc_sw128(sBh + (uint32_t)q * 2048, 8192, 1024)
+                                             : tc::make_desc_sw128(sBh + (uint32_t)q * 32, 16, 1024);
+          const uint64_t bl = Prod::kChMajor ? tc::make_desc_sw128(sBl + (uint32_t)q * 2048, 8192, 1024)
+                                             : tc::make_desc_sw128(sBl + (uint32_t)q * 32, 16, 1024);
+          mma3(tm + (uint32_t)(b * kPts), ah, al, bh, bl, idesc, k > 0 || q > 0);
+        }
+        tc::mma_commit_warp(&bar.empty[ring_s]);
+        if (++ring_s == nst) { ring_s = 0; ++ring_r; }
+      }
+      tc::mma_commit_warp(&bar.tmem_full[b]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<256>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dgrad: dX^T[128 in-ch x 128 pts] = W^T[128 x Cout] * dY^T[Cout x 128] per (tile, input-channel block); contraction
+// over the layer's output channels in chunks of 64.  PT: operands swapped, D[128 points x 128 in-ch], point-on-lane
+// epilogue (layer-1 scatter-add into grad_feats).
+// ---------------------------------------------------------------------------------------------------------------
+template <class PProd, class Epi, bool PT>
+__global__ void __launch_bounds__(kThreads, 1)
+x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat16* __restrict__ Wl, int Kp, Epi epi, int M,
+                int ncb, int nst, int wres) {
+  PCOE_V6_PROLOGUE(256)
+  const int nk = pp.C / 64;
+  const uint32_t sWres = smem0, wres_bytes = wres ? (uint32_t)nk * 2u * kPart : 0u;
+  const uint32_t sS = smem0 + wres_bytes, sbytes = wres ? 2u * kPart : 4u * kPart, xoff = wres ? 0u : 2u * kPart;
+  float* csm = reinterpret_cast<float*>(smem_gen + wres_bytes + (size_t)nst * sbytes);
+  const int cb = blockIdx.x % ncb, t0 = blockIdx.x / ncb, tstep = gridDim.x / ncb;
+  const int ntiles = (M + kPts - 1) / kPts;
+  const int my_items = t0 < ntiles ? (ntiles - t0 + tstep - 1) / tstep : 0;
+  zero_smem(sS, (uint32_t)nst * sbytes, tid, kThreads);
+  pp.init(csm, tid, kThreads);
+  const int eq = warp & 3, eh = (warp >> 2) & 1;
+  epi.init(csm + pp.nconst(), cb * 128 + eq * 32 + lane);
+  if (wres && tid < kProdThreads) {
+    for (int k = 0; k < nk; ++k) {
+      uint4 w[8];
+      wload_mn2(Wh, Wl, Kp, k * 64, cb * 128, tid, w);
+      wstore_mn2(sWres + (uint32_t)k * 2u * kPart, sWres + (uint32_t)k * 2u * kPart + kPart, tid, w);
+    }
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base;
+
+  if (warp < 8) {
+    int i = 0;
+    for (int tile = t0; tile < ntiles; tile += tstep, ++i) {
+      const int b = i & 1, u = i >> 1, m0 = tile * kPts;
+      tc::mbar_wait(&bar.tmem_full[b], (uint32_t)(u & 1));
+      tc::fence_after_sync();
+      if constexpr (!PT) {
+#pragma unroll 1
+        for (int j = eh * 2; j < eh * 2 + 2; ++j) {
+          float v[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(b * kPts + j * 32), v);
+          epi.block(v, tile, j, m0 + j * 32 < M);
+        }
+      } else {
+        const int row = m0 + eq * 32 + lane;
+#pragma unroll 1
+        for (int cbk = eh * 32; cbk < 128; cbk += 64) {
+          float v[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(b * kPts + cbk), v);
+          epi.block_pt(v, cb * 128 + cbk, row, row < M);
+        }
+      }
+      tc::fence_before_sync();
+      mbar_arrive_relaxed(&bar.tmem_empty[b]);
+    }
+    epi.finish();
+  } else if (warp < 16) {
+    const int g = tid - kEpiThreads;
+    constexpr int kXU = 4 / PProd::kUR;
+    const int wu = wres ? 0 : 1, upc = kXU + wu;
+    union RawU { typename PProd::Raw x; uint4 w[8]; __device__ RawU() {} };
+    struct Cur { int tile, k, u; };
+    auto adv = [&](Cur& c) { if (++c.u == upc) { c.u = 0; if (++c.k == nk) { c.k = 0; c.tile += tstep; } } };
+    Cur cl{t0, 0, 0}, cst = cl;
+    int ring_s = 0, ring_r = 0;
+    unit_pipeline<RawU>(my_items * nk * upc,
+        [&](int, RawU& r) {
+          const int xu = cl.u - wu;
+          if (xu < 0) wload_mn2(Wh, Wl, Kp, cl.k * 64, cb * 128, g, r.w);
+          else pp.template load<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * PProd::kUR, r.x);
+          adv(cl);
+        },
+        [&](int, const RawU& r) {
+          const uint32_t st = sS + (uint32_t)ring_s * sbytes;
+          if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
+          const int xu = cst.u - wu;
+          if (xu < 0) wstore_mn2(st, st + kPart, g, r.w);
+          else pp.template store<128>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * PProd::kUR, xu * 16 * PProd::kUR, 64, r.x, st + xoff, st + xoff + kPart);
+          if (cst.u == upc - 1) {
+            tc::fence_proxy_async();
+            mbar_arrive(&bar.full[ring_s]);
+            if (++ring_s == nst) { ring_s = 0; ++ring_r; }
+          }
+          adv(cst);
+        });
+  } else {
+    const uint32_t tm = tc::uniform_u32(tmem_base);
+    const uint32_t idesc = tc::make_idesc_bf16(128, 128, true, true);
+    int ring_s = 0, ring_r = 0, i = 0;
+    for (int tile = t0; tile < ntiles; tile += tstep, ++i) {
+      const int b = i & 1, u = i >> 1;
+      for (int k = 0; k < nk; ++k) {
+        tc::mbar_wait(&bar.full[ring_s], (uint32_t)(ring_r & 1));
+        if (k == 0 && u > 0) tc::mbar_wait(&bar.tmem_empty[b], (uint32_t)((u - 1) & 1));
+        tc::fence_after_sync();
+        const uint32_t st = sS + (uint32_t)ring_s * sbytes;
+        const uint32_t sWh = wres ? sWres + (uint32_t)k * 2u * kPart : st, sWl = sWh + kPart;
+        const uint32_t sPh = st + xoff, sPl = sPh + kPart;
+        for (int q = 0; q < 4; ++q) {
+          const uint64_t wh = tc::make_desc_sw128(sWh + (uint32_t)q * 2048, 8192, 1024), wl = tc::make_desc_sw128(sWl + (uint32_t)q * 2048, 8192, 1024);
+          const uint64_t ph = tc::make_desc_sw128(sPh + (uint32_t)q * 2048, 8192, 1024), pl = tc::make_desc_sw128(sPl + (uint32_t)q * 2048, 8192, 1024);
+          if constexpr (PT) mma3(tm + (uint32_t)(b * kPts), ph, pl, wh, wl, idesc, k > 0 || q > 0);
+          else mma3(tm + (uint32_t)(b * kPts), wh, wl, ph, pl, idesc, k > 0 || q > 0);
+        }
+        tc::mma_commit_warp(&bar.empty[ring_s]);
+        if (++ring_s == nst) { ring_s = 0; ++ring_r; }
+      }
+      tc::mma_commit_warp(&bar.tmem_full[b]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<256>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad: CTA (channel block, q block, split) accumulates dW[128 x nq] over its tiles in TMEM and adds it to global
+// memory at the end.  Stage = 64 points: [P hi | P lo | Q hi | Q lo], P = dy^T part [128 ch x 64 pts] (K-major),
+// Q = x_prev part, channel-major [128 ch x 64 pts] (K-major) or point-major [64 pts x 2 blocks of 64 ch] (MN-major).
+// ---------------------------------------------------------------------------------------------------------------
+template <class PProd, class QProd>
+__global__ void __launch_bounds__(kThreads, 1)
+x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_valid, int perm_d, int M, int tps, int nst) {
+  PCOE_V6_PROLOGUE(128)
+  const int cl0 = blockIdx.x * 128, qb = blockIdx.y;
+  const int ntiles = (M + kPts - 1) / kPts;
+  const int t0 = blockIdx.z * tps, t1 = min(ntiles, t0 + tps), nt = max(t1 - t0, 0);
+  const uint32_t sS = smem0, sbytes = 4u * kPart;
+  float* csm = reinterpret_cast<float*>(smem_gen + (size_t)nst * sbytes);
+  zero_smem(sS, (uint32_t)nst * sbytes, tid, kThreads);
+  pp.init(csm, tid, kThreads);
+  qp.init(csm + pp.nconst(), tid, kThreads);
+  int nq, nqu;                                               // columns of this q block; Q units per stage
+  if constexpr (QProd::kChMajor) {
+    nq = min(128, qp.C - qb * 128);
+    nqu = 4 / QProd::kUR;
+  } else {
+    nqu = min(2, qp.nchunks() - 2 * qb);
+    nq = 0;
+    for (int u = 0; u < nqu; ++u) nq += qp.chunk_k(2 * qb + u);
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  const int eq = warp & 3, eh = (warp >> 2) & 1;
+  constexpr int kPU = 4 / PProd::kUR;                        // P units per stage (128 rows / (32 * kUR))
+  const int ups = kPU + nqu, nstage = 2 * nt;                // units per stage; 64-point stages
+
+  if (warp < 8) {
+    if (nt > 0) {
+      tc::mbar_wait(&bar.tmem_full[0], 0u);
+      tc::fence_after_sync();
+      const int crow = cl0 + eq * 32 + lane;
+#pragma unroll 1
+      for (int cbk = eh * 32; cbk < nq; cbk += 64) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)cbk, v);   // may read past nq: unused columns
+        if (crow >= pp.C) continue;
+        float* dst = dW + (size_t)crow * ldo;
+        const int cb = qb * 128 + cbk;
+        if (perm_d < 0 && (ldo & 3) == 0 && cb + 32 <= cq_valid && cbk + 32 <= nq) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) red_add_v4(dst + cb + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            int c = cb + e;
+            if (c >= cq_valid || cbk + e >= nq) continue;
+            if (perm_d >= 0) c = c < perm_d ? c + 3 : c - perm_d;   // [feats | xyz] -> [xyz | feats]
+            atomicAdd(dst + c, v[e]);
+          }
+        }
+      }
+      tc::fence_before_sync();
+    }
+  } else if (warp < 16) {
+    const int g = tid - kEpiThreads;
+    union RawU { typename PProd::Raw p; typename QProd::Raw q; __device__ RawU() {} };
+    struct Cur { int u, m0; };
+    auto adv = [&](Cur& c) { if (++c.u == ups) { c.u = 0; c.m0 += 64; } };
+    Cur cl{0, t0 * kPts}, cst = cl;
+    int ring_s = 0, ring_r = 0;
+    unit_pipeline<RawU>(nstage * ups,
+        [&](int, RawU& r) {
+          if (cl.u < kPU) pp.template load<64>(g, cl.m0, cl0 + cl.u * 32 * PProd::kUR, r.p);
+          else if constexpr (QProd::kChMajor) qp.template load<64>(g, cl.m0, qb * 128 + (cl.u - kPU) * 32 * QProd::kUR, r.q);
+          else qp.template load<64>(g, cl.m0, 2 * qb + (cl.u - kPU), r.q);
+          adv(cl);
+        },
+        [&](int, const RawU& r) {
+          const uint32_t st = sS + (uint32_t)ring_s * sbytes;
+          if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
+          if (cst.u < kPU)
+            pp.template store<64>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, cst.u * 32 * PProd::kUR, 128, r.p, st, st + kPart);
+          else {
+            const int qu = cst.u - kPU;
+            if constexpr (QProd::kChMajor)
+              qp.template store<64>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, qu * 32 * QProd::kUR, 128, r.q, st + 2 * kPart, st + 3 * kPart);
+            else
+              qp.template store<64>(g, 2 * qb + qu, r.q, st + 2 * kPart + (uint32_t)qu * 8192u, st + 3 * kPart + (uint32_t)qu * 8192u);
+          }
+          if (cst.u == ups - 1) {
+            tc::fence_proxy_async();
+            mbar_arrive(&bar.full[ring_s]);
+            if (++ring_s == nst) { ring_s = 0; ++ring_r; }
+          }
+          adv(cst);
+        });
+  } else {
+    const uint32_t tm = tc::uniform_u32(tmem_base);
+    const uint32_t idesc = tc::make_idesc_bf16(128, nq, false, !QProd::kChMajor);
+    int ring_s = 0, ring_r = 0;
+    for (int h = 0; h < nstage; ++h) {
+      tc::mbar_wait(&bar.full[ring_s], (uint32_t)(ring_r & 1));
+      tc::fence_after_sync();
+      const uint32_t sPh = sS + (uint32_t)ring_s * sbytes, sPl = sPh + kPart, sQh = sPh + 2 * kPart, sQl = sPh + 3 * kPart;
+      for (int ks = 0; ks < 4; ++ks) {                        // 16 points per MMA
+        const uint64_t ah = tc::make_desc_sw128(sPh + (uint32_t)ks * 32, 16, 1024), al = tc::make_desc_sw128(sPl + (uint32_t)ks * 32, 16, 1024);
+        const uint64_t bh = QProd::kChMajor ? tc::make_desc_sw128(sQh + (uint32_t)ks * 32, 16, 1024)
+                                            : tc::make_desc_sw128(sQh + (uint32_t)ks * 2048, 8192, 1024);
+        const uint64_t bl = QProd::kChMajor ? tc::make_desc_sw128(sQl + (uint32_t)ks * 32, 16, 1024)
+                                            : tc::make_desc_sw128(sQl + (uint32_t)ks * 2048, 8192, 1024);
+        mma3(tm, ah, al, bh, bl, idesc, h > 0 || ks > 0);
+      }
+      tc::mma_commit_warp(&bar.empty[ring_s]);
+      if (++ring_s == nst) { ring_s = 0; ++ring_r; }
+    }
+    if (nt > 0) tc::mma_commit_warp(&bar.tmem_full[0]);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<128>(tmem);
+}
+
+}  // namespace v6
+}  // namespace pcoe

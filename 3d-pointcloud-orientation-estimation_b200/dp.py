@@ -39,6 +39,22 @@ class FlatGradBuffer:
     def zero_(self) -> None:
         self.flat.zero_()
 
+    def check_views(self) -> None:
+        """Every ``p.grad`` must still be a view into the flat buffer.  ``optimizer.zero_grad()`` with its default
+        ``set_to_none=True`` detaches them: autograd would then allocate fresh gradients and the all-reduce would
+        silently exchange a stale buffer.  Raises instead (use ``engine.zero_grad()`` / ``set_to_none=False``)."""
+        lo = self.flat.data_ptr()
+        hi = lo + self.flat.numel() * 4
+        off = 0
+        for p in self.params:
+            g = p.grad
+            if g is None or g.data_ptr() != lo + off * 4 or not (lo <= g.data_ptr() < hi):
+                raise RuntimeError(
+                    "pcoe.dp: a parameter's .grad no longer points into the flat gradient buffer (was "
+                    "optimizer.zero_grad(set_to_none=True) called?); call engine.zero_grad() or "
+                    "optimizer.zero_grad(set_to_none=False) instead")
+            off += p.numel()
+
     def nbytes(self) -> int:
         return self.flat.numel() * 4
 
@@ -76,6 +92,7 @@ class DataParallel:
                         dist.broadcast(b.data, src=0, group=process_group)
         self.grads = FlatGradBuffer(module)
         self._late_off, self._late_work = None, None
+        self._sync = True              # False inside no_sync(): micro-batch gradients accumulate locally
         if self.world > 1 and overlap:
             sa = [m for m in module.modules() if hasattr(m, "direct_grad_accumulation") and list(m.parameters())]
             if sa:
@@ -93,16 +110,38 @@ class DataParallel:
     def _reduce_tail_async(self) -> None:
         """Called by the last SA layer at the end of its backward: everything from its first parameter to the end
         of the flat buffer is final (autograd accumulates the trunk / head gradients before this node runs)."""
-        self._late_work = dist.all_reduce(self.grads.flat[self._late_off:], op=dist.ReduceOp.SUM, group=self.group,
-                                          async_op=True)
+        if self._late_work is not None:
+            # a second backward() before allreduce_grads() (gradient accumulation without no_sync, or an exception
+            # between the two): reducing the already-summed tail again would count the first micro-batch `world` times
+            raise RuntimeError("pcoe.dp: backward() ran twice before allreduce_grads(); wrap the extra micro-batches "
+                               "in `with engine.no_sync():` (gradient accumulation)")
+        if self._sync:
+            self._late_work = dist.all_reduce(self.grads.flat[self._late_off:], op=dist.ReduceOp.SUM, group=self.group,
+                                              async_op=True)
 
     def zero_grad(self) -> None:
         self.grads.zero_()
+
+    def no_sync(self):
+        """Context manager for gradient accumulation: backward() inside it adds into the flat buffer without
+        starting the overlapped exchange; the first backward() outside it (followed by ``allreduce_grads()``)
+        reduces the accumulated sum once."""
+        engine = self
+
+        class _NoSync:
+            def __enter__(self_inner):
+                self_inner.prev, engine._sync = engine._sync, False
+
+            def __exit__(self_inner, *exc):
+                engine._sync = self_inner.prev
+                return False
+        return _NoSync()
 
     def allreduce_grads(self) -> None:
         """grad <- mean over ranks (sum all-reduce of the flat buffer; scaled by 1/world here unless a
         pcoe.optim.FusedAdam built on this engine applies the factor in its step kernel)."""
         if self.world > 1:
+            self.grads.check_views()
             if self._late_work is not None:
                 dist.all_reduce(self.grads.flat[:self._late_off], op=dist.ReduceOp.SUM, group=self.group)
                 self._late_work.wait()

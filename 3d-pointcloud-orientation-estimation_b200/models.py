@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .sa import PointNetSetAbstraction
+from .sa import PointNetSetAbstraction, _dp_rank
 from .trunk import MvMTrunkHead
 
 # 8 horizontal directions, 45 degree steps starting from the original "forward" [0,0,-1]
@@ -222,7 +222,8 @@ class PointNetPPMvM(_Backbone):
                 if self._drop_counter is None or self._drop_counter.device != x.device:
                     raise RuntimeError("pcoe: run one eager training step before capturing (allocates the dropout counter)")
                 self._drop_counter.add_(1)
-                seed, counter = torch.initial_seed(), self._drop_counter
+                # data-parallel ranks share torch.initial_seed(): mix the rank in so that they draw different masks
+                seed, counter = torch.initial_seed() + 0x5DEECE66D * _dp_rank(), self._drop_counter
             else:
                 # eager: consume torch's CUDA generator like nn.Dropout would (reproducible under torch.manual_seed)
                 if self._drop_counter is None or self._drop_counter.device != x.device:

@@ -32,7 +32,7 @@ def _ptr(t) -> int | None:
 # sampling
 # ------------------------------------------------------------------------------------------------
 def farthest_point_sample(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor | None = None,
-                          return_xyz: bool = False):
+                          return_xyz: bool = False, int32: bool = False):
     """FPS indices (B,npoint) int64.  Reference: PointNet++Demo.py:8-29.
 
     ``start_idx`` (B,) is the first centroid of every cloud; the reference draws it with
@@ -49,7 +49,7 @@ def farthest_point_sample(xyz: torch.Tensor, npoint: int, start_idx: torch.Tenso
     oxyz = torch.empty(B, npoint, 3, dtype=torch.float32, device=xyz.device) if return_xyz else None
     _lib.check(_lib.load().pcoe_fps_f32(xyz.data_ptr(), B, N, npoint, start.data_ptr(), out.data_ptr(),
                                         _ptr(oxyz), _stream()))
-    idx = out.long()
+    idx = out if int32 else out.long()
     return (idx, oxyz) if return_xyz else idx
 
 

@@ -16,13 +16,22 @@ import torch.nn as nn
 from . import _lib, ops
 
 _DEFAULT_PRECISION = "fp32"
+PRECISIONS = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16, "bf16x3": _lib.PRECISION_BF16X3}
+_layer_seq = 0          # construction index of the SA layers of this process: deterministic Philox stream ids
+
+
+def _dp_rank() -> int:
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
 def set_default_precision(p: str) -> None:
-    """'fp32' (CUDA-core fp32 GEMMs, the parity mode) or 'bf16' (tcgen05 bf16 operands, fp32 accumulate)."""
+    """'fp32' (CUDA-core fp32 GEMMs), 'bf16x3' (tcgen05 with every operand split into two bf16 planes and three
+    MMAs per step, fp32 stored activations: fp32-class accuracy on the tensor pipe - the parity mode of the fast
+    path) or 'bf16' (tcgen05, plain bf16 operands and stored activations: fastest, stated tolerance)."""
     global _DEFAULT_PRECISION
-    if p not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if p not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
     _DEFAULT_PRECISION = p
 
 
@@ -89,7 +98,7 @@ class _SAFunction(torch.autograd.Function):
         train = module.training
         desc = _lib.SADesc(B=B, N=N, S=S, K=K, D=D, C1=Ws[0].size(0), C2=Ws[1].size(0), C3=Ws[2].size(0),
                            group_all=int(group_all), train=int(train),
-                           precision=_lib.PRECISION_BF16 if module.precision == "bf16" else _lib.PRECISION_FP32,
+                           precision=PRECISIONS[module.precision],
                            eps=module.bns[0].eps, momentum=module.bns[0].momentum or 0.1)
         P = _lib.SAParams()
         _fill3(P.W, Ws); _fill3(P.bias, bs); _fill3(P.gamma, gs); _fill3(P.beta, bes)
@@ -162,7 +171,7 @@ class PointNetSetAbstraction(nn.Module):
               or 'fps' (true farthest-point sampling, PointNet++Demo.py:8-29).
     grouper   'knn' (default; what the reference's ``query_ball_point`` computes, base.py:29-35) or
               'ball' (radius query of PointNet++Demo.py:49-70; needs ``radius``).
-    precision 'fp32' | 'bf16' | None (= pcoe default at call time).
+    precision 'fp32' | 'bf16x3' | 'bf16' | None (= pcoe default at call time); see set_default_precision.
     """
 
     def __init__(self, npoint, nsample, in_channel, mlp_channels, group_all=False, *,
@@ -179,8 +188,13 @@ class PointNetSetAbstraction(nn.Module):
         self.nsample = nsample
         self.group_all = group_all
         self.sampler, self.grouper, self.radius = sampler, grouper, radius
+        if precision is not None and precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
         self._precision = precision
         self._rng_counter = None
+        global _layer_seq
+        _layer_seq += 1
+        self._stream_id = _layer_seq              # reproducible across runs (unlike id(self)), distinct per layer
         # set by pcoe.dp.FlatGradBuffer: backward adds parameter gradients straight into p.grad
         self.direct_grad_accumulation = False
         self._after_backward = None                # pcoe.dp.DataParallel hook, called at the end of this layer's backward
@@ -210,10 +224,16 @@ class PointNetSetAbstraction(nn.Module):
             if self._rng_counter is None or self._rng_counter.device != xyz.device:
                 self._rng_counter = torch.zeros(1, dtype=torch.int64, device=xyz.device)
             self._rng_counter.add_(1)
-            return ops.random_subset(B, N, self.npoint, torch.initial_seed(), (id(self) & 0xFFFFFF) << 32, xyz.device,
+            # Philox stream = (layer construction index, data-parallel rank): same subsets for the same seed on every
+            # run, different subsets on different ranks and layers
+            offset = ((self._stream_id & 0xFFFF) << 48) | ((_dp_rank() & 0xFFFF) << 32)
+            return ops.random_subset(B, N, self.npoint, torch.initial_seed(), offset, xyz.device,
                                      self._rng_counter, xyz=xyz)
-        idx, new_xyz = ops.farthest_point_sample(xyz, self.npoint, return_xyz=True)   # the kernel gathers as it selects
-        return idx.to(torch.int32), new_xyz
+        # 'fps': the first centroid of every cloud is drawn ON THE DEVICE (torch's CUDA generator: no host sync, and a
+        # CUDA-graph replay draws fresh start points); ops.farthest_point_sample keeps the reference's host draw
+        start = torch.randint(0, N, (B,), device=xyz.device, dtype=torch.int32)
+        idx, new_xyz = ops.farthest_point_sample(xyz, self.npoint, start, return_xyz=True, int32=True)
+        return idx, new_xyz
 
     @staticmethod
     def _check_xyz(xyz):

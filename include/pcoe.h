@@ -119,7 +119,11 @@ int pcoe_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N, in
  * and its autograd.
  * ------------------------------------------------------------------------------------------ */
 
-enum { PCOE_PRECISION_FP32 = 0, PCOE_PRECISION_BF16 = 1 };
+/* FP32:   CUDA-core fp32 GEMMs (exact-arithmetic parity mode).
+ * BF16:   tcgen05, bf16 operands / bf16 stored activations, fp32 accumulate (throughput mode, stated tolerance).
+ * BF16X3: tcgen05, every operand split into two bf16 planes (hi + lo), three MMAs per step, fp32 stored
+ *         activations and fp32 transforms: fp32-class accuracy (2^-16 relative per product) on the tensor pipe. */
+enum { PCOE_PRECISION_FP32 = 0, PCOE_PRECISION_BF16 = 1, PCOE_PRECISION_BF16X3 = 2 };
 
 typedef struct pcoe_sa_desc {
   int32_t B;          /* clouds                                                               */
@@ -130,7 +134,7 @@ typedef struct pcoe_sa_desc {
   int32_t C1, C2, C3; /* output widths of the three 1x1 convolutions                          */
   int32_t group_all;  /* 1: one group of all N points, absolute xyz (pointnet_pp_8dir.py:23-26) */
   int32_t train;      /* 1: batch statistics + running-stat update; 0: running statistics     */
-  int32_t precision;  /* PCOE_PRECISION_FP32 (CUDA-core fp32) or PCOE_PRECISION_BF16 (tcgen05) */
+  int32_t precision;  /* PCOE_PRECISION_FP32 | PCOE_PRECISION_BF16 | PCOE_PRECISION_BF16X3 */
   float eps;          /* BatchNorm eps (1e-5 in the reference)                                */
   float momentum;     /* BatchNorm momentum (0.1 in the reference)                            */
 } pcoe_sa_desc;

@@ -126,8 +126,10 @@ int main() {
   const int Ns[] = {64, 128, 256}, Ks[] = {64, 128, 192};
   for (int N : Ns)
     for (int K : Ks) printf("K-major   N=%3d K=%3d  max_err=%g\n", N, K, run_case(0, N, K, 0));
-  for (int swap = 0; swap < 2; ++swap)
-    for (int N : Ns)
-      for (int K : Ks) printf("MN-major  N=%3d K=%3d swap=%d max_err=%g\n", N, K, swap, run_case(1, N, K, swap));
+  // swap = 1 (LBO/SBO exchanged) was the rejected layout hypothesis: its descriptors address memory outside the
+  // operand tiles (illegal access), so it is no longer run - the accepted layout is the one csrc/ uses.
+  for (int N : Ns)
+    for (int K : Ks) printf("MN-major  N=%3d K=%3d swap=%d max_err=%g\n", N, K, 0, run_case(1, N, K, 0));
+  printf("tc_probe: all cases done\n");
   return 0;
 }

@@ -284,3 +284,72 @@ def test_sa1_layer1_weight_gradient_from_the_layer2_epilogue(pcoe, cuda, monkeyp
     r_old = _rel(res["1"][1]["convs.0.weight"], sd0["sa.convs.0.weight"].grad)
     print(f"[dW1 vs fp64 oracle] epilogue path {r_new:.2e}, layer-1 kernel {r_old:.2e}")
     assert r_new < BF16_GRAD
+
+
+# ---- bf16x3 mode (tcgen05, split operands, fp32 stored activations): the fp32-accurate tensor-core mode ----------
+# every operand keeps 16 significant bits (hi + lo bf16 planes), the dropped lo*lo product is 2^-16 relative, the
+# accumulator is fp32: a layer output lands at ~1e-5 relative - below the 5e-5 .. 1.8e-4 the reference's own fp32 run
+# is away from its fp64 run - and the weight gradients (discontinuous in the forward values through the
+# max / ReLU routing) at the level of the CUDA-core fp32 mode.
+X3_FWD, X3_GRAD = 5e-5, 5e-3
+
+
+@pytest.mark.parametrize("shape", ["sa1", "sa2", "sa3"])
+def test_sa_bf16x3_tensor_core_vs_fp64_oracle(pcoe, cuda, shape):
+    torch.manual_seed(3)
+    B = 8
+    N, S, K, D, mlp, ga = dict(sa1=(1024, 128, 32, 0, [64, 64, 128], False), sa2=(128, 32, 32, 128, [128, 128, 256], False),
+                               sa3=(32, None, None, 256, [256, 512, 1024], True))[shape]
+    layer = pcoe.PointNetSetAbstraction(S, K, D, mlp, group_all=ga, precision="bf16x3").to(cuda).train()
+    g = torch.Generator().manual_seed(17)
+    with torch.no_grad():       # mixed-sign BatchNorm weights: negative channels pool through the group MINIMUM
+        for bn in layer.bns:
+            sign = torch.where(torch.rand(bn.weight.shape, generator=g) < 0.3, -1.0, 1.0)
+            bn.weight.copy_((0.5 + torch.rand(bn.weight.shape, generator=g)) * sign)
+            bn.bias.copy_(torch.rand(bn.bias.shape, generator=g) * 0.4 - 0.1)
+    xyz = torch.randn(B, N, 3, generator=g)
+    xyz = xyz / xyz.norm(dim=-1).amax(1).view(B, 1, 1)
+    pts = torch.randn(B, N, D, generator=g) if D else None
+    sd0 = sa_torch.clone_state({f"sa.{k}": v for k, v in layer.state_dict().items()}, dtype=torch.float64, requires_grad=True)
+    fps = None if ga else torch.stack([torch.randperm(N, generator=g)[:S] for _ in range(B)])
+    pts_c = pts.to(cuda).requires_grad_(True) if D else None
+    _, out = layer(xyz.to(cuda), pts_c, fps_idx=None if ga else fps.to(cuda))
+    grp = None if ga else layer.last_group_idx.long().cpu()
+    opts = pts.double().requires_grad_(True) if D else None
+    _, oy, _ = sa_torch.set_abstraction(sd0, "sa", xyz.double(), opts, group_all=ga, nsample=K, fps_idx=fps, group_idx=grp)
+    fwd = _rel(out, oy)
+    gout = torch.randn(out.shape, generator=g)
+    out.backward(gout.to(cuda))
+    oy.backward(gout.double())
+    rels = {n: _rel(p.grad, sd0[f"sa.{n}"].grad) for n, p in layer.named_parameters()
+            if not (n.startswith("convs") and n.endswith("bias"))}
+    if D:
+        rels["grad_feats"] = _rel(pts_c.grad, opts.grad)
+    print(f"\n[bf16x3 {shape}] fwd rel {fwd:.2e}; grad rel " + ", ".join(f"{k}={v:.1e}" for k, v in rels.items()))
+    assert fwd < X3_FWD
+    assert max(rels.values()) < X3_GRAD
+    for i in range(3):
+        for buf in ("running_mean", "running_var"):
+            assert torch.allclose(getattr(layer.bns[i], buf).cpu().double(), sd0[f"sa.bns.{i}.{buf}"], rtol=1e-4, atol=1e-5)
+        assert int(layer.bns[i].num_batches_tracked) == 1
+
+
+def test_sa_bf16x3_eval_and_ragged_tile(pcoe, cuda):
+    """Eval mode (running statistics folded) in bf16x3 equals the fp32 mode; B = 1 group-all gives M = 32 rows, a
+    quarter of one 128-point tile (the B = 1 inference shape of train.py:228-246 after SA2)."""
+    torch.manual_seed(5)
+    for (B, N, S, K, D, mlp, ga) in [(3, 256, 32, 32, 64, [64, 128, 128], False), (1, 32, None, None, 256, [256, 512, 1024], True)]:
+        a = pcoe.PointNetSetAbstraction(S, K, D, mlp, group_all=ga, precision="fp32").to(cuda)
+        b = pcoe.PointNetSetAbstraction(S, K, D, mlp, group_all=ga, precision="bf16x3").to(cuda)
+        with torch.no_grad():
+            for bn in a.bns:
+                bn.running_mean.normal_(0, 0.1); bn.running_var.uniform_(0.5, 1.5); bn.weight.uniform_(-1, 1.5)
+        b.load_state_dict(a.state_dict())
+        a.eval(); b.eval()
+        xyz = torch.rand(B, N, 3, device=cuda)
+        pts = torch.randn(B, N, D, device=cuda)
+        fps = None if ga else torch.stack([torch.randperm(N)[:S] for _ in range(B)]).to(cuda)
+        with torch.no_grad():
+            _, ya = a(xyz, pts, fps_idx=fps)
+            _, yb = b(xyz, pts, fps_idx=fps)
+        assert _rel(yb, ya) < X3_FWD, (B, N)
