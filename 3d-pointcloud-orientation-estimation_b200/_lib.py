@@ -45,6 +45,7 @@ SIGNATURES = {
     "pcoe_profile_report": (_I, [C.c_char_p, _SZ]),
     "pcoe_fps_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "pcoe_gather_points_f32": (_I, [_P, _I, _I, _I, _P, _I, _P, _P]),
+    "pcoe_host_randperm_subsets": (_I, [_P, _SZ, _I, _I, _I, _P]),
     "pcoe_random_subset": (_I, [_I, _I, _I, _U64, _U64, _P, _P, _P]),
     "pcoe_random_subset_xyz": (_I, [_I, _I, _I, _U64, _U64, _P, _P, _P, _P, _P]),
     "pcoe_knn_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),

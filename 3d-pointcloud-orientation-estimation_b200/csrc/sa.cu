@@ -408,47 +408,49 @@ static bool sa_x3_supported(const pcoe_sa_desc& d) {
 }
 struct Cfg6 { int nst, wres, grid; size_t smem; };
 // persistent (tile x channel-block) kernels: CTAs per channel block, resident weights or streamed, ring depth
-static Cfg6 cfg6(int nk, int ncb, int ntiles, size_t cbytes) {
+static Cfg6 cfg6(int nk, int ncb, int ntiles, size_t cbytes, int np) {
   Cfg6 c{};
   const int per = kNumSMs / ncb > 0 ? kNumSMs / ncb : 1;
   const int ctas = ntiles < per ? ntiles : per;
   c.grid = ctas * ncb;
-  const size_t avail = kSmemBudget6 - 1024 - cbytes, wb = (size_t)nk * 32768;
-  c.wres = (ntiles > ctas && wb + 2 * 32768 <= avail) ? 1 : 0;   // a CTA that sees one tile gains nothing from residency
-  const size_t ring = c.wres ? avail - wb : avail, sb = c.wres ? 32768 : 65536;
+  const size_t op = (size_t)np * 16384;   // one operand chunk, all planes
+  const size_t avail = kSmemBudget6 - 1024 - cbytes, wb = (size_t)nk * op;
+  c.wres = (ntiles > ctas && wb + 2 * op <= avail) ? 1 : 0;   // a CTA that sees one tile gains nothing from residency
+  const size_t ring = c.wres ? avail - wb : avail, sb = c.wres ? op : 2 * op;
   int n = (int)(ring / sb);
   c.nst = n > v6::kMaxStages6 ? v6::kMaxStages6 : n;
   c.smem = 1024 + (c.wres ? wb : 0) + (size_t)c.nst * sb + cbytes;
   return c;
 }
 
+constexpr int kFwdPlanes6 = 3;   // forward operands keep all 24 significant bits (6 MMAs per step), backward 16 (3 MMAs)
 template <class Prod, class Epi>
-static int launch_fwd6(const Prod& prod, const __nv_bfloat16* Wh, const __nv_bfloat16* Wl, int Kp, const Epi& epi, int M,
+static int launch_fwd6(const Prod& prod, const __nv_bfloat16* Wp, size_t wps, int Kp, const Epi& epi, int M,
                        int Cout, cudaStream_t st, const char* what) {
   const size_t cbytes = sizeof(float) * (size_t)(prod.nconst() + epi.nconst()) + 512;
   const int ncb = ceil_div(Cout, 128);
-  const Cfg6 c = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes);
+  const Cfg6 c = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes, kFwdPlanes6);
   if (c.nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
-  auto k = v6::x3_fwd_kernel<Prod, Epi>;
+  auto k = v6::x3_fwd_kernel<Prod, Epi, kFwdPlanes6>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
   LaunchScope ls(what, st);
-  k<<<c.grid, v4::kThreads, c.smem, st>>>(prod, Wh, Wl, Kp, epi, M, ncb, c.nst, c.wres);
+  k<<<c.grid, v4::kThreads, c.smem, st>>>(prod, Wp, wps, Kp, epi, M, ncb, c.nst, c.wres);
   return ls.done();
 }
 
 template <bool PT, class PProd, class Epi>
-static int launch_dgrad6(const PProd& pp, const __nv_bfloat16* Wh, const __nv_bfloat16* Wl, int Kp, const Epi& epi, int M,
+static int launch_dgrad6(const PProd& pp, const __nv_bfloat16* Wp, size_t wps, int Kp, const Epi& epi, int M,
                          int Cprev, cudaStream_t st, const char* what) {
   const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + epi.nconst()) + 512;
   const int ncb = ceil_div(Cprev, 128);
-  const Cfg6 c = cfg6(pp.C / 64, ncb, ceil_div(M, v4::kPts), cbytes);
+  const Cfg6 c = cfg6(pp.C / 64, ncb, ceil_div(M, v4::kPts), cbytes, 2);
   if (c.nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
   auto k = v6::x3_dgrad_kernel<PProd, Epi, PT>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
   LaunchScope ls(what, st);
-  k<<<c.grid, v4::kThreads, c.smem, st>>>(pp, Wh, Wl, Kp, epi, M, ncb, c.nst, c.wres);
+  k<<<c.grid, v4::kThreads, c.smem, st>>>(pp, Wp, wps, Kp, epi, M, ncb, c.nst, c.wres);
   return ls.done();
 }
 
@@ -478,8 +480,7 @@ static int convert_weights6(const pcoe_sa_desc& d, const SaLayout& L, const pcoe
   v6::ConvW6 w[3];
   int total = 0;
   for (int l = 0; l < 3; ++l) {
-    __nv_bfloat16* hi = (__nv_bfloat16*)(base + L.wb_off[l]);
-    w[l] = v6::ConvW6{P.W[l], hi, hi + (size_t)L.w4_rp[l] * L.w4_kp[l], Cs[l], Kin[l], L.w4_rp[l], L.w4_kp[l], l == 0 ? d.D : -1};
+    w[l] = v6::ConvW6{P.W[l], (__nv_bfloat16*)(base + L.wb_off[l]), Cs[l], Kin[l], L.w4_rp[l], L.w4_kp[l], l == 0 ? d.D : -1};
     total += L.w4_rp[l] * L.w4_kp[l];
   }
   LaunchScope ls("convert_weights_kernel", st);
@@ -650,17 +651,17 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
     if (L.v6) {   // bf16x3: split-operand tcgen05 kernels, fp32 activations (sa_tc6.cuh)
       PCOE_TRY(convert_weights6(d, L, P, wbase, st));
       auto wh = [&](int l) { return (const __nv_bfloat16*)(wbase + L.wb_off[l]); };
-      auto wl = [&](int l) { return wh(l) + (size_t)L.w4_rp[l] * L.w4_kp[l]; };
+      auto wps = [&](int l) { return (size_t)L.w4_rp[l] * L.w4_kp[l]; };
       v6::GatherFeat6 gp{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
       v6::StoreStats6 e0{}; e0.y = y[0]; e0.sums = sums[0]; e0.C = d.C1;
-      PCOE_TRY(launch_fwd6(gp, wh(0), wl(0), L.w4_kp[0], e0, M, d.C1, st, kname(d, kF1)));
+      PCOE_TRY(launch_fwd6(gp, wh(0), wps(0), L.w4_kp[0], e0, M, d.C1, st, kname(d, kF1)));
       v6::BnRelu6 p1{}; p1.y = y[0]; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.C = d.C1; p1.fin = mkfin(0);
       v6::StoreStats6 e1{}; e1.y = y[1]; e1.sums = sums[1]; e1.C = d.C2;
-      PCOE_TRY(launch_fwd6(p1, wh(1), wl(1), L.w4_kp[1], e1, M, d.C2, st, kname(d, kF2)));
+      PCOE_TRY(launch_fwd6(p1, wh(1), wps(1), L.w4_kp[1], e1, M, d.C2, st, kname(d, kF2)));
       v6::BnRelu6 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.C = d.C2; p2.fin = mkfin(1);
       v6::Group6 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
       e2.C = d.C3; e2.gamma = P.gamma[2];
-      PCOE_TRY(launch_fwd6(p2, wh(2), wl(2), L.w4_kp[2], e2, M, d.C3, st, kname(d, kF3)));
+      PCOE_TRY(launch_fwd6(p2, wh(2), wps(2), L.w4_kp[2], e2, M, d.C3, st, kname(d, kF3)));
       if (train) { if (sep_fin) PCOE_TRY(finalize(2)); else fin_out = mkfin(2); }
       done = true;
     }
@@ -920,7 +921,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   if constexpr (!TC) {
     if (L.v6) {   // bf16x3: streamed wgrad / persistent dgrad kernels with split operands (sa_tc6.cuh)
       auto wh = [&](int l) { return (const __nv_bfloat16*)(sv + L.wb_off[l]); };
-      auto wl = [&](int l) { return wh(l) + (size_t)L.w4_rp[l] * L.w4_kp[l]; };
+      auto wps = [&](int l) { return (size_t)L.w4_rp[l] * L.w4_kp[l]; };
       v6::DyLast6 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
       dy3.M = M; dy3.C = d.C3; dy3.fin = mkbfin(2, 1);   // the wgrad launch owns the parameter-gradient outputs
       v6::BnRelu6 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.C = d.C2;
@@ -928,7 +929,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       m2.dz = dz[1]; m2.sums = bs[1]; m2.C = d.C2;
       PCOE_TRY(launch_wgrad6(dy3, x2, Gr.dW[2], d.C2, d.C2, -1, M, ceil_div(d.C2, 128), st, kname(d, kWG3)));
       dy3.fin.write = 0;
-      PCOE_TRY(launch_dgrad6<false>(dy3, wh(2), wl(2), L.w4_kp[2], m2, M, d.C2, st, kname(d, kDG3)));
+      PCOE_TRY(launch_dgrad6<false>(dy3, wh(2), wps(2), L.w4_kp[2], m2, M, d.C2, st, kname(d, kDG3)));
       v6::Dy6 dy2{}; dy2.dz = dz[1]; dy2.y = y[1]; dy2.a = ca[1]; dy2.p = cp[1]; dy2.q = cq[1]; dy2.M = M; dy2.C = d.C2;
       dy2.fin = mkbfin(1, 1);
       v6::BnRelu6 x1{}; x1.y = y[0]; x1.scale = scale[0]; x1.shift = shift[0]; x1.M = M; x1.C = d.C1;
@@ -936,7 +937,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1;
       PCOE_TRY(launch_wgrad6(dy2, x1, Gr.dW[1], d.C1, d.C1, -1, M, ceil_div(d.C1, 128), st, kname(d, kWG2)));
       dy2.fin.write = 0;
-      PCOE_TRY(launch_dgrad6<false>(dy2, wh(1), wl(1), L.w4_kp[1], m1, M, d.C1, st, kname(d, kDG2)));
+      PCOE_TRY(launch_dgrad6<false>(dy2, wh(1), wps(1), L.w4_kp[1], m1, M, d.C1, st, kname(d, kDG2)));
       v6::Dy6 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.C = d.C1;
       dy1.fin = mkbfin(0, 1);
       v6::GatherFeat6 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
@@ -944,7 +945,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       dy1.fin.write = 0;
       if (d.D > 0 && grad_feats) {
         v4::Scatter4 se{grad_feats, nbr, d.N, d.S, d.D, d.group_all};
-        PCOE_TRY(launch_dgrad6<true>(dy1, wh(0), wl(0), L.w4_kp[0], se, M, d.D, st, kname(d, kDG1)));
+        PCOE_TRY(launch_dgrad6<true>(dy1, wh(0), wps(0), L.w4_kp[0], se, M, d.D, st, kname(d, kDG1)));
       }
       return PCOE_OK;
     }

@@ -37,7 +37,7 @@ struct SaLayout {
   bool v5;         // bf16 mode, wide layers that do not fit v4 (SA3): K-chunk-streamed kernels (sa_tc5.cuh), same
                    // HBM layouts as v2
   bool v6;         // bf16x3 mode (sa_tc6.cuh): fp32 tile-blocked channel-major activations [tile][C][128], two bf16
-                   // planes (hi, lo) of every weight image
+                   // planes (hi, mid, lo) of every weight image
   int Mld;         // rows rounded up to 128 (v2 / v5)
   int w4_rp[3], w4_kp[3];
   // v2 train: the last layer's pre-activations y3 are NOT stored; the forward accumulates the Gram matrix of the
@@ -102,7 +102,7 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
     L.wbt_rows[l] = (int)align_up(Kin[l], 128); L.wbt_k[l] = kpad(C[l]);
     L.wb_off[l] = L.wbt_off[l] = 0;
   }
-  const size_t planes = x3 ? 2 : 1;   // bf16x3: hi plane followed by lo plane
+  const size_t planes = x3 ? 3 : 1;   // bf16x3: hi, mid, lo planes (backward reads the first two)
   if ((tc || x3) && d.train)
     for (int l = 0; l < 3; ++l) {
       if (cm) { L.wb_off[l] = take(s, planes * 2 * L.w4_rp[l] * L.w4_kp[l]); continue; }

@@ -3,9 +3,14 @@
 // The reference computes its 1x1 convolutions in fp32 (models/pointnet_pp_8dir.py:40-41).  Plain bf16 operands
 // (sa_tc4/5.cuh) keep the loss within 1e-3 but move the max-pool / ReLU routing and with it the weight gradients by
 // tens of percent.  This mode keeps the tcgen05 pipeline and recovers fp32-class accuracy by SPLITTING
-// every operand into two bf16 planes, x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 significant bits), and
-// issuing three MMAs per step into the same fp32 TMEM accumulator:
-//        A*B  ~=  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi          (the dropped lo*lo term is 2^-16 relative)
+// every operand into bf16 planes and issuing one MMA per retained plane product into the same fp32 TMEM accumulator:
+//   backward GEMMs (dgrad, wgrad - linear in their operands once the routing is fixed): TWO planes,
+//        x = hi + lo,  hi = bf16(x), lo = bf16(x - hi)  (16 significant bits)
+//        A*B  ~=  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi                      (3 MMAs; dropped lo*lo is 2^-16 relative)
+//   forward GEMMs (their rounding noise decides the arg-max / ReLU routing, and a re-routed element moves the
+//   gradients by O(1): measured, 16-bit forward operands leave the weight gradients 1-3e-2 from the fp64 oracle,
+//   24-bit ones 4e-4 .. 4e-3): THREE planes, x = hi + mid + lo exactly (24 bits),
+//        A*B  ~=  hi*hi + (hi*mid + mid*hi) + (mid*mid + hi*lo + lo*hi)  (6 MMAs; dropped terms are 2^-24 relative)
 // Everything that is not an MMA operand stays fp32: activations live in HBM as fp32 (tile-blocked channel-major
 // [tile][C][128 points]), BatchNorm / ReLU / BatchNorm-backward transforms run in fp32 in the producers BEFORE the
 // split, batch statistics are fp64 sums of the fp32 accumulators.
@@ -46,9 +51,34 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& h, uint4& l) 
   split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y);
   split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
 }
+// (a, b) -> hi, mid, lo planes: a = hi + mid + lo exactly (three 8-bit pieces of the 24-bit significand)
+__device__ __forceinline__ void split3(float a, float b, uint32_t& h, uint32_t& m, uint32_t& l) {
+  h = bf2_pack(a, b);
+  const float ra = a - __uint_as_float(h << 16), rb = b - __uint_as_float(h & 0xFFFF0000u);
+  m = bf2_pack(ra, rb);
+  l = bf2_pack(ra - __uint_as_float(m << 16), rb - __uint_as_float(m & 0xFFFF0000u));
+}
+// 8 values -> NP planes, stored as 16-byte chunks at s0 + off + p * kPart (the planes of a part are consecutive)
+template <int NP>
+__device__ __forceinline__ void split_store8(const float (&v)[8], uint32_t s0, uint32_t off) {
+  if constexpr (NP == 2) {
+    uint4 h, l;
+    split8(v, h, l);
+    tc::sts128(s0 + off, h);
+    tc::sts128(s0 + off + kPart, l);
+  } else {
+    uint4 h, m, l;
+    split3(v[0], v[1], h.x, m.x, l.x); split3(v[2], v[3], h.y, m.y, l.y);
+    split3(v[4], v[5], h.z, m.z, l.z); split3(v[6], v[7], h.w, m.w, l.w);
+    tc::sts128(s0 + off, h);
+    tc::sts128(s0 + off + kPart, m);
+    tc::sts128(s0 + off + 2 * kPart, l);
+  }
+}
 
-// fp32 [C_out][C_in] -> two zero-padded bf16 planes [Rp][Kp]; perm_d >= 0: layer-1 column order [feats(perm_d) | xyz(3)]
-struct ConvW6 { const float* W; __nv_bfloat16* hi; __nv_bfloat16* lo; int cout, cin, Rp, Kp, perm_d; };
+// fp32 [C_out][C_in] -> three zero-padded bf16 planes [3][Rp][Kp] (hi, mid, lo; the backward kernels read the first
+// two); perm_d >= 0: layer-1 column order [feats(perm_d) | xyz(3)]
+struct ConvW6 { const float* W; __nv_bfloat16* planes; int cout, cin, Rp, Kp, perm_d; };
 __global__ void convert_weights6_kernel(ConvW6 a, ConvW6 b, ConvW6 c) {
   const ConvW6* L[3] = {&a, &b, &c};
   const int n0 = a.Rp * a.Kp / 8, n1 = b.Rp * b.Kp / 8, n2 = c.Rp * c.Kp / 8;
@@ -65,10 +95,13 @@ __global__ void convert_weights6_kernel(ConvW6 a, ConvW6 b, ConvW6 c) {
       if (w.perm_d >= 0) src = k < w.perm_d ? k + 3 : (k < w.perm_d + 3 ? k - w.perm_d : w.cin);
       v[u] = (r < w.cout && src < w.cin) ? __ldg(w.W + (size_t)r * w.cin + src) : 0.f;
     }
-    uint4 h, lo;
-    split8(v, h, lo);
-    reinterpret_cast<uint4*>(w.hi)[ee] = h;
-    reinterpret_cast<uint4*>(w.lo)[ee] = lo;
+    uint4 h, m, lo;
+    split3(v[0], v[1], h.x, m.x, lo.x); split3(v[2], v[3], h.y, m.y, lo.y);
+    split3(v[4], v[5], h.z, m.z, lo.z); split3(v[6], v[7], h.w, m.w, lo.w);
+    const size_t pl = (size_t)w.Rp * w.Kp / 8;
+    reinterpret_cast<uint4*>(w.planes)[ee] = h;
+    reinterpret_cast<uint4*>(w.planes)[pl + ee] = m;
+    reinterpret_cast<uint4*>(w.planes)[2 * pl + ee] = lo;
   }
 }
 
@@ -123,8 +156,8 @@ struct BnRelu6 {
       r.a[i][1] = rok ? __ldg(p + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  template <int PTS>
-  __device__ __forceinline__ void store(int g, int, int crow, int lrow, int lrows, const Raw& r, uint32_t shi, uint32_t slo) const {
+  template <int PTS, int NP>
+  __device__ __forceinline__ void store(int g, int, int crow, int lrow, int lrows, const Raw& r, uint32_t s0) const {
     const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
 #pragma unroll
     for (int i = 0; i < kUR; ++i) {
@@ -135,11 +168,7 @@ struct BnRelu6 {
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = fmaxf(fmaf(x[u], sc, sh), 0.f);
-      uint4 h, l;
-      split8(v, h, l);
-      const uint32_t off = cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk);
-      tc::sts128(shi + off, h);
-      tc::sts128(slo + off, l);
+      split_store8<NP>(v, s0, cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk));
     }
   }
 };
@@ -183,8 +212,8 @@ struct Dy6 {
       r.y[i][0] = rok ? __ldg(py) : z; r.y[i][1] = rok ? __ldg(py + 1) : z;
     }
   }
-  template <int PTS>
-  __device__ __forceinline__ void store(int g, int m0, int crow, int lrow, int lrows, const Raw& r, uint32_t shi, uint32_t slo) const {
+  template <int PTS, int NP>
+  __device__ __forceinline__ void store(int g, int m0, int crow, int lrow, int lrows, const Raw& r, uint32_t s0) const {
     const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
     const float okf = m0 + chunk * 8 < M ? 1.f : 0.f;     // points >= M contribute 0 to dW
 #pragma unroll
@@ -197,11 +226,7 @@ struct Dy6 {
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = fmaf(ca, d[u], fmaf(cp, yy[u], cq));
-      uint4 h, l;
-      split8(v, h, l);
-      const uint32_t off = cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk);
-      tc::sts128(shi + off, h);
-      tc::sts128(slo + off, l);
+      split_store8<NP>(v, s0, cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk));
     }
   }
 };
@@ -248,8 +273,8 @@ struct DyLast6 {
       r.sl[i] = rok ? (int)__ldg(slot + go + i * CM<PTS>::kRstep) : -1;
     }
   }
-  template <int PTS>
-  __device__ __forceinline__ void store(int g, int m0, int crow, int lrow, int lrows, const Raw& r, uint32_t shi, uint32_t slo) const {
+  template <int PTS, int NP>
+  __device__ __forceinline__ void store(int g, int m0, int crow, int lrow, int lrows, const Raw& r, uint32_t s0) const {
     const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
     const int m = m0 + chunk * 8;
     const float okf = m < M ? 1.f : 0.f;
@@ -264,11 +289,7 @@ struct DyLast6 {
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = fmaf(cp, yy[u], cq) + (u == sl ? add : 0.f);
-      uint4 h, l;
-      split8(v, h, l);
-      const uint32_t off = cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk);
-      tc::sts128(shi + off, h);
-      tc::sts128(slo + off, l);
+      split_store8<NP>(v, s0, cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk));
     }
   }
 };
@@ -308,27 +329,21 @@ struct GatherFeat6 {
       r.b[0] = make_float4(c[0], c[1], c[2], 0.f);
     }
   }
-  template <int PTS>
-  __device__ __forceinline__ void store(int g, int kb, const Raw& r, uint32_t shi, uint32_t slo) const {
+  template <int PTS, int NP>
+  __device__ __forceinline__ void store(int g, int kb, const Raw& r, uint32_t s0) const {
     if (kb < D / 64) {
       const int j = g & 7;
 #pragma unroll
       for (int i = 0; i < PTS / 32; ++i) {
         const float v[8] = {r.a[i].x, r.a[i].y, r.a[i].z, r.a[i].w, r.b[i].x, r.b[i].y, r.b[i].z, r.b[i].w};
-        uint4 h, l;
-        split8(v, h, l);
-        const uint32_t off = tc::sw128_off((g >> 3) + 32 * i, j * 8);
-        tc::sts128(shi + off, h);
-        tc::sts128(slo + off, l);
+        split_store8<NP>(v, s0, tc::sw128_off((g >> 3) + 32 * i, j * 8));
       }
     } else if (g < PTS) {
       const float v[8] = {gb.centred(r.a[0].x, r.b[0].x), gb.centred(r.a[0].y, r.b[0].y), gb.centred(r.a[0].z, r.b[0].z),
                           0.f, 0.f, 0.f, 0.f, 0.f};
-      uint4 h, l;
-      split8(v, h, l);
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      tc::sts128(shi + tc::sw128_off(g, 0), h); tc::sts128(shi + tc::sw128_off(g, 8), z);
-      tc::sts128(slo + tc::sw128_off(g, 0), l); tc::sts128(slo + tc::sw128_off(g, 8), z);
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      split_store8<NP>(v, s0, tc::sw128_off(g, 0));
+      split_store8<NP>(z, s0, tc::sw128_off(g, 8));
     }
   }
 };
@@ -449,43 +464,28 @@ struct MaskStats6 {
   }
 };
 
-// ---- weight-slice loads (both planes at once: 8 x 16 bytes per thread) -----------------------------------------
+// ---- weight-slice loads, one plane per call (4 x 16 bytes per thread) ---------------------------------------------
 // K-major slice [128 rows x 64 k] (forward A operand)
-__device__ __forceinline__ void wload_k2(const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat16* __restrict__ Wl, int Kp, int row0,
-                                         int k0, int g, uint4* w) {
+__device__ __forceinline__ void wload_k1(const __nv_bfloat16* __restrict__ W, int Kp, int row0, int k0, int g, uint4* w) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const size_t o = (size_t)(row0 + (g >> 3) + 32 * i) * Kp + k0 + (g & 7) * 8;
-    w[i] = __ldg(reinterpret_cast<const uint4*>(Wh + o));
-    w[4 + i] = __ldg(reinterpret_cast<const uint4*>(Wl + o));
-  }
+  for (int i = 0; i < 4; ++i)
+    w[i] = __ldg(reinterpret_cast<const uint4*>(W + (size_t)(row0 + (g >> 3) + 32 * i) * Kp + k0 + (g & 7) * 8));
 }
-__device__ __forceinline__ void wstore_k2(uint32_t shi, uint32_t slo, int g, const uint4* w) {
+__device__ __forceinline__ void wstore_k1(uint32_t saddr, int g, const uint4* w) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t off = tc::sw128_off((g >> 3) + 32 * i, (g & 7) * 8);
-    tc::sts128(shi + off, w[i]);
-    tc::sts128(slo + off, w[4 + i]);
-  }
+  for (int i = 0; i < 4; ++i) tc::sts128(saddr + tc::sw128_off((g >> 3) + 32 * i, (g & 7) * 8), w[i]);
 }
 // MN-major slice [64 k rows x 128 columns] = 2 blocks of [64 rows x 64 columns] (dgrad A operand)
-__device__ __forceinline__ void wload_mn2(const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat16* __restrict__ Wl, int Kp, int row0,
-                                          int col0, int g, uint4* w) {
+__device__ __forceinline__ void wload_mn1(const __nv_bfloat16* __restrict__ W, int Kp, int row0, int col0, int g, uint4* w) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const size_t o = (size_t)(row0 + (g >> 4) + 16 * i) * Kp + col0 + (g & 15) * 8;
-    w[i] = __ldg(reinterpret_cast<const uint4*>(Wh + o));
-    w[4 + i] = __ldg(reinterpret_cast<const uint4*>(Wl + o));
-  }
+  for (int i = 0; i < 4; ++i)
+    w[i] = __ldg(reinterpret_cast<const uint4*>(W + (size_t)(row0 + (g >> 4) + 16 * i) * Kp + col0 + (g & 15) * 8));
 }
-__device__ __forceinline__ void wstore_mn2(uint32_t shi, uint32_t slo, int g, const uint4* w) {
+__device__ __forceinline__ void wstore_mn1(uint32_t saddr, int g, const uint4* w) {
   const int j = g & 15;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t off = (uint32_t)(j >> 3) * 8192u + tc::sw128_off((g >> 4) + 16 * i, (j & 7) * 8);
-    tc::sts128(shi + off, w[i]);
-    tc::sts128(slo + off, w[4 + i]);
-  }
+  for (int i = 0; i < 4; ++i)
+    tc::sts128(saddr + (uint32_t)(j >> 3) * 8192u + tc::sw128_off((g >> 4) + 16 * i, (j & 7) * 8), w[i]);
 }
 
 struct Barriers6 {
@@ -508,25 +508,38 @@ struct Barriers6 {
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar.tmem_full[b], 1); tc::mbar_init(&bar.tmem_empty[b], kEpiThreads); } \
   }
 
-// the three split products of one 16-deep MMA step (small terms first)
-__device__ __forceinline__ void mma3(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc, bool acc) {
-  tc::mma_bf16_warp(d, al, bh, idesc, acc);
-  tc::mma_bf16_warp(d, ah, bl, idesc, true);
-  tc::mma_bf16_warp(d, ah, bh, idesc, true);
+// The retained plane products of one 16-deep MMA step, small terms first.  A / B: descriptors of plane 0; the planes of
+// an operand part are kPart bytes apart, i.e. +(kPart >> 4) in the descriptor's start-address field.
+template <int NP>
+__device__ __forceinline__ void mma_planes(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, bool acc) {
+  constexpr uint64_t P = kPart >> 4;
+  if constexpr (NP == 2) {
+    tc::mma_bf16_warp(d, a + P, b, idesc, acc);
+    tc::mma_bf16_warp(d, a, b + P, idesc, true);
+    tc::mma_bf16_warp(d, a, b, idesc, true);
+  } else {
+    tc::mma_bf16_warp(d, a + 2 * P, b, idesc, acc);       // lo  * hi
+    tc::mma_bf16_warp(d, a, b + 2 * P, idesc, true);      // hi  * lo
+    tc::mma_bf16_warp(d, a + P, b + P, idesc, true);      // mid * mid
+    tc::mma_bf16_warp(d, a + P, b, idesc, true);          // mid * hi
+    tc::mma_bf16_warp(d, a, b + P, idesc, true);          // hi  * mid
+    tc::mma_bf16_warp(d, a, b, idesc, true);              // hi  * hi
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// forward: Y^T[128 ch x 128 pts] = W[128 x Cin] * X^T[Cin x 128] per (tile, channel block).
-// smem: wres ? [W: nk x (hi 16K | lo 16K)][ring: nst x (X hi | X lo)] : [ring: nst x (W hi | W lo | X hi | X lo)]
+// forward (NP planes): Y^T[128 ch x 128 pts] = W[128 x Cin] * X^T[Cin x 128] per (tile, channel block).
+// smem: wres ? [W: nk x NP parts][ring: nst x (NP X parts)] : [ring: nst x (NP W parts | NP X parts)]
+// Wp = plane 0 of the weight image, wps = elements per plane.
 // ---------------------------------------------------------------------------------------------------------------
-template <class Prod, class Epi>
+template <class Prod, class Epi, int NP>
 __global__ void __launch_bounds__(kThreads, 1)
-x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat16* __restrict__ Wl, int Kp, Epi epi, int M,
-              int ncb, int nst, int wres) {
+x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wp, size_t wps, int Kp, Epi epi, int M, int ncb, int nst, int wres) {
   PCOE_V6_PROLOGUE(256)
   const int nk = prod.nchunks();
-  const uint32_t sWres = smem0, wres_bytes = wres ? (uint32_t)nk * 2u * kPart : 0u;
-  const uint32_t sS = smem0 + wres_bytes, sbytes = wres ? 2u * kPart : 4u * kPart, xoff = wres ? 0u : 2u * kPart;
+  constexpr uint32_t kOp = NP * kPart;                       // one operand chunk, all planes
+  const uint32_t sWres = smem0, wres_bytes = wres ? (uint32_t)nk * kOp : 0u;
+  const uint32_t sS = smem0 + wres_bytes, sbytes = wres ? kOp : 2u * kOp, xoff = wres ? 0u : kOp;
   float* csm = reinterpret_cast<float*>(smem_gen + wres_bytes + (size_t)nst * sbytes);
   const int cb = blockIdx.x % ncb, t0 = blockIdx.x / ncb, tstep = gridDim.x / ncb;
   const int ntiles = (M + kPts - 1) / kPts;
@@ -536,11 +549,13 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat
   const int eq = warp & 3, eh = (warp >> 2) & 1;
   epi.init(csm + prod.nconst(), cb * 128 + eq * 32 + lane);
   if (wres && tid < kProdThreads) {
-    for (int k = 0; k < nk; ++k) {
-      uint4 w[8];
-      wload_k2(Wh, Wl, Kp, cb * 128, k * 64, tid, w);
-      wstore_k2(sWres + (uint32_t)k * 2u * kPart, sWres + (uint32_t)k * 2u * kPart + kPart, tid, w);
-    }
+    for (int k = 0; k < nk; ++k)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        uint4 w[4];
+        wload_k1(Wp + (size_t)p * wps, Kp, cb * 128, k * 64, tid, w);
+        wstore_k1(sWres + (uint32_t)k * kOp + (uint32_t)p * kPart, tid, w);
+      }
   }
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -567,8 +582,8 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat
   } else if (warp < 16) {
     const int g = tid - kEpiThreads;
     constexpr int kXU = Prod::kChMajor ? 4 / Prod::kUR : 1;   // activation units per 64-channel chunk
-    const int wu = wres ? 0 : 1, upc = kXU + wu;
-    union RawU { typename Prod::Raw x; uint4 w[8]; __device__ RawU() {} };
+    const int wu = wres ? 0 : NP, upc = kXU + wu;             // streamed weights: one unit per plane
+    union RawU { typename Prod::Raw x; uint4 w[4]; __device__ RawU() {} };
     struct Cur { int tile, k, u; };
     auto adv = [&](Cur& c) { if (++c.u == upc) { c.u = 0; if (++c.k == nk) { c.k = 0; c.tile += tstep; } } };
     Cur cl{t0, 0, 0}, cst = cl;
@@ -576,7 +591,7 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat
     unit_pipeline<RawU>(my_items * nk * upc,
         [&](int, RawU& r) {
           const int xu = cl.u - wu;
-          if (xu < 0) wload_k2(Wh, Wl, Kp, cb * 128, cl.k * 64, g, r.w);
+          if (xu < 0) wload_k1(Wp + (size_t)cl.u * wps, Kp, cb * 128, cl.k * 64, g, r.w);
           else if constexpr (Prod::kChMajor) prod.template load<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * Prod::kUR, r.x);
           else prod.template load<128>(g, cl.tile * kPts, cl.k, r.x);
           adv(cl);
@@ -585,10 +600,10 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat
           const uint32_t st = sS + (uint32_t)ring_s * sbytes;
           if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
           const int xu = cst.u - wu;
-          if (xu < 0) wstore_k2(st, st + kPart, g, r.w);
+          if (xu < 0) wstore_k1(st + (uint32_t)cst.u * kPart, g, r.w);
           else if constexpr (Prod::kChMajor)
-            prod.template store<128>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * Prod::kUR, xu * 16 * Prod::kUR, 64, r.x, st + xoff, st + xoff + kPart);
-          else prod.template store<128>(g, cst.k, r.x, st + xoff, st + xoff + kPart);
+            prod.template store<128, NP>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * Prod::kUR, xu * 16 * Prod::kUR, 64, r.x, st + xoff);
+          else prod.template store<128, NP>(g, cst.k, r.x, st + xoff);
           if (cst.u == upc - 1) {
             tc::fence_proxy_async();
             mbar_arrive(&bar.full[ring_s]);
@@ -607,16 +622,13 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat
         if (k == 0 && u > 0) tc::mbar_wait(&bar.tmem_empty[b], (uint32_t)((u - 1) & 1));
         tc::fence_after_sync();
         const uint32_t st = sS + (uint32_t)ring_s * sbytes;
-        const uint32_t sAh = wres ? sWres + (uint32_t)k * 2u * kPart : st, sAl = sAh + kPart;
-        const uint32_t sBh = st + xoff, sBl = sBh + kPart;
+        const uint32_t sA = wres ? sWres + (uint32_t)k * kOp : st, sB = st + xoff;
         const int kk = prod.chunk_k(k);
         for (int q = 0; q < kk / 16; ++q) {
-          const uint64_t ah = tc::make_desc_sw128(sAh + (uint32_t)q * 32, 16, 1024), al = tc::make_desc_sw128(sAl + (uint32_t)q * 32, 16, 1024);
-          const uint64_t bh = Prod::kChMajor ? tc::make_desc_sw128(sBh + (uint32_t)q * 2048, 8192, 1024)
-                                             : tc::make_desc_sw128(sBh + (uint32_t)q * 32, 16, 1024);
-          const uint64_t bl = Prod::kChMajor ? tc::make_desc_sw128(sBl + (uint32_t)q * 2048, 8192, 1024)
-                                             : tc::make_desc_sw128(sBl + (uint32_t)q * 32, 16, 1024);
-          mma3(tm + (uint32_t)(b * kPts), ah, al, bh, bl, idesc, k > 0 || q > 0);
+          const uint64_t ad = tc::make_desc_sw128(sA + (uint32_t)q * 32, 16, 1024);
+          const uint64_t bd = Prod::kChMajor ? tc::make_desc_sw128(sB + (uint32_t)q * 2048, 8192, 1024)
+                                             : tc::make_desc_sw128(sB + (uint32_t)q * 32, 16, 1024);
+          mma_planes<NP>(tm + (uint32_t)(b * kPts), ad, bd, idesc, k > 0 || q > 0);
         }
         tc::mma_commit_warp(&bar.empty[ring_s]);
         if (++ring_s == nst) { ring_s = 0; ++ring_r; }
@@ -630,18 +642,19 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// dgrad: dX^T[128 in-ch x 128 pts] = W^T[128 x Cout] * dY^T[Cout x 128] per (tile, input-channel block); contraction
-// over the layer's output channels in chunks of 64.  PT: operands swapped, D[128 points x 128 in-ch], point-on-lane
-// epilogue (layer-1 scatter-add into grad_feats).
+// dgrad (2 planes): dX^T[128 in-ch x 128 pts] = W^T[128 x Cout] * dY^T[Cout x 128] per (tile, input-channel block);
+// contraction over the layer's output channels in chunks of 64.  PT: operands swapped, D[128 points x 128 in-ch],
+// point-on-lane epilogue (layer-1 scatter-add into grad_feats).
 // ---------------------------------------------------------------------------------------------------------------
 template <class PProd, class Epi, bool PT>
 __global__ void __launch_bounds__(kThreads, 1)
-x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloat16* __restrict__ Wl, int Kp, Epi epi, int M,
-                int ncb, int nst, int wres) {
+x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wp, size_t wps, int Kp, Epi epi, int M, int ncb, int nst, int wres) {
   PCOE_V6_PROLOGUE(256)
+  constexpr int NP = 2;
+  constexpr uint32_t kOp = NP * kPart;
   const int nk = pp.C / 64;
-  const uint32_t sWres = smem0, wres_bytes = wres ? (uint32_t)nk * 2u * kPart : 0u;
-  const uint32_t sS = smem0 + wres_bytes, sbytes = wres ? 2u * kPart : 4u * kPart, xoff = wres ? 0u : 2u * kPart;
+  const uint32_t sWres = smem0, wres_bytes = wres ? (uint32_t)nk * kOp : 0u;
+  const uint32_t sS = smem0 + wres_bytes, sbytes = wres ? kOp : 2u * kOp, xoff = wres ? 0u : kOp;
   float* csm = reinterpret_cast<float*>(smem_gen + wres_bytes + (size_t)nst * sbytes);
   const int cb = blockIdx.x % ncb, t0 = blockIdx.x / ncb, tstep = gridDim.x / ncb;
   const int ntiles = (M + kPts - 1) / kPts;
@@ -651,11 +664,13 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloa
   const int eq = warp & 3, eh = (warp >> 2) & 1;
   epi.init(csm + pp.nconst(), cb * 128 + eq * 32 + lane);
   if (wres && tid < kProdThreads) {
-    for (int k = 0; k < nk; ++k) {
-      uint4 w[8];
-      wload_mn2(Wh, Wl, Kp, k * 64, cb * 128, tid, w);
-      wstore_mn2(sWres + (uint32_t)k * 2u * kPart, sWres + (uint32_t)k * 2u * kPart + kPart, tid, w);
-    }
+    for (int k = 0; k < nk; ++k)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        uint4 w[4];
+        wload_mn1(Wp + (size_t)p * wps, Kp, k * 64, cb * 128, tid, w);
+        wstore_mn1(sWres + (uint32_t)k * kOp + (uint32_t)p * kPart, tid, w);
+      }
   }
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -692,8 +707,8 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloa
   } else if (warp < 16) {
     const int g = tid - kEpiThreads;
     constexpr int kXU = 4 / PProd::kUR;
-    const int wu = wres ? 0 : 1, upc = kXU + wu;
-    union RawU { typename PProd::Raw x; uint4 w[8]; __device__ RawU() {} };
+    const int wu = wres ? 0 : NP, upc = kXU + wu;
+    union RawU { typename PProd::Raw x; uint4 w[4]; __device__ RawU() {} };
     struct Cur { int tile, k, u; };
     auto adv = [&](Cur& c) { if (++c.u == upc) { c.u = 0; if (++c.k == nk) { c.k = 0; c.tile += tstep; } } };
     Cur cl{t0, 0, 0}, cst = cl;
@@ -701,7 +716,7 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloa
     unit_pipeline<RawU>(my_items * nk * upc,
         [&](int, RawU& r) {
           const int xu = cl.u - wu;
-          if (xu < 0) wload_mn2(Wh, Wl, Kp, cl.k * 64, cb * 128, g, r.w);
+          if (xu < 0) wload_mn1(Wp + (size_t)cl.u * wps, Kp, cl.k * 64, cb * 128, g, r.w);
           else pp.template load<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * PProd::kUR, r.x);
           adv(cl);
         },
@@ -709,8 +724,8 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloa
           const uint32_t st = sS + (uint32_t)ring_s * sbytes;
           if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
           const int xu = cst.u - wu;
-          if (xu < 0) wstore_mn2(st, st + kPart, g, r.w);
-          else pp.template store<128>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * PProd::kUR, xu * 16 * PProd::kUR, 64, r.x, st + xoff, st + xoff + kPart);
+          if (xu < 0) wstore_mn1(st + (uint32_t)cst.u * kPart, g, r.w);
+          else pp.template store<128, NP>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * PProd::kUR, xu * 16 * PProd::kUR, 64, r.x, st + xoff);
           if (cst.u == upc - 1) {
             tc::fence_proxy_async();
             mbar_arrive(&bar.full[ring_s]);
@@ -729,13 +744,12 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloa
         if (k == 0 && u > 0) tc::mbar_wait(&bar.tmem_empty[b], (uint32_t)((u - 1) & 1));
         tc::fence_after_sync();
         const uint32_t st = sS + (uint32_t)ring_s * sbytes;
-        const uint32_t sWh = wres ? sWres + (uint32_t)k * 2u * kPart : st, sWl = sWh + kPart;
-        const uint32_t sPh = st + xoff, sPl = sPh + kPart;
+        const uint32_t sW = wres ? sWres + (uint32_t)k * kOp : st, sP = st + xoff;
         for (int q = 0; q < 4; ++q) {
-          const uint64_t wh = tc::make_desc_sw128(sWh + (uint32_t)q * 2048, 8192, 1024), wl = tc::make_desc_sw128(sWl + (uint32_t)q * 2048, 8192, 1024);
-          const uint64_t ph = tc::make_desc_sw128(sPh + (uint32_t)q * 2048, 8192, 1024), pl = tc::make_desc_sw128(sPl + (uint32_t)q * 2048, 8192, 1024);
-          if constexpr (PT) mma3(tm + (uint32_t)(b * kPts), ph, pl, wh, wl, idesc, k > 0 || q > 0);
-          else mma3(tm + (uint32_t)(b * kPts), wh, wl, ph, pl, idesc, k > 0 || q > 0);
+          const uint64_t wd = tc::make_desc_sw128(sW + (uint32_t)q * 2048, 8192, 1024);
+          const uint64_t pd = tc::make_desc_sw128(sP + (uint32_t)q * 2048, 8192, 1024);
+          if constexpr (PT) mma_planes<NP>(tm + (uint32_t)(b * kPts), pd, wd, idesc, k > 0 || q > 0);
+          else mma_planes<NP>(tm + (uint32_t)(b * kPts), wd, pd, idesc, k > 0 || q > 0);
         }
         tc::mma_commit_warp(&bar.empty[ring_s]);
         if (++ring_s == nst) { ring_s = 0; ++ring_r; }
@@ -749,14 +763,15 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wh, const __nv_bfloa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// wgrad: CTA (channel block, q block, split) accumulates dW[128 x nq] over its tiles in TMEM and adds it to global
-// memory at the end.  Stage = 64 points: [P hi | P lo | Q hi | Q lo], P = dy^T part [128 ch x 64 pts] (K-major),
+// wgrad (2 planes): CTA (channel block, q block, split) accumulates dW[128 x nq] over its tiles in TMEM and adds it to
+// global memory at the end.  Stage = 64 points: [P hi | P lo | Q hi | Q lo], P = dy^T part [128 ch x 64 pts] (K-major),
 // Q = x_prev part, channel-major [128 ch x 64 pts] (K-major) or point-major [64 pts x 2 blocks of 64 ch] (MN-major).
 // ---------------------------------------------------------------------------------------------------------------
 template <class PProd, class QProd>
 __global__ void __launch_bounds__(kThreads, 1)
 x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_valid, int perm_d, int M, int tps, int nst) {
   PCOE_V6_PROLOGUE(128)
+  constexpr int NP = 2;
   const int cl0 = blockIdx.x * 128, qb = blockIdx.y;
   const int ntiles = (M + kPts - 1) / kPts;
   const int t0 = blockIdx.z * tps, t1 = min(ntiles, t0 + tps), nt = max(t1 - t0, 0);
@@ -828,13 +843,13 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
           const uint32_t st = sS + (uint32_t)ring_s * sbytes;
           if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
           if (cst.u < kPU)
-            pp.template store<64>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, cst.u * 32 * PProd::kUR, 128, r.p, st, st + kPart);
+            pp.template store<64, NP>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, cst.u * 32 * PProd::kUR, 128, r.p, st);
           else {
             const int qu = cst.u - kPU;
             if constexpr (QProd::kChMajor)
-              qp.template store<64>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, qu * 32 * QProd::kUR, 128, r.q, st + 2 * kPart, st + 3 * kPart);
+              qp.template store<64, NP>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, qu * 32 * QProd::kUR, 128, r.q, st + 2 * kPart);
             else
-              qp.template store<64>(g, 2 * qb + qu, r.q, st + 2 * kPart + (uint32_t)qu * 8192u, st + 3 * kPart + (uint32_t)qu * 8192u);
+              qp.template store<64, NP>(g, 2 * qb + qu, r.q, st + 2 * kPart + (uint32_t)qu * 8192u);
           }
           if (cst.u == ups - 1) {
             tc::fence_proxy_async();
@@ -850,14 +865,12 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
     for (int h = 0; h < nstage; ++h) {
       tc::mbar_wait(&bar.full[ring_s], (uint32_t)(ring_r & 1));
       tc::fence_after_sync();
-      const uint32_t sPh = sS + (uint32_t)ring_s * sbytes, sPl = sPh + kPart, sQh = sPh + 2 * kPart, sQl = sPh + 3 * kPart;
+      const uint32_t sP = sS + (uint32_t)ring_s * sbytes, sQ = sP + 2 * kPart;
       for (int ks = 0; ks < 4; ++ks) {                        // 16 points per MMA
-        const uint64_t ah = tc::make_desc_sw128(sPh + (uint32_t)ks * 32, 16, 1024), al = tc::make_desc_sw128(sPl + (uint32_t)ks * 32, 16, 1024);
-        const uint64_t bh = QProd::kChMajor ? tc::make_desc_sw128(sQh + (uint32_t)ks * 32, 16, 1024)
-                                            : tc::make_desc_sw128(sQh + (uint32_t)ks * 2048, 8192, 1024);
-        const uint64_t bl = QProd::kChMajor ? tc::make_desc_sw128(sQl + (uint32_t)ks * 32, 16, 1024)
-                                            : tc::make_desc_sw128(sQl + (uint32_t)ks * 2048, 8192, 1024);
-        mma3(tm, ah, al, bh, bl, idesc, h > 0 || ks > 0);
+        const uint64_t ad = tc::make_desc_sw128(sP + (uint32_t)ks * 32, 16, 1024);
+        const uint64_t bd = QProd::kChMajor ? tc::make_desc_sw128(sQ + (uint32_t)ks * 32, 16, 1024)
+                                            : tc::make_desc_sw128(sQ + (uint32_t)ks * 2048, 8192, 1024);
+        mma_planes<NP>(tm, ad, bd, idesc, h > 0 || ks > 0);
       }
       tc::mma_commit_warp(&bar.empty[ring_s]);
       if (++ring_s == nst) { ring_s = 0; ++ring_r; }

@@ -53,6 +53,21 @@ def farthest_point_sample(xyz: torch.Tensor, npoint: int, start_idx: torch.Tenso
     return (idx, oxyz) if return_xyz else idx
 
 
+def host_randperm_subsets(B: int, N: int, S: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``torch.stack([torch.randperm(N)[:S] for _ in range(B)])`` as (B,S) int32 on the HOST, bit-identical to torch and
+    consuming torch's global CPU generator exactly like those B calls (reference: models/pointnet_pp_8dir.py:28), but in
+    one C call (pcoe_host_randperm_subsets) instead of B Python-level randperm launches.  ``out``: optional (pinned)
+    int32 CPU tensor to fill."""
+    if out is None:
+        out = torch.empty(B, S, dtype=torch.int32)
+    if out.is_cuda or out.dtype != torch.int32 or not out.is_contiguous() or out.numel() != B * S:
+        raise ValueError("host_randperm_subsets: `out` must be a contiguous int32 CPU tensor of B*S elements")
+    state = torch.get_rng_state()
+    _lib.check(_lib.load().pcoe_host_randperm_subsets(state.data_ptr(), state.numel(), B, N, S, out.data_ptr()))
+    torch.set_rng_state(state)
+    return out
+
+
 def gather_points(points: torch.Tensor, idx32: torch.Tensor) -> torch.Tensor:
     """points (B,N,C) f32, idx (B,S) int32 -> (B,S,C).  Reference: models/base.py:4-14."""
     points = _req(points, torch.float32, "points")

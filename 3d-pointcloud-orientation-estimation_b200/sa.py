@@ -192,6 +192,8 @@ class PointNetSetAbstraction(nn.Module):
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
         self._precision = precision
         self._rng_counter = None
+        self._static_idx = None                    # set by pcoe.GraphedTrainStep (host-replayed subsets as a graph input)
+        self._last_draw_shape = None
         global _layer_seq
         _layer_seq += 1
         self._stream_id = _layer_seq              # reproducible across runs (unlike id(self)), distinct per layer
@@ -217,8 +219,15 @@ class PointNetSetAbstraction(nn.Module):
         """-> (idx32 (B,S), new_xyz (B,S,3) or None when the sampler does not gather)."""
         B, N, _ = xyz.shape
         if self.sampler == "randperm_host":
-            idx = torch.stack([torch.randperm(N)[:self.npoint] for _ in range(B)])
-            return idx.to(torch.int32).to(xyz.device, non_blocking=True), None
+            self._last_draw_shape = (B, N, self.npoint)
+            if self._static_idx is not None:
+                # pcoe.GraphedTrainStep owns the draw: it replays the reference's host generator before every graph
+                # replay and uploads the subsets into this static buffer (a graph input)
+                return self._static_idx, None
+            # the reference's torch.stack([torch.randperm(N)[:npoint] ...]) on torch's CPU generator, bit-identical
+            # (same subsets, same generator state afterwards), in one C call instead of B Python-level launches
+            idx = ops.host_randperm_subsets(B, N, self.npoint)
+            return idx.to(xyz.device, non_blocking=True), None
         if self.sampler == "randperm_device":
             # the call counter lives on the device so that a CUDA-graph replay draws new subsets
             if self._rng_counter is None or self._rng_counter.device != xyz.device:

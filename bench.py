@@ -10,9 +10,15 @@ A "step" is one optimisation step of the reference's training loop on one synthe
 train_multi_peaks_vonMises_KL.py:221-236.  Workload at N=1 = BASELINE.json configs[1]
 (PointNetPPMvM, 64 clouds x 1024 points per GPU); weak scaling over GPUs.
 
-One JSON line on stdout (rank 0).  `value`: inputs resident in HBM, device-side sampler, CUDA-event
-timed, L2 flushed between steps.  `e2e`: the drop-in module called with HOST tensors - pinned-host
-xyz + targets copied H2D every step, the reference's host-side randperm sampling, loss read back D2H.
+One JSON line on stdout (rank 0).  Both headline numbers run the SAME captured step (pcoe.GraphedTrainStep) in the
+`bf16x3` precision mode (split-operand tcgen05 kernels, fp32-class accuracy: the mode the T3 parity tests gate) with the
+REFERENCE's sampler: the random subsets of every step are replayed on torch's CPU generator (bit-identical to
+`torch.randperm`, models/pointnet_pp_8dir.py:28) and uploaded as graph inputs (40 KB per step).
+`value`: xyz + targets resident in HBM, CUDA-event timed per step, L2 flushed between steps.
+`e2e`: xyz + targets in pinned HOST memory, copied H2D inside the timed region every step (next batch's copy
+overlapped with the running step), loss read back D2H every step, wall-clock timed.
+`modes`: the same step in the other precision modes (plain bf16 = throughput mode with a stated tolerance; fp32 =
+CUDA-core kernels), so all three are on record.
 """
 from __future__ import annotations
 
@@ -99,7 +105,7 @@ def sa_shapes(B: int, N: int):
             (B * 32, 259, 256, 512, 1024, 32, 1, 32)]
 
 
-def kernel_work(B: int, N: int) -> dict:
+def kernel_work(B: int, N: int, precision: str = "bf16") -> dict:
     """Algorithmic work per STEP of every libpcoe kernel name: name -> (FLOPs, bytes).
     FLOPs = 2*M*Cin*Cout per GEMM (no padding / recompute).  Bytes = compulsory HBM traffic of the launch:
     every input it must read once and every output it must write once (bf16 activations, fp32 sources,
@@ -107,11 +113,12 @@ def kernel_work(B: int, N: int) -> dict:
     a kernel is whichever of FLOPs / tensor peak and bytes / HBM peak takes longer."""
     sh = sa_shapes(B, N)
     w = {}
+    esz = 2.0 if precision == "bf16" else 4.0                         # bf16x3 / fp32 store fp32 activations
     for li, s in enumerate(sh):
         M, c, Nin, S = s[0], s[1:5], s[5], s[6]
         G = M // 32
         g = lambda a, b: 2.0 * M * c[a] * c[b]
-        act = lambda k: 2.0 * M * c[k]                                # one bf16 activation tensor [M x C_k]
+        act = lambda k: esz * M * c[k]                                # one activation tensor [M x C_k]
         src = 4.0 * M + 4.0 * (M // (S * 32)) * Nin * c[0]             # neighbour indices + the gathered fp32 source, once
         pool = 10.0 * G * c[3]                                        # ymax, ymin (f32) + amax, amin (u8) per group
         t = f"sa{li + 1}_"
@@ -120,7 +127,7 @@ def kernel_work(B: int, N: int) -> dict:
         # SA1 / SA2 (v4 kernels): the last layer's pre-activations y3 are never stored - the forward accumulates the
         # Gram matrix of its input and the backward uses the sparse max-pool routing - so
         # act(3) is neither written by fwd_l3 nor read by bwd_l3.  SA3 (v5 kernels) still stores y3.
-        y3 = 0.0 if li < 2 else act(3)
+        y3 = 0.0 if (li < 2 and precision == "bf16") else act(3)
         # SA1 (no input features): dW1 is accumulated by the layer-2 backward epilogue (MaskStatsW1) - that kernel also
         # reads the indices + xyz (src) and does not write dz1; the layer-1 backward kernel does not run
         l2_extra = (src - act(1)) if li == 0 else 0.0
@@ -235,8 +242,9 @@ def run_ours(args):
         torch.backends.cuda.matmul.allow_tf32 = True
     peaks = load_peaks()
 
+    sampler = "randperm_host" if args.sampler == "host" else "randperm_device"
     torch.manual_seed(1000)
-    model = getattr(pcoe, cls)(sampler="randperm_device").to(dev).train()
+    model = getattr(pcoe, cls)(sampler=sampler).to(dev).train()
     engine = pcoe.dp.DataParallel(model, overlap=not args.no_overlap)
     if args.skip_allreduce:                              # diagnostic only: how much of the N>1 step is the exchange
         engine.allreduce_grads = lambda: None
@@ -288,7 +296,7 @@ def run_ours(args):
             graphed(*([resident[i][0]] + list(resident[i][1])))
     run = (lambda x, tg: graphed(x, *tg)) if graphed is not None else step
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    clock_sampler = ClockSampler(local) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = pcoe._lib.launch_count()
     t_wall0 = time.time()
@@ -307,7 +315,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    clocks = clock_sampler.stop(t_wall0, t_wall1) if clock_sampler else None
     value = world * B * args.steps / (dev_ms / 1e3)
 
     if args.timed_only:
@@ -326,6 +334,8 @@ def run_ours(args):
     # ---- end-to-end through the public API with host buffers ------------------------------------
     # (a) the graphed step fed from pinned host memory: H2D of xyz + targets, replay, loss D2H
     h2d = host[0][0].numel() * 4 + sum(t.numel() * t.element_size() for t in host[0][1])
+    if sampler == "randperm_host":                        # + the replayed subsets: (B,128) and (B,32) int32
+        h2d += 4 * B * (128 + 32)
     e2e_steps = max(3, min(args.steps, 100))
 
     def timed_e2e(fn):
@@ -355,13 +365,11 @@ def run_ours(args):
                 return loss
             graphed.prefetch(host[0][0], *host[0][1])
             e2e_value = timed_e2e(fed)
-    # (b) the eager drop-in call with the reference's host-generator sampling (index-exact mode)
-    for m in (model.sa1, model.sa2):
-        m.sampler = "randperm_host"
+    # (b) the plain eager drop-in call (no CUDA graph), same sampler: what a caller gets without GraphedTrainStep
+    if graphed is not None:
+        graphed.release()
     e2e_eager = timed_e2e(lambda i: step(host[i % NB][0].to(dev, non_blocking=True),
                                          tuple(t.to(dev, non_blocking=True) for t in host[i % NB][1])).detach())
-    for m in (model.sa1, model.sa2):
-        m.sampler = "randperm_device"
     if e2e_value is None:
         e2e_value = e2e_eager
 
@@ -379,7 +387,7 @@ def run_ours(args):
     pcoe._lib.profile(False)
     rep = pcoe._lib.profile_report()
     if rank == 0:
-        work = kernel_work(B, N)
+        work = kernel_work(B, N, args.precision)
         tot_ms = sum(ms for _, ms in rep.values())
         for name, (n, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
             ent = {"launches_per_step": n / psteps, "ms_per_step": ms / psteps, "share_of_libpcoe_time": ms / tot_ms}
@@ -398,7 +406,7 @@ def run_ours(args):
         top = max(cands, key=lambda n: kernels[n]["ms_per_step"] / kernels[n]["launches_per_step"]) if cands else None
         if top:
             k = kernels[top]
-            traffic = load_traffic().get(top) if (args.config == "c2" and args.precision == "bf16") else None
+            traffic = load_traffic().get(args.precision, {}).get(top) if args.config == "c2" else None
             roofline = {"kernel": top, "bound": k["bound"], "achieved": k["achieved"], "peak": peaks[k["bound"]],
                         "unit": k["unit"], "frac": k["frac"], "traffic": traffic, "peak_source": peaks["source"],
                         "avg_launch_ms": k["ms_per_step"] / k["launches_per_step"],
@@ -425,53 +433,63 @@ def run_ours(args):
         cpu = {"value": B * n_cpu / dt, "unit": "clouds/s", "cores": cores, "kind": "port",
                "sample": f"{n_cpu} full steps of {B} clouds after 1 warm-up (oracle port of the reference step, torch CPU fp32)"}
 
-    # ---- the fp32 parity mode of the same step, beside the headline (rank 0, N=1) -----------------
-    # `value` is the bf16 tensor-core mode (operands rounded to bf16: loss within 1e-3 of the fp32 mode, gradients
-    # within the stated bf16 tolerance).  The mode the <= 1e-3 loss / gradient parity tests run
-    # in is fp32 (CUDA-core GEMMs); its throughput on the same workload is reported here so both are on record.
-    parity = None
-    if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_parity_leg:
-        m32 = getattr(pcoe, cls)(sampler="randperm_device", precision="fp32").to(dev).train()
-        m32.load_state_dict(model.state_dict())
-        opt32 = torch.optim.Adam(m32.parameters(), lr=1e-3, fused=True)
-        p32 = list(m32.parameters())
+    # ---- the same step in the other precision modes (rank 0, N=1) ---------------------------------
+    # `value` is the mode named in config.precision.  The other modes are timed here on the same workload so that all
+    # three are on record: bf16x3 (parity-gated tensor-core mode), bf16 (throughput mode, stated tolerance), fp32
+    # (CUDA-core kernels).  Tensor-core modes: captured step, 30 replays; fp32: eager, 10 steps.
+    modes = None
+    if rank == 0 and world == 1 and not args.no_modes_leg:
+        modes = {args.precision: {"value": value, "ms_per_step": dev_ms / args.steps, "mode": "this run's `value`"}}
+        for prec in ("bf16x3", "bf16", "fp32"):
+            if prec == args.precision:
+                continue
+            m2 = getattr(pcoe, cls)(sampler="randperm_device", precision=prec).to(dev).train()
+            m2.load_state_dict(model.state_dict())
+            eng2 = pcoe.dp.DataParallel(m2)
+            opt2 = pcoe.optim.FusedAdam(eng2, lr=1e-3, max_grad_norm=clip, zero_grad_in_step=True)
 
-        def step32(x, tg):
-            opt32.zero_grad(set_to_none=False)
-            l = loss_of(kind, m32(x), tg, pcoe)
-            l.backward()
-            if clip is not None:
-                torch.nn.utils.clip_grad_norm_(p32, clip, foreach=True)
-            opt32.step()
+            def step2(x, tg):
+                l = loss_of(kind, m2(x), tg, pcoe)
+                l.backward()
+                opt2.step()
+                return l
 
-        for i in range(3):
-            step32(*resident[i % NB])
-        n32 = 20
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(n32):
-            step32(*resident[i % NB])
-        e1.record()
-        torch.cuda.synchronize()
-        ms32 = e0.elapsed_time(e1) / n32
-        parity = {"precision": "fp32", "value": B / (ms32 / 1e3), "unit": "clouds/s", "ms_per_step": ms32, "steps": n32,
-                  "mode": "eager (no CUDA graph), torch.optim.Adam(fused) + clip_grad_norm_",
-                  "note": "the mode the <=1e-3 loss/gradient parity tests and smoke() run in"}
-        del m32, opt32, p32
+            for i in range(3):
+                step2(*resident[i % NB])
+            n2, run2, how = 10, step2, "eager (no CUDA graph)"
+            if prec != "fp32":
+                g2 = pcoe.GraphedTrainStep(m2, lambda res, *tg: loss_of(kind, res, tg, pcoe), opt2, resident[0][0],
+                                           resident[0][1], clip_norm=clip, engine=eng2, warmup=1)
+                n2, run2, how = 30, (lambda x, tg: g2(x, *tg)), "captured step, device-side sampler"
+            for i in range(2):
+                run2(*resident[i % NB])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(n2):
+                run2(*resident[i % NB])
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / n2
+            modes[prec] = {"value": B / (ms2 / 1e3), "ms_per_step": ms2, "steps": n2, "mode": how + ", no L2 flush"}
+            del m2, eng2, opt2
 
     if rank == 0:
         line = {
             "metric": "train clouds/sec (1024 pts, fwd+bwd)", "value": value, "unit": "clouds/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (operands split into bf16 planes, fp32 accumulate and activations)"}[args.precision],
+            "data": "synthetic",
             "config": {"workload": WORKLOAD_NAMES[args.config], "clouds_per_gpu": B, "points": N,
                        "global_clouds_per_step": B * world, "parallelism": f"dp{world}",
                        "step": "zero_grad+fwd+loss+bwd+allreduce+clip+Adam",
                        "optimizer": "torch.optim.Adam(fused)+clip_grad_norm_" if args.torch_optimizer
-                       else "pcoe.optim.FusedAdam (clip+Adam+zero_grad, 2 launches)", "sampler_value": "randperm_device",
-                       "sampler_e2e": "randperm_host (reference-faithful)", "precision": args.precision,
+                       else "pcoe.optim.FusedAdam (clip+Adam+zero_grad, 2 launches)",
+                       "sampler": ("randperm_host: the reference's torch.randperm stream replayed on the host generator "
+                                   "(bit-identical), uploaded as graph inputs every step - used by `value` AND `e2e`")
+                       if sampler == "randperm_host" else "randperm_device (Philox subset kernel inside the graph; NOT the reference's stream)",
+                       "precision": args.precision,
                        "l2": "512 MiB buffer written between timed steps (flush outside the event pair)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -482,7 +500,7 @@ def run_ours(args):
             "cuda_graph": graphed is not None,
             "gpu_launches": int(launches),
             "gpu_launches_per_step": launches / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "fp32_parity_mode": parity, "kernels": kernels,
+            "roofline": roofline, "cpu_baseline": cpu, "modes": modes, "kernels": kernels,
             "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps,
             "grad_allreduce_bytes": engine.grads.nbytes() if world > 1 else 0,
         }
@@ -506,9 +524,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
-    ap.add_argument("--precision", choices=["fp32", "bf16"], default=os.environ.get("PCOE_PRECISION", "bf16"))
+    ap.add_argument("--precision", choices=["fp32", "bf16x3", "bf16"], default=os.environ.get("PCOE_PRECISION", "bf16x3"))
+    ap.add_argument("--sampler", choices=["host", "device"], default="host",
+                    help="host = the reference's randperm stream replayed on the CPU generator and fed to the graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-parity-leg", action="store_true", help="skip the fp32 parity-mode throughput leg")
+    ap.add_argument("--no-modes-leg", action="store_true", help="skip the throughput of the other precision modes")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: copy each batch H2D in line with its step")
     ap.add_argument("--torch-optimizer", action="store_true",

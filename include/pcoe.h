@@ -75,6 +75,14 @@ int pcoe_fps_f32(const float* xyz, int B, int N, int S, const int32_t* start_idx
 int pcoe_gather_points_f32(const float* src, int B, int N, int C, const int32_t* idx, int S,
                            float* out, void* stream);
 
+/* HOST function (no GPU work, all pointers are host pointers): exact replay of the reference's subset draw
+ *     torch.stack([torch.randperm(N)[:S] for _ in range(B)])          (models/pointnet_pp_8dir.py:28)
+ * on torch's CPU generator.  `rng_state` = the bytes of torch.get_rng_state() (mt19937 state, legacy layout), advanced
+ * in place exactly as B calls of torch.randperm(N) advance it - hand it back with torch.set_rng_state.  out_idx [B,S]
+ * i32 on the host (typically pinned, uploaded as a static input of the captured training step).  Bit-identical to
+ * torch (tests/test_host_rng_cpu.py), ~10x faster than the Python-level loop. */
+int pcoe_host_randperm_subsets(uint8_t* rng_state, size_t state_bytes, int B, int N, int S, int32_t* out_idx);
+
 /* Uniform random subset without replacement drawn on the device (partial Fisher-Yates, Philox-
  * style counter RNG keyed by (seed, call offset, cloud)).  Same distribution as the reference's
  * torch.randperm(N)[:S] (models/pointnet_pp_8dir.py:28; the on-device variant is

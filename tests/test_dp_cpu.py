@@ -93,3 +93,27 @@ def test_single_process_engine_is_a_no_op_allreduce():
     before = e.grads.flat.clone()
     e.allreduce_grads()
     assert torch.equal(before, e.grads.flat) and e.grads.nbytes() == 4 * sum(p.numel() for p in m.parameters())
+
+
+def test_overlapped_exchange_is_armed_once_per_step():
+    """a second backward() before allreduce_grads() must not all-reduce the already-summed tail again.
+    The hook raises unless the extra micro-batches run under no_sync(); FlatGradBuffer notices detached .grad views."""
+    import pytest
+    import torch
+    import pcoe
+
+    net = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.Linear(4, 2))
+    eng = pcoe.dp.DataParallel(net)                     # world 1: no process group needed
+    eng._late_off, eng._late_work = 4, object()         # as if the tail exchange of this step were in flight
+    with pytest.raises(RuntimeError, match="no_sync"):
+        eng._reduce_tail_async()
+    eng._late_work = None
+    with eng.no_sync():
+        assert eng._sync is False
+        eng._reduce_tail_async()                        # accumulation micro-batch: nothing is exchanged
+        assert eng._late_work is None
+    assert eng._sync is True
+    eng.grads.check_views()
+    torch.optim.SGD(net.parameters(), lr=0.1).zero_grad(set_to_none=True)
+    with pytest.raises(RuntimeError, match="flat gradient buffer"):
+        eng.grads.check_views()

@@ -180,3 +180,65 @@ def test_graphed_train_step_and_prefetched_feed(pcoe, cuda):
     g.prefetch(*host[2])
     l2 = float(g.step_prefetched())
     assert torch.equal(g.xyz.cpu(), host[2][0]) and l1 == l1 and l2 == l2
+
+
+def test_graphed_step_trains_on_the_reference_subsets(pcoe, cuda):
+    """GraphedTrainStep with the reference's own sampler (sampler="randperm_host", models/pointnet_pp_8dir.py:28): the
+    subsets are replayed on torch's CPU generator before every graph replay and uploaded as graph inputs, so a seeded
+    graphed run uses exactly the subsets of the seeded reference run: B x randperm(N) then B x randperm(128) per
+    forward, step after step - also through the double-buffered feed."""
+    B, N = 4, 512
+    torch.manual_seed(3)
+    model = pcoe.PointNetPPMvM(precision="bf16x3").to(cuda).train()          # default sampler = randperm_host
+    engine = pcoe.dp.DataParallel(model)
+    opt = pcoe.optim.FusedAdam(engine, lr=1e-3, max_grad_norm=1.0, zero_grad_in_step=True)
+    gt, K = pcoe.synthetic.mvm_targets(B, 0)
+    host = (pcoe.synthetic.clouds(1, B, N, 0).pin_memory(), gt.pin_memory(), K.to(torch.int32).pin_memory())
+    dev0 = tuple(t.to(cuda) for t in host)
+    loss_fn = lambda res, gt, K: pcoe.match_loss(res[0], res[1], res[2], gt, None, K).mean()
+    loss_fn(model(dev0[0]), dev0[1], dev0[2]).backward()
+    opt.step()
+    g = pcoe.GraphedTrainStep(model, loss_fn, opt, dev0[0], dev0[1:], clip_norm=1.0, engine=engine, warmup=1)
+
+    def reference_draws(n_forward):
+        return [(torch.stack([torch.randperm(N)[:128] for _ in range(B)]), torch.stack([torch.randperm(128)[:32] for _ in range(B)]))
+                for _ in range(n_forward)]
+
+    torch.manual_seed(42)
+    want = reference_draws(5)
+    torch.manual_seed(42)
+    for i in range(3):
+        loss = g(*host)
+        assert torch.equal(model.sa1.last_fps_idx.long().cpu(), want[i][0])
+        assert torch.equal(model.sa2.last_fps_idx.long().cpu(), want[i][1])
+        assert float(loss) == float(loss)
+    g.prefetch(*host)                                    # draws forward 3 now, consumed by the next step
+    g.step_prefetched()
+    torch.cuda.synchronize()
+    assert torch.equal(model.sa1.last_fps_idx.long().cpu(), want[3][0]) and torch.equal(model.sa2.last_fps_idx.long().cpu(), want[3][1])
+    g.release()
+    model(dev0[0])                                       # eager again: the layer draws for itself, same stream
+    assert torch.equal(model.sa1.last_fps_idx.long().cpu(), want[4][0])
+
+
+def test_graphed_step_with_true_fps_sampler_draws_new_start_points(pcoe, cuda):
+    """sampler="fps" inside a captured step: the first centroid of every cloud comes from torch's CUDA generator (no
+    host draw, no synchronising copy), so replays start from different points."""
+    torch.manual_seed(5)
+    B, N = 4, 512
+    model = pcoe.PointNetPP8Dir(sampler="fps", precision="bf16x3").to(cuda).train()
+    engine = pcoe.dp.DataParallel(model)
+    opt = pcoe.optim.FusedAdam(engine, lr=1e-3, zero_grad_in_step=True)
+    xyz = pcoe.synthetic.clouds(2, B, N, 0).to(cuda)
+    p8 = pcoe.synthetic.dir8_targets(B, pcoe.DIRS_8).to(cuda)
+    loss_fn = lambda res, p: pcoe.kl_loss_per_sample_from_logits(res, p).mean()
+    loss_fn(model(xyz), p8).backward()
+    opt.step()
+    g = pcoe.GraphedTrainStep(model, loss_fn, opt, xyz, (p8,), engine=engine, warmup=1)
+    firsts = []
+    for _ in range(6):
+        assert float(g(xyz, p8)) == float(g.loss)
+        firsts.append(model.sa1.last_fps_idx[:, 0].clone())
+        idx = model.sa1.last_fps_idx.long()
+        assert all(len(set(r.tolist())) == 128 for r in idx.cpu())          # FPS never repeats a point
+    assert len({tuple(f.tolist()) for f in firsts}) > 1
