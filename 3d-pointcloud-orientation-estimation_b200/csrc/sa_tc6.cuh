@@ -11,8 +11,8 @@
 //   gradients by O(1): measured, 16-bit forward operands leave the weight gradients 1-3e-2 from the fp64 oracle,
 //   24-bit ones 4e-4 .. 4e-3): THREE planes, x = hi + mid + lo exactly (24 bits),
 //        A*B  ~=  hi*hi + (hi*mid + mid*hi) + (mid*mid + hi*lo + lo*hi)  (6 MMAs; dropped terms are 2^-24 relative)
-// Everything that is not an MMA operand stays fp32: activations live in HBM as fp32 (tile-blocked channel-major
-// [tile][C][128 points]), BatchNorm / ReLU / BatchNorm-backward transforms run in fp32 in the producers BEFORE the
+// Everything that is not an MMA operand stays fp32: activations live in HBM as fp32 (tile-blocked, point-quad
+// interleaved: see act_off), BatchNorm / ReLU / BatchNorm-backward transforms run in fp32 in the producers BEFORE the
 // split, batch statistics are fp64 sums of the fp32 accumulators.
 //
 // Orientation, roles and operand images are those of sa_tc5.cuh (channels on the TMEM lanes; 17 warps: 8 epilogue,
@@ -106,25 +106,41 @@ __global__ void convert_weights6_kernel(ConvW6 a, ConvW6 b, ConvW6 c) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Channel-major producers.  One UNIT of the 256 producer threads covers PTS points x (kRstep * kUR) channel rows:
-// thread g owns the 8-point chunk g % (PTS/8) of rows r0 + i*kRstep, r0 = g / (PTS/8), i < kUR.
-//   PTS = 128 (forward / dgrad operand: 64-channel x 128-point part), kRstep = 16
-//   PTS = 64  (weight-gradient operand: 128-channel x 64-point part), kRstep = 32
-// load():  raw fp32 global loads only.   store(): fp32 transform -> split -> two swizzled 16-byte stores.
+// fp32 activations in HBM: tile-blocked and POINT-QUAD INTERLEAVED - element (tile, channel c, point p) of an
+// activation with C channels sits at float index
+//        ((tile * 32 + (p >> 2)) * C + c) * 4 + (p & 3)
+// i.e. inside a 128-point tile the 16-byte quads of four consecutive points are stored channel after channel.  Every
+// access pattern of these kernels is then fully coalesced with NO shared-memory staging: an epilogue thread (= one
+// channel, TMEM lane) holding 32 points writes eight float4, and for each of them the 32 lanes of the warp (32
+// consecutive channels) cover 512 contiguous bytes; a producer warp (lane = channel) reads the same way.  (With the
+// plain [tile][C][128] layout each warp-wide 16-byte store touched 32 different 128-byte lines: measured 4.3 us per
+// 128-point tile in the forward kernels, the stores alone ~2 us.)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t act_off(int tile, int C, int c, int quad) { return (((size_t)tile * 32 + quad) * C + c) * 4; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Channel-major producers.  One UNIT of the 256 producer threads covers R = (PTS == 128 ? 16 : 32) * kUR channel
+// rows x PTS points: thread g owns row g % R and the kUR 8-point chunks g / R + i * (256 / R), i < kUR (lanes of a warp
+// = consecutive channels: coalesced global loads, conflict-free swizzled shared-memory stores).
+//   PTS = 128 (forward / dgrad operand: 64-channel x 128-point part)     PTS = 64 (weight-gradient operand: 128 x 64)
+// load():  raw fp32 global loads only.   store(): fp32 transform -> split into NP bf16 planes -> swizzled 16-byte stores.
 // `m0` = first point row of the unit, `crow` = first channel, `lrow` = image row of `crow`, `lrows` = image rows.
 // ---------------------------------------------------------------------------------------------------------------
-template <int PTS>
+template <int PTS, int UR>
 struct CM {
-  static constexpr int kCpr = PTS / 8;
-  static constexpr int kRstep = kProdThreads / kCpr;
+  static constexpr int kR = (PTS == 128 ? 16 : 32) * UR;      // rows per unit
+  static constexpr int kCstep = kProdThreads / kR;            // chunk stride between a thread's items
 };
+__device__ __forceinline__ float4 ldg4_or0(const float* p, bool ok) {
+  return ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
 
 // relu(scale * y + shift) of the previous layer's pre-activations
 struct BnRelu6 {
   static constexpr bool kChMajor = true;
   static constexpr int kUR = 4;
   struct Raw { float4 a[kUR][2]; };
-  const float* __restrict__ y;        // tile-blocked fp32 [tile][C][128]
+  const float* __restrict__ y;        // fp32 activation (layout above)
   const float* __restrict__ scale;
   const float* __restrict__ shift;
   int M, C;
@@ -144,31 +160,31 @@ struct BnRelu6 {
   }
   template <int PTS>
   __device__ __forceinline__ void load(int g, int m0, int crow, Raw& r) const {
-    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
-    const int m = m0 + chunk * 8;
-    const bool ok = m < M;
-    const float* src = y + ((size_t)(m >> 7) * C + crow + r0) * 128 + (m & 127);
+    using G = CM<PTS, kUR>;
+    const int row = g % G::kR, c = crow + row, ch0 = g / G::kR;
+    const bool rok = c < C;
 #pragma unroll
     for (int i = 0; i < kUR; ++i) {
-      const bool rok = ok && crow + r0 + i * CM<PTS>::kRstep < C;
-      const float4* p = reinterpret_cast<const float4*>(src + (size_t)i * CM<PTS>::kRstep * 128);
-      r.a[i][0] = rok ? __ldg(p) : make_float4(0.f, 0.f, 0.f, 0.f);
-      r.a[i][1] = rok ? __ldg(p + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int m = m0 + (ch0 + i * G::kCstep) * 8;
+      const float* src = y + act_off(m >> 7, C, rok ? c : 0, (m & 127) >> 2);
+      const bool ok = rok && m < M;
+      r.a[i][0] = ldg4_or0(src, ok);
+      r.a[i][1] = ldg4_or0(src + (size_t)C * 4, ok);
     }
   }
   template <int PTS, int NP>
   __device__ __forceinline__ void store(int g, int, int crow, int lrow, int lrows, const Raw& r, uint32_t s0) const {
-    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
+    using G = CM<PTS, kUR>;
+    const int row = g % G::kR, c = crow + row, ch0 = g / G::kR;
+    if (c >= C) return;                           // rows beyond C stay zero from the one-time clear
+    const float sc = cs[c], sh = cs[C + c];
 #pragma unroll
     for (int i = 0; i < kUR; ++i) {
-      const int c = crow + r0 + i * CM<PTS>::kRstep;
-      if (c >= C) continue;                       // rows beyond C stay zero from the one-time clear
-      const float sc = cs[c], sh = cs[C + c];
       const float x[8] = {r.a[i][0].x, r.a[i][0].y, r.a[i][0].z, r.a[i][0].w, r.a[i][1].x, r.a[i][1].y, r.a[i][1].z, r.a[i][1].w};
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = fmaxf(fmaf(x[u], sc, sh), 0.f);
-      split_store8<NP>(v, s0, cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk));
+      split_store8<NP>(v, s0, cm_off(lrows, lrow + row, ch0 + i * G::kCstep));
     }
   }
 };
@@ -198,35 +214,35 @@ struct Dy6 {
   }
   template <int PTS>
   __device__ __forceinline__ void load(int g, int m0, int crow, Raw& r) const {
-    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
-    const int m = m0 + chunk * 8;
-    const bool ok = m < M;
-    const size_t off = ((size_t)(m >> 7) * C + crow + r0) * 128 + (m & 127);
+    using G = CM<PTS, kUR>;
+    const int row = g % G::kR, c = crow + row, ch0 = g / G::kR;
+    const bool rok = c < C;
 #pragma unroll
     for (int i = 0; i < kUR; ++i) {
-      const bool rok = ok && crow + r0 + i * CM<PTS>::kRstep < C;
-      const float4* pd = reinterpret_cast<const float4*>(dz + off + (size_t)i * CM<PTS>::kRstep * 128);
-      const float4* py = reinterpret_cast<const float4*>(y + off + (size_t)i * CM<PTS>::kRstep * 128);
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      r.d[i][0] = rok ? __ldg(pd) : z; r.d[i][1] = rok ? __ldg(pd + 1) : z;
-      r.y[i][0] = rok ? __ldg(py) : z; r.y[i][1] = rok ? __ldg(py + 1) : z;
+      const int m = m0 + (ch0 + i * G::kCstep) * 8;
+      const size_t off = act_off(m >> 7, C, rok ? c : 0, (m & 127) >> 2);
+      const bool ok = rok && m < M;
+      r.d[i][0] = ldg4_or0(dz + off, ok); r.d[i][1] = ldg4_or0(dz + off + (size_t)C * 4, ok);
+      r.y[i][0] = ldg4_or0(y + off, ok);  r.y[i][1] = ldg4_or0(y + off + (size_t)C * 4, ok);
     }
   }
   template <int PTS, int NP>
   __device__ __forceinline__ void store(int g, int m0, int crow, int lrow, int lrows, const Raw& r, uint32_t s0) const {
-    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
-    const float okf = m0 + chunk * 8 < M ? 1.f : 0.f;     // points >= M contribute 0 to dW
+    using G = CM<PTS, kUR>;
+    const int row = g % G::kR, c = crow + row, ch0 = g / G::kR;
+    if (c >= C) return;
+    const float ca0 = cs[c], cp0 = cs[C + c], cq0 = cs[2 * C + c];
 #pragma unroll
     for (int i = 0; i < kUR; ++i) {
-      const int c = crow + r0 + i * CM<PTS>::kRstep;
-      if (c >= C) continue;
-      const float ca = cs[c] * okf, cp = cs[C + c] * okf, cq = cs[2 * C + c] * okf;
+      const int chunk = ch0 + i * G::kCstep;
+      const float okf = m0 + chunk * 8 < M ? 1.f : 0.f;     // points >= M contribute 0 to dW
+      const float ca = ca0 * okf, cp = cp0 * okf, cq = cq0 * okf;
       const float d[8] = {r.d[i][0].x, r.d[i][0].y, r.d[i][0].z, r.d[i][0].w, r.d[i][1].x, r.d[i][1].y, r.d[i][1].z, r.d[i][1].w};
       const float yy[8] = {r.y[i][0].x, r.y[i][0].y, r.y[i][0].z, r.y[i][0].w, r.y[i][1].x, r.y[i][1].y, r.y[i][1].z, r.y[i][1].w};
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = fmaf(ca, d[u], fmaf(cp, yy[u], cq));
-      split_store8<NP>(v, s0, cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk));
+      split_store8<NP>(v, s0, cm_off(lrows, lrow + row, chunk));
     }
   }
 };
@@ -257,39 +273,37 @@ struct DyLast6 {
   }
   template <int PTS>
   __device__ __forceinline__ void load(int g, int m0, int crow, Raw& r) const {
-    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
-    const int m = m0 + chunk * 8;
-    const bool ok = m < M;
-    const int grp = (ok ? m : 0) >> 5;
-    const float* sy = y + ((size_t)(m >> 7) * C + crow + r0) * 128 + (m & 127);
-    const size_t go = (size_t)grp * C + crow + r0;
+    using G = CM<PTS, kUR>;
+    const int row = g % G::kR, c = crow + row, ch0 = g / G::kR;
+    const bool rok = c < C;
 #pragma unroll
     for (int i = 0; i < kUR; ++i) {
-      const bool rok = ok && crow + r0 + i * CM<PTS>::kRstep < C;
-      const float4* py = reinterpret_cast<const float4*>(sy + (size_t)i * CM<PTS>::kRstep * 128);
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      r.y[i][0] = rok ? __ldg(py) : z; r.y[i][1] = rok ? __ldg(py + 1) : z;
-      r.gv[i] = rok ? __ldg(gm + go + i * CM<PTS>::kRstep) : 0.f;
-      r.sl[i] = rok ? (int)__ldg(slot + go + i * CM<PTS>::kRstep) : -1;
+      const int m = m0 + (ch0 + i * G::kCstep) * 8;
+      const bool ok = rok && m < M;
+      const float* sy = y + act_off(m >> 7, C, rok ? c : 0, (m & 127) >> 2);
+      const size_t go = (size_t)((ok ? m : 0) >> 5) * C + (rok ? c : 0);
+      r.y[i][0] = ldg4_or0(sy, ok); r.y[i][1] = ldg4_or0(sy + (size_t)C * 4, ok);
+      r.gv[i] = ok ? __ldg(gm + go) : 0.f;
+      r.sl[i] = ok ? (int)__ldg(slot + go) : -1;
     }
   }
   template <int PTS, int NP>
   __device__ __forceinline__ void store(int g, int m0, int crow, int lrow, int lrows, const Raw& r, uint32_t s0) const {
-    const int chunk = g & (CM<PTS>::kCpr - 1), r0 = g / CM<PTS>::kCpr;
-    const int m = m0 + chunk * 8;
-    const float okf = m < M ? 1.f : 0.f;
-    const int j0 = m & 31;
+    using G = CM<PTS, kUR>;
+    const int row = g % G::kR, c = crow + row, ch0 = g / G::kR;
+    if (c >= C) return;
+    const float ca0 = cs[c], cp0 = cs[C + c], cq0 = cs[2 * C + c];
 #pragma unroll
     for (int i = 0; i < kUR; ++i) {
-      const int c = crow + r0 + i * CM<PTS>::kRstep;
-      if (c >= C) continue;
-      const float add = cs[c] * r.gv[i], cp = cs[C + c] * okf, cq = cs[2 * C + c] * okf;   // gv is 0 for points >= M
-      const int sl = r.sl[i] - j0;                // slot relative to this 8-point chunk
+      const int chunk = ch0 + i * G::kCstep, m = m0 + chunk * 8;
+      const float okf = m < M ? 1.f : 0.f;
+      const float add = ca0 * r.gv[i], cp = cp0 * okf, cq = cq0 * okf;   // gv is 0 for points >= M
+      const int sl = r.sl[i] - (m & 31);          // slot relative to this 8-point chunk
       const float yy[8] = {r.y[i][0].x, r.y[i][0].y, r.y[i][0].z, r.y[i][0].w, r.y[i][1].x, r.y[i][1].y, r.y[i][1].z, r.y[i][1].w};
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = fmaf(cp, yy[u], cq) + (u == sl ? add : 0.f);
-      split_store8<NP>(v, s0, cm_off(lrows, lrow + r0 + i * CM<PTS>::kRstep, chunk));
+      split_store8<NP>(v, s0, cm_off(lrows, lrow + row, chunk));
     }
   }
 };
@@ -350,15 +364,17 @@ struct GatherFeat6 {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Epilogues: thread = one channel (TMEM lane), v = 32 consecutive points (block j of the tile), fp32 outputs written
-// straight to the tile-blocked activation (128 contiguous bytes per thread and block).
+// straight to the quad-interleaved activation: eight float4 per thread, each warp-wide store 512 contiguous bytes.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store32_f32(float* dst, const float (&v)[32]) {
+__device__ __forceinline__ void store32_f32(float* y, int tile, int C, int c, int j, const float (&v)[32]) {
+  float* dst = y + act_off(tile, C, c, j * 8);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(dst + (size_t)q * C * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 struct StoreStats6 {
-  float* __restrict__ y;           // tile-blocked fp32
+  float* __restrict__ y;           // fp32 activation (quad-interleaved, see act_off)
   double* __restrict__ sums;       // [kRedCopies][2,C] or nullptr (eval)
   int C;
   int c;
@@ -367,7 +383,7 @@ struct StoreStats6 {
   __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; }
   __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid) {
     if (c >= C || !valid) return;
-    store32_f32(y + ((size_t)tile * C + c) * 128 + j * 32, v);
+    store32_f32(y, tile, C, c, j, v);
     sum_sumsq32(v, s0, s1);
   }
   __device__ __forceinline__ void finish() {
@@ -394,7 +410,7 @@ struct Group6 {   // last layer, K == 32: the 32 columns of a block are one grou
   __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; want_max = c < C ? !signbit(gamma[c]) : true; }
   __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid) {
     if (c >= C || !valid) return;
-    if (y) store32_f32(y + ((size_t)tile * C + c) * 128 + j * 32, v);
+    if (y) store32_f32(y, tile, C, c, j, v);
     sum_sumsq32(v, s0, s1);
     float ext;
     int arg;
@@ -430,15 +446,13 @@ struct MaskStats6 {
   }
   __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid) {
     if (c >= C || !valid) return;
-    const size_t o = ((size_t)tile * C + c) * 128 + j * 32;
-    const float4* py = reinterpret_cast<const float4*>(yprev + o);
-    float4* pd = reinterpret_cast<float4*>(dz + o);
+    const size_t o = act_off(tile, C, c, j * 8), qs = (size_t)C * 4;   // quad q of this block at o + q * qs
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {                 // two halves of 16 points: bounds the registers held by the y loads
       float4 yv[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) yv[q] = __ldg(py + 4 * h + q);
+      for (int q = 0; q < 4; ++q) yv[q] = __ldg(reinterpret_cast<const float4*>(yprev + o + (size_t)(4 * h + q) * qs));
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float yy[4] = {yv[q].x, yv[q].y, yv[q].z, yv[q].w};
@@ -450,7 +464,7 @@ struct MaskStats6 {
           a[u] += d[u];
           b[u] = fmaf(d[u], fmaf(yy[u], is, nmi), b[u]);
         }
-        pd[4 * h + q] = make_float4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<float4*>(dz + o + (size_t)(4 * h + q) * qs) = make_float4(d[0], d[1], d[2], d[3]);
       }
     }
     s0 += (a[0] + a[1]) + (a[2] + a[3]);
