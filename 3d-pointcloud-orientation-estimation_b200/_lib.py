@@ -34,6 +34,12 @@ class SAGrads(C.Structure):
     _fields_ = [(n, C.c_void_p * 3) for n in ("dW", "dbias", "dgamma", "dbeta")] + [("accumulate", C.c_int32)]
 
 
+class PointMlpDesc(C.Structure):
+    """pcoe_pointmlp_desc"""
+    _fields_ = [(n, C.c_int32) for n in ("M", "rows_per_cloud", "D", "use_xyz", "nlayers")] + \
+               [("C", C.c_int32 * 3), ("relu_last", C.c_int32), ("eps", C.c_float)]
+
+
 _P, _I, _F, _D, _U64, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_uint64, C.c_size_t
 
 # name -> (restype, argtypes); mirrors include/pcoe.h one to one
@@ -48,14 +54,19 @@ SIGNATURES = {
     "pcoe_host_randperm_subsets": (_I, [_P, _SZ, _I, _I, _I, _P]),
     "pcoe_random_subset": (_I, [_I, _I, _I, _U64, _U64, _P, _P, _P]),
     "pcoe_random_subset_xyz": (_I, [_I, _I, _I, _U64, _U64, _P, _P, _P, _P, _P]),
+    "pcoe_square_distance_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "pcoe_knn_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "pcoe_ball_query_f32": (_I, [_P, _P, _I, _I, _I, _I, _D, _P, _P]),
+    "pcoe_ball_query_multi_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "pcoe_sa_saved_bytes": (_SZ, [C.POINTER(SADesc)]),
     "pcoe_sa_workspace_bytes": (_SZ, [C.POINTER(SADesc)]),
     "pcoe_sa_forward": (_I, [C.POINTER(SADesc), _P, _P, _P, _P, C.POINTER(SAParams), _P, _P, _SZ,
                              _P, _SZ, _P]),
     "pcoe_sa_backward": (_I, [C.POINTER(SADesc), _P, _P, _P, _P, C.POINTER(SAParams), _P, _P, _P,
                               _SZ, _P, C.POINTER(SAGrads), _P, _SZ, _P]),
+    "pcoe_pointmlp_workspace_bytes": (_SZ, [C.POINTER(PointMlpDesc)]),
+    "pcoe_pointmlp_forward": (_I, [C.POINTER(PointMlpDesc), _P, _P, C.POINTER(SAParams), _P, _P, _SZ, _P]),
+    "pcoe_pointwise_linear_f32": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
     "pcoe_vm_kl_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "pcoe_mvm_match_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pcoe_soft_ce_fwd_bwd": (_I, [_P, _P, _I, _I, _P, _P, _P]),

@@ -348,6 +348,99 @@ ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_x
   }
 }
 
+// square_distance (models/base.py:20-27): dist[b,i,j] = -2 <src_i, dst_j> + |src_i|^2 + |dst_j|^2, the reference's
+// expanded form (it can come out slightly negative, as there).  One thread = one src row x 4 consecutive dst columns:
+// the (B,N,M) matrix is written once with 16-byte stores, which is all the HBM traffic there is (write-bound).
+__global__ void __launch_bounds__(256)
+square_distance_kernel(const float* __restrict__ src, const float* __restrict__ dst, int N, int M, int C,
+                       float* __restrict__ out) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j0 >= M) return;
+  const float* s = src + ((size_t)b * N + i) * C;
+  const float* d = dst + ((size_t)b * M + j0) * C;
+  float dot[4] = {0.f, 0.f, 0.f, 0.f}, nd[4] = {0.f, 0.f, 0.f, 0.f}, ns = 0.f;
+  const int nj = min(4, M - j0);
+  for (int c = 0; c < C; ++c) {
+    const float sv = __ldg(s + c);
+    ns = fmaf(sv, sv, ns);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (u < nj) {
+        const float dv = __ldg(d + (size_t)u * C + c);
+        dot[u] = fmaf(sv, dv, dot[u]);
+        nd[u] = fmaf(dv, dv, nd[u]);
+      }
+  }
+  float r[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) r[u] = (-2.f * dot[u] + ns) + nd[u];
+  float* o = out + ((size_t)b * N + i) * M + j0;
+  if (nj == 4 && ((((size_t)b * N + i) * M + j0) & 3) == 0) {
+    *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+  } else {
+    for (int u = 0; u < nj; ++u) o[u] = r[u];
+  }
+}
+
+// Multi-scale grouping: up to kMaxScales radii in ONE pass over the staged cloud.  The squared distance of a point to
+// the centroid is computed once and compared with every radius; each scale keeps its own hit count, so the result of
+// scale r is exactly what ball_query_kernel gives for (radius_r, nsample_r).  The scan stops when every scale is full.
+constexpr int kMaxScales = 4;
+struct BallScales {
+  int n;
+  float r2[kMaxScales];
+  int nsample[kMaxScales];
+  int32_t* out[kMaxScales];
+};
+__global__ void __launch_bounds__(kGroupWarps * 32)
+ball_query_multi_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S, BallScales sc) {
+  extern __shared__ float smem_f[];
+  float* sx = smem_f;
+  float* sy = sx + N;
+  float* sz = sy + N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  load_cloud_soa(xyz + (size_t)b * N * 3, N, sx, sy, sz);
+  __syncthreads();
+
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int s_begin = (blockIdx.x * kGroupWarps + warp) * kCentroidsPerWarp;
+  for (int s = s_begin; s < min(s_begin + kCentroidsPerWarp, S); ++s) {
+    const float* c = new_xyz + ((size_t)b * S + s) * 3;
+    const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
+    int cnt[kMaxScales], first[kMaxScales];
+#pragma unroll
+    for (int r = 0; r < kMaxScales; ++r) { cnt[r] = 0; first[r] = N; }
+    for (int base = 0; base < N; base += 32) {
+      bool open = false;
+#pragma unroll
+      for (int r = 0; r < kMaxScales; ++r) open |= r < sc.n && cnt[r] < sc.nsample[r];
+      if (!open) break;
+      const int i = base + lane;
+      const float d2 = i < N ? sqdist_rn(sx[i], sy[i], sz[i], cx, cy, cz) : 0.f;
+#pragma unroll
+      for (int r = 0; r < kMaxScales; ++r) {
+        if (r >= sc.n || cnt[r] >= sc.nsample[r]) continue;
+        const bool hit = i < N && !(d2 > sc.r2[r]);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (m) {
+          if (cnt[r] == 0) first[r] = base + __ffs(m) - 1;
+          const int slot = cnt[r] + __popc(m & lt_mask);
+          if (hit && slot < sc.nsample[r]) sc.out[r][((size_t)b * S + s) * sc.nsample[r] + slot] = i;
+          cnt[r] += __popc(m);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kMaxScales; ++r) {
+      if (r >= sc.n) continue;
+      int32_t* o = sc.out[r] + ((size_t)b * S + s) * sc.nsample[r];
+      for (int e = min(cnt[r], sc.nsample[r]) + lane; e < sc.nsample[r]; e += 32) o[e] = first[r];
+    }
+  }
+}
+
 static int group_smem(int N, int K, size_t* smem, int warps = kGroupWarps) {
   *smem = (size_t)N * 3 * sizeof(float) + (size_t)warps * ((K + 31) / 32 * 32) * 8;
   return *smem <= 200 * 1024;
@@ -408,5 +501,43 @@ extern "C" int pcoe_ball_query_f32(const float* xyz, const float* new_xyz, int B
   dim3 grid(ceil_div(S, kGroupWarps * kCentroidsPerWarp), B);
   LaunchScope ls("ball_query_kernel", (cudaStream_t)stream);
   ball_query_kernel<<<grid, kGroupWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, nsample, r2, out_idx);
+  return ls.done();
+}
+
+extern "C" int pcoe_square_distance_f32(const float* src, const float* dst, int B, int N, int M, int C, float* out,
+                                        void* stream) {
+  if (B <= 0 || N <= 0 || M <= 0 || C <= 0) return fail(PCOE_ERR_BAD_SHAPE, "square_distance: B=%d N=%d M=%d C=%d", B, N, M, C);
+  if (N > 65535 || B > 65535) return fail(PCOE_ERR_UNSUPPORTED, "square_distance: B=%d / N=%d exceed the grid limits", B, N);
+  if (!src || !dst || !out) return fail(PCOE_ERR_NULL, "square_distance: NULL pointer");
+  const int threads = M >= 1024 ? 256 : (M >= 256 ? 64 : 32);
+  dim3 grid(ceil_div(ceil_div(M, 4), threads), N, B);
+  LaunchScope ls("square_distance_kernel", (cudaStream_t)stream);
+  square_distance_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(src, dst, N, M, C, out);
+  return ls.done();
+}
+
+extern "C" int pcoe_ball_query_multi_f32(const float* xyz, const float* new_xyz, int B, int N, int S, int nscales,
+                                         const double* radius_host, const int* nsample_host, int32_t* const* out_idx_host,
+                                         void* stream) {
+  if (B <= 0 || N <= 0 || S <= 0) return fail(PCOE_ERR_BAD_SHAPE, "ball_query_multi: B=%d N=%d S=%d", B, N, S);
+  if (nscales < 1 || nscales > kMaxScales)
+    return fail(PCOE_ERR_UNSUPPORTED, "ball_query_multi: %d scales (1..%d supported)", nscales, kMaxScales);
+  if (!xyz || !new_xyz || !radius_host || !nsample_host || !out_idx_host) return fail(PCOE_ERR_NULL, "ball_query_multi: NULL pointer");
+  BallScales sc{};
+  sc.n = nscales;
+  for (int r = 0; r < nscales; ++r) {
+    if (nsample_host[r] <= 0) return fail(PCOE_ERR_BAD_SHAPE, "ball_query_multi: nsample[%d]=%d", r, nsample_host[r]);
+    if (!out_idx_host[r]) return fail(PCOE_ERR_NULL, "ball_query_multi: out_idx[%d] is NULL", r);
+    sc.r2[r] = (float)(radius_host[r] * radius_host[r]);
+    sc.nsample[r] = nsample_host[r];
+    sc.out[r] = out_idx_host[r];
+  }
+  size_t smem;
+  if (!group_smem(N, 0, &smem)) return fail(PCOE_ERR_UNSUPPORTED, "ball_query_multi: N=%d does not fit shared memory", N);
+  if (smem > 48 * 1024)
+    PCOE_CUDA(cudaFuncSetAttribute(ball_query_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(S, kGroupWarps * kCentroidsPerWarp), B);
+  LaunchScope ls("ball_query_multi_kernel", (cudaStream_t)stream);
+  ball_query_multi_kernel<<<grid, kGroupWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, sc);
   return ls.done();
 }

@@ -480,7 +480,7 @@ static int convert_weights6(const pcoe_sa_desc& d, const SaLayout& L, const pcoe
   v6::ConvW6 w[3];
   int total = 0;
   for (int l = 0; l < 3; ++l) {
-    w[l] = v6::ConvW6{P.W[l], (__nv_bfloat16*)(base + L.wb_off[l]), Cs[l], Kin[l], L.w4_rp[l], L.w4_kp[l], l == 0 ? d.D : -1};
+    w[l] = v6::ConvW6{P.W[l], (__nv_bfloat16*)(base + L.wb_off[l]), Cs[l], Kin[l], L.w4_rp[l], L.w4_kp[l], l == 0 ? d.D : -1, 3};
     total += L.w4_rp[l] * L.w4_kp[l];
   }
   LaunchScope ls("convert_weights_kernel", st);
@@ -652,7 +652,7 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       PCOE_TRY(convert_weights6(d, L, P, wbase, st));
       auto wh = [&](int l) { return (const __nv_bfloat16*)(wbase + L.wb_off[l]); };
       auto wps = [&](int l) { return (size_t)L.w4_rp[l] * L.w4_kp[l]; };
-      v6::GatherFeat6 gp{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
+      v6::GatherFeat6 gp{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D, 0};
       v6::StoreStats6 e0{}; e0.y = y[0]; e0.sums = sums[0]; e0.C = d.C1;
       PCOE_TRY(launch_fwd6(gp, wh(0), wps(0), L.w4_kp[0], e0, M, d.C1, st, kname(d, kF1)));
       v6::BnRelu6 p1{}; p1.y = y[0]; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.C = d.C1; p1.fin = mkfin(0);
@@ -940,7 +940,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       PCOE_TRY(launch_dgrad6<false>(dy2, wh(1), wps(1), L.w4_kp[1], m1, M, d.C1, st, kname(d, kDG2)));
       v6::Dy6 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.C = d.C1;
       dy1.fin = mkbfin(0, 1);
-      v6::GatherFeat6 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D};
+      v6::GatherFeat6 x0{v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M}, feats, d.D, 0};
       PCOE_TRY(launch_wgrad6(dy1, x0, Gr.dW[0], Cin, Cin, d.D, M, ceil_div(x0.nchunks(), 2), st, kname(d, kWG1)));
       dy1.fin.write = 0;
       if (d.D > 0 && grad_feats) {
@@ -975,6 +975,71 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
     ScatterEpi se{grad_feats, nbr, d.N, d.S, d.K, d.D, d.group_all};
     PCOE_TRY(dgrad(dy1, 0, se, kname(d, kDG1)));
   }
+  return PCOE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pointwise MLP stack + max over each cloud's points (inference): the conv1d(k=1) + BatchNorm(eval) [+ ReLU] chains of
+// the vanilla PointNet (models/pointnet.py: STN3d :22-28, STNkd :53-59, PointNetEncoder :93,102-105).  Runs the
+// split-operand tcgen05 forward kernels (sa_tc6.cuh) over all M = clouds * points rows with the identity grouping
+// (row = point, blocks of 32 consecutive points pooled by the last layer's epilogue), then reduces the blocks of a cloud.
+// ---------------------------------------------------------------------------------------------------------------
+struct PmLayout {
+  int nl, M, G, Cin0, Kp[3], Rp[3];
+  size_t y[2], stat[3], ymax, ymin, amax, amin, wb[3], total;
+};
+static PmLayout pm_layout(const pcoe_pointmlp_desc& d) {
+  PmLayout L{};
+  L.nl = d.nlayers; L.M = d.M; L.G = d.M / 32;
+  L.Cin0 = (d.use_xyz ? 3 : 0) + d.D;
+  auto take = [](size_t& cur, size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
+  size_t s = 0;
+  const size_t Mld = align_up((size_t)d.M, 128);
+  for (int l = 0; l < d.nlayers; ++l) {
+    const int kin = l == 0 ? L.Cin0 : d.C[l - 1];
+    L.Rp[l] = (int)align_up(d.C[l], 128);
+    L.Kp[l] = (int)align_up(l == 0 ? (d.D + (d.use_xyz ? 16 : 0)) : kin, 128);
+    if (l + 1 < d.nlayers) L.y[l] = take(s, Mld * d.C[l] * sizeof(float));
+    L.stat[l] = take(s, sizeof(float) * 4 * d.C[l]);
+    L.wb[l] = take(s, (size_t)3 * 2 * L.Rp[l] * L.Kp[l]);
+  }
+  const int CL = d.C[d.nlayers - 1];
+  L.ymax = take(s, sizeof(float) * (size_t)L.G * CL);
+  L.ymin = take(s, sizeof(float) * (size_t)L.G * CL);
+  L.amax = take(s, (size_t)L.G * CL);
+  L.amin = take(s, (size_t)L.G * CL);
+  L.total = s;
+  return L;
+}
+
+// out[b,c] = max over the cloud's blocks of act(scale * (scale >= 0 ? ymax : ymin) + shift)
+__global__ void pm_pool_kernel(const float* __restrict__ ymax, const float* __restrict__ ymin,
+                               const float* __restrict__ scale, const float* __restrict__ shift, int blocks_per_cloud,
+                               int C, int relu, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float a = scale[c], sh = shift[c];
+  const float* src = (!signbit(a) ? ymax : ymin) + (size_t)b * blocks_per_cloud * C + c;
+  // affine is monotone per channel: pool the raw extreme first, one FMA at the end
+  float ext = __ldg(src);
+  if (!signbit(a)) { for (int g = 1; g < blocks_per_cloud; ++g) ext = fmaxf(ext, __ldg(src + (size_t)g * C)); }
+  else { for (int g = 1; g < blocks_per_cloud; ++g) ext = fminf(ext, __ldg(src + (size_t)g * C)); }
+  const float v = fmaf(ext, a, sh);
+  out[(size_t)b * C + c] = relu ? fmaxf(v, 0.f) : v;
+}
+
+static int pm_validate(const pcoe_pointmlp_desc* d) {
+  if (!d) return fail(PCOE_ERR_NULL, "pointmlp: desc is NULL");
+  if (d->M <= 0 || d->rows_per_cloud <= 0 || d->M % d->rows_per_cloud != 0)
+    return fail(PCOE_ERR_BAD_SHAPE, "pointmlp: M=%d rows_per_cloud=%d", d->M, d->rows_per_cloud);
+  if (d->rows_per_cloud % 32 != 0)
+    return fail(PCOE_ERR_UNSUPPORTED, "pointmlp: rows_per_cloud=%d must be a multiple of 32 (pad a cloud by repeating a point)", d->rows_per_cloud);
+  if (d->nlayers < 2 || d->nlayers > 3) return fail(PCOE_ERR_UNSUPPORTED, "pointmlp: nlayers=%d (2 or 3)", d->nlayers);
+  if (d->D < 0 || d->D % 64 != 0 || (d->D == 0 && !d->use_xyz))
+    return fail(PCOE_ERR_UNSUPPORTED, "pointmlp: D=%d must be a multiple of 64 (or 0 with use_xyz)", d->D);
+  for (int l = 0; l < d->nlayers; ++l)
+    if (d->C[l] <= 0 || d->C[l] % 64 != 0) return fail(PCOE_ERR_UNSUPPORTED, "pointmlp: C[%d]=%d must be a multiple of 64", l, d->C[l]);
   return PCOE_OK;
 }
 
@@ -1052,4 +1117,108 @@ extern "C" int pcoe_sa_backward(const pcoe_sa_desc* desc, const float* xyz, cons
                                            *grads, workspace, (cudaStream_t)stream);
   return sa_backward_impl<float, false>(d, xyz, new_xyz, nbr, feats, *params, out, grad_out, saved, grad_feats, *grads,
                                  workspace, (cudaStream_t)stream);
+}
+
+extern "C" size_t pcoe_pointmlp_workspace_bytes(const pcoe_pointmlp_desc* desc) {
+  if (pm_validate(desc) != PCOE_OK) return 0;
+  return pm_layout(*desc).total;
+}
+
+extern "C" int pcoe_pointmlp_forward(const pcoe_pointmlp_desc* desc, const float* xyz, const float* feats,
+                                     const pcoe_sa_params* params, float* out, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  PCOE_TRY(pm_validate(desc));
+  const pcoe_pointmlp_desc& d = *desc;
+  if (!params || !out || !workspace) return fail(PCOE_ERR_NULL, "pointmlp: NULL pointer");
+  if (d.use_xyz && !xyz) return fail(PCOE_ERR_NULL, "pointmlp: xyz is NULL");
+  if (d.D > 0 && !feats) return fail(PCOE_ERR_NULL, "pointmlp: feats is NULL but D=%d", d.D);
+  for (int l = 0; l < d.nlayers; ++l)
+    if (!params->W[l] || !params->gamma[l] || !params->beta[l] || !params->running_mean[l] || !params->running_var[l])
+      return fail(PCOE_ERR_NULL, "pointmlp: parameter pointer of layer %d is NULL", l + 1);
+  const PmLayout L = pm_layout(d);
+  if (workspace_bytes < L.total) return fail(PCOE_ERR_WORKSPACE, "pointmlp: workspace %zu < %zu bytes", workspace_bytes, L.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const int nl = d.nlayers, M = d.M, CL = d.C[nl - 1];
+  float *scale[3], *shift[3];
+  for (int l = 0; l < nl; ++l) {
+    scale[l] = (float*)(ws + L.stat[l]); shift[l] = scale[l] + d.C[l];
+    LaunchScope ls("bn_finalize_kernel", st);
+    bn_finalize_kernel<<<ceil_div(d.C[l], 128), 128, 0, st>>>(nullptr, 1.0, d.C[l], params->gamma[l], params->beta[l],
+        params->bias[l], params->running_mean[l], params->running_var[l], d.eps, 0.f, 0, scale[l], shift[l], nullptr, nullptr);
+    PCOE_TRY(ls.done());
+  }
+  {
+    v6::ConvW6 w[3];
+    int total = 0;
+    for (int l = 0; l < 3; ++l) {
+      const int ll = l < nl ? l : nl - 1;            // unused third slot of a 2-layer stack: converts layer 2 again (tiny)
+      const int kin = ll == 0 ? L.Cin0 : d.C[ll - 1];
+      w[l] = v6::ConvW6{params->W[ll], (__nv_bfloat16*)(ws + L.wb[ll]), d.C[ll], kin, L.Rp[ll], L.Kp[ll], ll == 0 ? d.D : -1,
+                        d.use_xyz ? 3 : 0};
+      total += L.Rp[ll] * L.Kp[ll];
+    }
+    LaunchScope ls("convert_weights_kernel", st);
+    v6::convert_weights6_kernel<<<min(ceil_div(total / 8, 256), kNumSMs * 4), 256, 0, st>>>(w[0], w[1], w[2]);
+    PCOE_TRY(ls.done());
+  }
+  auto wh = [&](int l) { return (const __nv_bfloat16*)(ws + L.wb[l]); };
+  auto wps = [&](int l) { return (size_t)L.Rp[l] * L.Kp[l]; };
+  float* ymax = (float*)(ws + L.ymax);
+  float* ymin = (float*)(ws + L.ymin);
+  v6::Group6 eg{}; eg.y = nullptr; eg.sums = nullptr; eg.ymax = ymax; eg.ymin = ymin; eg.amax = (uint8_t*)(ws + L.amax);
+  eg.amin = (uint8_t*)(ws + L.amin); eg.C = CL; eg.gamma = params->gamma[nl - 1];
+  // identity grouping: group_all = 1 makes row r read point r with absolute coordinates
+  v6::GatherFeat6 gp{v4::GatherBase{d.use_xyz ? xyz : feats, nullptr, nullptr, d.rows_per_cloud, 1, 1, M}, feats, d.D, d.use_xyz ? 0 : 1};
+  float* y0 = (float*)(ws + L.y[0]);
+  v6::StoreStats6 e0{}; e0.y = y0; e0.sums = nullptr; e0.C = d.C[0];
+  PCOE_TRY(launch_fwd6(gp, wh(0), wps(0), L.Kp[0], e0, M, d.C[0], st, "pointmlp_l1"));
+  v6::BnRelu6 p1{}; p1.y = y0; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.C = d.C[0];
+  if (nl == 2) {
+    PCOE_TRY(launch_fwd6(p1, wh(1), wps(1), L.Kp[1], eg, M, d.C[1], st, "pointmlp_l2_pool"));
+  } else {
+    float* y1 = (float*)(ws + L.y[1]);
+    v6::StoreStats6 e1{}; e1.y = y1; e1.sums = nullptr; e1.C = d.C[1];
+    PCOE_TRY(launch_fwd6(p1, wh(1), wps(1), L.Kp[1], e1, M, d.C[1], st, "pointmlp_l2"));
+    v6::BnRelu6 p2{}; p2.y = y1; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.C = d.C[1];
+    PCOE_TRY(launch_fwd6(p2, wh(2), wps(2), L.Kp[2], eg, M, d.C[2], st, "pointmlp_l3_pool"));
+  }
+  LaunchScope ls("pm_pool_kernel", st);
+  pm_pool_kernel<<<dim3(ceil_div(CL, 128), M / d.rows_per_cloud), 128, 0, st>>>(ymax, ymin, scale[nl - 1], shift[nl - 1],
+                                                                              d.rows_per_cloud / 32, CL, d.relu_last, out);
+  return ls.done();
+}
+
+// y[m, :] = act(scale * (W x[m, :] + bias) ...) for a narrow input (Cin <= 8): the 3 -> 64 first layer of the PointNet
+// encoder, point-major output for the feature-transform bmm.  One thread per (point, 4 output channels).
+namespace pcoe {
+__global__ void pointwise_linear_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, int M, int Cin, int Cout, int relu, float* __restrict__ y) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = Cout / 4;
+  if (e >= (size_t)M * q) return;
+  const int m = (int)(e / q), c0 = (int)(e % q) * 4;
+  float xin[8];
+  for (int k = 0; k < Cin; ++k) xin[k] = __ldg(x + (size_t)m * Cin + k);
+  float r[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float acc = 0.f;
+    for (int k = 0; k < Cin; ++k) acc = fmaf(__ldg(W + (size_t)(c0 + u) * Cin + k), xin[k], acc);
+    acc = fmaf(acc, scale[c0 + u], shift[c0 + u]);
+    r[u] = relu ? fmaxf(acc, 0.f) : acc;
+  }
+  *reinterpret_cast<float4*>(y + (size_t)m * Cout + c0) = make_float4(r[0], r[1], r[2], r[3]);
+}
+}  // namespace pcoe
+
+extern "C" int pcoe_pointwise_linear_f32(const float* x, int M, int Cin, const float* W, const float* scale, const float* shift,
+                                         int Cout, int relu, float* y, void* stream) {
+  if (M <= 0 || Cin <= 0 || Cout <= 0) return fail(PCOE_ERR_BAD_SHAPE, "pointwise_linear: M=%d Cin=%d Cout=%d", M, Cin, Cout);
+  if (Cin > 8 || Cout % 4 != 0) return fail(PCOE_ERR_UNSUPPORTED, "pointwise_linear: Cin=%d (<= 8), Cout=%d (multiple of 4)", Cin, Cout);
+  if (!x || !W || !scale || !shift || !y) return fail(PCOE_ERR_NULL, "pointwise_linear: NULL pointer");
+  const size_t total = (size_t)M * (Cout / 4);
+  LaunchScope ls("pointwise_linear_kernel", (cudaStream_t)stream);
+  pointwise_linear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, W, scale, shift, M, Cin, Cout, relu, y);
+  return ls.done();
 }

@@ -77,8 +77,8 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], uint32_t s0, u
 }
 
 // fp32 [C_out][C_in] -> three zero-padded bf16 planes [3][Rp][Kp] (hi, mid, lo; the backward kernels read the first
-// two); perm_d >= 0: layer-1 column order [feats(perm_d) | xyz(3)]
-struct ConvW6 { const float* W; __nv_bfloat16* planes; int cout, cin, Rp, Kp, perm_d; };
+// two); perm_d >= 0: layer-1 column order [feats(perm_d) | xyz(xyz_cols)] (xyz_cols = 3, or 0 for a feature-only input)
+struct ConvW6 { const float* W; __nv_bfloat16* planes; int cout, cin, Rp, Kp, perm_d, xyz_cols; };
 __global__ void convert_weights6_kernel(ConvW6 a, ConvW6 b, ConvW6 c) {
   const ConvW6* L[3] = {&a, &b, &c};
   const int n0 = a.Rp * a.Kp / 8, n1 = b.Rp * b.Kp / 8, n2 = c.Rp * c.Kp / 8;
@@ -92,7 +92,7 @@ __global__ void convert_weights6_kernel(ConvW6 a, ConvW6 b, ConvW6 c) {
     for (int u = 0; u < 8; ++u) {
       const int k = k0 + u;
       int src = k;
-      if (w.perm_d >= 0) src = k < w.perm_d ? k + 3 : (k < w.perm_d + 3 ? k - w.perm_d : w.cin);
+      if (w.perm_d >= 0) src = k < w.perm_d ? k + w.xyz_cols : (k < w.perm_d + w.xyz_cols ? k - w.perm_d : w.cin);
       v[u] = (r < w.cout && src < w.cin) ? __ldg(w.W + (size_t)r * w.cin + src) : 0.f;
     }
     uint4 h, m, lo;
@@ -318,8 +318,9 @@ struct GatherFeat6 {
   GatherBase gb;
   const float* __restrict__ feats;
   int D;
+  int no_xyz;                         // 1: feature-only input (pointwise MLP stacks): the xyz block does not exist
   __host__ __device__ __forceinline__ int nconst() const { return 0; }
-  __host__ __device__ __forceinline__ int nchunks() const { return D / 64 + 1; }
+  __host__ __device__ __forceinline__ int nchunks() const { return D / 64 + (no_xyz ? 0 : 1); }
   __host__ __device__ __forceinline__ int chunk_k(int kb) const { return kb < D / 64 ? 64 : 16; }
   __device__ __forceinline__ void init(float*, int, int) {}
   template <int PTS>

@@ -100,6 +100,19 @@ def random_subset(B: int, N: int, S: int, seed: int, offset: int, device,
 # ------------------------------------------------------------------------------------------------
 # grouping
 # ------------------------------------------------------------------------------------------------
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """(B,N,C),(B,M,C) -> (B,N,M) f32.  Reference: models/base.py:20-27."""
+    src = _req(src, torch.float32, "src")
+    dst = _req(dst, torch.float32, "dst")
+    if src.dim() != 3 or dst.dim() != 3 or src.size(0) != dst.size(0) or src.size(2) != dst.size(2):
+        raise ValueError(f"square_distance: src {tuple(src.shape)} / dst {tuple(dst.shape)}")
+    B, N, Cc = src.shape
+    M = dst.size(1)
+    out = torch.empty(B, N, M, dtype=torch.float32, device=src.device)
+    _lib.check(_lib.load().pcoe_square_distance_f32(src.data_ptr(), dst.data_ptr(), B, N, M, Cc, out.data_ptr(), _stream()))
+    return out
+
+
 def knn_int32(new_xyz: torch.Tensor, xyz: torch.Tensor, nsample: int) -> torch.Tensor:
     new_xyz = _req(new_xyz, torch.float32, "new_xyz")
     xyz = _req(xyz, torch.float32, "xyz")
@@ -122,6 +135,24 @@ def ball_query_int32(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: to
     _lib.check(_lib.load().pcoe_ball_query_f32(xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, nsample,
                                                float(radius), out.data_ptr(), _stream()))
     return out
+
+
+def ball_query_multi_int32(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor):
+    """Multi-scale radius grouping in one launch: list of (B,S,nsample_r) int32, row r == ball_query_int32(radii[r],
+    nsamples[r], ...) bit for bit (query_ball_point, PointNet++Demo.py:49-70, per scale)."""
+    new_xyz = _req(new_xyz, torch.float32, "new_xyz")
+    xyz = _req(xyz, torch.float32, "xyz")
+    if len(radii) != len(nsamples) or not 1 <= len(radii) <= 4:
+        raise ValueError("ball_query_multi: 1..4 (radius, nsample) pairs")
+    B, N, _ = xyz.shape
+    S = new_xyz.size(1)
+    n = len(radii)
+    outs = [torch.empty(B, S, int(k), dtype=torch.int32, device=xyz.device) for k in nsamples]
+    r = (C.c_double * n)(*[float(x) for x in radii])
+    k = (C.c_int * n)(*[int(x) for x in nsamples])
+    o = (C.c_void_p * n)(*[t.data_ptr() for t in outs])
+    _lib.check(_lib.load().pcoe_ball_query_multi_f32(xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, n, r, k, o, _stream()))
+    return outs
 
 
 def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:

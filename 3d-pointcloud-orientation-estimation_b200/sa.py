@@ -51,12 +51,9 @@ def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 
 def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
-    """(B,N,M) squared distances.  Reference: models/base.py:20-27.  Kept for API completeness
-    (device torch ops); the hot path never materialises this matrix."""
-    dist = -2 * torch.matmul(src, dst.transpose(2, 1))
-    dist += torch.sum(src ** 2, dim=-1).unsqueeze(-1)
-    dist += torch.sum(dst ** 2, dim=-1).unsqueeze(1)
-    return dist
+    """(B,N,M) squared distances, ``-2 src.dst + |src|^2 + |dst|^2``.  Reference: models/base.py:20-27.
+    One libpcoe kernel (the matrix is written once); the hot path itself never materialises it."""
+    return ops.square_distance(src, dst)
 
 
 def query_ball_point(new_xyz: torch.Tensor, xyz: torch.Tensor, nsample: int) -> torch.Tensor:
@@ -96,9 +93,14 @@ class _SAFunction(torch.autograd.Function):
         D = 0 if feats is None else feats.size(2)
         Ws, bs, gs, bes = params[0::4], params[1::4], params[2::4], params[3::4]
         train = module.training
+        precision = module.precision
+        if precision == "bf16x3" and not (K == 32 and D % 64 == 0 and all(w.size(0) % 64 == 0 for w in Ws)):
+            # group sizes / widths the split-operand tcgen05 kernels do not cover run on the fp32 CUDA-core kernels
+            # (same accuracy class, still libpcoe on the GPU)
+            precision = "fp32"
         desc = _lib.SADesc(B=B, N=N, S=S, K=K, D=D, C1=Ws[0].size(0), C2=Ws[1].size(0), C3=Ws[2].size(0),
                            group_all=int(group_all), train=int(train),
-                           precision=PRECISIONS[module.precision],
+                           precision=PRECISIONS[precision],
                            eps=module.bns[0].eps, momentum=module.bns[0].momentum or 0.1)
         P = _lib.SAParams()
         _fill3(P.W, Ws); _fill3(P.bias, bs); _fill3(P.gamma, gs); _fill3(P.beta, bes)

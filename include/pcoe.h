@@ -103,6 +103,14 @@ int pcoe_random_subset_xyz(int B, int N, int S, uint64_t seed, uint64_t offset,
  * Grouping
  * ------------------------------------------------------------------------------------------ */
 
+/* Pairwise squared distances.  Replaces square_distance(src, dst), models/base.py:20-27:
+ *   out[b,i,j] = -2 <src[b,i], dst[b,j]> + |src[b,i]|^2 + |dst[b,j]|^2   (the reference's expanded form, fp32; like the
+ *   reference's it can be slightly negative for coincident points).  src [B,N,C], dst [B,M,C] -> out [B,N,M] f32.
+ * The hot path never materialises this matrix (pcoe_knn_f32 fuses it with the selection); this entry point exists for
+ * callers of the helper itself. */
+int pcoe_square_distance_f32(const float* src, const float* dst, int B, int N, int M, int C, float* out,
+                             void* stream);
+
 /* k nearest neighbours of every centroid.  Replaces query_ball_point(new_xyz, xyz, nsample) =
  * square_distance + topk(largest=False, sorted=False), models/base.py:20-35.
  *   xyz [B,N,3] f32, new_xyz [B,S,3] f32 -> out_idx [B,S,K] i32.
@@ -119,6 +127,15 @@ int pcoe_knn_f32(const float* xyz, const float* new_xyz, int B, int N, int S, in
  * Distances as in pcoe_fps_f32 (bit-exact contract).  out_idx [B,S,nsample] i32. */
 int pcoe_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N, int S, int nsample,
                         double radius, int32_t* out_idx, void* stream);
+
+/* Multi-scale (MSG-style) radius grouping: pcoe_ball_query_f32 for `nscales` (1..4) radii in one pass over the cloud
+ * (the cloud is staged in shared memory once, every squared distance is computed once and compared with every radius).
+ * out_idx_host[r] -> [B,S,nsample_host[r]] i32 device buffers; row r is bit-identical to
+ * pcoe_ball_query_f32(radius_host[r], nsample_host[r]).  Built from query_ball_point, PointNet++Demo.py:49-70, applied
+ * per scale.  The three `_host` arrays are HOST arrays of length nscales. */
+int pcoe_ball_query_multi_f32(const float* xyz, const float* new_xyz, int B, int N, int S, int nscales,
+                              const double* radius_host, const int* nsample_host, int32_t* const* out_idx_host,
+                              void* stream);
 
 /* --------------------------------------------------------------------------------------------
  * Set abstraction: gather + centre + 3 x (1x1 conv -> BatchNorm -> ReLU) + max over neighbours
@@ -198,6 +215,40 @@ int pcoe_sa_backward(const pcoe_sa_desc* desc, const float* xyz, const float* ne
                      const float* out, const float* grad_out, const void* saved,
                      size_t saved_bytes, float* grad_feats, const pcoe_sa_grads* grads,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Vanilla PointNet inference path (models/pointnet.py:6-129, eval mode)
+ * ------------------------------------------------------------------------------------------ */
+
+/* A pointwise MLP stack followed by the max over each cloud's points:
+ *     h = x;  for l < nlayers: h = BN_eval_l(W_l h + b_l), ReLU after every layer except - when relu_last == 0 - the last;
+ *     out[b, :] = max over the rows of cloud b of h
+ * i.e. STN3d / STNkd's conv1..3 + bn1..3 + torch.max (models/pointnet.py:24-27 / :55-58) and PointNetEncoder's
+ * conv1..3 + bn1..3 + torch.max (:93,102-104; bn3 without ReLU).  Same split-operand tcgen05 kernels as
+ * PCOE_PRECISION_BF16X3 set abstraction (24-bit operands, fp32 accumulate).
+ *   M              rows = clouds * rows_per_cloud;  rows_per_cloud must be a multiple of 32 (pad a cloud by repeating
+ *                  one of its points: the max does not change)
+ *   use_xyz, D     first-layer input = [xyz (3, when use_xyz) | feats (D)], D a multiple of 64 (0 allowed with use_xyz);
+ *                  W[0] is [C[0]][3*use_xyz + D] row-major in that column order
+ *   nlayers        2 or 3;  C[l] multiples of 64
+ *   params         W / bias / gamma / beta / running_mean / running_var of layers 0..nlayers-1 (bias entries may be NULL)
+ *   xyz [M,3], feats [M,D] f32 point-major;  out [M / rows_per_cloud, C[nlayers-1]] f32 */
+typedef struct pcoe_pointmlp_desc {
+  int32_t M, rows_per_cloud, D, use_xyz, nlayers;
+  int32_t C[3];
+  int32_t relu_last;
+  float eps;
+} pcoe_pointmlp_desc;
+size_t pcoe_pointmlp_workspace_bytes(const pcoe_pointmlp_desc* desc);
+int pcoe_pointmlp_forward(const pcoe_pointmlp_desc* desc, const float* xyz, const float* feats,
+                          const pcoe_sa_params* params, float* out, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* y[m,:] = act(scale * (W x[m,:]) + shift) for a narrow input: x [M,Cin] (Cin <= 8), W [Cout,Cin], per-channel
+ * scale / shift (BatchNorm eval folded with the conv bias), Cout a multiple of 4, y [M,Cout] point-major.  The 3 -> 64
+ * first layer of PointNetEncoder (models/pointnet.py:93) when its output feeds the feature transform. */
+int pcoe_pointwise_linear_f32(const float* x, int M, int Cin, const float* W, const float* scale, const float* shift,
+                              int Cout, int relu, float* y, void* stream);
 
 /* --------------------------------------------------------------------------------------------
  * Losses (value and gradient in one launch; gradients are d loss[b] / d input[b,...])

@@ -30,11 +30,14 @@ def knn_indices(new_xyz: torch.Tensor, xyz: torch.Tensor, k: int) -> torch.Tenso
 
 def set_abstraction(sd: dict, prefix: str, xyz: torch.Tensor, points, *, group_all: bool, nsample=None,
                     fps_idx=None, group_idx=None, training: bool = True, update_buffers: bool = True,
-                    eps: float = 1e-5, momentum: float = 0.1):
+                    eps: float = 1e-5, momentum: float = 0.1, names=("convs", "bns")):
     """One SA layer.  Follows PointNetSetAbstraction.forward, models/pointnet_pp_8dir.py:21-43.
     ``fps_idx`` (B,S) must be given for a non-global layer (the reference draws it from the CPU
     generator, :28 - see sampling.randperm_subset_replay); ``group_idx`` (B,S,K) overrides the kNN.
+    ``names`` = attribute names of the conv / BatchNorm lists (("mlp_convs", "mlp_bns") for PointNet++Demo.py's
+    SimpleSetAbstraction, whose MLP / pooling arithmetic :119-127 is the same).
     Returns (new_xyz, new_points, group_idx)."""
+    cn, bn_ = names
     B = xyz.shape[0]
     if group_all:
         new_xyz = torch.zeros(B, 1, 3, dtype=xyz.dtype)
@@ -50,18 +53,58 @@ def set_abstraction(sd: dict, prefix: str, xyz: torch.Tensor, points, *, group_a
             rows = torch.cat([rows, gather(points, group_idx)], -1)              # :34-35
     x = rows                                                                     # (B,S,K,C) channels last
     for l in range(3):
-        W = sd[f"{prefix}.convs.{l}.weight"].reshape(-1, x.shape[-1])            # (Cout,Cin,1,1)
-        x = x @ W.t() + sd[f"{prefix}.convs.{l}.bias"]                           # 1x1 conv, :41
-        rm, rv = sd[f"{prefix}.bns.{l}.running_mean"], sd[f"{prefix}.bns.{l}.running_var"]
+        W = sd[f"{prefix}.{cn}.{l}.weight"].reshape(-1, x.shape[-1])            # (Cout,Cin,1,1)
+        x = x @ W.t() + sd[f"{prefix}.{cn}.{l}.bias"]                           # 1x1 conv, :41
+        rm, rv = sd[f"{prefix}.{bn_}.{l}.running_mean"], sd[f"{prefix}.{bn_}.{l}.running_var"]
         if not update_buffers:
             rm, rv = rm.clone(), rv.clone()
         flat = x.reshape(-1, x.shape[-1])
-        flat = F.batch_norm(flat, rm, rv, sd[f"{prefix}.bns.{l}.weight"], sd[f"{prefix}.bns.{l}.bias"],
+        flat = F.batch_norm(flat, rm, rv, sd[f"{prefix}.{bn_}.{l}.weight"], sd[f"{prefix}.{bn_}.{l}.bias"],
                             training, momentum, eps)
         if training and update_buffers:
-            sd[f"{prefix}.bns.{l}.num_batches_tracked"] += 1
+            sd[f"{prefix}.{bn_}.{l}.num_batches_tracked"] += 1
         x = F.relu(flat).reshape(x.shape)
     return new_xyz, x.max(dim=2).values, group_idx                               # :42-43
+
+
+def ssg_layer(sd: dict, prefix: str, xyz, points, fps_idx, radius: float, nsample: int, training=True,
+              update_buffers=True, names=("mlp_convs", "mlp_bns")):
+    """SimpleSetAbstraction.forward, PointNet++Demo.py:96-129, channels-last: xyz (B,N,3), points (B,N,D) or None,
+    fps_idx (B,S) from the FPS oracle (:106), radius ball query (:109) from oracle.sampling.ball_query.
+    Returns (new_xyz (B,S,3), new_points (B,S,C), group_idx)."""
+    from . import sampling
+    new_xyz = gather(xyz, fps_idx)
+    gi = torch.from_numpy(sampling.ball_query(radius, nsample, xyz.detach().float().numpy(), new_xyz.detach().float().numpy()))
+    return set_abstraction(sd, prefix, xyz, points, group_all=False, fps_idx=fps_idx, group_idx=gi, training=training,
+                           update_buffers=update_buffers, names=names)
+
+
+def msg_layer(sd: dict, prefix: str, xyz, points, fps_idx, radii, nsamples, training=True, update_buffers=True):
+    """Multi-scale grouping: ssg_layer per (radius, nsample) on shared centroids, parameters under
+    ``{prefix}.conv_blocks.{i}`` / ``{prefix}.bn_blocks.{i}``, outputs concatenated along channels."""
+    outs = []
+    for i, (r, k) in enumerate(zip(radii, nsamples)):
+        sub = {}
+        for key, v in sd.items():
+            if key.startswith(f"{prefix}.conv_blocks.{i}."):
+                sub["b.mlp_convs." + key[len(f"{prefix}.conv_blocks.{i}."):]] = v
+            elif key.startswith(f"{prefix}.bn_blocks.{i}."):
+                sub["b.mlp_bns." + key[len(f"{prefix}.bn_blocks.{i}."):]] = v
+        new_xyz, o, _ = ssg_layer(sub, "b", xyz, points, fps_idx, r, k, training, update_buffers)
+        outs.append(o)
+    return new_xyz, torch.cat(outs, dim=-1)
+
+
+def ssg_cls_forward(sd: dict, x_cf: torch.Tensor, fps1, fps2, training=True, update_buffers=True, normal_channel=True):
+    """PointNetPlusPlusCls.forward, PointNet++Demo.py:212-240 (dropout as identity): x (B,C,N) channel-first."""
+    xyz = x_cf[:, :3].transpose(1, 2)
+    pts = x_cf[:, 3:].transpose(1, 2) if normal_channel else None
+    l1_xyz, l1, _ = ssg_layer(sd, "sa1", xyz, pts, fps1, 0.2, 32, training, update_buffers)
+    l2_xyz, l2, _ = ssg_layer(sd, "sa2", l1_xyz, l1, fps2, 0.4, 64, training, update_buffers)
+    _, l3, _ = set_abstraction(sd, "sa3", l2_xyz, l2, group_all=True, training=training, update_buffers=update_buffers,
+                               names=("mlp_convs", "mlp_bns"))
+    h = _bn_trunk(sd, l3.reshape(x_cf.shape[0], -1), training, update_buffers)
+    return F.log_softmax(h @ sd["fc3.weight"].t() + sd["fc3.bias"], dim=1)
 
 
 def sa_features(sd: dict, xyz: torch.Tensor, fps1, fps2, training=True, update_buffers=True, record=None):

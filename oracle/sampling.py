@@ -53,6 +53,17 @@ def ball_query(radius: float, nsample: int, xyz: np.ndarray, new_xyz: np.ndarray
     return out
 
 
+def square_distance(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
+    """(B,N,M) fp32.  Follows square_distance, models/base.py:20-27: -2 src @ dst^T, + sum(src^2), + sum(dst^2), in
+    that order, every step in fp32 (the matmul's internal summation order is the BLAS's: compare to ~1e-6)."""
+    src = np.asarray(src, dtype=np.float32)
+    dst = np.asarray(dst, dtype=np.float32)
+    d = np.float32(-2.0) * np.matmul(src, dst.transpose(0, 2, 1))
+    d = d + (src ** 2).sum(-1)[:, :, None]
+    d = d + (dst ** 2).sum(-1)[:, None, :]
+    return d.astype(np.float32)
+
+
 def knn(new_xyz: np.ndarray, xyz: np.ndarray, nsample: int):
     """k nearest neighbours as SETS.  Follows query_ball_point, models/base.py:29-35
     (square_distance :20-27 + topk(largest=False, sorted=False)).  The reference's row order is

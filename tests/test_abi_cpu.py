@@ -46,6 +46,21 @@ def test_argument_errors_without_gpu(pcoe):
                                               None, 3, None, None, None, None, 4, 0.7, 80.0, 1, None, None, None, None) == L.ERR_BAD_SHAPE
     assert lib.pcoe_heads_ln_relu_dropout_bwd(None, 4, 0.7, 80.0, 1, None, None, None, None, 3, None, None, None, None, None,
                                               None, None, None, 8, 256, 0.1, 1, None, None, None, None, None) == L.ERR_NULL
+    # round-2 entry points: square_distance, multi-scale ball query, pointwise MLP stack (vanilla PointNet)
+    import ctypes as C
+    assert lib.pcoe_square_distance_f32(None, None, 1, 0, 4, 3, None, None) == L.ERR_BAD_SHAPE
+    assert lib.pcoe_square_distance_f32(None, None, 1, 4, 4, 3, None, None) == L.ERR_NULL
+    r, k, o = (C.c_double * 5)(*[0.1] * 5), (C.c_int * 5)(*[8] * 5), (C.c_void_p * 5)()
+    assert lib.pcoe_ball_query_multi_f32(None, None, 1, 64, 4, 5, r, k, o, None) == L.ERR_UNSUPPORTED    # > 4 scales
+    assert lib.pcoe_ball_query_multi_f32(None, None, 1, 64, 4, 2, r, k, o, None) == L.ERR_NULL
+    pd = L.PointMlpDesc(M=2048, rows_per_cloud=1024, D=0, use_xyz=1, nlayers=3, C=(C.c_int32 * 3)(64, 128, 1024), relu_last=1, eps=1e-5)
+    assert lib.pcoe_pointmlp_workspace_bytes(C.byref(pd)) > 2048 * (64 + 128) * 4
+    pd.rows_per_cloud = 1000                                                  # not a multiple of 32 / does not divide M
+    assert lib.pcoe_pointmlp_workspace_bytes(C.byref(pd)) == 0
+    assert lib.pcoe_pointmlp_forward(C.byref(pd), None, None, None, None, None, 0, None) == L.ERR_BAD_SHAPE
+    pd.rows_per_cloud, pd.nlayers = 1024, 4
+    assert lib.pcoe_pointmlp_forward(C.byref(pd), None, None, None, None, None, 0, None) == L.ERR_UNSUPPORTED
+    assert lib.pcoe_pointwise_linear_f32(None, 8, 9, None, None, None, 64, 1, None, None) == L.ERR_UNSUPPORTED
     with pytest.raises(ValueError):
         L.check(L.ERR_BAD_SHAPE)
     with pytest.raises(NotImplementedError):
