@@ -1,5 +1,5 @@
 """B200-native PointNet++ set-abstraction hot path (drop-in for the reference's models/*.py)."""
-from . import _lib, ops, losses, sa, models, synthetic, dp, graph, optim, trunk, ssg_msg, pointnet  # noqa: F401
+from . import _lib, ops, losses, sa, models, synthetic, dp, graph, optim, trunk, ssg_msg, pointnet, data  # noqa: F401
 from .sa import (PointNetSetAbstraction, index_points, square_distance, query_ball_point,  # noqa: F401
                  set_default_precision, get_default_precision)
 from .models import (DIRS_8, PointNetPP8Dir, PointNetPPVonMises, PointNetPPMvM, PointNetPPXYZ,  # noqa: F401

@@ -67,6 +67,7 @@ SIGNATURES = {
     "pcoe_pointmlp_workspace_bytes": (_SZ, [C.POINTER(PointMlpDesc)]),
     "pcoe_pointmlp_forward": (_I, [C.POINTER(PointMlpDesc), _P, _P, C.POINTER(SAParams), _P, _P, _SZ, _P]),
     "pcoe_pointwise_linear_f32": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P, _P]),
+    "pcoe_resample_clouds_f32": (_I, [_P, _P, _I, _P, _I, _I, _U64, _U64, _P, _P, _P, _P]),
     "pcoe_vm_kl_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "pcoe_mvm_match_fwd_bwd": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pcoe_soft_ce_fwd_bwd": (_I, [_P, _P, _I, _I, _P, _P, _P]),

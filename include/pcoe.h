@@ -251,6 +251,22 @@ int pcoe_pointwise_linear_f32(const float* x, int M, int Cin, const float* W, co
                               int Cout, int relu, float* y, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Device-side input pipeline
+ * ------------------------------------------------------------------------------------------ */
+
+/* Builds a batch from a dataset resident in HBM: cloud `cloud_ids[b]` (rows offsets[c] .. offsets[c+1] of `points`) is
+ * resampled to `num` points.  Replaces sample_pts(arr, num) = arr[np.random.choice(len(arr), num, replace=len(arr) < num)]
+ * (dataloader_multi_peak_vonMises.py:21-26, dataloader_8dir_sampled.py:13-15, dataloader_single_peak_vonMises.py:12-14):
+ * n >= num -> uniform subset without replacement (ascending source order), n < num -> uniform draws with replacement;
+ * same distribution as numpy's, another random stream (keyed by seed and base_draw + *counter_dev * B + b, so a CUDA-graph
+ * replay that increments the counter draws fresh subsets).  Deterministic; oracle/data.py reproduces the indices.
+ *   points [total,3] f32, offsets [nclouds+1] i64, cloud_ids [B] i32 (values in [0,nclouds)),
+ *   out_xyz [B,num,3] f32, out_idx [B,num] i32 source row inside the cloud (may be NULL), counter_dev may be NULL. */
+int pcoe_resample_clouds_f32(const float* points, const int64_t* offsets, int nclouds, const int32_t* cloud_ids,
+                             int B, int num, uint64_t seed, uint64_t base_draw, const uint64_t* counter_dev,
+                             float* out_xyz, int32_t* out_idx, void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * Losses (value and gradient in one launch; gradients are d loss[b] / d input[b,...])
  * ------------------------------------------------------------------------------------------ */
 
