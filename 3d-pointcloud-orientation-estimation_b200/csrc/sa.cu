@@ -424,14 +424,14 @@ static Cfg6 cfg6(int nk, int ncb, int ntiles, size_t cbytes, int np) {
 }
 
 constexpr int kFwdPlanes6 = 3;   // forward operands keep all 24 significant bits (6 MMAs per step), backward 16 (3 MMAs)
-template <class Prod, class Epi>
+template <int NP = kFwdPlanes6, class Prod, class Epi>
 static int launch_fwd6(const Prod& prod, const __nv_bfloat16* Wp, size_t wps, int Kp, const Epi& epi, int M,
                        int Cout, cudaStream_t st, const char* what) {
   const size_t cbytes = sizeof(float) * (size_t)(prod.nconst() + epi.nconst()) + 512;
   const int ncb = ceil_div(Cout, 128);
-  const Cfg6 c = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes, kFwdPlanes6);
+  const Cfg6 c = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes, NP);
   if (c.nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
-  auto k = v6::x3_fwd_kernel<Prod, Epi, kFwdPlanes6>;
+  auto k = v6::x3_fwd_kernel<Prod, Epi, NP>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
   LaunchScope ls(what, st);
@@ -984,6 +984,9 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
 // split-operand tcgen05 forward kernels (sa_tc6.cuh) over all M = clouds * points rows with the identity grouping
 // (row = point, blocks of 32 consecutive points pooled by the last layer's epilogue), then reduces the blocks of a cloud.
 // ---------------------------------------------------------------------------------------------------------------
+// Inference has no gradient routing to protect (the max pool is continuous in the activations): two bf16 planes per operand
+// (16 significant bits, 3 MMAs per product, 2^-16 relative per product) instead of the training forward's three planes.
+constexpr int kPmPlanes = 2;
 struct PmLayout {
   int nl, M, G, Cin0, Kp[3], Rp[3];
   size_t y[2], stat[3], ymax, ymin, amax, amin, wb[3], total;
@@ -1172,16 +1175,16 @@ extern "C" int pcoe_pointmlp_forward(const pcoe_pointmlp_desc* desc, const float
   v6::GatherFeat6 gp{v4::GatherBase{d.use_xyz ? xyz : feats, nullptr, nullptr, d.rows_per_cloud, 1, 1, M}, feats, d.D, d.use_xyz ? 0 : 1};
   float* y0 = (float*)(ws + L.y[0]);
   v6::StoreStats6 e0{}; e0.y = y0; e0.sums = nullptr; e0.C = d.C[0];
-  PCOE_TRY(launch_fwd6(gp, wh(0), wps(0), L.Kp[0], e0, M, d.C[0], st, "pointmlp_l1"));
+  PCOE_TRY(launch_fwd6<kPmPlanes>(gp, wh(0), wps(0), L.Kp[0], e0, M, d.C[0], st, "pointmlp_l1"));
   v6::BnRelu6 p1{}; p1.y = y0; p1.scale = scale[0]; p1.shift = shift[0]; p1.M = M; p1.C = d.C[0];
   if (nl == 2) {
-    PCOE_TRY(launch_fwd6(p1, wh(1), wps(1), L.Kp[1], eg, M, d.C[1], st, "pointmlp_l2_pool"));
+    PCOE_TRY(launch_fwd6<kPmPlanes>(p1, wh(1), wps(1), L.Kp[1], eg, M, d.C[1], st, "pointmlp_l2_pool"));
   } else {
     float* y1 = (float*)(ws + L.y[1]);
     v6::StoreStats6 e1{}; e1.y = y1; e1.sums = nullptr; e1.C = d.C[1];
-    PCOE_TRY(launch_fwd6(p1, wh(1), wps(1), L.Kp[1], e1, M, d.C[1], st, "pointmlp_l2"));
+    PCOE_TRY(launch_fwd6<kPmPlanes>(p1, wh(1), wps(1), L.Kp[1], e1, M, d.C[1], st, "pointmlp_l2"));
     v6::BnRelu6 p2{}; p2.y = y1; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.C = d.C[1];
-    PCOE_TRY(launch_fwd6(p2, wh(2), wps(2), L.Kp[2], eg, M, d.C[2], st, "pointmlp_l3_pool"));
+    PCOE_TRY(launch_fwd6<kPmPlanes>(p2, wh(2), wps(2), L.Kp[2], eg, M, d.C[2], st, "pointmlp_l3_pool"));
   }
   LaunchScope ls("pm_pool_kernel", st);
   pm_pool_kernel<<<dim3(ceil_div(CL, 128), M / d.rows_per_cloud), 128, 0, st>>>(ymax, ymin, scale[nl - 1], shift[nl - 1],

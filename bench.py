@@ -38,12 +38,14 @@ CONFIGS = {  # name -> (kind, model class, clouds per GPU, points)
     "c2": ("mvm", "PointNetPPMvM", 64, 1024),
     "c3": ("8dir", "PointNetPP8Dir", 32, 2048),
     "c4": ("xyz", "PointNetPPXYZ", 32, 8192),
+    "c5": ("pointnet", "PointNet", 1024, 1024),       # inference sweep B = 1 .. 1024 (BASELINE configs[4])
 }
 WORKLOAD_NAMES = {
     "c1": "PointNet++ SSG single-peak von Mises KL head, 16 x 1024 pts per GPU, train step",
     "c2": "PointNet++ multi-peak mvM KL head (pointnet_pp_mvM.py), 64 x 1024 pts per GPU, train step",
     "c3": "PointNet++ 8-direction head, 32 x 2048 pts per GPU, train step",
     "c4": "Pointnet_pp_xyz at 8192 pts/cloud, 32 clouds per GPU, train step",
+    "c5": "PointNet vanilla (models/pointnet.py) inference sweep batch 1-1024 x 1024 pts, eval forward",
 }
 
 
@@ -151,6 +153,68 @@ def kernel_work(B: int, N: int, precision: str = "bf16") -> dict:
     w["random_subset_kernel"] = (0.0, float(sum(B * 4 * s[6] for s in sh[:2])))
     w["gather_points_kernel"] = (0.0, float(sum(B * (4 * s[6] + 24 * s[6]) for s in sh[:2])))
     return w
+
+
+def sampling_grouping_leg(pcoe, torch, dev, B, N, peaks, flush, iters=20):
+    """Stand-alone timing of the sampling / grouping / gather kernels at this config's shapes (north star: 'achieved HBM
+    GB/s for FPS / ball-query / gather').  Each kernel: `iters` launches, CUDA-event pair per launch, L2 flushed between
+    launches; bytes = SURVEY 8(d)'s algorithmic bytes per cloud x B (fp32 xyz, int32 indices, no re-reads).  FPS is
+    latency-bound by construction (S dependent arg-max steps per cloud), kNN / ball query are instruction-bound
+    (S*N distance evaluations + selection per cloud against ~50 KB of compulsory traffic): the HBM fraction is reported as
+    the north star asks, next to the instruction-side figure (distance evaluations per second)."""
+    xyz = pcoe.synthetic.clouds(7, B, N).to(dev)
+    S1, K = 128, 32
+    start = torch.zeros(B, dtype=torch.int32, device=dev)
+    fps_idx, new_xyz = pcoe.ops.farthest_point_sample(xyz, S1, start, return_xyz=True, int32=True)
+    l1_xyz = new_xyz
+    feats = torch.randn(B, S1, 128, device=dev)
+    idx2 = fps_idx[:, :32].clamp(max=S1 - 1).contiguous()
+    nbr = pcoe.ops.knn_int32(new_xyz, xyz, K)
+    out = {}
+
+    def timed(name, fn, nbytes, evals=None, note=None):
+        fn(); torch.cuda.synchronize()
+        ms = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        ms.sort()
+        t = ms[len(ms) // 2] * 1e-3
+        ent = {"us": t * 1e6, "algorithmic_bytes": nbytes, "gbs": nbytes / t / 1e9, "hbm_frac": nbytes / t / 1e9 / peaks["hbm"]}
+        if evals:
+            ent["distance_evals_per_s"] = evals / t
+        if note:
+            ent["note"] = note
+        out[name] = ent
+
+    timed(f"fps N={N} S={S1}", lambda: pcoe.ops.farthest_point_sample(xyz, S1, start, return_xyz=True, int32=True),
+          B * (12 * N + 16 * S1), evals=B * S1 * N, note="latency-bound: S dependent block-wide arg-max steps per cloud")
+    timed("fps N=128 S=32", lambda: pcoe.ops.farthest_point_sample(l1_xyz, 32, start, return_xyz=True, int32=True),
+          B * (12 * 128 + 16 * 32), evals=B * 32 * 128)
+    timed(f"knn N={N} S={S1} K={K}", lambda: pcoe.ops.knn_int32(new_xyz, xyz, K), B * (12 * N + 12 * S1 + 4 * S1 * K),
+          evals=B * S1 * N, note="instruction-bound: S*N distance evaluations + exact K-selection per cloud")
+    timed(f"ball_query N={N} S={S1} K={K} r=0.2", lambda: pcoe.ops.ball_query_int32(0.2, K, xyz, new_xyz),
+          B * (12 * N + 12 * S1 + 4 * S1 * K), evals=B * S1 * N)
+    timed(f"ball_query_multi N={N} S={S1} r=(0.1,0.2,0.4) K=(16,32,128)",
+          lambda: pcoe.ops.ball_query_multi_int32([0.1, 0.2, 0.4], [16, 32, 128], xyz, new_xyz),
+          B * (12 * N + 12 * S1 + 4 * S1 * (16 + 32 + 128)), evals=B * S1 * N)
+    timed(f"gather_points xyz S={S1}", lambda: pcoe.ops.gather_points(xyz, fps_idx), B * (4 * S1 + 24 * S1))
+    timed("gather_points feats (B,128,128)->(B,32,128)", lambda: pcoe.ops.gather_points(feats, idx2), B * (4 * 32 + 2 * 512 * 32))
+    grouped_idx = nbr.reshape(B, S1 * K)
+    timed(f"gather_points grouped xyz (B,{S1}*{K},3)", lambda: pcoe.ops.gather_points(xyz, grouped_idx),
+          B * (4 * S1 * K + 12 * N + 12 * S1 * K), note="the stand-alone grouped gather the fused SA kernels avoid")
+    timed(f"square_distance ({S1} x {N})", lambda: pcoe.square_distance(new_xyz, xyz), B * (12 * N + 12 * S1 + 4 * S1 * N),
+          note="write-bound: the (B,S,N) matrix once; the hot path never materialises it")
+    sizes = [N * 4] * B
+    cache = pcoe.data.PointCloudCache.from_arrays([pcoe.synthetic.clouds(9, 1, n)[0].numpy() for n in sizes],
+                                                 torch.zeros(B, 2).numpy(), kind="vm", device=dev)
+    ids = torch.arange(B, device=dev)
+    timed(f"resample_clouds n={4 * N}->{N}", lambda: cache.batch(ids, N, seed=1, draw=0), B * (12 * N + 12 * N),
+          note="device input pipeline: exact uniform subset per cloud (5 hash passes over n keys + ordered compaction)")
+    return out
 
 
 def load_traffic() -> dict:
@@ -474,6 +538,10 @@ def run_ours(args):
             modes[prec] = {"value": B / (ms2 / 1e3), "ms_per_step": ms2, "steps": n2, "mode": how + ", no L2 flush"}
             del m2, eng2, opt2
 
+    sg = None
+    if rank == 0 and world == 1 and not args.no_sampling_leg:
+        sg = sampling_grouping_leg(pcoe, torch, dev, B, N, peaks, flush)
+
     if rank == 0:
         line = {
             "metric": "train clouds/sec (1024 pts, fwd+bwd)", "value": value, "unit": "clouds/s", "n_gpus": world,
@@ -501,6 +569,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "gpu_launches_per_step": launches / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "modes": modes, "kernels": kernels,
+            "sampling_grouping": sg,
             "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps,
             "grad_allreduce_bytes": engine.grads.nbytes() if world > 1 else 0,
         }
@@ -517,6 +586,179 @@ def run_ours(args):
         os._exit(0)
 
 
+# ------------------------------------------------------------------------------------------------
+# c5: vanilla PointNet inference sweep (BASELINE configs[4]; not the headline metric - run with --config c5)
+# ------------------------------------------------------------------------------------------------
+def _pointnet_model(pcoe, torch):
+    torch.manual_seed(1000)
+    model = pcoe.PointNet(feature_transform=True)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():                                  # a trained checkpoint's BatchNorm state, not the identity
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.2, generator=g)
+                m.running_var.uniform_(0.5, 1.5, generator=g)
+                m.weight.uniform_(0.5, 1.5, generator=g)
+                m.bias.uniform_(-0.3, 0.3, generator=g)
+    return model.eval()
+
+
+def run_pointnet_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    import pcoe
+    from oracle import pointnet_torch, sa_torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = sa_torch.clone_state(_pointnet_model(pcoe, torch).state_dict())
+    Bc = 64
+    x = pcoe.synthetic.clouds(5, Bc, 1024)
+    with torch.no_grad():
+        for _ in range(max(1, args.warmup)):
+            pointnet_torch.pointnet_forward(sd, x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pointnet_torch.pointnet_forward(sd, x)
+        dt = time.perf_counter() - t0
+    v = Bc * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "inference clouds/sec (PointNet, 1024 pts, eval forward)", "value": v, "unit": "clouds/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES["c5"], "clouds_per_step": Bc, "points": 1024},
+        "cpu_baseline": {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} eval forwards of {Bc} clouds (oracle port of models/pointnet.py, torch CPU)"},
+        "e2e": {"value": v, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def run_pointnet(args):
+    import torch
+    import pcoe
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - this framework has no CPU path (use --impl reference)")
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    model = _pointnet_model(pcoe, torch).to(dev)
+    N = 1024
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    sweep = {}
+    steps = max(5, min(args.steps, 50))
+    clock_sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
+        x = pcoe.synthetic.clouds(5, B, N).to(dev)
+        with torch.no_grad():
+            for _ in range(max(3, args.warmup)):
+                y = model(x)
+            torch.cuda.synchronize()
+            # small batches are launch-bound: replay the forward from a CUDA graph (inputs copied into the static buffer)
+            graph, static_x, static_y = None, x.clone(), None
+            if B <= 64 and not args.no_graph:
+                try:
+                    sstream = torch.cuda.Stream()
+                    sstream.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(sstream):
+                        model(static_x)
+                    torch.cuda.current_stream().wait_stream(sstream)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        static_y = model(static_x)
+                except Exception as e:                      # capture is an optimisation, not the contract
+                    graph, static_y = None, None
+                    sys.stderr.write(f"c5: CUDA-graph capture failed at B={B}: {e}\n")
+            run = (lambda: graph.replay()) if graph is not None else (lambda: model(static_x))
+            for _ in range(2):
+                run()
+            l0 = pcoe._lib.launch_count()
+            model(static_x)
+            nl = pcoe._lib.launch_count() - l0
+            ms = []
+            for _ in range(steps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); run(); b.record()
+                torch.cuda.synchronize()
+                ms.append(a.elapsed_time(b))
+            ms.sort()
+            med = ms[len(ms) // 2]
+            # end to end: pinned host xyz -> device, forward, (B,3) result back
+            hx = pcoe.synthetic.clouds(6, B, N).pin_memory()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                static_x.copy_(hx, non_blocking=True)
+                if graph is not None:
+                    graph.replay()
+                    out = static_y.cpu()
+                else:
+                    out = model(static_x).cpu()
+            torch.cuda.synchronize()
+            e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+        sweep[str(B)] = {"latency_ms": med, "clouds_per_s": B / med * 1e3, "e2e_ms": e2e_ms, "e2e_clouds_per_s": B / e2e_ms * 1e3,
+                         "cuda_graph": graph is not None, "libpcoe_launches": int(nl)}
+        del graph
+    t_wall1 = time.time()
+    clocks = clock_sampler.stop(t_wall0, t_wall1) if clock_sampler else None
+    # per-kernel profile at B = 1024 -> roofline of the dominant kernel (the 128 -> 1024 layer + max pool)
+    B = 1024
+    x = pcoe.synthetic.clouds(5, B, N).to(dev)
+    pcoe._lib.profile(True)
+    with torch.no_grad():
+        for _ in range(3):
+            flush.zero_()
+            model(x)
+    torch.cuda.synchronize()
+    pcoe._lib.profile(False)
+    rep = pcoe._lib.profile_report()
+    kernels = {k: {"launches_per_step": n / 3, "ms_per_step": ms_ / 3} for k, (n, ms_) in sorted(rep.items(), key=lambda kv: -kv[1][1])}
+    M = B * N
+    roofline = None
+    if "pointmlp_l3_pool" in kernels:
+        k = kernels["pointmlp_l3_pool"]
+        t_s = k["ms_per_step"] / k["launches_per_step"] * 1e-3
+        flops = 2.0 * M * 128 * 1024
+        ach = flops / t_s / 1e12
+        roofline = {"kernel": "pointmlp_l3_pool (x3_fwd_kernel<BnRelu6, Group6, 2>)", "bound": "tensor", "achieved": ach,
+                    "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
+                    "peak_source": peaks["source"], "avg_launch_ms": t_s * 1e3, "algorithmic_flops": flops,
+                    "algorithmic_bytes": 4.0 * M * 128 + 10.0 * (M / 32) * 1024,
+                    "note": "algorithmic FLOPs = 2*M*128*1024 (one product per MAC); the kernel issues 3 tcgen05.mma per "
+                            "product (two bf16 planes per operand), so its tensor-pipe occupancy is 3x this fraction"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pointnet_torch, sa_torch
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = sa_torch.clone_state(model.state_dict())
+        xc = pcoe.synthetic.clouds(5, 64, N)
+        with torch.no_grad():
+            pointnet_torch.pointnet_forward(sd, xc)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                pointnet_torch.pointnet_forward(sd, xc)
+            dt = time.perf_counter() - t0
+        cpu = {"value": 64 * 3 / dt, "unit": "clouds/s", "cores": cores, "kind": "port",
+               "sample": "3 eval forwards of 64 clouds after 1 warm-up (oracle port of models/pointnet.py, torch CPU fp32)"}
+    if rank == 0:
+        top = sweep["1024"]
+        print(json.dumps({
+            "metric": "inference clouds/sec (PointNet, 1024 pts, eval forward)", "value": top["clouds_per_s"], "unit": "clouds/s",
+            "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": top["latency_ms"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (operands split into bf16 planes, fp32 accumulate and activations)", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES["c5"], "clouds_per_gpu": 1024, "points": N,
+                       "l2": "512 MiB buffer written between timed forwards (flush outside the event pair)",
+                       "value_is": "B = 1024 row of `sweep`"},
+            "clocks": clocks,
+            "e2e": {"value": top["e2e_clouds_per_s"], "unit": "clouds/s", "h2d_bytes_per_step": 1024 * N * 12, "d2h_bytes_per_step": 1024 * 12},
+            "gpu_launches": int(top["libpcoe_launches"]) * steps, "gpu_launches_per_step": int(top["libpcoe_launches"]),
+            "sweep": sweep, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -529,6 +771,7 @@ def main():
                     help="host = the reference's randperm stream replayed on the CPU generator and fed to the graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-modes-leg", action="store_true", help="skip the throughput of the other precision modes")
+    ap.add_argument("--no-sampling-leg", action="store_true", help="skip the stand-alone FPS / grouping / gather timings")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: copy each batch H2D in line with its step")
     ap.add_argument("--torch-optimizer", action="store_true",
@@ -540,7 +783,9 @@ def main():
                     help="warm-up + timed region only (for ncu captures): no e2e / per-kernel / CPU legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.config == "c5":
+        (run_pointnet_reference if args.impl == "reference" else run_pointnet)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

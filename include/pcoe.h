@@ -225,7 +225,8 @@ int pcoe_sa_backward(const pcoe_sa_desc* desc, const float* xyz, const float* ne
  *     out[b, :] = max over the rows of cloud b of h
  * i.e. STN3d / STNkd's conv1..3 + bn1..3 + torch.max (models/pointnet.py:24-27 / :55-58) and PointNetEncoder's
  * conv1..3 + bn1..3 + torch.max (:93,102-104; bn3 without ReLU).  Same split-operand tcgen05 kernels as
- * PCOE_PRECISION_BF16X3 set abstraction (24-bit operands, fp32 accumulate).
+ * PCOE_PRECISION_BF16X3 set abstraction with two bf16 planes per operand (16 significant bits, 3 MMAs per product, fp32
+ * accumulate and fp32 activations: ~1e-5 relative on the outputs).
  *   M              rows = clouds * rows_per_cloud;  rows_per_cloud must be a multiple of 32 (pad a cloud by repeating
  *                  one of its points: the max does not change)
  *   use_xyz, D     first-layer input = [xyz (3, when use_xyz) | feats (D)], D a multiple of 64 (0 allowed with use_xyz);
