@@ -813,8 +813,45 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
   constexpr int kPU = 4 / PProd::kUR;                        // P units per stage (128 rows / (32 * kUR))
   const int ups = kPU + nqu, nstage = 2 * nt;                // units per stage; 64-point stages
 
-  if (warp < 8) {
-    if (nt > 0) {
+  if (warp < 16) {
+    // Both warp groups (0-7 and 8-15) are producers: the accumulator is read only once, after the last stage, so the
+    // "epilogue" warps would otherwise idle for the whole kernel.  Group gsel builds the stages h = gsel, gsel + 2, ...
+    // (each stage still gets its kProdThreads arrivals from one group), which doubles the loads in flight per SM.
+    const int gsel = warp >> 3, g = tid & (kProdThreads - 1);
+    union RawU { typename PProd::Raw p; typename QProd::Raw q; __device__ RawU() {} };
+    struct Cur { int u, m0; };
+    auto adv = [&](Cur& c) { if (++c.u == ups) { c.u = 0; c.m0 += 128; } };
+    Cur cl{0, t0 * kPts + gsel * 64}, cst = cl;
+    int ring_s = gsel % nst, ring_r = gsel / nst;
+    const int my_stages = (nstage - gsel + 1) / 2;
+    unit_pipeline<RawU>(my_stages * ups,
+        [&](int, RawU& r) {
+          if (cl.u < kPU) pp.template load<64>(g, cl.m0, cl0 + cl.u * 32 * PProd::kUR, r.p);
+          else if constexpr (QProd::kChMajor) qp.template load<64>(g, cl.m0, qb * 128 + (cl.u - kPU) * 32 * QProd::kUR, r.q);
+          else qp.template load<64>(g, cl.m0, 2 * qb + (cl.u - kPU), r.q);
+          adv(cl);
+        },
+        [&](int, const RawU& r) {
+          const uint32_t st = sS + (uint32_t)ring_s * sbytes;
+          if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
+          if (cst.u < kPU)
+            pp.template store<64, NP>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, cst.u * 32 * PProd::kUR, 128, r.p, st);
+          else {
+            const int qu = cst.u - kPU;
+            if constexpr (QProd::kChMajor)
+              qp.template store<64, NP>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, qu * 32 * QProd::kUR, 128, r.q, st + 2 * kPart);
+            else
+              qp.template store<64, NP>(g, 2 * qb + qu, r.q, st + 2 * kPart + (uint32_t)qu * 8192u);
+          }
+          if (cst.u == ups - 1) {
+            tc::fence_proxy_async();
+            mbar_arrive(&bar.full[ring_s]);
+            ring_s += 2;
+            while (ring_s >= nst) { ring_s -= nst; ++ring_r; }
+          }
+          adv(cst);
+        });
+    if (warp < 8 && nt > 0) {
       tc::mbar_wait(&bar.tmem_full[0], 0u);
       tc::fence_after_sync();
       const int crow = cl0 + eq * 32 + lane;
@@ -840,39 +877,6 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
       }
       tc::fence_before_sync();
     }
-  } else if (warp < 16) {
-    const int g = tid - kEpiThreads;
-    union RawU { typename PProd::Raw p; typename QProd::Raw q; __device__ RawU() {} };
-    struct Cur { int u, m0; };
-    auto adv = [&](Cur& c) { if (++c.u == ups) { c.u = 0; c.m0 += 64; } };
-    Cur cl{0, t0 * kPts}, cst = cl;
-    int ring_s = 0, ring_r = 0;
-    unit_pipeline<RawU>(nstage * ups,
-        [&](int, RawU& r) {
-          if (cl.u < kPU) pp.template load<64>(g, cl.m0, cl0 + cl.u * 32 * PProd::kUR, r.p);
-          else if constexpr (QProd::kChMajor) qp.template load<64>(g, cl.m0, qb * 128 + (cl.u - kPU) * 32 * QProd::kUR, r.q);
-          else qp.template load<64>(g, cl.m0, 2 * qb + (cl.u - kPU), r.q);
-          adv(cl);
-        },
-        [&](int, const RawU& r) {
-          const uint32_t st = sS + (uint32_t)ring_s * sbytes;
-          if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
-          if (cst.u < kPU)
-            pp.template store<64, NP>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, cst.u * 32 * PProd::kUR, 128, r.p, st);
-          else {
-            const int qu = cst.u - kPU;
-            if constexpr (QProd::kChMajor)
-              qp.template store<64, NP>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, qu * 32 * QProd::kUR, 128, r.q, st + 2 * kPart);
-            else
-              qp.template store<64, NP>(g, 2 * qb + qu, r.q, st + 2 * kPart + (uint32_t)qu * 8192u);
-          }
-          if (cst.u == ups - 1) {
-            tc::fence_proxy_async();
-            mbar_arrive(&bar.full[ring_s]);
-            if (++ring_s == nst) { ring_s = 0; ++ring_r; }
-          }
-          adv(cst);
-        });
   } else {
     const uint32_t tm = tc::uniform_u32(tmem_base);
     const uint32_t idesc = tc::make_idesc_bf16(128, nq, false, !QProd::kChMajor);
