@@ -408,14 +408,14 @@ static bool sa_x3_supported(const pcoe_sa_desc& d) {
 }
 struct Cfg6 { int nst, wres, grid; size_t smem; };
 // persistent (tile x channel-block) kernels: CTAs per channel block, resident weights or streamed, ring depth
-static Cfg6 cfg6(int nk, int ncb, int ntiles, size_t cbytes, int np) {
+static Cfg6 cfg6(int nk, int ncb, int ntiles, size_t cbytes, int np, int min_ring = 2) {
   Cfg6 c{};
   const int per = kNumSMs / ncb > 0 ? kNumSMs / ncb : 1;
   const int ctas = ntiles < per ? ntiles : per;
   c.grid = ctas * ncb;
   const size_t op = (size_t)np * 16384;   // one operand chunk, all planes
   const size_t avail = kSmemBudget6 - 1024 - cbytes, wb = (size_t)nk * op;
-  c.wres = (ntiles > ctas && wb + 2 * op <= avail) ? 1 : 0;   // a CTA that sees one tile gains nothing from residency
+  c.wres = (ntiles > ctas && wb + min_ring * op <= avail) ? 1 : 0;   // a CTA that sees one tile gains nothing from residency
   const size_t ring = c.wres ? avail - wb : avail, sb = c.wres ? op : 2 * op;
   int n = (int)(ring / sb);
   c.nst = n > v6::kMaxStages6 ? v6::kMaxStages6 : n;
@@ -424,14 +424,33 @@ static Cfg6 cfg6(int nk, int ncb, int ntiles, size_t cbytes, int np) {
 }
 
 constexpr int kFwdPlanes6 = 3;   // forward operands keep all 24 significant bits (6 MMAs per step), backward 16 (3 MMAs)
+// PCOE_X3_ASYNC=0 (debug / A-B timing): register pipeline everywhere
+static bool x3_async_enabled() {
+  static const bool on = [] { const char* e = getenv("PCOE_X3_ASYNC"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <int NP = kFwdPlanes6, class Prod, class Epi>
 static int launch_fwd6(const Prod& prod, const __nv_bfloat16* Wp, size_t wps, int Kp, const Epi& epi, int M,
                        int Cout, cudaStream_t st, const char* what) {
   const size_t cbytes = sizeof(float) * (size_t)(prod.nconst() + epi.nconst()) + 512;
   const int ncb = ceil_div(Cout, 128);
+  if constexpr (Prod::kAsync) {
+    // resident weights + room for the raw staging ring: the producers copy their fp32 operands with cp.async
+    const size_t raw = (size_t)v6::kRawDepth * Prod::kRawItems * v6::kRawItemBytes;
+    const Cfg6 ca = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes + raw, NP, 1);
+    if (x3_async_enabled() && ca.wres && ca.nst >= 1) {
+      auto k = v6::x3_fwd_kernel<Prod, Epi, NP, true>;
+      static bool attr = false;
+      if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
+      LaunchScope ls(what, st);
+      k<<<ca.grid, v4::kThreads, ca.smem, st>>>(prod, Wp, wps, Kp, epi, M, ncb, ca.nst, ca.wres);
+      return ls.done();
+    }
+  }
   const Cfg6 c = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes, NP);
   if (c.nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
-  auto k = v6::x3_fwd_kernel<Prod, Epi, NP>;
+  auto k = v6::x3_fwd_kernel<Prod, Epi, NP, false>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
   LaunchScope ls(what, st);
@@ -444,9 +463,21 @@ static int launch_dgrad6(const PProd& pp, const __nv_bfloat16* Wp, size_t wps, i
                          int Cprev, cudaStream_t st, const char* what) {
   const size_t cbytes = sizeof(float) * (size_t)(pp.nconst() + epi.nconst()) + 512;
   const int ncb = ceil_div(Cprev, 128);
+  {
+    const size_t raw = (size_t)v6::kRawDepth * PProd::kRawItems * v6::kRawItemBytes;
+    const Cfg6 ca = cfg6(pp.C / 64, ncb, ceil_div(M, v4::kPts), cbytes + raw, 2, 1);
+    if (x3_async_enabled() && ca.wres && ca.nst >= 1) {
+      auto k = v6::x3_dgrad_kernel<PProd, Epi, PT, true>;
+      static bool attr = false;
+      if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
+      LaunchScope ls(what, st);
+      k<<<ca.grid, v4::kThreads, ca.smem, st>>>(pp, Wp, wps, Kp, epi, M, ncb, ca.nst, ca.wres);
+      return ls.done();
+    }
+  }
   const Cfg6 c = cfg6(pp.C / 64, ncb, ceil_div(M, v4::kPts), cbytes, 2);
   if (c.nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
-  auto k = v6::x3_dgrad_kernel<PProd, Epi, PT>;
+  auto k = v6::x3_dgrad_kernel<PProd, Epi, PT, false>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
   LaunchScope ls(what, st);

@@ -135,6 +135,60 @@ __device__ __forceinline__ float4 ldg4_or0(const float* p, bool ok) {
   return ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// ---- asynchronous raw staging (LDGSTS) ---------------------------------------------------------------------------
+// The register pipeline keeps ONE unit of global loads in flight per producer thread while the previous one is
+// transformed; measured, the producers then spend most of their time on the long scoreboard (2.4 us per 32 KB unit at
+// 17 warps per SM).  The channel-major producers can instead copy their raw fp32 operands global -> shared with
+// cp.async into a per-thread ring of kRawDepth units ([unit][item][thread] x 16 bytes: every thread reads back exactly
+// what it copied, so no barrier is involved - cp.async.wait_group orders a thread's own copies), which keeps
+// kRawDepth - 1 units (64 KB per SM at depth 3) in flight without holding registers.
+constexpr int kRawDepth = 3;
+constexpr uint32_t kRawItemBytes = kProdThreads * 16u;        // one 16-byte item of every producer thread = 4 KB
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, bool ok) {
+  const int sz = ok ? 16 : 0;                                  // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g, bool ok) {
+  const int sz = ok ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+// slot of (item, thread g) inside a raw unit
+__device__ __forceinline__ uint32_t raw_slot(uint32_t unit_base, int item, int g) { return unit_base + (uint32_t)(item * kProdThreads + g) * 16u; }
+
+// kRawDepth-deep pipeline over W units: issue(w, slot) enqueues the async copies of unit w, consume(w, slot) runs when
+// they have landed
+template <class IssueF, class ConsumeF>
+__device__ __forceinline__ void async_pipeline(int W, uint32_t raw0, uint32_t kRawUnit, IssueF issue, ConsumeF consume) {
+  if (W <= 0) return;
+#pragma unroll
+  for (int w = 0; w < kRawDepth - 1; ++w) {
+    if (w < W) issue(w, raw0 + (uint32_t)w * kRawUnit);
+    cp_async_commit();
+  }
+  int ri = kRawDepth - 1, rc = 0;                              // ring slots of the next issue / the next consume
+  for (int w = 0; w < W; ++w) {
+    if (w + kRawDepth - 1 < W) issue(w + kRawDepth - 1, raw0 + (uint32_t)ri * kRawUnit);
+    cp_async_commit();                                          // one group per iteration, empty or not
+    cp_async_wait<kRawDepth - 1>();                             // all but the newest kRawDepth-1 groups: unit w has landed
+    consume(w, raw0 + (uint32_t)rc * kRawUnit);
+    if (++ri == kRawDepth) ri = 0;
+    if (++rc == kRawDepth) rc = 0;
+  }
+}
+
 // relu(scale * y + shift) of the previous layer's pre-activations
 struct BnRelu6 {
   static constexpr bool kChMajor = true;
@@ -171,6 +225,27 @@ struct BnRelu6 {
       r.a[i][0] = ldg4_or0(src, ok);
       r.a[i][1] = ldg4_or0(src + (size_t)C * 4, ok);
     }
+  }
+  static constexpr bool kAsync = true;
+  template <int PTS>
+  __device__ __forceinline__ void load_async(int g, int m0, int crow, uint32_t ub) const {
+    using G = CM<PTS, kUR>;
+    const int row = g % G::kR, c = crow + row, ch0 = g / G::kR;
+    const bool rok = c < C;
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      const int m = m0 + (ch0 + i * G::kCstep) * 8;
+      const float* src = y + act_off(m >> 7, C, rok ? c : 0, (m & 127) >> 2);
+      const bool ok = rok && m < M;
+      cp_async16(raw_slot(ub, 2 * i, g), src, ok);
+      cp_async16(raw_slot(ub, 2 * i + 1, g), src + (size_t)C * 4, ok);
+    }
+  }
+  static constexpr int kRawItems = 8;
+  template <int PTS>
+  __device__ __forceinline__ void fetch(int g, int, int, uint32_t ub, Raw& r) const {
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) { r.a[i][0] = lds128f(raw_slot(ub, 2 * i, g)); r.a[i][1] = lds128f(raw_slot(ub, 2 * i + 1, g)); }
   }
   template <int PTS, int NP>
   __device__ __forceinline__ void store(int g, int, int crow, int lrow, int lrows, const Raw& r, uint32_t s0) const {
@@ -224,6 +299,30 @@ struct Dy6 {
       const bool ok = rok && m < M;
       r.d[i][0] = ldg4_or0(dz + off, ok); r.d[i][1] = ldg4_or0(dz + off + (size_t)C * 4, ok);
       r.y[i][0] = ldg4_or0(y + off, ok);  r.y[i][1] = ldg4_or0(y + off + (size_t)C * 4, ok);
+    }
+  }
+  static constexpr bool kAsync = true;
+  template <int PTS>
+  __device__ __forceinline__ void load_async(int g, int m0, int crow, uint32_t ub) const {
+    using G = CM<PTS, kUR>;
+    const int row = g % G::kR, c = crow + row, ch0 = g / G::kR;
+    const bool rok = c < C;
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      const int m = m0 + (ch0 + i * G::kCstep) * 8;
+      const size_t off = act_off(m >> 7, C, rok ? c : 0, (m & 127) >> 2);
+      const bool ok = rok && m < M;
+      cp_async16(raw_slot(ub, 4 * i, g), dz + off, ok);     cp_async16(raw_slot(ub, 4 * i + 1, g), dz + off + (size_t)C * 4, ok);
+      cp_async16(raw_slot(ub, 4 * i + 2, g), y + off, ok);  cp_async16(raw_slot(ub, 4 * i + 3, g), y + off + (size_t)C * 4, ok);
+    }
+  }
+  static constexpr int kRawItems = 8;
+  template <int PTS>
+  __device__ __forceinline__ void fetch(int g, int, int, uint32_t ub, Raw& r) const {
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      r.d[i][0] = lds128f(raw_slot(ub, 4 * i, g));     r.d[i][1] = lds128f(raw_slot(ub, 4 * i + 1, g));
+      r.y[i][0] = lds128f(raw_slot(ub, 4 * i + 2, g)); r.y[i][1] = lds128f(raw_slot(ub, 4 * i + 3, g));
     }
   }
   template <int PTS, int NP>
@@ -287,6 +386,41 @@ struct DyLast6 {
       r.sl[i] = ok ? (int)__ldg(slot + go) : -1;
     }
   }
+  // raw unit: items 0..7 = y (two 16-byte quads per chunk), item 8 = [gm x 4], item 9 = [slot word x 4]
+  static constexpr bool kAsync = true;
+  template <int PTS>
+  __device__ __forceinline__ void load_async(int g, int m0, int crow, uint32_t ub) const {
+    using G = CM<PTS, kUR>;
+    const int row = g % G::kR, c = crow + row, ch0 = g / G::kR;
+    const bool rok = c < C;
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      const int m = m0 + (ch0 + i * G::kCstep) * 8;
+      const bool ok = rok && m < M;
+      const float* sy = y + act_off(m >> 7, C, rok ? c : 0, (m & 127) >> 2);
+      const size_t go = (size_t)((ok ? m : 0) >> 5) * C + (rok ? c : 0);
+      cp_async16(raw_slot(ub, 2 * i, g), sy, ok);
+      cp_async16(raw_slot(ub, 2 * i + 1, g), sy + (size_t)C * 4, ok);
+      cp_async4(raw_slot(ub, 8, g) + 4u * i, gm + go, ok);
+      cp_async4(raw_slot(ub, 9, g) + 4u * i, slot + (go & ~(size_t)3), ok);    // the aligned word that holds the byte
+    }
+  }
+  static constexpr int kRawItems = 10;
+  template <int PTS>
+  __device__ __forceinline__ void fetch(int g, int m0, int crow, uint32_t ub, Raw& r) const {
+    using G = CM<PTS, kUR>;
+    const int row = g % G::kR, c = crow + row, ch0 = g / G::kR;
+    const bool rok = c < C;
+#pragma unroll
+    for (int i = 0; i < kUR; ++i) {
+      const int m = m0 + (ch0 + i * G::kCstep) * 8;
+      const bool ok = rok && m < M;
+      r.y[i][0] = lds128f(raw_slot(ub, 2 * i, g)); r.y[i][1] = lds128f(raw_slot(ub, 2 * i + 1, g));
+      r.gv[i] = __uint_as_float(lds32(raw_slot(ub, 8, g) + 4u * i));
+      const uint32_t w = lds32(raw_slot(ub, 9, g) + 4u * i);
+      r.sl[i] = ok ? (int)((w >> (8 * (c & 3))) & 255u) : -1;                  // C % 4 == 0: byte index = c & 3
+    }
+  }
   template <int PTS, int NP>
   __device__ __forceinline__ void store(int g, int m0, int crow, int lrow, int lrows, const Raw& r, uint32_t s0) const {
     using G = CM<PTS, kUR>;
@@ -313,6 +447,8 @@ struct DyLast6 {
 // D == 0 (SA1) is the xyz block alone.  Thread g owns the 8-channel unit g & 7 of rows (g >> 3) + 32 i, i < PTS/32.
 struct GatherFeat6 {
   static constexpr bool kChMajor = false;
+  static constexpr bool kAsync = false;
+  static constexpr int kRawItems = 0;
   static constexpr int kUR = 4;       // unused (point-major): one unit per 64-channel block
   struct Raw { float4 a[4], b[4]; };
   GatherBase gb;
@@ -547,15 +683,17 @@ __device__ __forceinline__ void mma_planes(uint32_t d, uint64_t a, uint64_t b, u
 // smem: wres ? [W: nk x NP parts][ring: nst x (NP X parts)] : [ring: nst x (NP W parts | NP X parts)]
 // Wp = plane 0 of the weight image, wps = elements per plane.
 // ---------------------------------------------------------------------------------------------------------------
-template <class Prod, class Epi, int NP>
+template <class Prod, class Epi, int NP, bool ASYNC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wp, size_t wps, int Kp, Epi epi, int M, int ncb, int nst, int wres) {
   PCOE_V6_PROLOGUE(256)
   const int nk = prod.nchunks();
   constexpr uint32_t kOp = NP * kPart;                       // one operand chunk, all planes
+  constexpr uint32_t kRawUnit = ASYNC ? (uint32_t)Prod::kRawItems * kRawItemBytes : 0u, kRawBytes = kRawDepth * kRawUnit;
   const uint32_t sWres = smem0, wres_bytes = wres ? (uint32_t)nk * kOp : 0u;
   const uint32_t sS = smem0 + wres_bytes, sbytes = wres ? kOp : 2u * kOp, xoff = wres ? 0u : kOp;
-  float* csm = reinterpret_cast<float*>(smem_gen + wres_bytes + (size_t)nst * sbytes);
+  const uint32_t sRaw = sS + (uint32_t)nst * sbytes;          // ASYNC: raw fp32 staging ring (requires wres)
+  float* csm = reinterpret_cast<float*>(smem_gen + wres_bytes + (size_t)nst * sbytes + kRawBytes);
   const int cb = blockIdx.x % ncb, t0 = blockIdx.x / ncb, tstep = gridDim.x / ncb;
   const int ntiles = (M + kPts - 1) / kPts;
   const int my_items = t0 < ntiles ? (ntiles - t0 + tstep - 1) / tstep : 0;
@@ -603,29 +741,43 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wp, size_t wps, int K
     auto adv = [&](Cur& c) { if (++c.u == upc) { c.u = 0; if (++c.k == nk) { c.k = 0; c.tile += tstep; } } };
     Cur cl{t0, 0, 0}, cst = cl;
     int ring_s = 0, ring_r = 0;
-    unit_pipeline<RawU>(my_items * nk * upc,
-        [&](int, RawU& r) {
-          const int xu = cl.u - wu;
-          if (xu < 0) wload_k1(Wp + (size_t)cl.u * wps, Kp, cb * 128, cl.k * 64, g, r.w);
-          else if constexpr (Prod::kChMajor) prod.template load<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * Prod::kUR, r.x);
-          else prod.template load<128>(g, cl.tile * kPts, cl.k, r.x);
-          adv(cl);
-        },
-        [&](int, const RawU& r) {
-          const uint32_t st = sS + (uint32_t)ring_s * sbytes;
-          if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
-          const int xu = cst.u - wu;
-          if (xu < 0) wstore_k1(st + (uint32_t)cst.u * kPart, g, r.w);
-          else if constexpr (Prod::kChMajor)
-            prod.template store<128, NP>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * Prod::kUR, xu * 16 * Prod::kUR, 64, r.x, st + xoff);
-          else prod.template store<128, NP>(g, cst.k, r.x, st + xoff);
-          if (cst.u == upc - 1) {
-            tc::fence_proxy_async();
-            mbar_arrive(&bar.full[ring_s]);
-            if (++ring_s == nst) { ring_s = 0; ++ring_r; }
-          }
-          adv(cst);
-        });
+    auto store_unit = [&](const RawU& r) {
+      const uint32_t st = sS + (uint32_t)ring_s * sbytes;
+      if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
+      const int xu = cst.u - wu;
+      if (xu < 0) wstore_k1(st + (uint32_t)cst.u * kPart, g, r.w);
+      else if constexpr (Prod::kChMajor)
+        prod.template store<128, NP>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * Prod::kUR, xu * 16 * Prod::kUR, 64, r.x, st + xoff);
+      else prod.template store<128, NP>(g, cst.k, r.x, st + xoff);
+      if (cst.u == upc - 1) {
+        tc::fence_proxy_async();
+        mbar_arrive(&bar.full[ring_s]);
+        if (++ring_s == nst) { ring_s = 0; ++ring_r; }
+      }
+      adv(cst);
+    };
+    if constexpr (ASYNC) {   // resident weights, channel-major activations: raw operands staged with cp.async
+      async_pipeline(my_items * nk * upc, sRaw, kRawUnit,
+          [&](int, uint32_t ub) {
+            prod.template load_async<128>(g, cl.tile * kPts, cl.k * 64 + cl.u * 16 * Prod::kUR, ub);
+            adv(cl);
+          },
+          [&](int, uint32_t ub) {
+            RawU r;
+            prod.template fetch<128>(g, cst.tile * kPts, cst.k * 64 + cst.u * 16 * Prod::kUR, ub, r.x);
+            store_unit(r);
+          });
+    } else {
+      unit_pipeline<RawU>(my_items * nk * upc,
+          [&](int, RawU& r) {
+            const int xu = cl.u - wu;
+            if (xu < 0) wload_k1(Wp + (size_t)cl.u * wps, Kp, cb * 128, cl.k * 64, g, r.w);
+            else if constexpr (Prod::kChMajor) prod.template load<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * Prod::kUR, r.x);
+            else prod.template load<128>(g, cl.tile * kPts, cl.k, r.x);
+            adv(cl);
+          },
+          [&](int, const RawU& r) { store_unit(r); });
+    }
   } else {   // warp 16: MMA issue, warp-uniform loop, one elected lane issues
     const uint32_t tm = tc::uniform_u32(tmem_base);
     const uint32_t idesc = tc::make_idesc_bf16(128, kPts, false, Prod::kChMajor);
@@ -661,16 +813,18 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wp, size_t wps, int K
 // contraction over the layer's output channels in chunks of 64.  PT: operands swapped, D[128 points x 128 in-ch],
 // point-on-lane epilogue (layer-1 scatter-add into grad_feats).
 // ---------------------------------------------------------------------------------------------------------------
-template <class PProd, class Epi, bool PT>
+template <class PProd, class Epi, bool PT, bool ASYNC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wp, size_t wps, int Kp, Epi epi, int M, int ncb, int nst, int wres) {
   PCOE_V6_PROLOGUE(256)
   constexpr int NP = 2;
   constexpr uint32_t kOp = NP * kPart;
+  constexpr uint32_t kRawUnit = ASYNC ? (uint32_t)PProd::kRawItems * kRawItemBytes : 0u, kRawBytes = kRawDepth * kRawUnit;
   const int nk = pp.C / 64;
   const uint32_t sWres = smem0, wres_bytes = wres ? (uint32_t)nk * kOp : 0u;
   const uint32_t sS = smem0 + wres_bytes, sbytes = wres ? kOp : 2u * kOp, xoff = wres ? 0u : kOp;
-  float* csm = reinterpret_cast<float*>(smem_gen + wres_bytes + (size_t)nst * sbytes);
+  const uint32_t sRaw = sS + (uint32_t)nst * sbytes;
+  float* csm = reinterpret_cast<float*>(smem_gen + wres_bytes + (size_t)nst * sbytes + kRawBytes);
   const int cb = blockIdx.x % ncb, t0 = blockIdx.x / ncb, tstep = gridDim.x / ncb;
   const int ntiles = (M + kPts - 1) / kPts;
   const int my_items = t0 < ntiles ? (ntiles - t0 + tstep - 1) / tstep : 0;
@@ -728,26 +882,40 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wp, size_t wps, int 
     auto adv = [&](Cur& c) { if (++c.u == upc) { c.u = 0; if (++c.k == nk) { c.k = 0; c.tile += tstep; } } };
     Cur cl{t0, 0, 0}, cst = cl;
     int ring_s = 0, ring_r = 0;
-    unit_pipeline<RawU>(my_items * nk * upc,
-        [&](int, RawU& r) {
-          const int xu = cl.u - wu;
-          if (xu < 0) wload_mn1(Wp + (size_t)cl.u * wps, Kp, cl.k * 64, cb * 128, g, r.w);
-          else pp.template load<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * PProd::kUR, r.x);
-          adv(cl);
-        },
-        [&](int, const RawU& r) {
-          const uint32_t st = sS + (uint32_t)ring_s * sbytes;
-          if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
-          const int xu = cst.u - wu;
-          if (xu < 0) wstore_mn1(st + (uint32_t)cst.u * kPart, g, r.w);
-          else pp.template store<128, NP>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * PProd::kUR, xu * 16 * PProd::kUR, 64, r.x, st + xoff);
-          if (cst.u == upc - 1) {
-            tc::fence_proxy_async();
-            mbar_arrive(&bar.full[ring_s]);
-            if (++ring_s == nst) { ring_s = 0; ++ring_r; }
-          }
-          adv(cst);
-        });
+    auto store_unit = [&](const RawU& r) {
+      const uint32_t st = sS + (uint32_t)ring_s * sbytes;
+      if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
+      const int xu = cst.u - wu;
+      if (xu < 0) wstore_mn1(st + (uint32_t)cst.u * kPart, g, r.w);
+      else pp.template store<128, NP>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * PProd::kUR, xu * 16 * PProd::kUR, 64, r.x, st + xoff);
+      if (cst.u == upc - 1) {
+        tc::fence_proxy_async();
+        mbar_arrive(&bar.full[ring_s]);
+        if (++ring_s == nst) { ring_s = 0; ++ring_r; }
+      }
+      adv(cst);
+    };
+    if constexpr (ASYNC) {
+      async_pipeline(my_items * nk * upc, sRaw, kRawUnit,
+          [&](int, uint32_t ub) {
+            pp.template load_async<128>(g, cl.tile * kPts, cl.k * 64 + cl.u * 16 * PProd::kUR, ub);
+            adv(cl);
+          },
+          [&](int, uint32_t ub) {
+            RawU r;
+            pp.template fetch<128>(g, cst.tile * kPts, cst.k * 64 + cst.u * 16 * PProd::kUR, ub, r.x);
+            store_unit(r);
+          });
+    } else {
+      unit_pipeline<RawU>(my_items * nk * upc,
+          [&](int, RawU& r) {
+            const int xu = cl.u - wu;
+            if (xu < 0) wload_mn1(Wp + (size_t)cl.u * wps, Kp, cl.k * 64, cb * 128, g, r.w);
+            else pp.template load<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * PProd::kUR, r.x);
+            adv(cl);
+          },
+          [&](int, const RawU& r) { store_unit(r); });
+    }
   } else {
     const uint32_t tm = tc::uniform_u32(tmem_base);
     const uint32_t idesc = tc::make_idesc_bf16(128, 128, true, true);
