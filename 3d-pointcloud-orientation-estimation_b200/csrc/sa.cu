@@ -439,7 +439,9 @@ static int launch_fwd6(const Prod& prod, const __nv_bfloat16* Wp, size_t wps, in
     // resident weights + room for the raw staging ring: the producers copy their fp32 operands with cp.async
     const size_t raw = (size_t)v6::kRawDepth * Prod::kRawItems * v6::kRawItemBytes;
     const Cfg6 ca = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes + raw, NP, 1);
-    if (x3_async_enabled() && ca.wres && ca.nst >= 1) {
+    // never trade weight residency for the staging ring (measured: SA2 forward 42 -> 58 us when its weights are streamed)
+    const bool keeps_res = ca.wres || !cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes, NP).wres;
+    if (x3_async_enabled() && ca.nst >= 1 && keeps_res) {
       auto k = v6::x3_fwd_kernel<Prod, Epi, NP, true>;
       static bool attr = false;
       if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
@@ -466,7 +468,9 @@ static int launch_dgrad6(const PProd& pp, const __nv_bfloat16* Wp, size_t wps, i
   {
     const size_t raw = (size_t)v6::kRawDepth * PProd::kRawItems * v6::kRawItemBytes;
     const Cfg6 ca = cfg6(pp.C / 64, ncb, ceil_div(M, v4::kPts), cbytes + raw, 2, 1);
-    if (x3_async_enabled() && ca.wres && ca.nst >= 1) {
+    // dgrad (two planes): the staging ring beats weight residency (SA2 dgrad3: 74 us resident + register pipeline,
+    // 50 us streamed + cp.async ring)
+    if (x3_async_enabled() && ca.nst >= 1) {
       auto k = v6::x3_dgrad_kernel<PProd, Epi, PT, true>;
       static bool attr = false;
       if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
@@ -494,11 +498,26 @@ static int launch_wgrad6(const PProd& pp, const QProd& qp, float* dW, int ldo, i
   splits = splits < 1 ? 1 : (splits > ntiles ? ntiles : splits);
   const int tps = ceil_div(ntiles, splits);
   splits = ceil_div(ntiles, tps);
+  if constexpr (PProd::kAsync && QProd::kAsync) {
+    constexpr int items = PProd::kRawItems > QProd::kRawItems ? PProd::kRawItems : QProd::kRawItems;
+    const size_t raw = (size_t)v6::kRawDepth * items * v6::kRawItemBytes;
+    int na = (int)((kSmemBudget6 - 1024 - cbytes - raw) / 65536);
+    na = na > v6::kMaxStages6 ? v6::kMaxStages6 : na;
+    if (x3_async_enabled() && na >= 1) {
+      const size_t smem = 1024 + (size_t)na * 65536 + raw + cbytes;
+      auto k = v6::x3_wgrad_kernel<PProd, QProd, true>;
+      static bool attr = false;
+      if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
+      LaunchScope ls(what, st);
+      k<<<dim3(clb, nqb, splits), v4::kThreads, smem, st>>>(pp, qp, dW, ldo, cq_valid, perm_d, M, tps, na);
+      return ls.done();
+    }
+  }
   int nst = (int)((kSmemBudget6 - 1024 - cbytes) / 65536);
   nst = nst > v6::kMaxStages6 ? v6::kMaxStages6 : nst;
   if (nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
   const size_t smem = 1024 + (size_t)nst * 65536 + cbytes;
-  auto k = v6::x3_wgrad_kernel<PProd, QProd>;
+  auto k = v6::x3_wgrad_kernel<PProd, QProd, false>;
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
   LaunchScope ls(what, st);

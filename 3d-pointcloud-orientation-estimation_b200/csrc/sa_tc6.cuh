@@ -639,6 +639,23 @@ __device__ __forceinline__ void wstore_mn1(uint32_t saddr, int g, const uint4* w
     tc::sts128(saddr + (uint32_t)(j >> 3) * 8192u + tc::sw128_off((g >> 4) + 16 * i, (j & 7) * 8), w[i]);
 }
 
+// the same slices copied asynchronously into raw-ring items 0..3 of the thread (streamed weights on the cp.async path)
+__device__ __forceinline__ void wload_k1_async(const __nv_bfloat16* __restrict__ W, int Kp, int row0, int k0, int g, uint32_t ub) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cp_async16(raw_slot(ub, i, g), W + (size_t)(row0 + (g >> 3) + 32 * i) * Kp + k0 + (g & 7) * 8, true);
+}
+__device__ __forceinline__ void wload_mn1_async(const __nv_bfloat16* __restrict__ W, int Kp, int row0, int col0, int g, uint32_t ub) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cp_async16(raw_slot(ub, i, g), W + (size_t)(row0 + (g >> 4) + 16 * i) * Kp + col0 + (g & 15) * 8, true);
+}
+__device__ __forceinline__ void wfetch(uint32_t ub, int g, uint4* w) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 v = lds128f(raw_slot(ub, i, g));
+    w[i] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+  }
+}
+
 struct Barriers6 {
   uint64_t full[kMaxStages6];
   uint64_t empty[kMaxStages6];
@@ -692,7 +709,7 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wp, size_t wps, int K
   constexpr uint32_t kRawUnit = ASYNC ? (uint32_t)Prod::kRawItems * kRawItemBytes : 0u, kRawBytes = kRawDepth * kRawUnit;
   const uint32_t sWres = smem0, wres_bytes = wres ? (uint32_t)nk * kOp : 0u;
   const uint32_t sS = smem0 + wres_bytes, sbytes = wres ? kOp : 2u * kOp, xoff = wres ? 0u : kOp;
-  const uint32_t sRaw = sS + (uint32_t)nst * sbytes;          // ASYNC: raw fp32 staging ring (requires wres)
+  const uint32_t sRaw = sS + (uint32_t)nst * sbytes;          // ASYNC: raw staging ring
   float* csm = reinterpret_cast<float*>(smem_gen + wres_bytes + (size_t)nst * sbytes + kRawBytes);
   const int cb = blockIdx.x % ncb, t0 = blockIdx.x / ncb, tstep = gridDim.x / ncb;
   const int ntiles = (M + kPts - 1) / kPts;
@@ -759,12 +776,16 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wp, size_t wps, int K
     if constexpr (ASYNC) {   // resident weights, channel-major activations: raw operands staged with cp.async
       async_pipeline(my_items * nk * upc, sRaw, kRawUnit,
           [&](int, uint32_t ub) {
-            prod.template load_async<128>(g, cl.tile * kPts, cl.k * 64 + cl.u * 16 * Prod::kUR, ub);
+            const int xu = cl.u - wu;
+            if (xu < 0) wload_k1_async(Wp + (size_t)cl.u * wps, Kp, cb * 128, cl.k * 64, g, ub);
+            else prod.template load_async<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * Prod::kUR, ub);
             adv(cl);
           },
           [&](int, uint32_t ub) {
             RawU r;
-            prod.template fetch<128>(g, cst.tile * kPts, cst.k * 64 + cst.u * 16 * Prod::kUR, ub, r.x);
+            const int xu = cst.u - wu;
+            if (xu < 0) wfetch(ub, g, r.w);
+            else prod.template fetch<128>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * Prod::kUR, ub, r.x);
             store_unit(r);
           });
     } else {
@@ -898,12 +919,16 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wp, size_t wps, int 
     if constexpr (ASYNC) {
       async_pipeline(my_items * nk * upc, sRaw, kRawUnit,
           [&](int, uint32_t ub) {
-            pp.template load_async<128>(g, cl.tile * kPts, cl.k * 64 + cl.u * 16 * PProd::kUR, ub);
+            const int xu = cl.u - wu;
+            if (xu < 0) wload_mn1_async(Wp + (size_t)cl.u * wps, Kp, cl.k * 64, cb * 128, g, ub);
+            else pp.template load_async<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * PProd::kUR, ub);
             adv(cl);
           },
           [&](int, uint32_t ub) {
             RawU r;
-            pp.template fetch<128>(g, cst.tile * kPts, cst.k * 64 + cst.u * 16 * PProd::kUR, ub, r.x);
+            const int xu = cst.u - wu;
+            if (xu < 0) wfetch(ub, g, r.w);
+            else pp.template fetch<128>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * PProd::kUR, ub, r.x);
             store_unit(r);
           });
     } else {
@@ -950,16 +975,19 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wp, size_t wps, int 
 // global memory at the end.  Stage = 64 points: [P hi | P lo | Q hi | Q lo], P = dy^T part [128 ch x 64 pts] (K-major),
 // Q = x_prev part, channel-major [128 ch x 64 pts] (K-major) or point-major [64 pts x 2 blocks of 64 ch] (MN-major).
 // ---------------------------------------------------------------------------------------------------------------
-template <class PProd, class QProd>
+template <class PProd, class QProd, bool ASYNC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_valid, int perm_d, int M, int tps, int nst) {
   PCOE_V6_PROLOGUE(128)
   constexpr int NP = 2;
+  constexpr int kRawItemsPQ = PProd::kRawItems > QProd::kRawItems ? PProd::kRawItems : QProd::kRawItems;
+  constexpr uint32_t kRawUnit = ASYNC ? (uint32_t)kRawItemsPQ * kRawItemBytes : 0u, kRawBytes = kRawDepth * kRawUnit;
   const int cl0 = blockIdx.x * 128, qb = blockIdx.y;
   const int ntiles = (M + kPts - 1) / kPts;
   const int t0 = blockIdx.z * tps, t1 = min(ntiles, t0 + tps), nt = max(t1 - t0, 0);
   const uint32_t sS = smem0, sbytes = 4u * kPart;
-  float* csm = reinterpret_cast<float*>(smem_gen + (size_t)nst * sbytes);
+  const uint32_t sRaw = sS + (uint32_t)nst * sbytes;
+  float* csm = reinterpret_cast<float*>(smem_gen + (size_t)nst * sbytes + kRawBytes);
   zero_smem(sS, (uint32_t)nst * sbytes, tid, kThreads);
   pp.init(csm, tid, kThreads);
   qp.init(csm + pp.nconst(), tid, kThreads);
@@ -985,9 +1013,43 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
     // Both warp groups (0-7 and 8-15) are producers: the accumulator is read only once, after the last stage, so the
     // "epilogue" warps would otherwise idle for the whole kernel.  Group gsel builds the stages h = gsel, gsel + 2, ...
     // (each stage still gets its kProdThreads arrivals from one group), which doubles the loads in flight per SM.
-    const int gsel = warp >> 3, g = tid & (kProdThreads - 1);
+    const int g = tid & (kProdThreads - 1);
     union RawU { typename PProd::Raw p; typename QProd::Raw q; __device__ RawU() {} };
     struct Cur { int u, m0; };
+    if constexpr (ASYNC) {
+      // one producer group (warps 8-15), raw operands staged with cp.async kRawDepth units deep (see async_pipeline)
+      if (warp >= 8) {
+        auto adv = [&](Cur& c) { if (++c.u == ups) { c.u = 0; c.m0 += 64; } };
+        Cur cl{0, t0 * kPts}, cst = cl;
+        int ring_s = 0, ring_r = 0;
+        async_pipeline(nstage * ups, sRaw, kRawUnit,
+            [&](int, uint32_t ub) {
+              if (cl.u < kPU) pp.template load_async<64>(g, cl.m0, cl0 + cl.u * 32 * PProd::kUR, ub);
+              else qp.template load_async<64>(g, cl.m0, qb * 128 + (cl.u - kPU) * 32 * QProd::kUR, ub);
+              adv(cl);
+            },
+            [&](int, uint32_t ub) {
+              RawU r;
+              const uint32_t st = sS + (uint32_t)ring_s * sbytes;
+              if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
+              if (cst.u < kPU) {
+                pp.template fetch<64>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, ub, r.p);
+                pp.template store<64, NP>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, cst.u * 32 * PProd::kUR, 128, r.p, st);
+              } else {
+                const int qu = cst.u - kPU;
+                qp.template fetch<64>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, ub, r.q);
+                qp.template store<64, NP>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, qu * 32 * QProd::kUR, 128, r.q, st + 2 * kPart);
+              }
+              if (cst.u == ups - 1) {
+                tc::fence_proxy_async();
+                mbar_arrive(&bar.full[ring_s]);
+                if (++ring_s == nst) { ring_s = 0; ++ring_r; }
+              }
+              adv(cst);
+            });
+      }
+    } else {
+    const int gsel = warp >> 3;
     auto adv = [&](Cur& c) { if (++c.u == ups) { c.u = 0; c.m0 += 128; } };
     Cur cl{0, t0 * kPts + gsel * 64}, cst = cl;
     int ring_s = gsel % nst, ring_r = gsel / nst;
@@ -1019,6 +1081,7 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
           }
           adv(cst);
         });
+    }
     if (warp < 8 && nt > 0) {
       tc::mbar_wait(&bar.tmem_full[0], 0u);
       tc::fence_after_sync();
