@@ -447,8 +447,8 @@ struct DyLast6 {
 // D == 0 (SA1) is the xyz block alone.  Thread g owns the 8-channel unit g & 7 of rows (g >> 3) + 32 i, i < PTS/32.
 struct GatherFeat6 {
   static constexpr bool kChMajor = false;
-  static constexpr bool kAsync = false;
-  static constexpr int kRawItems = 0;
+  static constexpr bool kAsync = true;
+  static constexpr int kRawItems = 8;
   static constexpr int kUR = 4;       // unused (point-major): one unit per 64-channel block
   struct Raw { float4 a[4], b[4]; };
   GatherBase gb;
@@ -478,6 +478,45 @@ struct GatherFeat6 {
       if (g < PTS && m0 + g < gb.M) gb.load_xyz_raw(m0 + g, gb.point_of(m0 + g), v, c);
       r.a[0] = make_float4(v[0], v[1], v[2], 0.f);
       r.b[0] = make_float4(c[0], c[1], c[2], 0.f);
+    }
+  }
+  // cp.async path: the neighbour indices are read synchronously (L2-resident int32 rows, shared by the 8 threads of a
+  // point), the gathered 512-byte feature rows / xyz triples are copied asynchronously.
+  // feature block: items 2i, 2i+1 = the two 16-byte halves of row i's 8-channel unit; xyz block: item 0 = point, item 1 = centroid
+  template <int PTS>
+  __device__ __forceinline__ void load_async(int g, int m0, int kb, uint32_t ub) const {
+    if (kb < D / 64) {
+      const int j = g & 7;
+#pragma unroll
+      for (int i = 0; i < PTS / 32; ++i) {
+        const int row = m0 + (g >> 3) + 32 * i;
+        const bool ok = row < gb.M;
+        const float* src = feats + (size_t)(ok ? gb.point_of(row) : 0) * D + kb * 64 + j * 8;
+        cp_async16(raw_slot(ub, 2 * i, g), src, ok);
+        cp_async16(raw_slot(ub, 2 * i + 1, g), src + 4, ok);
+      }
+    } else if (g < PTS) {
+      const int row = m0 + g;
+      const bool ok = row < gb.M;
+      const int pt = ok ? gb.point_of(row) : 0;
+      const float* px = gb.xyz + (size_t)pt * 3;
+      const float* pc = gb.group_all ? px : gb.new_xyz + (size_t)((ok ? row : 0) >> 5) * 3;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        cp_async4(raw_slot(ub, 0, g) + 4u * u, px + u, ok);
+        cp_async4(raw_slot(ub, 1, g) + 4u * u, pc + u, ok && !gb.group_all);
+      }
+    }
+  }
+  template <int PTS>
+  __device__ __forceinline__ void fetch(int g, int, int kb, uint32_t ub, Raw& r) const {
+    if (kb < D / 64) {
+#pragma unroll
+      for (int i = 0; i < PTS / 32; ++i) { r.a[i] = lds128f(raw_slot(ub, 2 * i, g)); r.b[i] = lds128f(raw_slot(ub, 2 * i + 1, g)); }
+    } else if (g < PTS) {
+      r.a[0] = lds128f(raw_slot(ub, 0, g));      // .w holds stale bytes: only x, y, z are used
+      r.b[0] = lds128f(raw_slot(ub, 1, g));
+      if (gb.group_all) r.b[0] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   template <int PTS, int NP>
@@ -778,14 +817,16 @@ x3_fwd_kernel(Prod prod, const __nv_bfloat16* __restrict__ Wp, size_t wps, int K
           [&](int, uint32_t ub) {
             const int xu = cl.u - wu;
             if (xu < 0) wload_k1_async(Wp + (size_t)cl.u * wps, Kp, cb * 128, cl.k * 64, g, ub);
-            else prod.template load_async<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * Prod::kUR, ub);
+            else if constexpr (Prod::kChMajor) prod.template load_async<128>(g, cl.tile * kPts, cl.k * 64 + xu * 16 * Prod::kUR, ub);
+            else prod.template load_async<128>(g, cl.tile * kPts, cl.k, ub);
             adv(cl);
           },
           [&](int, uint32_t ub) {
             RawU r;
             const int xu = cst.u - wu;
             if (xu < 0) wfetch(ub, g, r.w);
-            else prod.template fetch<128>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * Prod::kUR, ub, r.x);
+            else if constexpr (Prod::kChMajor) prod.template fetch<128>(g, cst.tile * kPts, cst.k * 64 + xu * 16 * Prod::kUR, ub, r.x);
+            else prod.template fetch<128>(g, cst.tile * kPts, cst.k, ub, r.x);
             store_unit(r);
           });
     } else {
@@ -1025,7 +1066,8 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
         async_pipeline(nstage * ups, sRaw, kRawUnit,
             [&](int, uint32_t ub) {
               if (cl.u < kPU) pp.template load_async<64>(g, cl.m0, cl0 + cl.u * 32 * PProd::kUR, ub);
-              else qp.template load_async<64>(g, cl.m0, qb * 128 + (cl.u - kPU) * 32 * QProd::kUR, ub);
+              else if constexpr (QProd::kChMajor) qp.template load_async<64>(g, cl.m0, qb * 128 + (cl.u - kPU) * 32 * QProd::kUR, ub);
+              else qp.template load_async<64>(g, cl.m0, 2 * qb + (cl.u - kPU), ub);
               adv(cl);
             },
             [&](int, uint32_t ub) {
@@ -1037,8 +1079,13 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
                 pp.template store<64, NP>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, cst.u * 32 * PProd::kUR, 128, r.p, st);
               } else {
                 const int qu = cst.u - kPU;
-                qp.template fetch<64>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, ub, r.q);
-                qp.template store<64, NP>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, qu * 32 * QProd::kUR, 128, r.q, st + 2 * kPart);
+                if constexpr (QProd::kChMajor) {
+                  qp.template fetch<64>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, ub, r.q);
+                  qp.template store<64, NP>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, qu * 32 * QProd::kUR, 128, r.q, st + 2 * kPart);
+                } else {
+                  qp.template fetch<64>(g, cst.m0, 2 * qb + qu, ub, r.q);
+                  qp.template store<64, NP>(g, 2 * qb + qu, r.q, st + 2 * kPart + (uint32_t)qu * 8192u);
+                }
               }
               if (cst.u == ups - 1) {
                 tc::fence_proxy_async();

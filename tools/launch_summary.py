@@ -12,9 +12,9 @@ import sys
 def short(name: str) -> str:
     name = name.replace("void ", "")
     fn = name.split("<")[0].split("(")[0]
-    if fn.startswith(("pcoe::", "v4::", "v5::")):          # ncu drops the outer namespace of nested ones
+    if fn.startswith(("pcoe::", "v4::", "v5::", "v6::")):          # ncu drops the outer namespace of nested ones
         targs = name[len(fn):].split(">(")[0] if "<" in name else ""
-        args = re.findall(r"(?:pcoe|v4|v5)::(\w+)", targs)
+        args = re.findall(r"(?:pcoe|v4|v5|v6)::(\w+)", targs)
         fn = fn if fn.startswith("pcoe::") else "pcoe::" + fn
         return f"{fn}<{','.join(args)}>" if args else fn
     return fn[:70]
