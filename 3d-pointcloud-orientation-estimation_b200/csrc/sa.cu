@@ -439,9 +439,10 @@ static int launch_fwd6(const Prod& prod, const __nv_bfloat16* Wp, size_t wps, in
     // resident weights + room for the raw staging ring: the producers copy their fp32 operands with cp.async
     const size_t raw = (size_t)v6::kRawDepth * Prod::kRawItems * v6::kRawItemBytes;
     const Cfg6 ca = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes + raw, NP, 1);
-    // never trade weight residency for the staging ring (measured: SA2 forward 42 -> 58 us when its weights are streamed)
-    const bool keeps_res = ca.wres || !cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes, NP).wres;
-    if (x3_async_enabled() && ca.nst >= 1 && keeps_res) {
+    // never trade weight residency for the staging ring (measured: SA2 forward 42 -> 58 us when its weights are
+    // streamed): order of preference = ring + resident weights, resident weights alone, ring + streamed weights
+    const bool res_alone = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes, NP, 1).wres;
+    if (x3_async_enabled() && ca.nst >= 1 && (ca.wres || !res_alone)) {
       auto k = v6::x3_fwd_kernel<Prod, Epi, NP, true>;
       static bool attr = false;
       if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
@@ -450,7 +451,7 @@ static int launch_fwd6(const Prod& prod, const __nv_bfloat16* Wp, size_t wps, in
       return ls.done();
     }
   }
-  const Cfg6 c = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes, NP);
+  const Cfg6 c = cfg6(prod.nchunks(), ncb, ceil_div(M, v4::kPts), cbytes, NP, 1);
   if (c.nst < 1) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
   auto k = v6::x3_fwd_kernel<Prod, Epi, NP, false>;
   static bool attr = false;

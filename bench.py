@@ -497,6 +497,29 @@ def run_ours(args):
         cpu = {"value": B * n_cpu / dt, "unit": "clouds/s", "cores": cores, "kind": "port",
                "sample": f"{n_cpu} full steps of {B} clouds after 1 warm-up (oracle port of the reference step, torch CPU fp32)"}
 
+    # ---- the reference algorithm in torch eager ON THE SAME GPU (rank 0, N=1) -----------------------------------------
+    # The reference's scripts run on CUDA when it is available (train_multi_peaks_vonMises_KL.py:27).  The reference tree
+    # does not travel to the GPU box, so this leg runs the oracle port of its training step (oracle/step.py: the same
+    # torch ops - gather, cdist-style kNN + topk, conv-as-matmul, batch_norm, max, host randperm, host Hungarian) on
+    # this device: the like-for-like "stock PyTorch on a B200" number next to `value`.
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.step import OracleTrainer
+        tr = OracleTrainer(kind, {k: v.detach().cpu() for k, v in model.state_dict().items()}, device=dev)
+        gb = [(x, tuple(t.long() if not t.is_floating_point() else t for t in tg)) for x, tg in resident[:4]]
+        for i in range(2):
+            tr.step(*gb[i])
+        torch.cuda.synchronize()
+        n_g = 10
+        t0 = time.perf_counter()
+        for i in range(n_g):
+            tr.step(*gb[i % 4])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        gpu_eager = {"value": B * n_g / dt, "unit": "clouds/s", "ms_per_step": 1e3 * dt / n_g, "kind": "port",
+                     "sample": f"{n_g} full steps of {B} clouds after 2 warm-ups: oracle port of the reference step in torch eager "
+                               "on this GPU (fp32, host randperm + host Hungarian as the reference), inputs resident"}
+
     # ---- the same step in the other precision modes (rank 0, N=1) ---------------------------------
     # `value` is the mode named in config.precision.  The other modes are timed here on the same workload so that all
     # three are on record: bf16x3 (parity-gated tensor-core mode), bf16 (throughput mode, stated tolerance), fp32
@@ -568,7 +591,7 @@ def run_ours(args):
             "cuda_graph": graphed is not None,
             "gpu_launches": int(launches),
             "gpu_launches_per_step": launches / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "modes": modes, "kernels": kernels,
+            "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_port": gpu_eager, "modes": modes, "kernels": kernels,
             "sampling_grouping": sg,
             "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps,
             "grad_allreduce_bytes": engine.grads.nbytes() if world > 1 else 0,

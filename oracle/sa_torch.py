@@ -40,7 +40,7 @@ def set_abstraction(sd: dict, prefix: str, xyz: torch.Tensor, points, *, group_a
     cn, bn_ = names
     B = xyz.shape[0]
     if group_all:
-        new_xyz = torch.zeros(B, 1, 3, dtype=xyz.dtype)
+        new_xyz = torch.zeros(B, 1, 3, dtype=xyz.dtype, device=xyz.device)
         rows = xyz.unsqueeze(1)                                                  # :24 absolute xyz
         if points is not None:
             rows = torch.cat([rows, points.unsqueeze(1)], -1)                    # :25
@@ -177,11 +177,12 @@ def model_forward(kind: str, sd: dict, xyz: torch.Tensor, fps1, fps2, training=T
     raise ValueError(kind)
 
 
-def clone_state(sd: dict, dtype=None, requires_grad: bool = False) -> dict:
-    """Detached copy of a state dict on the CPU (floating tensors optionally cast / made leaves)."""
+def clone_state(sd: dict, dtype=None, requires_grad: bool = False, device="cpu") -> dict:
+    """Detached copy of a state dict on the CPU - or on `device` for bench.py's eager-CUDA run of the port - (floating
+    tensors optionally cast / made leaves)."""
     out = {}
     for k, v in sd.items():
-        t = v.detach().cpu().clone()
+        t = v.detach().cpu().clone().to(device)
         if t.is_floating_point():
             if dtype is not None:
                 t = t.to(dtype)

@@ -10,9 +10,13 @@ from . import losses, sa_torch
 
 
 class OracleTrainer:
-    def __init__(self, kind: str, state_dict: dict, lr: float = 1e-3, dropout_p: float | None = None):
+    def __init__(self, kind: str, state_dict: dict, lr: float = 1e-3, dropout_p: float | None = None, device="cpu"):
+        """device = "cpu" (the cpu_baseline / --impl reference legs) or a CUDA device: the same torch-eager restatement of
+        the reference step run on the GPU, i.e. what the reference's own scripts do when CUDA is available
+        (train_multi_peaks_vonMises_KL.py:27: device = cuda if available)."""
         self.kind = kind
-        self.sd = sa_torch.clone_state(state_dict, requires_grad=True)
+        self.device = torch.device(device)
+        self.sd = sa_torch.clone_state(state_dict, requires_grad=True, device=self.device)
         self.params = [v for k, v in self.sd.items() if v.requires_grad]
         self.opt = torch.optim.Adam(self.params, lr=lr)
         self.dropout_p = {"mvm": 0.4}.get(kind, 0.5) if dropout_p is None else dropout_p
@@ -21,8 +25,8 @@ class OracleTrainer:
         B, N, _ = xyz.shape
         self.opt.zero_grad(set_to_none=True)
         # the reference draws its random subsets on the host generator (pointnet_pp_8dir.py:28)
-        fps1 = torch.stack([torch.randperm(N)[:128] for _ in range(B)])
-        fps2 = torch.stack([torch.randperm(128)[:32] for _ in range(B)])
+        fps1 = torch.stack([torch.randperm(N)[:128] for _ in range(B)]).to(self.device)
+        fps2 = torch.stack([torch.randperm(128)[:32] for _ in range(B)]).to(self.device)
         res = sa_torch.model_forward(self.kind, self.sd, xyz, fps1, fps2, training=True, dropout_p=self.dropout_p)
         if self.kind == "mvm":
             loss = losses.match_loss(res[0], res[1], res[2], targets[0], targets[1]).mean()
