@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 
-_DEFAULT_PRECISION = "fp32"
+_DEFAULT_PRECISION = "bf16x3"
 PRECISIONS = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16, "bf16x3": _lib.PRECISION_BF16X3}
 _layer_seq = 0          # construction index of the SA layers of this process: deterministic Philox stream ids
 
@@ -26,9 +26,10 @@ def _dp_rank() -> int:
 
 
 def set_default_precision(p: str) -> None:
-    """'fp32' (CUDA-core fp32 GEMMs), 'bf16x3' (tcgen05 with every operand split into two bf16 planes and three
-    MMAs per step, fp32 stored activations: fp32-class accuracy on the tensor pipe - the parity mode of the fast
-    path) or 'bf16' (tcgen05, plain bf16 operands and stored activations: fastest, stated tolerance)."""
+    """'bf16x3' (the default: tcgen05 with every operand split into bf16 planes - three planes / six MMAs per product in
+    the forward, two / three in the backward -, fp32 stored activations: fp32-class accuracy on the tensor pipe, the
+    mode the parity tests gate; layer shapes it does not cover run on the fp32 kernels), 'fp32' (CUDA-core fp32 GEMMs)
+    or 'bf16' (tcgen05, plain bf16 operands and stored activations: fastest, stated tolerance, not parity-gated)."""
     global _DEFAULT_PRECISION
     if p not in PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")

@@ -248,6 +248,34 @@ def loss_of(kind: str, res, tg, pcoe):
     return sum((r ** 2).sum() for r in res)
 
 
+def _leave_multirank(torch, dist, graphs=()):
+    """Orderly multi-rank exit: final barrier, drop the captured graphs (they hold references to the NCCL communicator),
+    then destroy_process_group().  That call has been observed to hang on this stack (torch 2.11 / NCCL 2.28) while a
+    captured graph was alive, so it runs under a watchdog: if it has not returned after 20 s the rank leaves with
+    os._exit(0) - after the JSON line has been flushed, so a stuck teardown can never cost the measurement."""
+    import gc
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    for g in graphs:
+        try:
+            if g is not None and getattr(g, "graph", None) is not None:
+                g.graph.reset()
+        except Exception:
+            pass
+    gc.collect()
+    torch.cuda.synchronize()
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
+        dist.destroy_process_group()
+    finally:
+        t.cancel()
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
     """The reference algorithm (oracle port, torch CPU) on the box's host cores; rank 0 only."""
@@ -386,13 +414,8 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": dev_ms / args.steps, "gpu_launches": int(launches),
                               "precision": args.precision, "timed_only": True}), flush=True)
-        if world > 1:                                    # same clean multi-rank exit as the full run (see the end)
-            torch.cuda.synchronize()
-            dist.barrier()
-            torch.cuda.synchronize()
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
+        if world > 1:                                    # same multi-rank exit as the full run (see the end)
+            _leave_multirank(torch, dist, (graphed,))
         return
 
     # ---- end-to-end through the public API with host buffers ------------------------------------
@@ -598,15 +621,7 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        # The NCCL communicator is referenced by the captured CUDA graph; tearing it down through
-        # destroy_process_group() was observed to hang on this stack (torch 2.11 / NCCL 2.28), so the
-        # ranks leave right after the final barrier.
-        os._exit(0)
+        _leave_multirank(torch, dist, (graphed,))
 
 
 # ------------------------------------------------------------------------------------------------
