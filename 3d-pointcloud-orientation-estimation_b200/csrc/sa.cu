@@ -531,7 +531,8 @@ static int convert_weights6(const pcoe_sa_desc& d, const SaLayout& L, const pcoe
   v6::ConvW6 w[3];
   int total = 0;
   for (int l = 0; l < 3; ++l) {
-    w[l] = v6::ConvW6{P.W[l], (__nv_bfloat16*)(base + L.wb_off[l]), Cs[l], Kin[l], L.w4_rp[l], L.w4_kp[l], l == 0 ? d.D : -1, 3};
+    w[l] = v6::ConvW6{P.W[l], (__nv_bfloat16*)(base + L.wb_off[l]), Cs[l], Kin[l], L.w4_rp[l], L.w4_kp[l], l == 0 ? d.D : -1, 3,
+                      (l >= 1 && Kin[l] == 64 && L.w4_kp[l] == 128) ? 1 : 0};
     total += L.w4_rp[l] * L.w4_kp[l];
   }
   LaunchScope ls("convert_weights_kernel", st);
@@ -776,7 +777,13 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
   if constexpr (TC) v4path = L.v2;
   // the v4 kernels accumulate dW into copies (dw_combine_kernel writes / adds into dW at the end); the copies follow
   // the batch sums in the workspace: one memset node for both
-  PCOE_CUDA(cudaMemsetAsync(ws + L.wb_sums[0], 0, L.wb_sums_bytes + (v4path ? L.wb_dwc_bytes : 0), st));
+  // bf16x3, SA1: dW1 comes out of the layer-2 dgrad epilogue (MaskStatsW6); PCOE_SA_BWD_L1_KERNEL=1 = the separate kernel
+  bool w1_epi6 = false;
+  if constexpr (!TC) {
+    const char* keep_env = getenv("PCOE_SA_BWD_L1_KERNEL");
+    w1_epi6 = L.v6 && d.D == 0 && !d.group_all && d.C1 == 64 && !(keep_env && keep_env[0] == '1');
+  }
+  PCOE_CUDA(cudaMemsetAsync(ws + L.wb_sums[0], 0, L.wb_sums_bytes + ((v4path || w1_epi6) ? L.wb_dwc_bytes : 0), st));
   if (v4path) {
   } else if (!Gr.accumulate) {
     for (int l = 0; l < 3; ++l)
@@ -988,6 +995,16 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       m1.dz = dz[0]; m1.sums = bs[0]; m1.C = d.C1;
       PCOE_TRY(launch_wgrad6(dy2, x1, Gr.dW[1], d.C1, d.C1, -1, M, ceil_div(d.C1, 128), st, kname(d, kWG2)));
       dy2.fin.write = 0;
+      if (w1_epi6) {
+        v6::MaskStatsW6 mw{}; mw.yprev = y[0]; mw.scale = scale[0]; mw.shift = shift[0]; mw.mean = mean[0]; mw.invstd = invstd[0];
+        mw.sums = bs[0]; mw.C = d.C1; mw.gb = v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M};
+        mw.acc = (float*)(ws + L.wb_dwc[0]); mw.g0 = (float*)(ws + L.wb_g0);
+        PCOE_TRY(launch_dgrad6<false>(dy2, wh(1), wps(1), L.w4_kp[1], mw, M, d.C1, st, kname(d, kDG2)));
+        LaunchScope ls("dw1_finalize_kernel", st);
+        v6::dw1_finalize6_kernel<<<ceil_div(d.C1 * 3, 128), 128, 0, st>>>(mw.acc, mw.g0, P.W[0], mkbfin(0, 1), d.C1, Gr.dW[0],
+                                                                          Gr.accumulate);
+        return ls.done();
+      }
       PCOE_TRY(launch_dgrad6<false>(dy2, wh(1), wps(1), L.w4_kp[1], m1, M, d.C1, st, kname(d, kDG2)));
       v6::Dy6 dy1{}; dy1.dz = dz[0]; dy1.y = y[0]; dy1.a = ca[0]; dy1.p = cp[0]; dy1.q = cq[0]; dy1.M = M; dy1.C = d.C1;
       dy1.fin = mkbfin(0, 1);
@@ -1209,7 +1226,7 @@ extern "C" int pcoe_pointmlp_forward(const pcoe_pointmlp_desc* desc, const float
       const int ll = l < nl ? l : nl - 1;            // unused third slot of a 2-layer stack: converts layer 2 again (tiny)
       const int kin = ll == 0 ? L.Cin0 : d.C[ll - 1];
       w[l] = v6::ConvW6{params->W[ll], (__nv_bfloat16*)(ws + L.wb[ll]), d.C[ll], kin, L.Rp[ll], L.Kp[ll], ll == 0 ? d.D : -1,
-                        d.use_xyz ? 3 : 0};
+                        d.use_xyz ? 3 : 0, 0};
       total += L.Rp[ll] * L.Kp[ll];
     }
     LaunchScope ls("convert_weights_kernel", st);

@@ -135,10 +135,14 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   L.wb_sums_bytes = b - L.wb_sums[0];
   for (int l = 0; l < 3; ++l) {
     L.dwc_ld[l] = l == 0 ? (Kin[0] + 15) / 16 * 16 : Kin[l];       // = the Q operand's channel extent (multiple of 16)
-    L.wb_dwc[l] = L.v2 ? take(b, sizeof(float) * (size_t)kRedCopies * C[l] * L.dwc_ld[l]) : 0;
+    // v6 (bf16x3), no input features: layer 1's dz1^T x0 accumulator of the MaskStatsW6 epilogue, [kRedCopies][C1][4]
+    const bool w6 = L.v6 && l == 0 && d.D == 0 && !d.group_all && d.C1 == 64;
+    L.wb_dwc[l] = L.v2 ? take(b, sizeof(float) * (size_t)kRedCopies * C[l] * L.dwc_ld[l])
+                       : (w6 ? take(b, sizeof(float) * (size_t)kRedCopies * C[l] * 4) : 0);
   }
-  L.wb_g0 = L.v2 ? take(b, sizeof(float) * 16 * kRedCopies) : 0;
-  L.wb_dwc_bytes = L.v2 ? b - L.wb_dwc[0] : 0;
+  const bool w6 = L.v6 && d.D == 0 && !d.group_all && d.C1 == 64;
+  L.wb_g0 = (L.v2 || w6) ? take(b, sizeof(float) * 16 * kRedCopies) : 0;
+  L.wb_dwc_bytes = L.v2 ? b - L.wb_dwc[0] : (w6 ? b - L.wb_dwc[0] : 0);
   for (int l = 0; l < 3; ++l) L.wb_consts[l] = take(b, sizeof(float) * 3 * C[l]);
   L.wb_gmimg = L.wb_rvec = L.wb_gsum = L.wb_l3e = 0;
   if (L.l3s) {

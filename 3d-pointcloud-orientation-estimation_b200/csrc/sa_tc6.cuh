@@ -78,7 +78,9 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], uint32_t s0, u
 
 // fp32 [C_out][C_in] -> three zero-padded bf16 planes [3][Rp][Kp] (hi, mid, lo; the backward kernels read the first
 // two); perm_d >= 0: layer-1 column order [feats(perm_d) | xyz(xyz_cols)] (xyz_cols = 3, or 0 for a feature-only input)
-struct ConvW6 { const float* W; __nv_bfloat16* planes; int cout, cin, Rp, Kp, perm_d, xyz_cols; };
+// dup_cols: image columns 64..127 repeat columns 0..63 (64-wide inputs: the dgrad's TMEM lanes 64..127 then carry the same
+// input channels, two epilogue threads per channel - MaskStatsW6; the forward only reads columns 0..63)
+struct ConvW6 { const float* W; __nv_bfloat16* planes; int cout, cin, Rp, Kp, perm_d, xyz_cols, dup_cols; };
 __global__ void convert_weights6_kernel(ConvW6 a, ConvW6 b, ConvW6 c) {
   const ConvW6* L[3] = {&a, &b, &c};
   const int n0 = a.Rp * a.Kp / 8, n1 = b.Rp * b.Kp / 8, n2 = c.Rp * c.Kp / 8;
@@ -90,7 +92,7 @@ __global__ void convert_weights6_kernel(ConvW6 a, ConvW6 b, ConvW6 c) {
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int k = k0 + u;
+      const int k = (w.dup_cols && k0 + u < 128) ? ((k0 + u) & 63) : k0 + u;
       int src = k;
       if (w.perm_d >= 0) src = k < w.perm_d ? k + w.xyz_cols : (k < w.perm_d + w.xyz_cols ? k - w.perm_d : w.cin);
       v[u] = (r < w.cout && src < w.cin) ? __ldg(w.W + (size_t)r * w.cin + src) : 0.f;
@@ -550,6 +552,8 @@ __device__ __forceinline__ void store32_f32(float* y, int tile, int C, int c, in
 }
 
 struct StoreStats6 {
+  static constexpr bool kPre = false;
+  static constexpr bool kHalf = false;
   float* __restrict__ y;           // fp32 activation (quad-interleaved, see act_off)
   double* __restrict__ sums;       // [kRedCopies][2,C] or nullptr (eval)
   int C;
@@ -571,6 +575,8 @@ struct StoreStats6 {
 };
 
 struct Group6 {   // last layer, K == 32: the 32 columns of a block are one group
+  static constexpr bool kPre = false;
+  static constexpr bool kHalf = false;
   float* __restrict__ y;           // tile-blocked fp32, or nullptr (eval)
   double* __restrict__ sums;
   float* __restrict__ ymax;        // [G,C]
@@ -604,6 +610,8 @@ struct Group6 {   // last layer, K == 32: the 32 columns of a block are one grou
 
 // dz_prev^T = dx^T * [z_prev > 0]; sums of dz_prev and dz_prev * xhat_prev per channel
 struct MaskStats6 {
+  static constexpr bool kPre = false;
+  static constexpr bool kHalf = false;
   const float* __restrict__ yprev;   // tile-blocked fp32
   const float* __restrict__ scale;
   const float* __restrict__ shift;
@@ -653,6 +661,146 @@ struct MaskStats6 {
     atomicAdd(dst + C + c, (double)s1);
   }
 };
+
+
+// SA1 (no input features): layer 1 has no data gradient, only dW1 [C1 x 3] = dy1^T x0 with dy1 = a1 dz1 + p1 y1 + q1 and
+// y1 = W1 x0, i.e.  dW1 = a1 (dz1^T x0) + p1 W1 (x0^T x0) + q1 (sum x0)^T.  The layer-2 dgrad epilogue holds dz1 in
+// registers (one channel per thread), so it accumulates dz1^T x0 itself in fp32: dz1 is never written, the layer-1
+// weight-gradient kernel (a full pass over dz1 and y1 for a 64 x 3 result) does not run.  pre() parks the 32 point
+// offsets of the warp's blocks in shared memory before the wait for the accumulator; one warp per block also
+// accumulates x0^T x0 and sum x0.  dw1_finalize6_kernel applies (a1, p1, q1) once the batch sums are complete.
+struct MaskStatsW6 {
+  static constexpr bool kPre = true;
+  static constexpr bool kHalf = true;   // C == 64 only: lanes 64..127 repeat the channels (ConvW6::dup_cols), 16 points per thread
+  int half;
+  const float* __restrict__ yprev;   // y1, fp32 activation layout
+  const float* __restrict__ scale;
+  const float* __restrict__ shift;
+  const float* __restrict__ mean;
+  const float* __restrict__ invstd;
+  double* __restrict__ sums;
+  int C;
+  GatherBase gb;
+  float* __restrict__ acc;           // [kRedCopies][C][4]: dz1^T x0 in columns 0..2
+  float* __restrict__ g0;            // [kRedCopies][16]: xx xy xz yy yz zz sx sy sz
+  int c, eq;
+  float s0, s1, sc, sh, is, nmi;
+  float A0, A1, A2;
+  float G[9];
+  float4* xs;                        // shared memory: [warp][2 blocks][32 points] (x, y, z, 0)
+  float4 yq[2][4];                   // y1 of this thread's 2 x 16 points, loaded by pre() before the accumulator wait
+  __host__ __device__ __forceinline__ int nconst() const { return 8 * 2 * 32 * 4; }
+  __device__ __forceinline__ void init(float* csm, int ch) {
+    xs = reinterpret_cast<float4*>(csm) + (threadIdx.x >> 5) * 64;   // csm is 16-byte aligned
+    c = ch & 63; half = (ch >> 6) & 1;
+    eq = (threadIdx.x >> 5) & 3; s0 = s1 = 0.f; A0 = A1 = A2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) G[i] = 0.f;
+    const bool ok = c < C;
+    sc = ok ? scale[c] : 0.f; sh = ok ? shift[c] : 0.f; is = ok ? invstd[c] : 0.f; nmi = ok ? -mean[c] * is : 0.f;
+  }
+  __device__ __forceinline__ void pre(int tile, int eh, int M) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int row = tile * kPts + (2 * eh + it) * 32 + lane;
+      float o[3] = {0.f, 0.f, 0.f};
+      if (row < M) {
+        float x[3], cc[3];
+        gb.load_xyz_raw(row, gb.point_of(row), x, cc);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) o[u] = gb.centred(x[u], cc[u]);       // the forward's x0, bit for bit
+      }
+      xs[it * 32 + lane] = make_float4(o[0], o[1], o[2], 0.f);           // read back by this warp only
+      const int j = 2 * eh + it;
+      const bool ok = tile * kPts + j * 32 < M;
+      const size_t yo = act_off(tile, C, c, j * 8 + half * 4), qs = (size_t)C * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) yq[it][q] = ldg4_or0(yprev + yo + (size_t)q * qs, ok);
+    }
+    __syncwarp();
+  }
+  // v = the accumulator's columns j*32 + half*16 .. +15 (16 points of block j) of channel c
+  __device__ __forceinline__ void block16(float (&v)[16], int tile, int j, bool valid) {
+    const int it = j & 1;
+    const float4* xp = xs + it * 32;
+    if (valid) {
+      float4 yv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) yv[q] = yq[it][q];
+      float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+      float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float yy[4] = {yv[q].x, yv[q].y, yv[q].z, yv[q].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = 4 * q + u;
+          const bool on = fmaf(yy[u], sc, sh) > 0.f;
+          const float d = on ? v[i] : 0.f;
+          a[u] += d;
+          b[u] = fmaf(d, fmaf(yy[u], is, nmi), b[u]);
+          const float4 x0 = xp[half * 16 + i];                            // broadcast 16-byte load
+          t0[u] = fmaf(d, x0.x, t0[u]); t1[u] = fmaf(d, x0.y, t1[u]); t2[u] = fmaf(d, x0.z, t2[u]);
+        }
+      }
+      s0 += (a[0] + a[1]) + (a[2] + a[3]);
+      s1 += (b[0] + b[1]) + (b[2] + b[3]);
+      A0 += (t0[0] + t0[1]) + (t0[2] + t0[3]); A1 += (t1[0] + t1[1]) + (t1[2] + t1[3]); A2 += (t2[0] + t2[1]) + (t2[2] + t2[3]);
+      if (eq == 3) {   // one warp per block: x0^T x0 and sum x0 of this lane's point (zero beyond M)
+        const float4 own = xp[threadIdx.x & 31];
+        G[0] = fmaf(own.x, own.x, G[0]); G[1] = fmaf(own.x, own.y, G[1]); G[2] = fmaf(own.x, own.z, G[2]);
+        G[3] = fmaf(own.y, own.y, G[3]); G[4] = fmaf(own.y, own.z, G[4]); G[5] = fmaf(own.z, own.z, G[5]);
+        G[6] += own.x; G[7] += own.y; G[8] += own.z;
+      }
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    const int cp = blockIdx.x % kRedCopies;
+    if (c < C) {
+      double* dst = sums + (size_t)cp * 2 * C;
+      atomicAdd(dst + c, (double)s0);
+      atomicAdd(dst + C + c, (double)s1);
+      float* ad = acc + ((size_t)cp * C + c) * 4;
+      atomicAdd(ad, A0); atomicAdd(ad + 1, A1); atomicAdd(ad + 2, A2);
+    }
+    if (eq == 3) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        float t = G[i];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, m);
+        if ((threadIdx.x & 31) == 0) atomicAdd(g0 + cp * 16 + i, t);
+      }
+    }
+  }
+};
+
+// dW1[c][k] (+)= a_c A[c][k] + p_c sum_j W1[c][j] G0[j][k] + q_c s[k]   (W1 fp32 [C][3]); thread (c, k = 0) also writes
+// the layer's dgamma / dbeta through fin.eval
+__global__ void dw1_finalize6_kernel(const float* __restrict__ acc, const float* __restrict__ g0, const float* __restrict__ W1,
+                                     BnBwdFin fin, int C, float* __restrict__ dW, int accumulate) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= C * 3) return;
+  const int r = e / 3, k = e - r * 3;
+  float A = 0.f, G[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) G[i] = 0.f;
+#pragma unroll
+  for (int g = 0; g < kRedCopies; ++g) {
+    A += acc[((size_t)g * C + r) * 4 + k];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) G[i] += g0[g * 16 + i];
+  }
+  float ca, cp, cq;
+  fin.eval(r, C, k == 0, ca, cp, cq);
+  const float w0 = W1[r * 3], w1 = W1[r * 3 + 1], w2 = W1[r * 3 + 2];
+  const float gk0 = k == 0 ? G[0] : (k == 1 ? G[1] : G[2]);     // G0 rows: (xx xy xz), (xy yy yz), (xz yz zz)
+  const float gk1 = k == 0 ? G[1] : (k == 1 ? G[3] : G[4]);
+  const float gk2 = k == 0 ? G[2] : (k == 1 ? G[4] : G[5]);
+  const float s = ca * A + cp * (w0 * gk0 + w1 * gk1 + w2 * gk2) + cq * G[6 + k];
+  dW[e] = accumulate ? dW[e] + s : s;
+}
 
 // ---- weight-slice loads, one plane per call (4 x 16 bytes per thread) ---------------------------------------------
 // K-major slice [128 rows x 64 k] (forward A operand)
@@ -913,14 +1061,24 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wp, size_t wps, int 
     int i = 0;
     for (int tile = t0; tile < ntiles; tile += tstep, ++i) {
       const int b = i & 1, u = i >> 1, m0 = tile * kPts;
+      if constexpr (!PT) { if constexpr (Epi::kPre) epi.pre(tile, eh, M); }
       tc::mbar_wait(&bar.tmem_full[b], (uint32_t)(u & 1));
       tc::fence_after_sync();
       if constexpr (!PT) {
+        if constexpr (Epi::kHalf) {   // two threads per channel: 16 of a block's 32 points each
 #pragma unroll 1
-        for (int j = eh * 2; j < eh * 2 + 2; ++j) {
-          float v[32];
-          tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(b * kPts + j * 32), v);
-          epi.block(v, tile, j, m0 + j * 32 < M);
+          for (int j = eh * 2; j < eh * 2 + 2; ++j) {
+            float v[16];
+            tc::tmem_ld16(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(b * kPts + j * 32 + (eq >> 1) * 16), v);
+            epi.block16(v, tile, j, m0 + j * 32 < M);
+          }
+        } else {
+#pragma unroll 1
+          for (int j = eh * 2; j < eh * 2 + 2; ++j) {
+            float v[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(eq * 32) << 16) + (uint32_t)(b * kPts + j * 32), v);
+            epi.block(v, tile, j, m0 + j * 32 < M);
+          }
         }
       } else {
         const int row = m0 + eq * 32 + lane;

@@ -13,6 +13,10 @@ import csv
 import json
 import sys
 
+ORDER_X3 = (["knn_kernel(sa1)", "sa1_fwd_l1", "sa1_fwd_l2", "sa1_fwd_l3", "knn_kernel(sa2)", "sa2_fwd_l1", "sa2_fwd_l2", "sa2_fwd_l3",
+             "sa3_fwd_l1", "sa3_fwd_l2", "sa3_fwd_l3"] +
+            [f"sa{l}_bwd_{k}{i}" for l in (3, 2) for i in (3, 2, 1) for k in ("wgrad", "dgrad")] +
+            ["sa1_bwd_wgrad3", "sa1_bwd_dgrad3", "sa1_bwd_wgrad2", "sa1_bwd_dgrad2", "sa1_bwd_wgrad1"])   # bf16x3: -k regex:'x3_|knn_k32'
 ORDER = (["knn_kernel(sa1)", "sa1_fwd_l1", "sa1_fwd_l2", "sa1_fwd_l3", "knn_kernel(sa2)", "sa2_fwd_l1", "sa2_fwd_l2",
           "sa2_fwd_l3", "sa3_fwd_l1", "sa3_fwd_l2", "sa3_fwd_l3", "sa3_bwd_wgrad3", "sa3_bwd_dgrad3", "sa3_bwd_wgrad2",
           "sa3_bwd_dgrad2", "sa3_bwd_wgrad1", "sa3_bwd_dgrad1", "sa2_bwd_l3", "sa2_bwd_l2", "sa2_bwd_l1", "sa1_bwd_l3",
@@ -34,6 +38,10 @@ def to_bytes(v: float, unit: str) -> float:
 
 def main():
     raw, out_txt, out_json = sys.argv[1:4]
+    mode = sys.argv[4] if len(sys.argv) > 4 else "bf16"
+    global ORDER
+    if mode == "bf16x3":
+        ORDER = ORDER_X3
     rows = list(csv.reader(open(raw)))
     hdr, units = rows[0], rows[1]
     ci = {h: i for i, h in enumerate(hdr)}
@@ -60,7 +68,15 @@ def main():
         traffic[name] = rd + wr
         lines.append(f"{name:18s} " + " ".join(f"{v:9.2f}" for v in vals) + "   " + r[ci["Kernel Name"]][:70])
     open(out_txt, "w").write("\n".join(lines) + "\n")
-    json.dump(traffic, open(out_json, "w"), indent=1, sort_keys=True)
+    # traffic.json is keyed by precision mode: {"bf16": {kernel: bytes}, "bf16x3": {...}}
+    try:
+        allt = json.load(open(out_json))
+        if allt and not isinstance(next(iter(allt.values())), dict):
+            allt = {"bf16": allt}
+    except Exception:
+        allt = {}
+    allt[mode] = traffic
+    json.dump(allt, open(out_json, "w"), indent=1, sort_keys=True)
     print("\n".join(lines))
 
 
