@@ -9,24 +9,38 @@
 namespace pcoe {
 
 constexpr int kGroupWarps = 8;         // warps per CTA
-constexpr int kCentroidsPerWarp = 4;   // centroids a warp walks through sequentially
+constexpr int kCentroidsPerWarp = 4;   // most centroids a warp walks through sequentially
+// Centroids per warp of the ball-query kernels: up to kCentroidsPerWarp (the cloud is staged once per CTA), fewer when the
+// grid would not fill the GPU - at 32 clouds x 128 centroids of 8192 points, 4 per warp gave 128 CTAs on 148 SMs
+// (ncu: 9 % warps active, 121 us); 1 per warp gives 512 CTAs.
+static int ball_cpw(int B, int S) {
+  const long long tasks = (long long)B * S;
+  long long c = tasks / ((long long)kGroupWarps * 2 * kNumSMs);
+  return (int)(c < 1 ? 1 : (c > kCentroidsPerWarp ? kCentroidsPerWarp : c));
+}
 
 __device__ __forceinline__ void load_cloud_soa(const float* __restrict__ cloud, int N, float* sx,
                                                float* sy, float* sz) {
   // N*3 floats, 16-byte vectorised when the cloud base allows it (always for 4 | 3N and aligned B).
   const int total = N * 3;
   if ((((uintptr_t)cloud) & 15) == 0) {
+    // four points = twelve floats = three 16-byte loads per thread and step: no division, all loads of a step in flight
     const float4* c4 = reinterpret_cast<const float4*>(cloud);
-    for (int q = threadIdx.x; q < total / 4; q += blockDim.x) {
-      float4 v = __ldg(c4 + q);
-      float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        int i = q * 4 + u, p = i / 3, c = i - p * 3;
-        (c == 0 ? sx : (c == 1 ? sy : sz))[p] = vv[u];
+    for (int t = threadIdx.x; t < N / 4; t += blockDim.x) {
+      const float4 a = __ldg(c4 + 3 * t), b = __ldg(c4 + 3 * t + 1), c = __ldg(c4 + 3 * t + 2);
+      const int p = 4 * t;
+      if ((N & 3) == 0) {   // sy, sz 16-byte aligned: one conflict-free 16-byte store per coordinate
+        *reinterpret_cast<float4*>(sx + p) = make_float4(a.x, a.w, b.z, c.y);
+        *reinterpret_cast<float4*>(sy + p) = make_float4(a.y, b.x, b.w, c.z);
+        *reinterpret_cast<float4*>(sz + p) = make_float4(a.z, b.y, c.x, c.w);
+      } else {
+        sx[p] = a.x;     sy[p] = a.y;     sz[p] = a.z;
+        sx[p + 1] = a.w; sy[p + 1] = b.x; sz[p + 1] = b.y;
+        sx[p + 2] = b.z; sy[p + 2] = b.w; sz[p + 2] = c.x;
+        sx[p + 3] = c.y; sy[p + 3] = c.z; sz[p + 3] = c.w;
       }
     }
-    for (int i = (total / 4) * 4 + threadIdx.x; i < total; i += blockDim.x) {
+    for (int i = (N / 4) * 12 + threadIdx.x; i < total; i += blockDim.x) {
       int p = i / 3, c = i - p * 3;
       (c == 0 ? sx : (c == 1 ? sy : sz))[p] = __ldg(cloud + i);
     }
@@ -316,7 +330,7 @@ knn_k32_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
 // Ball query: ascending-index scan, the first `nsample` hits, padded with the first hit.
 __global__ void __launch_bounds__(kGroupWarps * 32)
 ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S,
-                  int nsample, float r2, int32_t* __restrict__ out_idx) {
+                  int nsample, float r2, int32_t* __restrict__ out_idx, int cpw) {
   extern __shared__ float smem_f[];
   float* sx = smem_f;
   float* sy = sx + N;
@@ -326,8 +340,8 @@ ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_x
   load_cloud_soa(xyz + (size_t)b * N * 3, N, sx, sy, sz);
   __syncthreads();
 
-  const int s_begin = (blockIdx.x * kGroupWarps + warp) * kCentroidsPerWarp;
-  for (int s = s_begin; s < min(s_begin + kCentroidsPerWarp, S); ++s) {
+  const int s_begin = (blockIdx.x * kGroupWarps + warp) * cpw;
+  for (int s = s_begin; s < min(s_begin + cpw, S); ++s) {
     const float* c = new_xyz + ((size_t)b * S + s) * 3;
     const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
     int32_t* o = out_idx + ((size_t)b * S + s) * nsample;
@@ -394,7 +408,7 @@ struct BallScales {
   int32_t* out[kMaxScales];
 };
 __global__ void __launch_bounds__(kGroupWarps * 32)
-ball_query_multi_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S, BallScales sc) {
+ball_query_multi_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S, BallScales sc, int cpw) {
   extern __shared__ float smem_f[];
   float* sx = smem_f;
   float* sy = sx + N;
@@ -405,8 +419,8 @@ ball_query_multi_kernel(const float* __restrict__ xyz, const float* __restrict__
   __syncthreads();
 
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int s_begin = (blockIdx.x * kGroupWarps + warp) * kCentroidsPerWarp;
-  for (int s = s_begin; s < min(s_begin + kCentroidsPerWarp, S); ++s) {
+  const int s_begin = (blockIdx.x * kGroupWarps + warp) * cpw;
+  for (int s = s_begin; s < min(s_begin + cpw, S); ++s) {
     const float* c = new_xyz + ((size_t)b * S + s) * 3;
     const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
     int cnt[kMaxScales], first[kMaxScales];
@@ -437,6 +451,49 @@ ball_query_multi_kernel(const float* __restrict__ xyz, const float* __restrict__
       if (r >= sc.n) continue;
       int32_t* o = sc.out[r] + ((size_t)b * S + s) * sc.nsample[r];
       for (int e = min(cnt[r], sc.nsample[r]) + lane; e < sc.nsample[r]; e += 32) o[e] = first[r];
+    }
+  }
+}
+
+// C == 3 (every call site of the reference): one thread = 4 src rows x 4 consecutive dst points.  The 12 dst floats are
+// three 16-byte loads, reused for the 4 rows; 16 outputs leave as four 16-byte stores.
+__global__ void __launch_bounds__(256)
+square_distance3_kernel(const float* __restrict__ src, const float* __restrict__ dst, int N, int M, float* __restrict__ out) {
+  const int b = blockIdx.z, i0 = blockIdx.y * 4;
+  const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j0 >= M) return;
+  const float* d = dst + ((size_t)b * M + j0) * 3;
+  float dv[12];
+  if (j0 + 4 <= M && ((((size_t)b * M + j0) * 3) & 3) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(d)), bq = __ldg(reinterpret_cast<const float4*>(d) + 1),
+                 c = __ldg(reinterpret_cast<const float4*>(d) + 2);
+    dv[0] = a.x; dv[1] = a.y; dv[2] = a.z; dv[3] = a.w; dv[4] = bq.x; dv[5] = bq.y; dv[6] = bq.z; dv[7] = bq.w;
+    dv[8] = c.x; dv[9] = c.y; dv[10] = c.z; dv[11] = c.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 12; ++e) dv[e] = j0 + e / 3 < M ? __ldg(d + e) : 0.f;
+  }
+  float nd[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) nd[u] = fmaf(dv[3 * u + 2], dv[3 * u + 2], fmaf(dv[3 * u + 1], dv[3 * u + 1], dv[3 * u] * dv[3 * u]));
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + r;
+    if (i >= N) break;
+    const float* sp = src + ((size_t)b * N + i) * 3;
+    const float sx = __ldg(sp), sy = __ldg(sp + 1), sz = __ldg(sp + 2);
+    const float ns = fmaf(sz, sz, fmaf(sy, sy, sx * sx));
+    float o4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float dot = fmaf(sz, dv[3 * u + 2], fmaf(sy, dv[3 * u + 1], sx * dv[3 * u]));
+      o4[u] = (-2.f * dot + ns) + nd[u];
+    }
+    float* o = out + ((size_t)b * N + i) * M + j0;
+    if (j0 + 4 <= M && ((((size_t)b * N + i) * M + j0) & 3) == 0) {
+      *reinterpret_cast<float4*>(o) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    } else {
+      for (int u = 0; u < 4 && j0 + u < M; ++u) o[u] = o4[u];
     }
   }
 }
@@ -498,9 +555,10 @@ extern "C" int pcoe_ball_query_f32(const float* xyz, const float* new_xyz, int B
   if (smem > 48 * 1024)
     PCOE_CUDA(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const float r2 = (float)(radius * radius);  // Python double r**2, cast to the tensor dtype
-  dim3 grid(ceil_div(S, kGroupWarps * kCentroidsPerWarp), B);
+  const int cpw = ball_cpw(B, S);
+  dim3 grid(ceil_div(S, kGroupWarps * cpw), B);
   LaunchScope ls("ball_query_kernel", (cudaStream_t)stream);
-  ball_query_kernel<<<grid, kGroupWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, nsample, r2, out_idx);
+  ball_query_kernel<<<grid, kGroupWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, nsample, r2, out_idx, cpw);
   return ls.done();
 }
 
@@ -510,9 +568,14 @@ extern "C" int pcoe_square_distance_f32(const float* src, const float* dst, int 
   if (N > 65535 || B > 65535) return fail(PCOE_ERR_UNSUPPORTED, "square_distance: B=%d / N=%d exceed the grid limits", B, N);
   if (!src || !dst || !out) return fail(PCOE_ERR_NULL, "square_distance: NULL pointer");
   const int threads = M >= 1024 ? 256 : (M >= 256 ? 64 : 32);
-  dim3 grid(ceil_div(ceil_div(M, 4), threads), N, B);
   LaunchScope ls("square_distance_kernel", (cudaStream_t)stream);
-  square_distance_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(src, dst, N, M, C, out);
+  if (C == 3) {
+    dim3 grid(ceil_div(ceil_div(M, 4), threads), ceil_div(N, 4), B);
+    square_distance3_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(src, dst, N, M, out);
+  } else {
+    dim3 grid(ceil_div(ceil_div(M, 4), threads), N, B);
+    square_distance_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(src, dst, N, M, C, out);
+  }
   return ls.done();
 }
 
@@ -536,8 +599,9 @@ extern "C" int pcoe_ball_query_multi_f32(const float* xyz, const float* new_xyz,
   if (!group_smem(N, 0, &smem)) return fail(PCOE_ERR_UNSUPPORTED, "ball_query_multi: N=%d does not fit shared memory", N);
   if (smem > 48 * 1024)
     PCOE_CUDA(cudaFuncSetAttribute(ball_query_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(S, kGroupWarps * kCentroidsPerWarp), B);
+  const int cpw = ball_cpw(B, S);
+  dim3 grid(ceil_div(S, kGroupWarps * cpw), B);
   LaunchScope ls("ball_query_multi_kernel", (cudaStream_t)stream);
-  ball_query_multi_kernel<<<grid, kGroupWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, sc);
+  ball_query_multi_kernel<<<grid, kGroupWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, sc, cpw);
   return ls.done();
 }

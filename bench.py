@@ -586,7 +586,9 @@ def run_ours(args):
 
     sg = None
     if rank == 0 and world == 1 and not args.no_sampling_leg:
-        sg = sampling_grouping_leg(pcoe, torch, dev, B, N, peaks, flush)
+        sg = {f"{B} clouds x {N} points": sampling_grouping_leg(pcoe, torch, dev, B, N, peaks, flush)}
+        if (B, N) != (32, 8192):                          # the FPS / ball-query stress shape of BASELINE configs[3]
+            sg["32 clouds x 8192 points"] = sampling_grouping_leg(pcoe, torch, dev, 32, 8192, peaks, flush)
 
     if rank == 0:
         line = {

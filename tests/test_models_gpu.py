@@ -317,3 +317,34 @@ def test_baseline_configs_c3_c4_shapes(pcoe, cuda, cls, B, N):
     g32 = torch.cat([p.grad.flatten() for p in outs[0][1].sa1.parameters() if p.grad is not None]).norm()
     g16 = torch.cat([p.grad.flatten() for p in outs[1][1].sa1.parameters() if p.grad is not None]).norm()
     assert torch.isfinite(g16) and 0.5 < float(g16 / g32) < 2.0
+
+
+def test_single_cloud_full_resolution_eval_inference(pcoe, cuda):
+    """The reference's inference call (train.py:228-246): ONE whole cloud (all ~10 000 vertices, no resampling) through
+    PointNetPPXYZ_Schedmit in eval mode.  Checked against the torch-CPU oracle on the same checkpoint and the same
+    host-generator subsets, with non-trivial running statistics (a trained checkpoint's BatchNorm state)."""
+    B, N = 1, 10000
+    torch.manual_seed(77)
+    model = pcoe.PointNetPPXYZ_Schedmit()
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                m.running_mean.normal_(0, 0.1, generator=g)
+                m.running_var.uniform_(0.5, 1.5, generator=g)
+                m.weight.uniform_(0.5, 1.5, generator=g)
+                m.bias.uniform_(-0.2, 0.2, generator=g)
+    sd = sa_torch.clone_state(model.state_dict(), dtype=torch.float64)
+    model = model.to(cuda).eval()
+    xyz = pcoe.synthetic.clouds(11, B, N)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        vy, vz = model(xyz.to(cuda))
+    fps1, fps2 = model.sa1.last_fps_idx.long().cpu(), model.sa2.last_fps_idx.long().cpu()
+    torch.manual_seed(5)                                     # the reference's draw order: sa1 then sa2 (:28)
+    assert torch.equal(fps1, torch.stack([torch.randperm(N)[:128] for _ in range(B)]))
+    assert torch.equal(fps2, torch.stack([torch.randperm(128)[:32] for _ in range(B)]))
+    oy, oz = sa_torch.model_forward("schedmit", sd, xyz.double(), fps1, fps2, training=False, update_buffers=False)
+    assert vy.shape == (1, 3) and vz.shape == (1, 3)
+    assert float((vy.cpu().double() - oy).abs().max()) < 1e-3 and float((vz.cpu().double() - oz).abs().max()) < 1e-3
+    assert abs(float(vy.norm()) - 1.0) < 1e-5               # unit vectors (F.normalize, Pointnet_pp_xyz_Schedmit.py:88-90)
