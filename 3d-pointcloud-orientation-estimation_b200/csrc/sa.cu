@@ -12,6 +12,7 @@
 #include "sa_tc4.cuh"
 #include "sa_tc5.cuh"
 #include "sa_tc6.cuh"
+#include "pm_tma.cuh"
 #include "sa_layout.h"
 #include <type_traits>
 
@@ -1057,7 +1058,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
 constexpr int kPmPlanes = 2;
 struct PmLayout {
   int nl, M, G, Cin0, Kp[3], Rp[3];
-  size_t y[2], stat[3], ymax, ymin, amax, amin, wb[3], total;
+  size_t y[2], stat[3], ymax, ymin, amax, amin, wb[3], xin, total;   // y[l]: fp32 activation OR the two-plane operand image (same bytes)
 };
 static PmLayout pm_layout(const pcoe_pointmlp_desc& d) {
   PmLayout L{};
@@ -1074,6 +1075,7 @@ static PmLayout pm_layout(const pcoe_pointmlp_desc& d) {
     L.stat[l] = take(s, sizeof(float) * 4 * d.C[l]);
     L.wb[l] = take(s, (size_t)3 * 2 * L.Rp[l] * L.Kp[l]);
   }
+  L.xin = d.D > 0 ? take(s, Mld * d.D * sizeof(float)) : 0;       // packed input image of a feature stack (TMA path)
   const int CL = d.C[d.nlayers - 1];
   L.ymax = take(s, sizeof(float) * (size_t)L.G * CL);
   L.ymin = take(s, sizeof(float) * (size_t)L.G * CL);
@@ -1190,6 +1192,71 @@ extern "C" int pcoe_sa_backward(const pcoe_sa_desc* desc, const float* xyz, cons
                                  workspace, (cudaStream_t)stream);
 }
 
+// ---- TMA-fed path (pm_tma.cuh): epilogue-produced operand planes, bulk async copies, no producer warps ---------------
+template <class Epi, bool CHMAJOR>
+static int launch_pm_layer(const uint8_t* ximg, int nk, const __nv_bfloat16* Wp, size_t wps, int Kp, const Epi& epi, int M,
+                           int Cout, cudaStream_t st, const char* what) {
+  const int ncb = ceil_div(Cout, 128), ntiles = ceil_div(M, v4::kPts);
+  const int per = kNumSMs / ncb > 0 ? kNumSMs / ncb : 1;
+  const int grid = (ntiles < per ? ntiles : per) * ncb;
+  const size_t tb = (size_t)nk * pm::kOpB, fixed = 1024 + tb + epi.stage_bytes();
+  if (fixed + tb > kSmemBudget6) return fail(PCOE_ERR_UNSUPPORTED, "%s: layer does not fit shared memory", what);
+  int nst = (int)((kSmemBudget6 - fixed) / tb);
+  nst = nst > pm::kPmStages ? pm::kPmStages : nst;
+  auto k = pm::pm_layer_kernel<Epi, CHMAJOR>;
+  static bool attr = false;
+  if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
+  LaunchScope ls(what, st);
+  k<<<grid, pm::kPmThreads, fixed + (size_t)nst * tb, st>>>(ximg, nk, Wp, wps, Kp, epi, M, ncb, nst);
+  return ls.done();
+}
+
+static bool pm_tma_enabled() {
+  static const bool on = [] { const char* e = getenv("PCOE_PM_TMA"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+static int pointmlp_forward_tma(const pcoe_pointmlp_desc& d, const PmLayout& L, const float* xyz, const float* feats,
+                                const pcoe_sa_params& P, float* const* scale, float* const* shift, char* ws, cudaStream_t st) {
+  const int nl = d.nlayers, M = d.M, CL = d.C[nl - 1];
+  const size_t ntiles = (size_t)ceil_div(M, v4::kPts);
+  auto wh = [&](int l) { return (const __nv_bfloat16*)(ws + L.wb[l]); };
+  auto wps = [&](int l) { return (size_t)L.Rp[l] * L.Kp[l]; };
+  pm::PoolPm pool{(float*)(ws + L.ymax), (float*)(ws + L.ymin), P.gamma[nl - 1], CL, 0, true};
+  const uint8_t* cur;            // operand image feeding the next MMA layer
+  int cur_nk, first;             // its 64-channel chunks; index of the next MMA layer
+  bool chmajor;
+  if (d.use_xyz) {               // layer 0 on the CUDA cores (K = 3), writes layer 1's channel-major operand image
+    uint8_t* img0 = (uint8_t*)(ws + L.y[0]);
+    const size_t threads = ntiles * (size_t)(d.C[0] >> 6) * 1024;
+    LaunchScope ls("pointmlp_first_xyz", st);
+    pm::pm_first_xyz_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(xyz, M, P.W[0], scale[0], shift[0], d.C[0], 1, img0);
+    PCOE_TRY(ls.done());
+    cur = img0; cur_nk = d.C[0] >> 6; first = 1; chmajor = true;
+  } else {                       // feature stack: pack the point-major rows into a K-major operand image
+    uint8_t* xin = (uint8_t*)(ws + L.xin);
+    const size_t total = ntiles * v4::kPts * (size_t)(d.D >> 3);
+    LaunchScope ls("pointmlp_pack_rows", st);
+    pm::pm_pack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feats, M, d.D, xin);
+    PCOE_TRY(ls.done());
+    cur = xin; cur_nk = d.D >> 6; first = 0; chmajor = false;
+  }
+  for (int l = first; l < nl; ++l) {
+    const bool last = l == nl - 1;
+    if (!last) {
+      pm::StorePlanesPm ep{(uint8_t*)(ws + L.y[l]), scale[l], shift[l], d.C[l], 1, 0, 0.f, 0.f};
+      if (chmajor) PCOE_TRY((launch_pm_layer<pm::StorePlanesPm, true>(cur, cur_nk, wh(l), wps(l), L.Kp[l], ep, M, d.C[l], st, l == 1 ? "pointmlp_l2" : "pointmlp_l1")));
+      else PCOE_TRY((launch_pm_layer<pm::StorePlanesPm, false>(cur, cur_nk, wh(l), wps(l), L.Kp[l], ep, M, d.C[l], st, l == 1 ? "pointmlp_l2" : "pointmlp_l1")));
+      cur = (const uint8_t*)(ws + L.y[l]); cur_nk = d.C[l] >> 6; chmajor = true;
+    } else {
+      const char* nm = nl == 2 ? "pointmlp_l2_pool" : "pointmlp_l3_pool";
+      if (chmajor) PCOE_TRY((launch_pm_layer<pm::PoolPm, true>(cur, cur_nk, wh(l), wps(l), L.Kp[l], pool, M, CL, st, nm)));
+      else PCOE_TRY((launch_pm_layer<pm::PoolPm, false>(cur, cur_nk, wh(l), wps(l), L.Kp[l], pool, M, CL, st, nm)));
+    }
+  }
+  return PCOE_OK;
+}
+
 extern "C" size_t pcoe_pointmlp_workspace_bytes(const pcoe_pointmlp_desc* desc) {
   if (pm_validate(desc) != PCOE_OK) return 0;
   return pm_layout(*desc).total;
@@ -1237,6 +1304,15 @@ extern "C" int pcoe_pointmlp_forward(const pcoe_pointmlp_desc* desc, const float
   auto wps = [&](int l) { return (size_t)L.Rp[l] * L.Kp[l]; };
   float* ymax = (float*)(ws + L.ymax);
   float* ymin = (float*)(ws + L.ymin);
+  // default: epilogue-produced operand planes + bulk async copies (pm_tma.cuh); [xyz | feats] inputs and PCOE_PM_TMA=0
+  // take the producer-warp kernels below
+  if (pm_tma_enabled() && !(d.use_xyz && d.D > 0) && (!d.use_xyz || d.C[0] % 64 == 0)) {
+    PCOE_TRY(pointmlp_forward_tma(d, L, xyz, feats, *params, scale, shift, ws, st));
+    LaunchScope lsp("pm_pool_kernel", st);
+    pm_pool_kernel<<<dim3(ceil_div(CL, 128), M / d.rows_per_cloud), 128, 0, st>>>(ymax, ymin, scale[nl - 1], shift[nl - 1],
+                                                                                d.rows_per_cloud / 32, CL, d.relu_last, out);
+    return lsp.done();
+  }
   v6::Group6 eg{}; eg.y = nullptr; eg.sums = nullptr; eg.ymax = ymax; eg.ymin = ymin; eg.amax = (uint8_t*)(ws + L.amax);
   eg.amin = (uint8_t*)(ws + L.amin); eg.C = CL; eg.gamma = params->gamma[nl - 1];
   // identity grouping: group_all = 1 makes row r read point r with absolute coordinates

@@ -762,12 +762,14 @@ def run_pointnet(args):
         t_s = k["ms_per_step"] / k["launches_per_step"] * 1e-3
         flops = 2.0 * M * 128 * 1024
         ach = flops / t_s / 1e12
-        roofline = {"kernel": "pointmlp_l3_pool (x3_fwd_kernel<BnRelu6, Group6, 2>)", "bound": "tensor", "achieved": ach,
+        roofline = {"kernel": "pointmlp_l3_pool (pm_layer_kernel<PoolPm, true>: TMA-fed 128 -> 1024 layer + max pool)", "bound": "tensor", "achieved": ach,
                     "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
                     "peak_source": peaks["source"], "avg_launch_ms": t_s * 1e3, "algorithmic_flops": flops,
                     "algorithmic_bytes": 4.0 * M * 128 + 10.0 * (M / 32) * 1024,
+                    "tensor_pipe_occupancy": 3.0 * ach / peaks["tensor"],
                     "note": "algorithmic FLOPs = 2*M*128*1024 (one product per MAC); the kernel issues 3 tcgen05.mma per "
-                            "product (two bf16 planes per operand), so its tensor-pipe occupancy is 3x this fraction"}
+                            "product (two bf16 planes per operand: 16 significant bits), so the tensor pipe is busy 3x this "
+                            "fraction of the (sustained) peak - `tensor_pipe_occupancy`"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import pointnet_torch, sa_torch
