@@ -712,7 +712,7 @@ static int sa_forward_impl(const pcoe_sa_desc& d, const float* xyz, const float*
       v6::StoreStats6 e1{}; e1.y = y[1]; e1.sums = sums[1]; e1.C = d.C2;
       PCOE_TRY(launch_fwd6(p1, wh(1), wps(1), L.w4_kp[1], e1, M, d.C2, st, kname(d, kF2)));
       v6::BnRelu6 p2{}; p2.y = y[1]; p2.scale = scale[1]; p2.shift = shift[1]; p2.M = M; p2.C = d.C2; p2.fin = mkfin(1);
-      v6::Group6 e2{}; e2.y = y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
+      v6::Group6 e2{}; e2.y = (__nv_bfloat16*)y[2]; e2.sums = sums[2]; e2.ymax = ymax; e2.ymin = ymin; e2.amax = amax; e2.amin = amin;
       e2.C = d.C3; e2.gamma = P.gamma[2];
       PCOE_TRY(launch_fwd6(p2, wh(2), wps(2), L.w4_kp[2], e2, M, d.C3, st, kname(d, kF3)));
       if (train) { if (sep_fin) PCOE_TRY(finalize(2)); else fin_out = mkfin(2); }
@@ -981,7 +981,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
     if (L.v6) {   // bf16x3: streamed wgrad / persistent dgrad kernels with split operands (sa_tc6.cuh)
       auto wh = [&](int l) { return (const __nv_bfloat16*)(sv + L.wb_off[l]); };
       auto wps = [&](int l) { return (size_t)L.w4_rp[l] * L.w4_kp[l]; };
-      v6::DyLast6 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
+      v6::DyLast6 dy3{}; dy3.gm = gm; dy3.slot = slot; dy3.y = (const __nv_bfloat16*)y[2]; dy3.a = ca[2]; dy3.p = cp[2]; dy3.q = cq[2];
       dy3.M = M; dy3.C = d.C3; dy3.fin = mkbfin(2, 1);   // the wgrad launch owns the parameter-gradient outputs
       v6::BnRelu6 x2{}; x2.y = y[1]; x2.scale = scale[1]; x2.shift = shift[1]; x2.M = M; x2.C = d.C2;
       v6::MaskStats6 m2{}; m2.yprev = y[1]; m2.scale = scale[1]; m2.shift = shift[1]; m2.mean = mean[1]; m2.invstd = invstd[1];

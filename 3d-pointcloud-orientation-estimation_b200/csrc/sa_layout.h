@@ -87,7 +87,8 @@ inline SaLayout sa_layout(const pcoe_sa_desc& d) {
   }
 
   size_t s = 0;
-  for (int l = 0; l < 3; ++l) L.sv_y[l] = (l == 2 && L.l3s) ? 0 : take(s, rows_ld * C[l] * L.esz);
+  // v6 (bf16x3): y3 is stored as bf16 (sa_tc6.cuh, act16_off) - its only reader is the dense BatchNorm-backward term
+  for (int l = 0; l < 3; ++l) L.sv_y[l] = (l == 2 && L.l3s) ? 0 : take(s, rows_ld * C[l] * ((l == 2 && L.v6) ? 2 : L.esz));
   L.sv_gram = L.sv_gram_bytes = 0;
   if (L.l3s) {
     L.sv_gram_bytes = sizeof(float) * (size_t)kRedCopies * d.C2 * L.gram_ld;

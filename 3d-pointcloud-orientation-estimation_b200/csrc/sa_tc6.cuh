@@ -119,6 +119,12 @@ __global__ void convert_weights6_kernel(ConvW6 a, ConvW6 b, ConvW6 c) {
 // 128-point tile in the forward kernels, the stores alone ~2 us.)
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ size_t act_off(int tile, int C, int c, int quad) { return (((size_t)tile * 32 + quad) * C + c) * 4; }
+// The LAST layer's pre-activations y3 are stored as bf16 in the same interleaving with 8-point octets (16 bytes):
+// element (tile, c, p) at bf16 index ((tile * 16 + (p >> 3)) * C + c) * 8 + (p & 7).  y3 never feeds a forward GEMM and
+// takes no ReLU-mask decision (the routing is the saved arg-max slot): its only reader is the dense BatchNorm-backward
+// term p * y3 + q of dy3, where an independent 2^-9 relative rounding per element averages out over the contraction
+// (measured: weight gradients unchanged at the 1e-5 level, tests/test_sa_gpu.py) - half the bytes of the largest tensor.
+__device__ __forceinline__ size_t act16_off(int tile, int C, int c, int octet) { return (((size_t)tile * 16 + octet) * C + c) * 8; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Channel-major producers.  One UNIT of the 256 producer threads covers R = (PTS == 128 ? 16 : 32) * kUR channel
@@ -352,10 +358,10 @@ struct Dy6 {
 struct DyLast6 {
   static constexpr bool kChMajor = true;
   static constexpr int kUR = 4;
-  struct Raw { float4 y[kUR][2]; float gv[kUR]; int sl[kUR]; };
+  struct Raw { uint4 y[kUR]; float gv[kUR]; int sl[kUR]; };      // y: 8 bf16 per chunk
   const float* __restrict__ gm;       // [G,C]
   const uint8_t* __restrict__ slot;   // [G,C]
-  const float* __restrict__ y;
+  const __nv_bfloat16* __restrict__ y;   // bf16 (act16_off)
   const float* __restrict__ a;
   const float* __restrict__ p;
   const float* __restrict__ q;
@@ -381,14 +387,14 @@ struct DyLast6 {
     for (int i = 0; i < kUR; ++i) {
       const int m = m0 + (ch0 + i * G::kCstep) * 8;
       const bool ok = rok && m < M;
-      const float* sy = y + act_off(m >> 7, C, rok ? c : 0, (m & 127) >> 2);
+      const __nv_bfloat16* sy = y + act16_off(m >> 7, C, rok ? c : 0, (m & 127) >> 3);
       const size_t go = (size_t)((ok ? m : 0) >> 5) * C + (rok ? c : 0);
-      r.y[i][0] = ldg4_or0(sy, ok); r.y[i][1] = ldg4_or0(sy + (size_t)C * 4, ok);
+      r.y[i] = ok ? __ldg(reinterpret_cast<const uint4*>(sy)) : make_uint4(0u, 0u, 0u, 0u);
       r.gv[i] = ok ? __ldg(gm + go) : 0.f;
       r.sl[i] = ok ? (int)__ldg(slot + go) : -1;
     }
   }
-  // raw unit: items 0..7 = y (two 16-byte quads per chunk), item 8 = [gm x 4], item 9 = [slot word x 4]
+  // raw unit: items 0..3 = y (one 16-byte octet per chunk), item 4 = [gm x 4], item 5 = [slot word x 4]
   static constexpr bool kAsync = true;
   template <int PTS>
   __device__ __forceinline__ void load_async(int g, int m0, int crow, uint32_t ub) const {
@@ -399,15 +405,14 @@ struct DyLast6 {
     for (int i = 0; i < kUR; ++i) {
       const int m = m0 + (ch0 + i * G::kCstep) * 8;
       const bool ok = rok && m < M;
-      const float* sy = y + act_off(m >> 7, C, rok ? c : 0, (m & 127) >> 2);
+      const __nv_bfloat16* sy = y + act16_off(m >> 7, C, rok ? c : 0, (m & 127) >> 3);
       const size_t go = (size_t)((ok ? m : 0) >> 5) * C + (rok ? c : 0);
-      cp_async16(raw_slot(ub, 2 * i, g), sy, ok);
-      cp_async16(raw_slot(ub, 2 * i + 1, g), sy + (size_t)C * 4, ok);
-      cp_async4(raw_slot(ub, 8, g) + 4u * i, gm + go, ok);
-      cp_async4(raw_slot(ub, 9, g) + 4u * i, slot + (go & ~(size_t)3), ok);    // the aligned word that holds the byte
+      cp_async16(raw_slot(ub, i, g), sy, ok);
+      cp_async4(raw_slot(ub, 4, g) + 4u * i, gm + go, ok);
+      cp_async4(raw_slot(ub, 5, g) + 4u * i, slot + (go & ~(size_t)3), ok);    // the aligned word that holds the byte
     }
   }
-  static constexpr int kRawItems = 10;
+  static constexpr int kRawItems = 6;
   template <int PTS>
   __device__ __forceinline__ void fetch(int g, int m0, int crow, uint32_t ub, Raw& r) const {
     using G = CM<PTS, kUR>;
@@ -417,9 +422,10 @@ struct DyLast6 {
     for (int i = 0; i < kUR; ++i) {
       const int m = m0 + (ch0 + i * G::kCstep) * 8;
       const bool ok = rok && m < M;
-      r.y[i][0] = lds128f(raw_slot(ub, 2 * i, g)); r.y[i][1] = lds128f(raw_slot(ub, 2 * i + 1, g));
-      r.gv[i] = __uint_as_float(lds32(raw_slot(ub, 8, g) + 4u * i));
-      const uint32_t w = lds32(raw_slot(ub, 9, g) + 4u * i);
+      const float4 t = lds128f(raw_slot(ub, i, g));
+      r.y[i] = make_uint4(__float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z), __float_as_uint(t.w));
+      r.gv[i] = __uint_as_float(lds32(raw_slot(ub, 4, g) + 4u * i));
+      const uint32_t w = lds32(raw_slot(ub, 5, g) + 4u * i);
       r.sl[i] = ok ? (int)((w >> (8 * (c & 3))) & 255u) : -1;                  // C % 4 == 0: byte index = c & 3
     }
   }
@@ -435,7 +441,10 @@ struct DyLast6 {
       const float okf = m < M ? 1.f : 0.f;
       const float add = ca0 * r.gv[i], cp = cp0 * okf, cq = cq0 * okf;   // gv is 0 for points >= M
       const int sl = r.sl[i] - (m & 31);          // slot relative to this 8-point chunk
-      const float yy[8] = {r.y[i][0].x, r.y[i][0].y, r.y[i][0].z, r.y[i][0].w, r.y[i][1].x, r.y[i][1].y, r.y[i][1].z, r.y[i][1].w};
+      const uint32_t yw[4] = {r.y[i].x, r.y[i].y, r.y[i].z, r.y[i].w};
+      float yy[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { yy[2 * u] = __uint_as_float(yw[u] << 16); yy[2 * u + 1] = __uint_as_float(yw[u] & 0xFFFF0000u); }
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = fmaf(cp, yy[u], cq) + (u == sl ? add : 0.f);
@@ -577,7 +586,7 @@ struct StoreStats6 {
 struct Group6 {   // last layer, K == 32: the 32 columns of a block are one group
   static constexpr bool kPre = false;
   static constexpr bool kHalf = false;
-  float* __restrict__ y;           // tile-blocked fp32, or nullptr (eval)
+  __nv_bfloat16* __restrict__ y;   // bf16 activation (act16_off), or nullptr (eval / inference)
   double* __restrict__ sums;
   float* __restrict__ ymax;        // [G,C]
   float* __restrict__ ymin;
@@ -592,7 +601,14 @@ struct Group6 {   // last layer, K == 32: the 32 columns of a block are one grou
   __device__ __forceinline__ void init(float*, int ch) { c = ch; s0 = s1 = 0.f; want_max = c < C ? !signbit(gamma[c]) : true; }
   __device__ __forceinline__ void block(float (&v)[32], int tile, int j, bool valid) {
     if (c >= C || !valid) return;
-    if (y) store32_f32(y, tile, C, c, j, v);
+    if (y) {
+      __nv_bfloat16* dst = y + act16_off(tile, C, c, j * 4);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const float t[8] = {v[8 * o], v[8 * o + 1], v[8 * o + 2], v[8 * o + 3], v[8 * o + 4], v[8 * o + 5], v[8 * o + 6], v[8 * o + 7]};
+        *reinterpret_cast<uint4*>(dst + (size_t)o * C * 8) = tc::pack8_bf16(t);
+      }
+    }
     sum_sumsq32(v, s0, s1);
     float ext;
     int arg;

@@ -130,6 +130,8 @@ def kernel_work(B: int, N: int, precision: str = "bf16") -> dict:
         # Gram matrix of its input and the backward uses the sparse max-pool routing - so
         # act(3) is neither written by fwd_l3 nor read by bwd_l3.  SA3 (v5 kernels) still stores y3.
         y3 = 0.0 if (li < 2 and precision == "bf16") else act(3)
+        if precision == "bf16x3":
+            y3 = 2.0 * M * c[3]                                       # bf16x3 stores the last layer's pre-activations as bf16
         # SA1 (no input features): dW1 is accumulated by the layer-2 backward epilogue (MaskStatsW1) - that kernel also
         # reads the indices + xyz (src) and does not write dz1; the layer-1 backward kernel does not run
         l2_extra = (src - act(1)) if li == 0 else 0.0
@@ -141,8 +143,8 @@ def kernel_work(B: int, N: int, precision: str = "bf16") -> dict:
             t + "bwd_l2": (2 * g(1, 2) + (g(0, 1) if li == 0 else 0.0), 2 * act(2) + act(1) + act(1) + l2_extra),
             t + "bwd_l1": (g(0, 1) + dg1, 2 * act(1) + src + scat),
             # v5 / first-generation path: separate kernels
-            t + "bwd_wgrad3": (g(2, 3), act(3) + act(2) + 5.0 * G * c[3]),
-            t + "bwd_dgrad3": (g(2, 3), act(3) + act(2) + 5.0 * G * c[3] + act(2)),
+            t + "bwd_wgrad3": (g(2, 3), y3 + act(2) + 5.0 * G * c[3]),
+            t + "bwd_dgrad3": (g(2, 3), y3 + act(2) + 5.0 * G * c[3] + act(2)),
             t + "bwd_wgrad2": (g(1, 2), 2 * act(2) + act(1)),
             # bf16x3 SA1: the layer-2 dgrad epilogue also accumulates dW1 (MaskStatsW6): it reads the indices + xyz and does
             # not write dz1; the layer-1 wgrad kernel does not run

@@ -16,7 +16,8 @@ import sys
 ORDER_X3 = (["knn_kernel(sa1)", "sa1_fwd_l1", "sa1_fwd_l2", "sa1_fwd_l3", "knn_kernel(sa2)", "sa2_fwd_l1", "sa2_fwd_l2", "sa2_fwd_l3",
              "sa3_fwd_l1", "sa3_fwd_l2", "sa3_fwd_l3"] +
             [f"sa{l}_bwd_{k}{i}" for l in (3, 2) for i in (3, 2, 1) for k in ("wgrad", "dgrad")] +
-            ["sa1_bwd_wgrad3", "sa1_bwd_dgrad3", "sa1_bwd_wgrad2", "sa1_bwd_dgrad2", "sa1_bwd_wgrad1"])   # bf16x3: -k regex:'x3_|knn_k32'
+            ["sa1_bwd_wgrad3", "sa1_bwd_dgrad3", "sa1_bwd_wgrad2", "sa1_bwd_dgrad2"])   # bf16x3: -k regex:'x3_|knn_k32' (dW1 of SA1 comes
+                                                                                        # out of sa1_bwd_dgrad2's epilogue: no wgrad1 launch)
 ORDER = (["knn_kernel(sa1)", "sa1_fwd_l1", "sa1_fwd_l2", "sa1_fwd_l3", "knn_kernel(sa2)", "sa2_fwd_l1", "sa2_fwd_l2",
           "sa2_fwd_l3", "sa3_fwd_l1", "sa3_fwd_l2", "sa3_fwd_l3", "sa3_bwd_wgrad3", "sa3_bwd_dgrad3", "sa3_bwd_wgrad2",
           "sa3_bwd_dgrad2", "sa3_bwd_wgrad1", "sa3_bwd_dgrad1", "sa2_bwd_l3", "sa2_bwd_l2", "sa2_bwd_l1", "sa1_bwd_l3",
