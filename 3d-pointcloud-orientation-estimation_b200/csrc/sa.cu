@@ -997,7 +997,7 @@ static int sa_backward_impl(const pcoe_sa_desc& d, const float* xyz, const float
       PCOE_TRY(launch_wgrad6(dy2, x1, Gr.dW[1], d.C1, d.C1, -1, M, ceil_div(d.C1, 128), st, kname(d, kWG2)));
       dy2.fin.write = 0;
       if (w1_epi6) {
-        v6::MaskStatsW6 mw{}; mw.yprev = y[0]; mw.scale = scale[0]; mw.shift = shift[0]; mw.mean = mean[0]; mw.invstd = invstd[0];
+        v6::MaskStatsW6 mw{}; mw.W1 = P.W[0]; mw.scale = scale[0]; mw.shift = shift[0]; mw.mean = mean[0]; mw.invstd = invstd[0];
         mw.sums = bs[0]; mw.C = d.C1; mw.gb = v4::GatherBase{xyz, new_xyz, nbr, d.N, d.S, d.group_all, M};
         mw.acc = (float*)(ws + L.wb_dwc[0]); mw.g0 = (float*)(ws + L.wb_g0);
         PCOE_TRY(launch_dgrad6<false>(dy2, wh(1), wps(1), L.w4_kp[1], mw, M, d.C1, st, kname(d, kDG2)));

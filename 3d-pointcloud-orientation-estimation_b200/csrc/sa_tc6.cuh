@@ -689,7 +689,9 @@ struct MaskStatsW6 {
   static constexpr bool kPre = true;
   static constexpr bool kHalf = true;   // C == 64 only: lanes 64..127 repeat the channels (ConvW6::dup_cols), 16 points per thread
   int half;
-  const float* __restrict__ yprev;   // y1, fp32 activation layout
+  const float* __restrict__ W1;      // layer-1 weights fp32 [C][3]: y1 = W1 x0 is recomputed (3 FMAs) instead of read back -
+                                     // the same value as the forward's 24-bit-operand MMA to an ulp; the conv bias is not
+                                     // part of y1 in train mode (BatchNorm cancels it)
   const float* __restrict__ scale;
   const float* __restrict__ shift;
   const float* __restrict__ mean;
@@ -700,11 +702,14 @@ struct MaskStatsW6 {
   float* __restrict__ acc;           // [kRedCopies][C][4]: dz1^T x0 in columns 0..2
   float* __restrict__ g0;            // [kRedCopies][16]: xx xy xz yy yz zz sx sy sz
   int c, eq;
-  float s0, s1, sc, sh, is, nmi;
+  float s0, s1, sc, sh, is, nmi, w0, w1, w2;
   float A0, A1, A2;
   float G[9];
   float4* xs;                        // shared memory: [warp][2 blocks][32 points] (x, y, z, 0)
-  float4 yq[2][4];                   // y1 of this thread's 2 x 16 points, loaded by pre() before the accumulator wait
+  // software pipeline of the gather (index -> coordinates are dependent loads): while tile i is processed, the
+  // coordinates of tile i+1 and the neighbour indices of tile i+2 are in flight
+  float xv[2][3], cv[2][3];          // raw point / centroid of this lane's 2 points of the NEXT tile to be parked
+  int pt_n[2];                       // xyz row of this lane's 2 points of the tile after that (-1: beyond M)
   __host__ __device__ __forceinline__ int nconst() const { return 8 * 2 * 32 * 4; }
   __device__ __forceinline__ void init(float* csm, int ch) {
     xs = reinterpret_cast<float4*>(csm) + (threadIdx.x >> 5) * 64;   // csm is 16-byte aligned
@@ -714,26 +719,41 @@ struct MaskStatsW6 {
     for (int i = 0; i < 9; ++i) G[i] = 0.f;
     const bool ok = c < C;
     sc = ok ? scale[c] : 0.f; sh = ok ? shift[c] : 0.f; is = ok ? invstd[c] : 0.f; nmi = ok ? -mean[c] * is : 0.f;
+    w0 = ok ? W1[c * 3] : 0.f; w1 = ok ? W1[c * 3 + 1] : 0.f; w2 = ok ? W1[c * 3 + 2] : 0.f;
   }
-  __device__ __forceinline__ void pre(int tile, int eh, int M) {
+  __device__ __forceinline__ void load_idx(int tile, int eh, int M) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       const int row = tile * kPts + (2 * eh + it) * 32 + lane;
-      float o[3] = {0.f, 0.f, 0.f};
-      if (row < M) {
-        float x[3], cc[3];
-        gb.load_xyz_raw(row, gb.point_of(row), x, cc);
-#pragma unroll
-        for (int u = 0; u < 3; ++u) o[u] = gb.centred(x[u], cc[u]);       // the forward's x0, bit for bit
-      }
-      xs[it * 32 + lane] = make_float4(o[0], o[1], o[2], 0.f);           // read back by this warp only
-      const int j = 2 * eh + it;
-      const bool ok = tile * kPts + j * 32 < M;
-      const size_t yo = act_off(tile, C, c, j * 8 + half * 4), qs = (size_t)C * 4;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) yq[it][q] = ldg4_or0(yprev + yo + (size_t)q * qs, ok);
+      pt_n[it] = row < M ? gb.point_of(row) : -1;
     }
+  }
+  __device__ __forceinline__ void load_xyz(int tile, int eh) {        // uses pt_n (of this tile)
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int row = tile * kPts + (2 * eh + it) * 32 + lane;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) xv[it][u] = cv[it][u] = 0.f;
+      if (pt_n[it] >= 0) gb.load_xyz_raw(row, pt_n[it], xv[it], cv[it]);
+    }
+  }
+  // before the first tile: coordinates of tile t0 and indices of tile t1 requested
+  __device__ __forceinline__ void prime(int t0, int t1, int eh, int M) {
+    load_idx(t0, eh, M);
+    load_xyz(t0, eh);
+    load_idx(t1, eh, M);
+  }
+  // tile = the tile about to be processed; t1 / t2 = the next two tiles of this CTA (may lie beyond the last tile)
+  __device__ __forceinline__ void pre(int tile, int t1, int t2, int eh, int M) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int it = 0; it < 2; ++it)   // the forward's x0, bit for bit; (0, 0, 0) beyond M
+      xs[it * 32 + lane] = make_float4(gb.centred(xv[it][0], cv[it][0]), gb.centred(xv[it][1], cv[it][1]),
+                                       gb.centred(xv[it][2], cv[it][2]), 0.f);
+    load_xyz(t1, eh);                // pt_n holds t1's rows (requested one tile ago)
+    load_idx(t2, eh, M);
     __syncwarp();
   }
   // v = the accumulator's columns j*32 + half*16 .. +15 (16 points of block j) of channel c
@@ -741,24 +761,17 @@ struct MaskStatsW6 {
     const int it = j & 1;
     const float4* xp = xs + it * 32;
     if (valid) {
-      float4 yv[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) yv[q] = yq[it][q];
       float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
       float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float yy[4] = {yv[q].x, yv[q].y, yv[q].z, yv[q].w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = 4 * q + u;
-          const bool on = fmaf(yy[u], sc, sh) > 0.f;
-          const float d = on ? v[i] : 0.f;
-          a[u] += d;
-          b[u] = fmaf(d, fmaf(yy[u], is, nmi), b[u]);
-          const float4 x0 = xp[half * 16 + i];                            // broadcast 16-byte load
-          t0[u] = fmaf(d, x0.x, t0[u]); t1[u] = fmaf(d, x0.y, t1[u]); t2[u] = fmaf(d, x0.z, t2[u]);
-        }
+      for (int i = 0; i < 16; ++i) {
+        const float4 x0 = xp[half * 16 + i];                              // broadcast 16-byte load
+        const float yy = fmaf(w2, x0.z, fmaf(w1, x0.y, w0 * x0.x));       // y1 = W1 x0
+        const bool on = fmaf(yy, sc, sh) > 0.f;
+        const float d = on ? v[i] : 0.f;
+        a[i & 3] += d;
+        b[i & 3] = fmaf(d, fmaf(yy, is, nmi), b[i & 3]);
+        t0[i & 3] = fmaf(d, x0.x, t0[i & 3]); t1[i & 3] = fmaf(d, x0.y, t1[i & 3]); t2[i & 3] = fmaf(d, x0.z, t2[i & 3]);
       }
       s0 += (a[0] + a[1]) + (a[2] + a[3]);
       s1 += (b[0] + b[1]) + (b[2] + b[3]);
@@ -1075,9 +1088,10 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wp, size_t wps, int 
 
   if (warp < 8) {
     int i = 0;
+    if constexpr (!PT) { if constexpr (Epi::kPre) epi.prime(t0, t0 + tstep, eh, M); }
     for (int tile = t0; tile < ntiles; tile += tstep, ++i) {
       const int b = i & 1, u = i >> 1, m0 = tile * kPts;
-      if constexpr (!PT) { if constexpr (Epi::kPre) epi.pre(tile, eh, M); }
+      if constexpr (!PT) { if constexpr (Epi::kPre) epi.pre(tile, tile + tstep, tile + 2 * tstep, eh, M); }
       tc::mbar_wait(&bar.tmem_full[b], (uint32_t)(u & 1));
       tc::fence_after_sync();
       if constexpr (!PT) {

@@ -146,9 +146,9 @@ def kernel_work(B: int, N: int, precision: str = "bf16") -> dict:
             t + "bwd_wgrad3": (g(2, 3), y3 + act(2) + 5.0 * G * c[3]),
             t + "bwd_dgrad3": (g(2, 3), y3 + act(2) + 5.0 * G * c[3] + act(2)),
             t + "bwd_wgrad2": (g(1, 2), 2 * act(2) + act(1)),
-            # bf16x3 SA1: the layer-2 dgrad epilogue also accumulates dW1 (MaskStatsW6): it reads the indices + xyz and does
-            # not write dz1; the layer-1 wgrad kernel does not run
-            t + "bwd_dgrad2": ((g(1, 2) + g(0, 1), 2 * act(2) + act(1) + src) if (li == 0 and precision == "bf16x3")
+            # bf16x3 SA1: the layer-2 dgrad epilogue also accumulates dW1 (MaskStatsW6): it reads the indices + xyz, recomputes
+            # y1 = W1 x0 instead of reading it and does not write dz1; the layer-1 wgrad kernel does not run
+            t + "bwd_dgrad2": ((g(1, 2) + 2 * g(0, 1), 2 * act(2) + src) if (li == 0 and precision == "bf16x3")
                                else (g(1, 2), 2 * act(2) + act(1) + act(1))),
             t + "bwd_wgrad1": (g(0, 1), 2 * act(1) + src), t + "bwd_dgrad1": (dg1, 2 * act(1) + scat)})
     grp = float(sum(B * (12 * s[5] + 12 * s[6] + 4 * s[6] * s[7]) for s in sh[:2]))
