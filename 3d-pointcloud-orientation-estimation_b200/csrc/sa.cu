@@ -501,17 +501,27 @@ static int launch_wgrad6(const PProd& pp, const QProd& qp, float* dW, int ldo, i
   const int tps = ceil_div(ntiles, splits);
   splits = ceil_div(ntiles, tps);
   if constexpr (PProd::kAsync && QProd::kAsync) {
-    constexpr int items = PProd::kRawItems > QProd::kRawItems ? PProd::kRawItems : QProd::kRawItems;
-    const size_t raw = (size_t)v6::kRawDepth * items * v6::kRawItemBytes;
-    int na = (int)((kSmemBudget6 - 1024 - cbytes - raw) / 65536);
-    na = na > v6::kMaxStages6 ? v6::kMaxStages6 : na;
-    if (x3_async_enabled() && na >= 1) {
+    // two producer groups (P units / Q units), each on its own cp.async ring: deepest pair of rings that fits beside
+    // one operand stage
+    const size_t up = (size_t)PProd::kRawItems * v6::kRawItemBytes, uq = (size_t)QProd::kRawItems * v6::kRawItemBytes;
+    const size_t room = kSmemBudget6 - 1024 - cbytes - 65536;
+    int dP = 0, dQ = 0;
+    if (kSmemBudget6 > 1024 + cbytes + 65536) {
+      if (3 * up + 3 * uq <= room) { dP = 3; dQ = 3; }
+      else if (3 * up + 2 * uq <= room) { dP = 3; dQ = 2; }
+      else if (2 * up + 3 * uq <= room) { dP = 2; dQ = 3; }
+      else if (2 * up + 2 * uq <= room) { dP = 2; dQ = 2; }
+    }
+    if (x3_async_enabled() && dP) {
+      const size_t raw = dP * up + dQ * uq;
+      int na = (int)((kSmemBudget6 - 1024 - cbytes - raw) / 65536);
+      na = na > v6::kMaxStages6 ? v6::kMaxStages6 : na;
       const size_t smem = 1024 + (size_t)na * 65536 + raw + cbytes;
       auto k = v6::x3_wgrad_kernel<PProd, QProd, true>;
       static bool attr = false;
       if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
       LaunchScope ls(what, st);
-      k<<<dim3(clb, nqb, splits), v4::kThreads, smem, st>>>(pp, qp, dW, ldo, cq_valid, perm_d, M, tps, na);
+      k<<<dim3(clb, nqb, splits), v4::kThreads, smem, st>>>(pp, qp, dW, ldo, cq_valid, perm_d, M, tps, na, dP * 16 + dQ);
       return ls.done();
     }
   }
@@ -523,7 +533,7 @@ static int launch_wgrad6(const PProd& pp, const QProd& qp, float* dW, int ldo, i
   static bool attr = false;
   if (!attr) { PCOE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget6)); attr = true; }
   LaunchScope ls(what, st);
-  k<<<dim3(clb, nqb, splits), v4::kThreads, smem, st>>>(pp, qp, dW, ldo, cq_valid, perm_d, M, tps, nst);
+  k<<<dim3(clb, nqb, splits), v4::kThreads, smem, st>>>(pp, qp, dW, ldo, cq_valid, perm_d, M, tps, nst, 0);
   return ls.done();
 }
 

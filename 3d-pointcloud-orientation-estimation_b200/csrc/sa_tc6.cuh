@@ -178,7 +178,7 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t unit_base, int item, int g
 
 // kRawDepth-deep pipeline over W units: issue(w, slot) enqueues the async copies of unit w, consume(w, slot) runs when
 // they have landed
-template <class IssueF, class ConsumeF>
+template <int kRawDepth = 3, class IssueF, class ConsumeF>
 __device__ __forceinline__ void async_pipeline(int W, uint32_t raw0, uint32_t kRawUnit, IssueF issue, ConsumeF consume) {
   if (W <= 0) return;
 #pragma unroll
@@ -1206,11 +1206,13 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wp, size_t wps, int 
 // ---------------------------------------------------------------------------------------------------------------
 template <class PProd, class QProd, bool ASYNC = false>
 __global__ void __launch_bounds__(kThreads, 1)
-x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_valid, int perm_d, int M, int tps, int nst) {
+x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_valid, int perm_d, int M, int tps, int nst, int depths) {
   PCOE_V6_PROLOGUE(128)
   constexpr int NP = 2;
-  constexpr int kRawItemsPQ = PProd::kRawItems > QProd::kRawItems ? PProd::kRawItems : QProd::kRawItems;
-  constexpr uint32_t kRawUnit = ASYNC ? (uint32_t)kRawItemsPQ * kRawItemBytes : 0u, kRawBytes = kRawDepth * kRawUnit;
+  // ASYNC: raw staging rings of the two producer groups, depths = dP * 16 + dQ (see the producer branch)
+  const uint32_t kRawBytes = ASYNC ? ((uint32_t)(depths >> 4) * (uint32_t)PProd::kRawItems + (uint32_t)(depths & 15) * (uint32_t)QProd::kRawItems) * kRawItemBytes : 0u;
+  if (ASYNC && tid == 0)
+    for (int s = 0; s < kMaxStages6; ++s) tc::mbar_init(&bar.full[s], 2 * kProdThreads);   // both groups arrive
   const int cl0 = blockIdx.x * 128, qb = blockIdx.y;
   const int ntiles = (M + kPts - 1) / kPts;
   const int t0 = blockIdx.z * tps, t1 = min(ntiles, t0 + tps), nt = max(t1 - t0, 0);
@@ -1246,43 +1248,51 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
     union RawU { typename PProd::Raw p; typename QProd::Raw q; __device__ RawU() {} };
     struct Cur { int u, m0; };
     if constexpr (ASYNC) {
-      // one producer group (warps 8-15), raw operands staged with cp.async kRawDepth units deep (see async_pipeline)
-      if (warp >= 8) {
-        auto adv = [&](Cur& c) { if (++c.u == ups) { c.u = 0; c.m0 += 64; } };
-        Cur cl{0, t0 * kPts}, cst = cl;
-        int ring_s = 0, ring_r = 0;
-        async_pipeline(nstage * ups, sRaw, kRawUnit,
-            [&](int, uint32_t ub) {
-              if (cl.u < kPU) pp.template load_async<64>(g, cl.m0, cl0 + cl.u * 32 * PProd::kUR, ub);
-              else if constexpr (QProd::kChMajor) qp.template load_async<64>(g, cl.m0, qb * 128 + (cl.u - kPU) * 32 * QProd::kUR, ub);
-              else qp.template load_async<64>(g, cl.m0, 2 * qb + (cl.u - kPU), ub);
-              adv(cl);
-            },
-            [&](int, uint32_t ub) {
-              RawU r;
-              const uint32_t st = sS + (uint32_t)ring_s * sbytes;
-              if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
-              if (cst.u < kPU) {
-                pp.template fetch<64>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, ub, r.p);
-                pp.template store<64, NP>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, cst.u * 32 * PProd::kUR, 128, r.p, st);
-              } else {
-                const int qu = cst.u - kPU;
-                if constexpr (QProd::kChMajor) {
-                  qp.template fetch<64>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, ub, r.q);
-                  qp.template store<64, NP>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, qu * 32 * QProd::kUR, 128, r.q, st + 2 * kPart);
-                } else {
-                  qp.template fetch<64>(g, cst.m0, 2 * qb + qu, ub, r.q);
-                  qp.template store<64, NP>(g, 2 * qb + qu, r.q, st + 2 * kPart + (uint32_t)qu * 8192u);
-                }
-              }
-              if (cst.u == ups - 1) {
-                tc::fence_proxy_async();
-                mbar_arrive(&bar.full[ring_s]);
-                if (++ring_s == nst) { ring_s = 0; ++ring_r; }
-              }
-              adv(cst);
-            });
-      }
+      // Both warp groups produce, each through its own cp.async ring: warps 8-15 build the P (dy) units, warps 0-7 the
+      // Q (x_prev) units of every stage (the accumulator is read once, after the last stage, so warps 0-7 would otherwise
+      // idle; ncu: the 8-warp version was bound by the producers' instruction throughput, not by latency).  A stage is
+      // complete when both groups have arrived (full barrier = 2 x kProdThreads).  Ring depths: `depths` = dP * 16 + dQ.
+      const bool isP = warp >= 8;
+      const int dP = depths >> 4, dQ = depths & 15;
+      const int nu = isP ? kPU : nqu;
+      const uint32_t rawP = sRaw, rawQ = sRaw + (uint32_t)dP * (uint32_t)PProd::kRawItems * kRawItemBytes;
+      struct Cur2 { int u, m0; };
+      Cur2 cl{0, t0 * kPts}, cst = cl;
+      auto adv = [&](Cur2& c) { if (++c.u == nu) { c.u = 0; c.m0 += 64; } };
+      int ring_s = 0, ring_r = 0;
+      auto issue = [&](int, uint32_t ub) {
+        if (isP) pp.template load_async<64>(g, cl.m0, cl0 + cl.u * 32 * PProd::kUR, ub);
+        else if constexpr (QProd::kChMajor) qp.template load_async<64>(g, cl.m0, qb * 128 + cl.u * 32 * QProd::kUR, ub);
+        else qp.template load_async<64>(g, cl.m0, 2 * qb + cl.u, ub);
+        adv(cl);
+      };
+      auto consume = [&](int, uint32_t ub) {
+        RawU r;
+        const uint32_t st = sS + (uint32_t)ring_s * sbytes;
+        if (cst.u == 0 && ring_r > 0) tc::mbar_wait(&bar.empty[ring_s], (uint32_t)((ring_r - 1) & 1));
+        if (isP) {
+          pp.template fetch<64>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, ub, r.p);
+          pp.template store<64, NP>(g, cst.m0, cl0 + cst.u * 32 * PProd::kUR, cst.u * 32 * PProd::kUR, 128, r.p, st);
+        } else {
+          const int qu = cst.u;
+          if constexpr (QProd::kChMajor) {
+            qp.template fetch<64>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, ub, r.q);
+            qp.template store<64, NP>(g, cst.m0, qb * 128 + qu * 32 * QProd::kUR, qu * 32 * QProd::kUR, 128, r.q, st + 2 * kPart);
+          } else {
+            qp.template fetch<64>(g, cst.m0, 2 * qb + qu, ub, r.q);
+            qp.template store<64, NP>(g, 2 * qb + qu, r.q, st + 2 * kPart + (uint32_t)qu * 8192u);
+          }
+        }
+        if (cst.u == nu - 1) {
+          tc::fence_proxy_async();
+          mbar_arrive(&bar.full[ring_s]);
+          if (++ring_s == nst) { ring_s = 0; ++ring_r; }
+        }
+        adv(cst);
+      };
+      const uint32_t unitB = (uint32_t)(isP ? PProd::kRawItems : QProd::kRawItems) * kRawItemBytes;
+      if ((isP ? dP : dQ) == 3) async_pipeline<3>(nstage * nu, isP ? rawP : rawQ, unitB, issue, consume);
+      else async_pipeline<2>(nstage * nu, isP ? rawP : rawQ, unitB, issue, consume);
     } else {
     const int gsel = warp >> 3;
     auto adv = [&](Cur& c) { if (++c.u == ups) { c.u = 0; c.m0 += 128; } };
