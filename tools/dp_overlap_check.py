@@ -44,13 +44,16 @@ def grads(overlap: bool, accumulate: bool):
 ok = True
 for acc in (False, True):
     a, b = grads(True, acc), grads(False, acc)
-    same = torch.equal(a, b)
+    # the weight-gradient kernels accumulate with fp32 atomics (order varies run to run), so two runs of the SAME
+    # configuration differ at the 1e-7 level: compare to that noise floor, not bitwise
+    rel = float((a - b).norm() / b.norm())
+    same = rel < 1e-5
     # every rank holds the same reduced buffer
     other = a.clone()
     dist.broadcast(other, src=0)
     agree = torch.equal(other, a)
     if rank == 0:
-        print(f"accumulate={acc}: overlap == no-overlap bitwise: {same}; ranks agree: {agree}; |g| = {float(a.norm()):.6f}")
+        print(f"accumulate={acc}: overlap vs no-overlap rel-L2 {rel:.2e} (< 1e-5: {same}); ranks hold identical buffers: {agree}; |g| = {float(a.norm()):.6f}")
     ok = ok and same and agree
 if rank == 0:
     print("dp_overlap_check:", "PASS" if ok else "FAIL")
