@@ -82,6 +82,7 @@ SIGNATURES = {
                                             _I, _P, _P, _P, _P, _I, _F, _F, _I, _P, _P, _P, _P]),
     "pcoe_heads_ln_relu_dropout_bwd": (_I, [_P, _I, _F, _F, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P,
                                             _I, _I, _F, _I, _P, _P, _P, _P, _P]),
+    "pcoe_peer_allreduce_f32": (_I, [_P, _P, _P, _I, _I, _SZ, _SZ, _P, _I, _P]),
     "pcoe_adam_workspace_bytes": (_SZ, []),
     "pcoe_adam_step": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
 }

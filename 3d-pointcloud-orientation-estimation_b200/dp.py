@@ -10,6 +10,8 @@ Works with any torch.distributed backend (NCCL over NVLink on the B200 box, gloo
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -18,12 +20,17 @@ class FlatGradBuffer:
     """Re-points every ``p.grad`` into one contiguous fp32 buffer so that autograd accumulates in
     place and the whole gradient is reduced by a single collective (5.86-5.88 MB for these models)."""
 
-    def __init__(self, module: torch.nn.Module):
+    def __init__(self, module: torch.nn.Module, alloc=None):
+        """``alloc(n_floats, device) -> tensor`` overrides the allocation (pcoe.dp.PeerExchange: symmetric memory that
+        every rank of the node maps); the buffer is padded to a multiple of 4 floats for 16-byte accesses."""
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("module has no trainable parameters")
         dev, total = self.params[0].device, sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.total = total
+        padded = (total + 3) // 4 * 4
+        self.total = total
+        self.flat = torch.zeros(padded, dtype=torch.float32, device=dev) if alloc is None else alloc(padded, dev)
         off = 0
         for p in self.params:
             if p.dtype != torch.float32 or p.device != dev:
@@ -56,7 +63,57 @@ class FlatGradBuffer:
             off += p.numel()
 
     def nbytes(self) -> int:
-        return self.flat.numel() * 4
+        """Bytes of gradient payload (the ≤ 3 floats of 16-byte padding at the end stay zero and are not counted)."""
+        return self.total * 4
+
+
+class PeerExchange:
+    """Sum-all-reduce of (a slice of) the flat gradient buffer over NVLink peer memory: libpcoe's two-shot kernel
+    (csrc/peer.cu) on torch's symmetric memory (every rank maps every peer's buffer and a small signal pad).  One node,
+    <= 8 ranks, CUDA only; CUDA-graph capturable (flag epochs live on the device)."""
+
+    def __init__(self, group=None, max_ctas: int = 64, multicast: bool | None = None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        self._C, self._symm = C, symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("PeerExchange: at most 8 ranks (one NVSwitch node)")
+        self.max_ctas = max_ctas
+        if multicast is None:
+            multicast = os.environ.get("PCOE_PEER_MULTICAST", "1") != "0"
+        self._want_mc, self.mc_ptr = multicast, 0
+        self.flat = None
+        self.stream = torch.cuda.Stream()
+
+    def alloc(self, n: int, device) -> torch.Tensor:
+        symm = self._symm
+        self.flat = symm.empty(n, dtype=torch.float32, device=device)
+        self.flat.zero_()
+        self._hb = symm.rendezvous(self.flat, self.group)
+        self.pad = symm.empty(64, dtype=torch.int32, device=device)
+        self.pad.zero_()
+        self._hp = symm.rendezvous(self.pad, self.group)
+        self.ctl = torch.zeros(16, dtype=torch.int32, device=device)
+        C = self._C
+        self._bufs = (C.c_void_p * self.world)(*[int(p) for p in self._hb.buffer_ptrs])
+        self._pads = (C.c_void_p * self.world)(*[int(p) for p in self._hp.buffer_ptrs])
+        if self._want_mc:                              # NVSwitch multicast mapping, when the fabric offers one
+            try:
+                self.mc_ptr = int(getattr(self._hb, "multicast_ptr", 0) or 0)
+            except Exception:
+                self.mc_ptr = 0
+        torch.cuda.synchronize()
+        dist.barrier(self.group)                       # every rank's pad / buffer is zeroed before the first flag lands
+        return self.flat
+
+    def all_reduce_(self, lo: int, hi: int, stream=None) -> None:
+        """flat[lo:hi] <- sum over ranks, enqueued on `stream` (default: the current stream).  lo, hi multiples of 4."""
+        from . import _lib
+        st = torch.cuda.current_stream() if stream is None else stream
+        _lib.check(_lib.load().pcoe_peer_allreduce_f32(self._bufs, self._pads, self.mc_ptr or None, self.rank, self.world, lo, hi - lo,
+                                                       self.ctl.data_ptr(), self.max_ctas, st.cuda_stream))
 
 
 def shard_bounds(total: int, world: int, rank: int) -> tuple[int, int]:
@@ -77,7 +134,10 @@ class DataParallel:
     is all-reduced asynchronously while sa2 / sa1 run their backward; ``allreduce_grads()`` then reduces the small
     head of the buffer and joins.  Both collectives are captured by ``pcoe.GraphedTrainStep``."""
 
-    def __init__(self, module: torch.nn.Module, process_group=None, broadcast_buffers: bool = True, overlap: bool = True):
+    def __init__(self, module: torch.nn.Module, process_group=None, broadcast_buffers: bool = True, overlap: bool = True,
+                 exchange: str = "nccl"):
+        """exchange: 'nccl' (torch.distributed all-reduce: any backend), 'peer' (libpcoe's NVLink peer-memory kernel,
+        PeerExchange) or 'auto' ('peer' when it can be set up - CUDA, <= 8 ranks, symmetric memory - else 'nccl')."""
         self.module = module
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -90,7 +150,27 @@ class DataParallel:
                 if broadcast_buffers:
                     for b in module.buffers():
                         dist.broadcast(b.data, src=0, group=process_group)
-        self.grads = FlatGradBuffer(module)
+        if exchange not in ("nccl", "peer", "auto"):
+            raise ValueError(f"pcoe.dp: exchange={exchange!r} (expected 'nccl', 'peer' or 'auto')")
+        self.peer = None
+        if self.world > 1 and exchange in ("peer", "auto") and next(module.parameters()).is_cuda:
+            err = None
+            try:
+                self.peer = PeerExchange(process_group)
+                self.grads = FlatGradBuffer(module, alloc=self.peer.alloc)
+            except Exception as e:                                # no symmetric memory on this system / across nodes
+                err = e
+            # the choice is collective: one rank without a mapping sends every rank to the torch.distributed path
+            ok = torch.tensor([0 if err is not None else 1], device=next(module.parameters()).device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+            if int(ok) == 0:
+                if exchange == "peer":
+                    raise RuntimeError(f"pcoe.dp: peer-memory exchange unavailable on at least one rank ({err})")
+                import warnings
+                warnings.warn(f"pcoe.dp: peer-memory exchange unavailable ({err}); using the torch.distributed all-reduce")
+                self.peer = None
+        if self.peer is None:
+            self.grads = FlatGradBuffer(module)
         self._late_off, self._late_work = None, None
         self._sync = True              # False inside no_sync(): micro-batch gradients accumulate locally
         if self.world > 1 and overlap:
@@ -103,6 +183,7 @@ class DataParallel:
                     if p is first_param:
                         break
                     off += p.numel()
+                off = (off + 3) // 4 * 4     # 16-byte aligned boundary, rounded UP: the tail bucket holds only final gradients
                 if 0 < off < self.grads.flat.numel():
                     self._late_off = off
                     last._after_backward = self._reduce_tail_async
@@ -116,8 +197,15 @@ class DataParallel:
             raise RuntimeError("pcoe.dp: backward() ran twice before allreduce_grads(); wrap the extra micro-batches "
                                "in `with engine.no_sync():` (gradient accumulation)")
         if self._sync:
-            self._late_work = dist.all_reduce(self.grads.flat[self._late_off:], op=dist.ReduceOp.SUM, group=self.group,
-                                              async_op=True)
+            if self.peer is not None:
+                # side stream: the tail's exchange runs beside the remaining backward kernels
+                side = self.peer.stream
+                side.wait_stream(torch.cuda.current_stream())
+                self.peer.all_reduce_(self._late_off, self.grads.flat.numel(), side)
+                self._late_work = side
+            else:
+                self._late_work = dist.all_reduce(self.grads.flat[self._late_off:], op=dist.ReduceOp.SUM, group=self.group,
+                                                  async_op=True)
 
     def zero_grad(self) -> None:
         self.grads.zero_()
@@ -142,7 +230,17 @@ class DataParallel:
         pcoe.optim.FusedAdam built on this engine applies the factor in its step kernel)."""
         if self.world > 1:
             self.grads.check_views()
-            if self._late_work is not None:
+            if self.peer is not None:
+                cur = torch.cuda.current_stream()
+                if self._late_work is not None:               # head bucket behind the tail on the side stream, then join
+                    side = self._late_work
+                    side.wait_stream(cur)
+                    self.peer.all_reduce_(0, self._late_off, side)
+                    cur.wait_stream(side)
+                    self._late_work = None
+                else:
+                    self.peer.all_reduce_(0, self.grads.flat.numel(), cur)
+            elif self._late_work is not None:
                 dist.all_reduce(self.grads.flat[:self._late_off], op=dist.ReduceOp.SUM, group=self.group)
                 self._late_work.wait()
                 self._late_work = None

@@ -49,7 +49,7 @@ class FusedAdam:
         if not flat_g.is_cuda:
             raise RuntimeError("pcoe.optim.FusedAdam runs on CUDA only (no CPU fallback)")
         dev = flat_g.device
-        self.flat_p = torch.empty_like(flat_g)
+        self.flat_p = torch.zeros(flat_g.numel(), dtype=torch.float32, device=dev)   # (the gradient buffer may be padded / symmetric)
         off = 0
         with torch.no_grad():
             for p in self.params:
@@ -58,8 +58,8 @@ class FusedAdam:
                 view.copy_(p.data)
                 p.data = view                      # parameters now live in the flat buffer
                 off += n
-        self.exp_avg = torch.zeros_like(flat_g)
-        self.exp_avg_sq = torch.zeros_like(flat_g)
+        self.exp_avg = torch.zeros(flat_g.numel(), dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(flat_g.numel(), dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)   # ||g|| before clipping, last step
         self._ws = torch.zeros(_lib.load().pcoe_adam_workspace_bytes(), dtype=torch.uint8, device=dev)

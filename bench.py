@@ -343,7 +343,7 @@ def run_ours(args):
     sampler = "randperm_host" if args.sampler == "host" else "randperm_device"
     torch.manual_seed(1000)
     model = getattr(pcoe, cls)(sampler=sampler).to(dev).train()
-    engine = pcoe.dp.DataParallel(model, overlap=not args.no_overlap)
+    engine = pcoe.dp.DataParallel(model, overlap=not args.no_overlap, exchange=args.exchange)
     if args.skip_allreduce:                              # diagnostic only: how much of the N>1 step is the exchange
         engine.allreduce_grads = lambda: None
         engine._late_off = None
@@ -626,6 +626,7 @@ def run_ours(args):
             "sampling_grouping": sg,
             "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps,
             "grad_allreduce_bytes": engine.grads.nbytes() if world > 1 else 0,
+            "grad_exchange": ("peer (libpcoe two-shot all-reduce over NVLink symmetric memory)" if engine.peer is not None else "nccl") if world > 1 else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -825,6 +826,8 @@ def main():
     ap.add_argument("--torch-optimizer", action="store_true",
                     help="torch.optim.Adam(fused) + clip_grad_norm_ instead of pcoe.optim.FusedAdam")
     ap.add_argument("--trunk-tf32", action="store_true", help="TF32 tensor-core cuBLAS kernels for the torch.nn trunk")
+    ap.add_argument("--exchange", choices=["nccl", "peer", "auto"], default=os.environ.get("PCOE_EXCHANGE", "nccl"),
+                    help="gradient exchange at N > 1: torch.distributed (NCCL) all-reduce or libpcoe's NVLink peer-memory kernel")
     ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after backward instead of two overlapped buckets")
     ap.add_argument("--skip-allreduce", action="store_true", help="diagnostic: N>1 without the gradient exchange (INVALID as a result)")
     ap.add_argument("--timed-only", action="store_true",

@@ -392,6 +392,23 @@ int pcoe_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                    float grad_scale, int zero_grad, int64_t* step_dev, float* grad_norm_dev, void* workspace,
                    void* stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink peer memory ("allreduce for the MLP gradients only")
+ * ------------------------------------------------------------------------------------------ */
+
+/* In-place sum-all-reduce of n floats at float offset `offset` of a SYMMETRIC buffer: bufs_host[p] is THIS process's
+ * mapping of rank p's buffer, pads_host[p] of rank p's signal pad (>= 32 uint32, zeroed once before the first call;
+ * torch.distributed._symmetric_memory provides both).  Two-shot with a pushed second shot: every rank announces its
+ * gradients (flag A), rank r sums slice r over the ranks in rank order and stores the sum into every rank's buffer, then
+ * the ranks exchange "pushes landed" flags (B); when the launch completes nobody touches this rank's buffer any more.
+ * mc_buf: NVSwitch multicast mapping of the same buffer (multimem.ld_reduce / multimem.st do the sum and the broadcast
+ * in the switch) or NULL for plain peer loads / stores.  Every rank of the node must make the same sequence of calls.
+ * ctl_dev: 16 uint32 of this rank's device memory, zeroed once (the launch epoch lives there, so the call can be captured
+ * in a CUDA graph and replayed).  offset, n multiples of 4; world <= 8.  The two `_host` arrays are HOST arrays of
+ * `world` device pointers.  max_ctas <= 0: 64. */
+int pcoe_peer_allreduce_f32(const void* const* bufs_host, const void* const* pads_host, const void* mc_buf, int rank,
+                            int world, size_t offset, size_t n, uint32_t* ctl_dev, int max_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

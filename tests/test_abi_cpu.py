@@ -61,6 +61,13 @@ def test_argument_errors_without_gpu(pcoe):
     pd.rows_per_cloud, pd.nlayers = 1024, 4
     assert lib.pcoe_pointmlp_forward(C.byref(pd), None, None, None, None, None, 0, None) == L.ERR_UNSUPPORTED
     assert lib.pcoe_pointwise_linear_f32(None, 8, 9, None, None, None, 64, 1, None, None) == L.ERR_UNSUPPORTED
+    # gradient exchange over peer memory: rank / world, NULL tables, 16-byte granularity
+    two = (C.c_void_p * 2)(0x1000, 0x2000)
+    assert lib.pcoe_peer_allreduce_f32(two, two, None, 2, 2, 0, 8, 0x1000, 0, None) == L.ERR_BAD_SHAPE     # rank >= world
+    assert lib.pcoe_peer_allreduce_f32(two, two, None, 0, 9, 0, 8, 0x1000, 0, None) == L.ERR_BAD_SHAPE     # > 8 ranks
+    assert lib.pcoe_peer_allreduce_f32(None, two, None, 0, 2, 0, 8, 0x1000, 0, None) == L.ERR_NULL
+    assert lib.pcoe_peer_allreduce_f32(two, two, None, 0, 2, 2, 8, 0x1000, 0, None) == L.ERR_BAD_SHAPE     # offset % 4
+    assert lib.pcoe_peer_allreduce_f32(two, two, None, 0, 2, 0, 0, 0x1000, 0, None) == L.OK                # n == 0: nothing to do
     with pytest.raises(ValueError):
         L.check(L.ERR_BAD_SHAPE)
     with pytest.raises(NotImplementedError):

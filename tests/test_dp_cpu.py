@@ -95,6 +95,22 @@ def test_single_process_engine_is_a_no_op_allreduce():
     assert torch.equal(before, e.grads.flat) and e.grads.nbytes() == 4 * sum(p.numel() for p in m.parameters())
 
 
+def test_exchange_choice_and_padded_flat_buffer():
+    """exchange='auto' on CPU parameters keeps the torch.distributed path; an unknown name is refused; the flat buffer is
+    padded to 16 bytes (the peer-memory kernel moves float4) and the padding never counts as payload."""
+    import pytest
+    import pcoe
+    m = _Toy()
+    e = pcoe.dp.DataParallel(m, exchange="auto")
+    assert e.peer is None
+    with pytest.raises(ValueError):
+        pcoe.dp.DataParallel(_Toy(), exchange="mpi")
+    total = sum(p.numel() for p in m.parameters())
+    assert e.grads.flat.numel() == (total + 3) // 4 * 4 and e.grads.nbytes() == 4 * total
+    opt = pcoe.optim.FusedAdam if hasattr(pcoe, "optim") else None
+    assert opt is not None
+
+
 def test_overlapped_exchange_is_armed_once_per_step():
     """a second backward() before allreduce_grads() must not all-reduce the already-summed tail again.
     The hook raises unless the extra micro-batches run under no_sync(); FlatGradBuffer notices detached .grad views."""

@@ -20,12 +20,15 @@ dist.init_process_group("nccl", device_id=dev)
 B, N = 16, 1024
 
 
-def grads(overlap: bool, accumulate: bool):
+EXCHANGE = os.environ.get("PCOE_EXCHANGE", "nccl")
+
+
+def grads(overlap: bool, accumulate: bool, exchange: str = "nccl"):
     torch.manual_seed(1000)
     model = pcoe.PointNetPPMvM(p_drop=0.0).to(dev).train()
     with torch.no_grad():
         model.head_mu.weight.normal_(0, 0.05)
-    eng = pcoe.dp.DataParallel(model, overlap=overlap)
+    eng = pcoe.dp.DataParallel(model, overlap=overlap, exchange=exchange)
     eng.zero_grad()
     micro = 2 if accumulate else 1
     for m in range(micro):
@@ -43,7 +46,7 @@ def grads(overlap: bool, accumulate: bool):
 
 ok = True
 for acc in (False, True):
-    a, b = grads(True, acc), grads(False, acc)
+    a, b = grads(True, acc, EXCHANGE), grads(False, acc, "nccl")
     # the weight-gradient kernels accumulate with fp32 atomics (order varies run to run), so two runs of the SAME
     # configuration differ at the 1e-7 level: compare to that noise floor, not bitwise
     rel = float((a - b).norm() / b.norm())
@@ -53,7 +56,7 @@ for acc in (False, True):
     dist.broadcast(other, src=0)
     agree = torch.equal(other, a)
     if rank == 0:
-        print(f"accumulate={acc}: overlap vs no-overlap rel-L2 {rel:.2e} (< 1e-5: {same}); ranks hold identical buffers: {agree}; |g| = {float(a.norm()):.6f}")
+        print(f"[{EXCHANGE}] accumulate={acc}: overlap vs no-overlap (nccl) rel-L2 {rel:.2e} (< 1e-5: {same}); ranks hold identical buffers: {agree}; |g| = {float(a.norm()):.6f}")
     ok = ok and same and agree
 if rank == 0:
     print("dp_overlap_check:", "PASS" if ok else "FAIL")
