@@ -14,7 +14,6 @@
 #include "sa_tc6.cuh"
 #include "pm_tma.cuh"
 #include "sa_layout.h"
-#include <type_traits>
 
 namespace pcoe {
 
@@ -502,8 +501,8 @@ static int launch_wgrad6(const PProd& pp, const QProd& qp, float* dW, int ldo, i
   splits = ceil_div(ntiles, tps);
   if constexpr (PProd::kAsync && QProd::kAsync) {
     // two producer groups (P units / Q units), each on its own cp.async ring: deepest pair of rings that fits beside
-    // one operand stage
-    const size_t up = (size_t)PProd::kRawItems * v6::kRawItemBytes, uq = (size_t)QProd::kRawItems * v6::kRawItemBytes;
+    // one operand stage (a 64-point Q unit of the gather producer is half the size of its 128-point forward unit)
+    const size_t up = (size_t)PProd::kRawItems * v6::kRawItemBytes, uq = (size_t)QProd::kRawItems64 * v6::kRawItemBytes;
     const size_t room = kSmemBudget6 - 1024 - cbytes - 65536;
     int dP = 0, dQ = 0;
     if (kSmemBudget6 > 1024 + cbytes + 65536) {

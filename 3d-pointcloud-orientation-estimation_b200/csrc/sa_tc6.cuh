@@ -250,6 +250,7 @@ struct BnRelu6 {
     }
   }
   static constexpr int kRawItems = 8;
+  static constexpr int kRawItems64 = kRawItems;
   template <int PTS>
   __device__ __forceinline__ void fetch(int g, int, int, uint32_t ub, Raw& r) const {
 #pragma unroll
@@ -460,6 +461,7 @@ struct GatherFeat6 {
   static constexpr bool kChMajor = false;
   static constexpr bool kAsync = true;
   static constexpr int kRawItems = 8;
+  static constexpr int kRawItems64 = 4;   // items of a 64-point unit (wgrad Q operand): two per 32 rows
   static constexpr int kUR = 4;       // unused (point-major): one unit per 64-channel block
   struct Raw { float4 a[4], b[4]; };
   GatherBase gb;
@@ -1199,6 +1201,25 @@ x3_dgrad_kernel(PProd pp, const __nv_bfloat16* __restrict__ Wp, size_t wps, int 
   if (warp == 0) tc::tmem_dealloc<256>(tmem);
 }
 
+// p[0..32) += v[0..32): scalar reductions up to the first 16-byte boundary, red.v4 from there, scalars for the rest
+template <int A>
+__device__ __forceinline__ void red_add_row32_at(float* p, const float (&v)[32]) {
+#pragma unroll
+  for (int e = 0; e < A; ++e) atomicAdd(p + e, v[e]);
+  constexpr int NV = (32 - A) / 4;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) red_add_v4(p + A + 4 * q, v[A + 4 * q], v[A + 4 * q + 1], v[A + 4 * q + 2], v[A + 4 * q + 3]);
+#pragma unroll
+  for (int e = A + 4 * NV; e < 32; ++e) atomicAdd(p + e, v[e]);
+}
+__device__ __forceinline__ void red_add_row32(float* p, const float (&v)[32]) {
+  const uint32_t lead = ((16u - ((uint32_t)(uintptr_t)p & 15u)) & 15u) >> 2;   // floats before the boundary
+  if (lead == 0) red_add_row32_at<0>(p, v);
+  else if (lead == 1) red_add_row32_at<1>(p, v);
+  else if (lead == 2) red_add_row32_at<2>(p, v);
+  else red_add_row32_at<3>(p, v);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // wgrad (2 planes): CTA (channel block, q block, split) accumulates dW[128 x nq] over its tiles in TMEM and adds it to
 // global memory at the end.  Stage = 64 points: [P hi | P lo | Q hi | Q lo], P = dy^T part [128 ch x 64 pts] (K-major),
@@ -1209,8 +1230,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_valid, int perm_d, int M, int tps, int nst, int depths) {
   PCOE_V6_PROLOGUE(128)
   constexpr int NP = 2;
+  constexpr uint32_t kUnitP = (uint32_t)PProd::kRawItems * kRawItemBytes;
   // ASYNC: raw staging rings of the two producer groups, depths = dP * 16 + dQ (see the producer branch)
-  const uint32_t kRawBytes = ASYNC ? ((uint32_t)(depths >> 4) * (uint32_t)PProd::kRawItems + (uint32_t)(depths & 15) * (uint32_t)QProd::kRawItems) * kRawItemBytes : 0u;
+  constexpr uint32_t kUnitQ = (uint32_t)QProd::kRawItems64 * kRawItemBytes;
+  const uint32_t kRawBytes = ASYNC ? (uint32_t)(depths >> 4) * kUnitP + (uint32_t)(depths & 15) * kUnitQ : 0u;
   if (ASYNC && tid == 0)
     for (int s = 0; s < kMaxStages6; ++s) tc::mbar_init(&bar.full[s], 2 * kProdThreads);   // both groups arrive
   const int cl0 = blockIdx.x * 128, qb = blockIdx.y;
@@ -1255,7 +1278,7 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
       const bool isP = warp >= 8;
       const int dP = depths >> 4, dQ = depths & 15;
       const int nu = isP ? kPU : nqu;
-      const uint32_t rawP = sRaw, rawQ = sRaw + (uint32_t)dP * (uint32_t)PProd::kRawItems * kRawItemBytes;
+      const uint32_t rawP = sRaw, rawQ = sRaw + (uint32_t)dP * kUnitP;
       struct Cur2 { int u, m0; };
       Cur2 cl{0, t0 * kPts}, cst = cl;
       auto adv = [&](Cur2& c) { if (++c.u == nu) { c.u = 0; c.m0 += 64; } };
@@ -1290,7 +1313,7 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
         }
         adv(cst);
       };
-      const uint32_t unitB = (uint32_t)(isP ? PProd::kRawItems : QProd::kRawItems) * kRawItemBytes;
+      const uint32_t unitB = isP ? kUnitP : kUnitQ;
       if ((isP ? dP : dQ) == 3) async_pipeline<3>(nstage * nu, isP ? rawP : rawQ, unitB, issue, consume);
       else async_pipeline<2>(nstage * nu, isP ? rawP : rawQ, unitB, issue, consume);
     } else {
@@ -1338,9 +1361,11 @@ x3_wgrad_kernel(PProd pp, QProd qp, float* __restrict__ dW, int ldo, int cq_vali
         if (crow >= pp.C) continue;
         float* dst = dW + (size_t)crow * ldo;
         const int cb = qb * 128 + cbk;
-        if (perm_d < 0 && (ldo & 3) == 0 && cb + 32 <= cq_valid && cbk + 32 <= nq) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) red_add_v4(dst + cb + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        if (cb + 32 <= cq_valid && cbk + 32 <= nq && (perm_d < 0 || cb + 32 <= perm_d)) {
+          // 32 consecutive destination columns (shifted by the 3 xyz columns under the layer-1 permutation): vector
+          // reductions wherever the row's address allows - every CTA of the grid adds into the same dW, and the
+          // number of L2 reduction operations is what the tail of this kernel costs
+          red_add_row32(dst + cb + (perm_d >= 0 ? 3 : 0), v);
         } else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {

@@ -72,7 +72,10 @@ class PeerExchange:
     (csrc/peer.cu) on torch's symmetric memory (every rank maps every peer's buffer and a small signal pad).  One node,
     <= 8 ranks, CUDA only; CUDA-graph capturable (flag epochs live on the device)."""
 
-    def __init__(self, group=None, max_ctas: int = 64, multicast: bool | None = None):
+    def __init__(self, group=None, max_ctas: int | None = None, multicast: bool | None = None):
+        """max_ctas: grid cap of the exchange kernel (default: 16 with an NVSwitch multicast mapping - one load and one
+        store per element saturate early - else 64).  multicast: use the multicast mapping when the fabric offers one
+        (default: yes, PCOE_PEER_MULTICAST=0 disables)."""
         import ctypes as C
         import torch.distributed._symmetric_memory as symm
         self._C, self._symm = C, symm
@@ -104,6 +107,8 @@ class PeerExchange:
                 self.mc_ptr = int(getattr(self._hb, "multicast_ptr", 0) or 0)
             except Exception:
                 self.mc_ptr = 0
+        if self.max_ctas is None:
+            self.max_ctas = 16 if self.mc_ptr else 64
         torch.cuda.synchronize()
         dist.barrier(self.group)                       # every rank's pad / buffer is zeroed before the first flag lands
         return self.flat
@@ -135,7 +140,7 @@ class DataParallel:
     head of the buffer and joins.  Both collectives are captured by ``pcoe.GraphedTrainStep``."""
 
     def __init__(self, module: torch.nn.Module, process_group=None, broadcast_buffers: bool = True, overlap: bool = True,
-                 exchange: str = "nccl"):
+                 exchange: str = "auto"):
         """exchange: 'nccl' (torch.distributed all-reduce: any backend), 'peer' (libpcoe's NVLink peer-memory kernel,
         PeerExchange) or 'auto' ('peer' when it can be set up - CUDA, <= 8 ranks, symmetric memory - else 'nccl')."""
         self.module = module

@@ -826,7 +826,7 @@ def main():
     ap.add_argument("--torch-optimizer", action="store_true",
                     help="torch.optim.Adam(fused) + clip_grad_norm_ instead of pcoe.optim.FusedAdam")
     ap.add_argument("--trunk-tf32", action="store_true", help="TF32 tensor-core cuBLAS kernels for the torch.nn trunk")
-    ap.add_argument("--exchange", choices=["nccl", "peer", "auto"], default=os.environ.get("PCOE_EXCHANGE", "nccl"),
+    ap.add_argument("--exchange", choices=["nccl", "peer", "auto"], default=os.environ.get("PCOE_EXCHANGE", "auto"),
                     help="gradient exchange at N > 1: torch.distributed (NCCL) all-reduce or libpcoe's NVLink peer-memory kernel")
     ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after backward instead of two overlapped buckets")
     ap.add_argument("--skip-allreduce", action="store_true", help="diagnostic: N>1 without the gradient exchange (INVALID as a result)")
