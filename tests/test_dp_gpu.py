@@ -27,9 +27,12 @@ def test_peer_allreduce_matches_nccl_exactly(world):
     assert r.returncode == 0 and "peer_worker: PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-def test_training_gradients_peer_vs_nccl_world2():
-    """Overlapped two-bucket exchange through the peer kernel == one torch.distributed all-reduce after backward."""
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_training_gradients_overlap_vs_single_allreduce_world2(exchange):
+    """the overlapped two-bucket exchange (through NCCL or through the peer kernel), with and without
+    gradient accumulation under no_sync(), == one torch.distributed all-reduce after backward; every rank holds the
+    same reduced buffer."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _run(2, "tools/dp_overlap_check.py", {"PCOE_EXCHANGE": "peer"}, port=29641)
+    r = _run(2, "tools/dp_overlap_check.py", {"PCOE_EXCHANGE": exchange}, port=29641 + (exchange == "peer"))
     assert r.returncode == 0 and "dp_overlap_check: PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
