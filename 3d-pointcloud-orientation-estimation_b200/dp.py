@@ -6,7 +6,9 @@ losses, so the batch is sharded with no data-path collective; the only exchange 
 mean.  BatchNorm batch statistics and running buffers stay rank-local (the north star: "allreduce
 for the MLP gradients only"), i.e. every rank behaves exactly like the reference run on its shard.
 
-Works with any torch.distributed backend (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+The exchange itself: libpcoe's peer-memory kernel on one NVLink node (PeerExchange, csrc/peer.cu: the flat buffer
+lives in symmetric memory, two flag exchanges and one pass over the data per call), or any torch.distributed backend
+(NCCL across nodes, gloo in the CPU tests) - ``DataParallel(exchange="auto" | "peer" | "nccl")``.
 """
 from __future__ import annotations
 
@@ -29,7 +31,6 @@ class FlatGradBuffer:
         dev, total = self.params[0].device, sum(p.numel() for p in self.params)
         self.total = total
         padded = (total + 3) // 4 * 4
-        self.total = total
         self.flat = torch.zeros(padded, dtype=torch.float32, device=dev) if alloc is None else alloc(padded, dev)
         off = 0
         for p in self.params:
