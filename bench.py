@@ -19,6 +19,9 @@ REFERENCE's sampler: the random subsets of every step are replayed on torch's CP
 overlapped with the running step), loss read back D2H every step, wall-clock timed.
 `modes`: the same step in the other precision modes (plain bf16 = throughput mode with a stated tolerance; fp32 =
 CUDA-core kernels), so all three are on record.
+N > 1: the gradient exchange inside the captured step is libpcoe's NVLink peer-memory all-reduce (csrc/peer.cu) when the
+ranks can map each other's memory, else torch.distributed's (`--exchange auto|peer|nccl`; `config.grad_exchange` says
+which one ran).
 """
 from __future__ import annotations
 
