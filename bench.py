@@ -20,7 +20,7 @@ overlapped with the running step), loss read back D2H every step, wall-clock tim
 `modes`: the same step in the other precision modes (plain bf16 = throughput mode with a stated tolerance; fp32 =
 CUDA-core kernels), so all three are on record.
 N > 1: the gradient exchange inside the captured step is libpcoe's NVLink peer-memory all-reduce (csrc/peer.cu) when the
-ranks can map each other's memory, else torch.distributed's (`--exchange auto|peer|nccl`; `config.grad_exchange` says
+ranks can map each other's memory, else torch.distributed's (`--exchange auto|peer|nccl`; the `grad_exchange` key says
 which one ran).
 """
 from __future__ import annotations
