@@ -76,7 +76,7 @@ class PeerExchange:
     def __init__(self, group=None, max_ctas: int | None = None, multicast: bool | None = None):
         """max_ctas: grid cap of the exchange kernel (default: 16 with an NVSwitch multicast mapping - one load and one
         store per element saturate early - else 64).  multicast: use the multicast mapping when the fabric offers one
-        (default: yes, PCOE_PEER_MULTICAST=0 disables)."""
+        (default: with more than 2 ranks; PCOE_PEER_MULTICAST=0 / 1 overrides)."""
         import ctypes as C
         import torch.distributed._symmetric_memory as symm
         self._C, self._symm = C, symm
@@ -86,7 +86,10 @@ class PeerExchange:
             raise ValueError("PeerExchange: at most 8 ranks (one NVSwitch node)")
         self.max_ctas = max_ctas
         if multicast is None:
-            multicast = os.environ.get("PCOE_PEER_MULTICAST", "1") != "0"
+            # with one peer the switch-side reduction saves nothing (one remote load either way) and the plain P2P loop
+            # with 64 CTAs is the faster one (23 vs 28-42 us for the whole buffer, profiles/r02_scaling.txt)
+            env = os.environ.get("PCOE_PEER_MULTICAST")
+            multicast = (env != "0") if env is not None else self.world > 2
         self._want_mc, self.mc_ptr = multicast, 0
         self.flat = None
         self.stream = torch.cuda.Stream()
